@@ -1,0 +1,557 @@
+// dwdf_api.cu — host side of libdwdf.so: validates and lowers the element tree to the flat program
+// the kernels consume, builds the TMA descriptors, sizes and launches the kernels, and implements
+// the extern "C" surface of include/dwdf.h. No torch, no Python: plain C++ over the CUDA runtime.
+#include "../../include/dwdf.h"
+#include "dwdf_kernels.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include <cudaTypedefs.h>
+
+using namespace dwdf;
+
+struct dwdf_program
+{
+    std::vector<dwdf_node> nodes;
+    dwdf_circuit_desc desc;
+    bool is_clipper = false;
+    ClipDesc clip {};
+    ClipVariant variant {};
+    TreeProgram tree {};
+    int n_states = 0;
+};
+
+namespace
+{
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches { 0 };
+std::atomic<int> g_use_tma { 1 };
+
+int fail (int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start (ap, fmt);
+    vsnprintf (g_err, sizeof (g_err), fmt, ap);
+    va_end (ap);
+    return code;
+}
+
+int cuda_fail (cudaError_t e, const char* what)
+{
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+        return fail (DWDF_ERR_NO_DEVICE, "%s: %s (libdwdf has no CPU fallback)", what, cudaGetErrorString (e));
+    return fail (DWDF_ERR_CUDA, "%s: %s", what, cudaGetErrorString (e));
+}
+
+#define DWDF_CUDA(call) \
+    do \
+    { \
+        cudaError_t e__ = (call); \
+        if (e__ != cudaSuccess) \
+            return cuda_fail (e__, #call); \
+    } while (0)
+
+// ---- TMA descriptors ----------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder ()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] () -> PFN_cuTensorMapEncodeTiled_v12000 {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint ("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (PFN_cuTensorMapEncodeTiled_v12000) p;
+    }();
+    return fn;
+}
+
+// (B, T) fp32 batch-major tensor, tiles of [32 sequences x tile_t samples]; rows of a tile are
+// tile_t*4 = 128 or 64 bytes and use the matching swizzle so that 32 lanes reading the same
+// 16-byte chunk index of their own rows hit 32 distinct banks.
+bool make_map (CUtensorMap* m, const float* base, int64_t B, int64_t T, int tile_t)
+{
+    auto enc = tensor_map_encoder ();
+    if (enc == nullptr)
+        return false;
+    const cuuint64_t dims[2] = { (cuuint64_t) T, (cuuint64_t) B };
+    const cuuint64_t strides[1] = { (cuuint64_t) T * 4 };
+    const cuuint32_t box[2] = { (cuuint32_t) tile_t, 32 };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUtensorMapSwizzle sw = tile_t == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    return enc (m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*> (base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool tma_usable (const void* a, const void* b, const void* c, int64_t B, int64_t T)
+{
+    if (! g_use_tma.load () || T % 4 != 0 || T < 4 || B < 1)
+        return false;
+    for (const void* p : { a, b, c })
+        if (p != nullptr && ((uintptr_t) p & 15u) != 0)
+            return false;
+    return tensor_map_encoder () != nullptr;
+}
+
+// ---- tree validation / lowering ---------------------------------------------------------------------
+bool is_leaf (int k) { return k == DWDF_RESISTOR || k == DWDF_CAPACITOR || k == DWDF_RESISTIVE_VS; }
+
+int64_t n_groups (int64_t B) { return (B + 31) / 32; }
+int64_t n_segments (int64_t T) { return (T + kSeg - 1) / kSeg; }
+} // namespace
+
+extern "C" {
+
+const char* dwdf_last_error (void) { return g_err; }
+const char* dwdf_build_info (void) { return "libdwdf " "v1 sm_100a cuda-12.9 tma+mbarrier fp32 no-cpu-fallback"; }
+int64_t dwdf_launch_count (void) { return g_launches.load (); }
+int dwdf_set_tma (int enable) { return g_use_tma.exchange (enable ? 1 : 0); }
+
+int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_circuit_desc* d, dwdf_program** out)
+{
+    if (out == nullptr || nodes == nullptr || d == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (n_nodes < 1 || n_nodes > DWDF_MAX_NODES)
+        return fail (DWDF_ERR_INVALID, "n_nodes %d outside [1, %d]", n_nodes, DWDF_MAX_NODES);
+    if (d->n_params < 1 || d->n_params > DWDF_MAX_PARAMS)
+        return fail (DWDF_ERR_INVALID, "n_params %d outside [1, %d]", d->n_params, DWDF_MAX_PARAMS);
+    if (! (d->fs > 0.0f))
+        return fail (DWDF_ERR_INVALID, "sample rate must be positive");
+    std::vector<int> parents (n_nodes, 0);
+    int n_states = 0;
+    for (int i = 0; i < n_nodes; ++i)
+    {
+        const dwdf_node& n = nodes[i];
+        if (n.kind < DWDF_RESISTOR || n.kind > DWDF_INVERTER)
+            return fail (DWDF_ERR_INVALID, "node %d: unknown kind %d", i, n.kind);
+        if (is_leaf (n.kind))
+        {
+            if (n.param < 0 || n.param >= d->n_params)
+                return fail (DWDF_ERR_INVALID, "node %d: leaf parameter slot %d outside [0, %d)", i, n.param, d->n_params);
+            if (n.kind == DWDF_CAPACITOR)
+                ++n_states;
+        }
+        else
+        {
+            const int need = n.kind == DWDF_INVERTER ? 1 : 2;
+            const int ch[2] = { n.child1, n.child2 };
+            for (int k = 0; k < need; ++k)
+            {
+                if (ch[k] < 0 || ch[k] >= i)
+                    return fail (DWDF_ERR_INVALID, "node %d: child %d must precede it (post-order)", i, ch[k]);
+                ++parents[ch[k]];
+            }
+        }
+    }
+    for (int i = 0; i < n_nodes - 1; ++i)
+        if (parents[i] != 1)
+            return fail (DWDF_ERR_INVALID, "node %d has %d parents (the circuit must be a tree whose top is the last node)", i, parents[i]);
+    if (d->probe < 0 || d->probe >= n_nodes)
+        return fail (DWDF_ERR_INVALID, "probe node %d out of range", d->probe);
+    if (d->ordering != DWDF_ORDER_PLUGIN && d->ordering != DWDF_ORDER_PYTHON)
+        return fail (DWDF_ERR_INVALID, "unknown ordering %d", d->ordering);
+    if (d->r_node >= n_nodes || (d->r_node >= 0 && nodes[d->r_node].kind != DWDF_RESISTOR && nodes[d->r_node].kind != DWDF_RESISTIVE_VS))
+        return fail (DWDF_ERR_INVALID, "r_node must be a Resistor or ResistiveVoltageSource leaf");
+    if (d->root_kind == DWDF_ROOT_DIODE_PAIR)
+    {
+        if (d->source < 0 || d->source >= n_nodes || nodes[d->source].kind != DWDF_RESISTIVE_VS)
+            return fail (DWDF_ERR_INVALID, "diode-pair circuits are driven through a ResistiveVoltageSource leaf (source = %d)", d->source);
+        if (d->root_mode < DWDF_MODE_APPROX || d->root_mode > DWDF_MODE_APPROX_GOOD)
+            return fail (DWDF_ERR_INVALID, "unknown root mode %d", d->root_mode);
+        if (d->param_Is < 0 || d->param_Is >= d->n_params || d->param_nabla < 0 || d->param_nabla >= d->n_params)
+            return fail (DWDF_ERR_INVALID, "diode parameter slots out of range");
+        if (! (d->Vt > 0.0f) || ! (d->n_up > 0.0f) || ! (d->n_down > 0.0f))
+            return fail (DWDF_ERR_INVALID, "Vt, n_up, n_down must be positive");
+        if (d->root_mode == DWDF_MODE_APPROX_GOOD && (d->n_up != 1.0f || d->n_down != 1.0f))
+            return fail (DWDF_ERR_UNSUPPORTED, "the eq.18 'Good' law is defined for a symmetric pair only");
+    }
+    else if (d->root_kind != DWDF_ROOT_IDEAL_VS)
+        return fail (DWDF_ERR_INVALID, "unknown root kind %d", d->root_kind);
+
+    dwdf_program* p = new (std::nothrow) dwdf_program;
+    if (p == nullptr)
+        return fail (DWDF_ERR_INVALID, "out of memory");
+    p->nodes.assign (nodes, nodes + n_nodes);
+    p->desc = *d;
+    p->n_states = n_states;
+
+    // flat program for the interpreter
+    TreeProgram& t = p->tree;
+    t.n_nodes = n_nodes;
+    int st = 0;
+    for (int i = 0; i < 16; ++i)
+    {
+        t.kind[i] = i < n_nodes ? nodes[i].kind : 0;
+        t.c1[i] = i < n_nodes ? nodes[i].child1 : -1;
+        t.c2[i] = i < n_nodes ? nodes[i].child2 : -1;
+        t.param[i] = i < n_nodes ? nodes[i].param : -1;
+        t.state_of[i] = (i < n_nodes && nodes[i].kind == DWDF_CAPACITOR) ? st++ : -1;
+    }
+    t.root_kind = d->root_kind;
+    t.root_mode = d->root_mode;
+    t.pyorder = d->ordering == DWDF_ORDER_PYTHON;
+    t.probe = d->probe;
+    t.source = d->source;
+    t.r_node = d->r_node;
+    t.slot_Is = d->param_Is;
+    t.slot_nabla = d->param_nabla;
+    t.n_params = d->n_params;
+    t.n_iter = d->newton_max_iter;
+    t.fs = d->fs;
+    t.Vt = d->Vt;
+    t.n_up = d->n_up;
+    t.n_down = d->n_down;
+    t.tol = d->newton_tol;
+    t.n_states = n_states;
+
+    // the diode clipper: Parallel(P1 = ResistiveVs, P2 = Capacitor) + DiodePair, probe on the capacitor
+    const bool clip_shape = d->root_kind == DWDF_ROOT_DIODE_PAIR && n_nodes == 3 && nodes[0].kind == DWDF_RESISTIVE_VS && nodes[1].kind == DWDF_CAPACITOR && nodes[2].kind == DWDF_PARALLEL
+                            && nodes[2].child1 == 0 && nodes[2].child2 == 1 && d->source == 0 && d->probe == 1 && d->r_node < 0 && d->root_mode != DWDF_MODE_APPROX_GOOD;
+    if (clip_shape)
+    {
+        const int s[4] = { nodes[0].param, nodes[1].param, d->param_Is, d->param_nabla };
+        bool distinct = true;
+        for (int a = 0; a < 4; ++a)
+            for (int b = a + 1; b < 4; ++b)
+                distinct = distinct && s[a] != s[b];
+        if (distinct)
+        {
+            p->is_clipper = true;
+            p->clip = ClipDesc { d->fs, d->Vt, d->n_up, d->n_down, d->newton_tol, d->newton_max_iter, s[0], s[1], s[2], s[3] };
+            p->variant = ClipVariant { d->root_mode == DWDF_MODE_EXACT ? kModeExact : kModeApprox, ! (d->n_up == 1.0f && d->n_down == 1.0f), d->ordering == DWDF_ORDER_PYTHON };
+        }
+    }
+    *out = p;
+    return DWDF_OK;
+}
+
+int dwdf_program_destroy (dwdf_program* prog)
+{
+    delete prog;
+    return DWDF_OK;
+}
+
+int dwdf_program_is_clipper (const dwdf_program* prog) { return prog != nullptr && prog->is_clipper ? 1 : 0; }
+int dwdf_program_n_states (const dwdf_program* prog) { return prog == nullptr ? 0 : (prog->is_clipper ? 1 : prog->n_states + 1); }
+
+size_t dwdf_ckpt_bytes (const dwdf_program* prog, int64_t B, int64_t T)
+{
+    if (prog == nullptr || B <= 0 || T <= 0)
+        return 0;
+    if (prog->is_clipper)
+        return (size_t) (n_segments (T) * B) * sizeof (float);
+    return 16; // the interpreter's adjoint keeps its own tape in the workspace
+}
+
+size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
+{
+    if (prog == nullptr || B <= 0 || T <= 0)
+        return 0;
+    size_t bytes = ((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256 * 256 + 256;
+    if (! prog->is_clipper) // per-sample tape of the interpreter adjoint: (n_states + 1) floats per sample
+        bytes += (size_t) B * (size_t) T * (size_t) (prog->n_states + 1) * sizeof (float);
+    return bytes;
+}
+
+static int check_batch (const dwdf_program* prog, const void* params, const void* x, int64_t B, int64_t T)
+{
+    if (prog == nullptr || params == nullptr || x == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if (B < 0 || T < 0 || T > (int64_t) 1 << 30 || B > (int64_t) 1 << 36)
+        return fail (DWDF_ERR_INVALID, "bad batch shape (%lld, %lld)", (long long) B, (long long) T);
+    return DWDF_OK;
+}
+
+static int forward_impl (const dwdf_program* prog, const float* params, const float* x, const float* r, float* y, float* z_ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream)
+{
+    if (int rc = check_batch (prog, params, x, B, T))
+        return rc;
+    if (y == nullptr)
+        return fail (DWDF_ERR_INVALID, "null output");
+    if (B == 0 || T == 0)
+        return DWDF_OK;
+    if ((prog->desc.r_node >= 0) != (r != nullptr))
+        return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
+    if (prog->is_clipper)
+    {
+        ClipTmaMaps maps;
+        const bool tma = tma_usable (x, y, nullptr, B, T) && make_map (&maps.x, x, B, T, 32) && make_map (&maps.y, y, B, T, 32);
+        DWDF_CUDA (launch_clipper_forward (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, state, B, T, stream));
+    }
+    else
+    {
+        DWDF_CUDA (launch_tree_forward (prog->tree, params, x, r, y, state, B, T, stream));
+    }
+    g_launches.fetch_add (1);
+    return DWDF_OK;
+}
+
+int dwdf_forward (const dwdf_program* prog, const float* params, const float* x, const float* r, float* y, float* z_ckpt, int64_t B, int64_t T, void* stream)
+{
+    return forward_impl (prog, params, x, r, y, z_ckpt, nullptr, B, T, (cudaStream_t) stream);
+}
+
+int dwdf_process_block (const dwdf_program* prog, const float* params, const float* x, const float* r, float* y, float* state, int64_t B, int64_t T, void* stream)
+{
+    if (state == nullptr)
+        return fail (DWDF_ERR_INVALID, "null state");
+    return forward_impl (prog, params, x, r, y, nullptr, state, B, T, (cudaStream_t) stream);
+}
+
+static int backward_impl (bool raw_only, const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t) stream_;
+    if (int rc = check_batch (prog, params, x, B, T))
+        return rc;
+    if (gy_or_target == nullptr || out == nullptr || workspace == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if (grad_mode != DWDF_GRAD_UPSTREAM && grad_mode != DWDF_GRAD_TARGET)
+        return fail (DWDF_ERR_INVALID, "unknown grad mode %d", grad_mode);
+    if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
+        return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
+    if (workspace_bytes < dwdf_workspace_bytes (prog, B, T))
+        return fail (DWDF_ERR_WORKSPACE, "workspace of %zu bytes, need %zu", workspace_bytes, dwdf_workspace_bytes (prog, B, T));
+    if (B == 0 || T == 0)
+        return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
+    if (prog->desc.root_kind == DWDF_ROOT_DIODE_PAIR && prog->desc.root_mode == DWDF_MODE_APPROX_GOOD)
+        return fail (DWDF_ERR_UNSUPPORTED, "the 'Good' diode law is forward only");
+    const bool target = grad_mode == DWDF_GRAD_TARGET;
+    const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
+    const double count = (double) B * (double) (T - sk);
+    double* partials = (double*) workspace;
+    if (prog->is_clipper)
+    {
+        if (z_ckpt == nullptr)
+            return fail (DWDF_ERR_INVALID, "the clipper adjoint replays from the checkpoints dwdf_forward wrote: z_ckpt is null");
+        ClipTmaMaps maps;
+        const bool tma = gx == nullptr && tma_usable (x, gy_or_target, nullptr, B, T) && make_map (&maps.x, x, B, T, kSeg) && make_map (&maps.y, gy_or_target, B, T, kSeg);
+        DWDF_CUDA (launch_clipper_adjoint (prog->variant, tma, &maps, prog->clip, params, x, z_ckpt, gy_or_target, target, sk, gx, partials, B, T, stream));
+        DWDF_CUDA (launch_clipper_finalize (prog->clip, params, partials, n_groups (B), nullptr, raw_only, target, loss_kind, count, out, stream));
+    }
+    else
+    {
+        if (gx != nullptr)
+            return fail (DWDF_ERR_UNSUPPORTED, "dL/dx is available for the diode-clipper program only");
+        if (r != nullptr)
+            return fail (DWDF_ERR_UNSUPPORTED, "gradients with a per-sample resistance channel are not implemented");
+        float* tape = (float*) ((char*) workspace + (((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256) * 256);
+        DWDF_CUDA (launch_tree_adjoint (prog->tree, params, x, r, gy_or_target, target, sk, partials, tape, B, T, stream));
+        DWDF_CUDA (launch_tree_finalize (prog->tree, params, partials, n_groups (B), nullptr, raw_only, target, loss_kind, count, out, stream));
+    }
+    g_launches.fetch_add (2);
+    return DWDF_OK;
+}
+
+int dwdf_backward (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
+{
+    return backward_impl (false, prog, params, x, r, z_ckpt, gy_or_target, grad_mode, loss_kind, skip, gx, out, workspace, workspace_bytes, B, T, stream);
+}
+
+int dwdf_backward_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int64_t skip, float* gx, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
+{
+    return backward_impl (true, prog, params, x, r, z_ckpt, gy_or_target, grad_mode, DWDF_LOSS_MSE, skip, gx, raw, workspace, workspace_bytes, B, T, stream);
+}
+
+int dwdf_finalize (const dwdf_program* prog, const float* params, int32_t grad_mode, int32_t loss_kind, double* raw_inout, void* stream)
+{
+    if (prog == nullptr || params == nullptr || raw_inout == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    const bool target = grad_mode == DWDF_GRAD_TARGET;
+    if (prog->is_clipper)
+        DWDF_CUDA (launch_clipper_finalize (prog->clip, params, nullptr, 0, raw_inout, false, target, loss_kind, 0.0, raw_inout, (cudaStream_t) stream));
+    else
+        DWDF_CUDA (launch_tree_finalize (prog->tree, params, nullptr, 0, raw_inout, false, target, loss_kind, 0.0, raw_inout, (cudaStream_t) stream));
+    g_launches.fetch_add (1);
+    return DWDF_OK;
+}
+
+static int train_impl (bool raw_only, const dwdf_program* prog, const float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t) stream_;
+    if (int rc = check_batch (prog, params, x, B, T))
+        return rc;
+    if (target == nullptr || out == nullptr || workspace == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if (! prog->is_clipper || r != nullptr)
+        return fail (DWDF_ERR_UNSUPPORTED, "the fused training pass exists for the diode-clipper program only");
+    if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
+        return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
+    if (workspace_bytes < dwdf_workspace_bytes (prog, B, T))
+        return fail (DWDF_ERR_WORKSPACE, "workspace of %zu bytes, need %zu", workspace_bytes, dwdf_workspace_bytes (prog, B, T));
+    if (B == 0 || T == 0)
+        return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
+    const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
+    double* partials = (double*) workspace;
+    ClipTmaMaps maps[2];
+    bool tma = tma_usable (x, target, y, B, T) && make_map (&maps[0].x, x, B, T, 32) && make_map (&maps[0].y, target, B, T, 32);
+    if (tma && y != nullptr)
+        tma = make_map (&maps[1].y, y, B, T, 32);
+    else if (tma)
+        maps[1].y = maps[0].y;
+    DWDF_CUDA (launch_clipper_train (prog->variant, tma, maps, prog->clip, params, x, target, sk, y, partials, B, T, stream));
+    DWDF_CUDA (launch_clipper_finalize (prog->clip, params, partials, n_groups (B), nullptr, raw_only, true, loss_kind, (double) B * (double) (T - sk), out, stream));
+    g_launches.fetch_add (2);
+    return DWDF_OK;
+}
+
+int dwdf_train_pass (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
+{
+    return train_impl (false, prog, params, x, r, target, loss_kind, skip, y, out, workspace, workspace_bytes, B, T, stream);
+}
+
+int dwdf_train_pass_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* target, int64_t skip, float* y, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
+{
+    return train_impl (true, prog, params, x, r, target, DWDF_LOSS_MSE, skip, y, raw, workspace, workspace_bytes, B, T, stream);
+}
+
+int dwdf_adam_step (float* params, const double* out, float* m, float* v, int32_t* step, int32_t n_params, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, double grad_scale, const float* lo, const float* hi, void* stream)
+{
+    if (params == nullptr || out == nullptr || m == nullptr || v == nullptr || step == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if (n_params < 1 || n_params > DWDF_MAX_PARAMS)
+        return fail (DWDF_ERR_INVALID, "n_params out of range");
+    DWDF_CUDA (launch_adam (params, out, m, v, step, n_params, lr, lr_per_slot, beta1, beta2, eps, grad_scale, lo, hi, (cudaStream_t) stream));
+    g_launches.fetch_add (1);
+    return DWDF_OK;
+}
+
+// ---- end-to-end calls with host buffers ----------------------------------------------------------
+// Library-owned device arena (grow-only, one per process) and a small set of streams: the batch is
+// cut into row chunks so that the host->device copy of chunk k+1, the kernels of chunk k and the
+// device->host copy of chunk k-1 overlap (PCIe is full duplex; the copy engines run beside the SMs).
+namespace
+{
+struct Arena
+{
+    std::mutex mu;
+    char* dev = nullptr;
+    size_t cap = 0;
+    cudaStream_t streams[3] = { nullptr, nullptr, nullptr };
+    cudaEvent_t done[3] = { nullptr, nullptr, nullptr };
+    cudaEvent_t params_ready = nullptr;
+    int ensure (size_t bytes)
+    {
+        if (streams[0] == nullptr)
+        {
+            DWDF_CUDA (cudaEventCreateWithFlags (&params_ready, cudaEventDisableTiming));
+            for (int i = 0; i < 3; ++i)
+            {
+                DWDF_CUDA (cudaStreamCreateWithFlags (&streams[i], cudaStreamNonBlocking));
+                DWDF_CUDA (cudaEventCreateWithFlags (&done[i], cudaEventDisableTiming));
+            }
+        }
+        if (bytes <= cap)
+            return DWDF_OK;
+        if (dev != nullptr)
+            DWDF_CUDA (cudaFree (dev));
+        dev = nullptr;
+        cap = 0;
+        DWDF_CUDA (cudaMalloc ((void**) &dev, bytes));
+        cap = bytes;
+        return DWDF_OK;
+    }
+};
+Arena g_arena;
+size_t align256 (size_t n) { return (n + 255) / 256 * 256; }
+constexpr int64_t kChunkRows = 4096; // rows per pipelined chunk (64 MiB of x at T = 4096)
+} // namespace
+
+int dwdf_forward_host (const dwdf_program* prog, const float* params_host, const float* x_host, const float* r_host, float* y_host, int64_t B, int64_t T)
+{
+    if (int rc = check_batch (prog, params_host, x_host, B, T))
+        return rc;
+    if (y_host == nullptr)
+        return fail (DWDF_ERR_INVALID, "null output");
+    if (B == 0 || T == 0)
+        return DWDF_OK;
+    std::lock_guard<std::mutex> lock (g_arena.mu);
+    const size_t row = (size_t) T * sizeof (float), bt = (size_t) B * row;
+    const size_t off_x = 256, off_y = off_x + align256 (bt), off_r = off_y + align256 (bt);
+    if (int rc = g_arena.ensure (off_r + (r_host != nullptr ? align256 (bt) : 0)))
+        return rc;
+    float* d_params = (float*) g_arena.dev;
+    float *d_x = (float*) (g_arena.dev + off_x), *d_y = (float*) (g_arena.dev + off_y), *d_r = r_host != nullptr ? (float*) (g_arena.dev + off_r) : nullptr;
+    DWDF_CUDA (cudaMemcpyAsync (d_params, params_host, sizeof (float) * prog->desc.n_params, cudaMemcpyHostToDevice, g_arena.streams[0]));
+    DWDF_CUDA (cudaEventRecord (g_arena.params_ready, g_arena.streams[0]));
+    int k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += kChunkRows, ++k)
+    {
+        const int64_t nb = B - b0 < kChunkRows ? B - b0 : kChunkRows;
+        cudaStream_t s = g_arena.streams[k % 3];
+        if (k < 3 && k > 0)
+            DWDF_CUDA (cudaStreamWaitEvent (s, g_arena.params_ready, 0)); // parameters uploaded
+        DWDF_CUDA (cudaMemcpyAsync (d_x + b0 * T, x_host + b0 * T, (size_t) nb * row, cudaMemcpyHostToDevice, s));
+        if (d_r != nullptr)
+            DWDF_CUDA (cudaMemcpyAsync (d_r + b0 * T, r_host + b0 * T, (size_t) nb * row, cudaMemcpyHostToDevice, s));
+        if (int rc = forward_impl (prog, d_params, d_x + b0 * T, d_r != nullptr ? d_r + b0 * T : nullptr, d_y + b0 * T, nullptr, nullptr, nb, T, s))
+            return rc;
+        DWDF_CUDA (cudaMemcpyAsync (y_host + b0 * T, d_y + b0 * T, (size_t) nb * row, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 3; ++i)
+        DWDF_CUDA (cudaStreamSynchronize (g_arena.streams[i]));
+    return DWDF_OK;
+}
+
+int dwdf_grad_host (const dwdf_program* prog, const float* params_host, const float* x_host, const float* r_host, const float* g_host, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* y_host, double* out_host, int64_t B, int64_t T)
+{
+    if (int rc = check_batch (prog, params_host, x_host, B, T))
+        return rc;
+    if (g_host == nullptr || out_host == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if (! prog->is_clipper || r_host != nullptr)
+        return fail (DWDF_ERR_UNSUPPORTED, "dwdf_grad_host covers the diode-clipper program; use the device API for other trees");
+    if (B == 0 || T == 0)
+        return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
+    std::lock_guard<std::mutex> lock (g_arena.mu);
+    const bool target = grad_mode == DWDF_GRAD_TARGET;
+    const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
+    const size_t row = (size_t) T * sizeof (float), bt = (size_t) B * row;
+    const size_t ck = align256 ((size_t) (n_segments (T) * B) * sizeof (float));
+    const size_t pb = align256 ((size_t) (n_groups (B) + B / kChunkRows + 2) * kPartialStride * sizeof (double));
+    const size_t off_out = 256, off_x = 1024, off_g = off_x + align256 (bt), off_y = off_g + align256 (bt), off_ck = off_y + align256 (bt), off_p = off_ck + ck;
+    if (int rc = g_arena.ensure (off_p + pb))
+        return rc;
+    float* d_params = (float*) g_arena.dev;
+    double* d_out = (double*) (g_arena.dev + off_out);
+    float *d_x = (float*) (g_arena.dev + off_x), *d_g = (float*) (g_arena.dev + off_g), *d_y = (float*) (g_arena.dev + off_y), *d_ck = (float*) (g_arena.dev + off_ck);
+    double* d_part = (double*) (g_arena.dev + off_p);
+    DWDF_CUDA (cudaMemcpyAsync (d_params, params_host, sizeof (float) * prog->desc.n_params, cudaMemcpyHostToDevice, g_arena.streams[0]));
+    DWDF_CUDA (cudaEventRecord (g_arena.params_ready, g_arena.streams[0]));
+    int k = 0;
+    int64_t group0 = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += kChunkRows, ++k)
+    {
+        const int64_t nb = B - b0 < kChunkRows ? B - b0 : kChunkRows;
+        cudaStream_t s = g_arena.streams[k % 3];
+        if (k < 3 && k > 0)
+            DWDF_CUDA (cudaStreamWaitEvent (s, g_arena.params_ready, 0));
+        DWDF_CUDA (cudaMemcpyAsync (d_x + b0 * T, x_host + b0 * T, (size_t) nb * row, cudaMemcpyHostToDevice, s));
+        DWDF_CUDA (cudaMemcpyAsync (d_g + b0 * T, g_host + b0 * T, (size_t) nb * row, cudaMemcpyHostToDevice, s));
+        float* ckc = d_ck + (size_t) n_segments (T) * b0; // each chunk owns a (segments, nb) checkpoint block
+        if (int rc = forward_impl (prog, d_params, d_x + b0 * T, nullptr, d_y + b0 * T, ckc, nullptr, nb, T, s))
+            return rc;
+        if (y_host != nullptr)
+            DWDF_CUDA (cudaMemcpyAsync (y_host + b0 * T, d_y + b0 * T, (size_t) nb * row, cudaMemcpyDeviceToHost, s));
+        ClipTmaMaps maps;
+        const bool tma = tma_usable (d_x + b0 * T, d_g + b0 * T, nullptr, nb, T) && make_map (&maps.x, d_x + b0 * T, nb, T, kSeg) && make_map (&maps.y, d_g + b0 * T, nb, T, kSeg);
+        DWDF_CUDA (launch_clipper_adjoint (prog->variant, tma, &maps, prog->clip, d_params, d_x + b0 * T, ckc, d_g + b0 * T, target, sk, nullptr, d_part + group0 * kPartialStride, nb, T, s));
+        g_launches.fetch_add (1);
+        group0 += n_groups (nb);
+        DWDF_CUDA (cudaEventRecord (g_arena.done[k % 3], s));
+    }
+    // join on stream 0, reduce, read back
+    for (int i = 1; i < 3; ++i)
+        DWDF_CUDA (cudaStreamWaitEvent (g_arena.streams[0], g_arena.done[i], 0));
+    DWDF_CUDA (launch_clipper_finalize (prog->clip, d_params, d_part, group0, nullptr, false, target, loss_kind, (double) B * (double) (T - sk), d_out, g_arena.streams[0]));
+    g_launches.fetch_add (1);
+    DWDF_CUDA (cudaMemcpyAsync (out_host, d_out, DWDF_OUT_LEN * sizeof (double), cudaMemcpyDeviceToHost, g_arena.streams[0]));
+    for (int i = 0; i < 3; ++i)
+        DWDF_CUDA (cudaStreamSynchronize (g_arena.streams[i]));
+    return DWDF_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,70 @@
+// dwdf_kernels.h — host-callable launchers of the CUDA kernels (internal; the public surface is
+// include/dwdf.h). Each launcher enqueues on `stream` and returns the cudaError_t of the launch.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "dwdf_math.cuh"
+
+namespace dwdf
+{
+
+constexpr int kSeg = 16; // capacitor-state checkpoint spacing [samples]; also the adjoint's segment
+constexpr int kPartialStride = 8; // doubles per sequence-group in the clipper partials buffer
+constexpr int kTreePartialStride = 24; // ... in the tree interpreter partials buffer
+// partial sums one warp (32 sequences) hands to the finalize kernel
+enum : int
+{
+    kAccGamma = 0, // sum G dz'/dgamma
+    kAccEll = 1, // sum G dz'/d ell,  ell = ln(Rp Is)
+    kAccV = 2, // sum G dz'/dV
+    kAccSse = 3, // sum (y - target)^2
+    kAccSt2 = 4 // sum target^2
+};
+
+struct ClipVariant
+{
+    int mode; // kModeApprox / kModeExact
+    bool general; // N_up / N_down law
+    bool pyorder; // probe after tree.incident
+};
+
+// TMA descriptors of one launch (valid only when use_tma)
+struct ClipTmaMaps
+{
+    CUtensorMap x, y; // forward: 32 x 32 tiles, 128-byte swizzle; adjoint: 16 x 32 tiles, 64-byte swizzle
+};
+
+cudaError_t launch_clipper_forward (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, float* y, float* ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream);
+
+// adjoint: raw sums per group of 32 sequences into partials[(group0 + group) * kPartialStride + k]
+cudaError_t launch_clipper_adjoint (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* ckpt, const float* g, bool target, int64_t skip, float* gx, double* partials, int64_t B, int64_t T, cudaStream_t stream);
+
+// fused training pass: forward + loss + parameter sensitivities in one sweep
+cudaError_t launch_clipper_train (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* target, int64_t skip, float* y, double* partials, int64_t B, int64_t T, cudaStream_t stream);
+
+// fixed-order reduction of the partials + chain rule to (Is, nabla, R, C) + loss -> out[DWDF_OUT_LEN]
+cudaError_t launch_clipper_finalize (const ClipDesc& desc, const float* params, const double* partials, int64_t n_groups, const double* raw_in, bool raw_only, bool target, int loss_kind, double count, double* out, cudaStream_t stream);
+
+cudaError_t launch_adam (float* params, const double* out, float* m, float* v, int32_t* step, int n_params, float lr, const float* lr_vec, float beta1, float beta2, float eps, double grad_scale, const float* lo, const float* hi, cudaStream_t stream);
+
+// ---- generic tree interpreter -----------------------------------------------------------------
+struct TreeProgram // by-value kernel argument (fits the 4 KB parameter space comfortably)
+{
+    int n_nodes;
+    int kind[16], c1[16], c2[16], param[16];
+    int root_kind, root_mode, pyorder, probe, source, r_node;
+    int slot_Is, slot_nabla, n_params, n_iter;
+    float fs, Vt, n_up, n_down, tol;
+    int n_states;
+    int state_of[16]; // capacitor node -> state index
+};
+
+cudaError_t launch_tree_forward (const TreeProgram& p, const float* params, const float* x, const float* r, float* y, float* state, int64_t B, int64_t T, cudaStream_t stream);
+// reverse-mode gradient of the interpreter (linear trees closed by an ideal voltage source or a
+// diode pair): per-sequence tape in `tape` (device scratch), raw dL/dparam partials per group.
+cudaError_t launch_tree_adjoint (const TreeProgram& p, const float* params, const float* x, const float* r, const float* g, bool target, int64_t skip, double* partials, float* tape, int64_t B, int64_t T, cudaStream_t stream);
+cudaError_t launch_tree_finalize (const TreeProgram& p, const float* params, const double* partials, int64_t n_groups, const double* raw_in, bool raw_only, bool target, int loss_kind, double count, double* out, cudaStream_t stream);
+
+} // namespace dwdf

@@ -1,0 +1,363 @@
+// dwdf_math.cuh — scalar arithmetic of the WDF hot path, written for the sm_100a FMA/ALU pipes.
+//
+// What is computed follows the reference (cited per function); how it is computed does not:
+// floor/ldexp are done with round-down magic-number adds and integer adds on the exponent field
+// instead of float<->int conversions (the conversion/MUFU pipe issues at 1/8 the FMA rate),
+// divisions are MUFU.RCP + FMUL, every select is branch-free, polynomials are FMA Horner chains.
+//
+// The functions are __host__ __device__ so that tests/ can compile the same source with g++ and
+// check the logic against the oracle on a machine without a GPU; the product only ever calls them
+// from kernels.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define DWDF_HD __host__ __device__ __forceinline__
+#else
+#define DWDF_HD inline
+#endif
+
+namespace dwdf
+{
+
+// ---- bit casts / primitives -----------------------------------------------------------------
+DWDF_HD float i2f (int32_t i)
+{
+#if defined(__CUDA_ARCH__)
+    return __int_as_float (i);
+#else
+    float f;
+    std::memcpy (&f, &i, 4);
+    return f;
+#endif
+}
+DWDF_HD int32_t f2i (float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_int (f);
+#else
+    int32_t i;
+    std::memcpy (&i, &f, 4);
+    return i;
+#endif
+}
+// reciprocal: one MUFU.RCP (<= 1 ulp) on the device
+DWDF_HD float rcp (float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+// x + y rounded toward -inf (FADD.RM)
+DWDF_HD float add_rd (float x, float y)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd_rd (x, y);
+#else
+    double s = (double) x + (double) y; // exact in double for the magnitudes used here
+    float f = (float) s;
+    if ((double) f > s)
+        f = std::nextafterf (f, -INFINITY);
+    return f;
+#endif
+}
+DWDF_HD float fma_ (float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn (a, b, c);
+#else
+    return std::fmaf (a, b, c);
+#endif
+}
+
+// ---- omega.h: the "approx" Wright-omega ----------------------------------------------------
+// exp_approx, omega.h:99-116 (with pow2_approx :83-92): 2^floor(x') * cubic(x' - floor(x')),
+// x' = max(-126, x * log2(e)).
+//   floor: x' + 1.5*2^23 rounded DOWN leaves floor(x') in the low mantissa bits (one FADD.RM),
+//   ldexp: (bits << 23) added to the polynomial's exponent field (the magic constant's own bits
+//          shift out).
+// Differs from the reference only at negative integer x', where omega.h's truncation quirk picks
+// (l = x'-1, f = 1) and this picks (l = x', f = 0): both are 2^x' to 1.3e-5 (cubic end-point error).
+DWDF_HD float exp_approx_scaled (float xp) // takes x' = x * log2(e)
+{
+    const float kMagic = 12582912.0f; // 1.5 * 2^23
+    xp = fmaxf (xp, -126.0f);
+    const float t = add_rd (xp, kMagic);
+    const float l = t - kMagic;
+    const float f = xp - l;
+    const float p = fma_ (f, fma_ (f, fma_ (f, 0.07944154167983575f, 0.2274112777602189f), 0.6931471805599453f), 1.0f);
+    return i2f (f2i (p) + (int32_t) ((uint32_t) f2i (t) << 23));
+}
+DWDF_HD float exp_approx (float x) { return exp_approx_scaled (1.442695040888963f * x); }
+
+// log_approx, omega.h:49-63 (with log2_approx :33-42), for x > 0: ln2 * (exponent + cubic(mantissa)).
+//   exponent as float without I2F: (bits >> 23) OR'ed into the mantissa of 2^23, minus (2^23 + 127).
+DWDF_HD float log_approx_pos (float x)
+{
+    const int32_t bits = f2i (x);
+    const float m = i2f ((bits & 0x007fffff) | 0x3f800000);
+    const float e = i2f ((bits >> 23) | 0x4b000000) - 8388735.0f;
+    const float p = fma_ (m, fma_ (m, fma_ (m, 0.1640425613334452f, -1.098865286222744f), 3.148297929334117f), -2.213475204444817f);
+    return 0.693147180559945f * (e + p);
+}
+
+// omega3, omega.h:159-169
+DWDF_HD float omega3_approx (float x)
+{
+    const float cub = fma_ (x, fma_ (x, fma_ (x, -1.314293149877800e-3f, 4.775931364975583e-2f), 3.631952663804445e-1f), 6.313183464296682e-1f);
+    const float lg = x - log_approx_pos (x);
+    float y = x < 8.0f ? cub : lg;
+    y = x < -3.341459552768620f ? 0.0f : y;
+    return y;
+}
+
+// omega4, omega.h:172-177: omega3 + one Newton step on  w - exp(x - w)
+DWDF_HD float omega4_approx (float x)
+{
+    const float y = omega3_approx (x);
+    const float e = exp_approx (x - y);
+    return y - (y - e) * rcp (y + 1.0f);
+}
+
+constexpr float kOmega3Zero = -3.341459552768620f; // below this omega3 == 0 and omega4(x) == exp_approx(x)
+
+// ---- "exact" Wright-omega in fp32 ---------------------------------------------------------------
+// Replaces Toms917DiodePair.h:64-67 (float -> complex<double> TOMS-917 -> float) and
+// scipy.special.wrightomega (diode_pretraining.py:57-58). Same published algorithm (Lawrence,
+// Corless & Jeffrey, ACM TOMS 917) restricted to the real axis, where only three of its regions
+// are reachable (toms917.cpp:240-261,290-296): a series start, then Fritsch-Shafer-Crowley
+// iterations (toms917.cpp:345-364). Evaluated in fp32: one FSC iteration already reaches fp32
+// round-off (measured <= 3e-7 relative on x in [-60, 300]); n_iter (default 2, like TOMS-917)
+// and tol bound the refinement ("Newton tolerance").
+//   For x <= -2 the residual x - w - ln(w) cancels catastrophically in fp32; there w = e^x * s and
+//   ln(w) = x + log1p(s - 1) exactly, so r = -(w + log1p(s - 1)) has no cancellation.
+DWDF_HD float fsc_step (float w, float r)
+{
+    const float wp1 = w + 1.0f;
+    const float q = 2.0f * wp1 * fma_ (0.66666666666666667f, r, wp1);
+    const float e = (r * (q - r)) / (wp1 * fma_ (-2.0f, r, q));
+    return fma_ (w, e, w);
+}
+
+DWDF_HD float omega_exact (float x, int n_iter, float tol)
+{
+    float w;
+    if (x <= -2.0f)
+    { // series in e^x
+        const float e = expf (x);
+        const float sig = e * fma_ (e, fma_ (e, fma_ (e, 5.2083333333333333f, -2.6666666666666667f), 1.5f), -1.0f);
+        w = fma_ (e, sig, e);
+        if (x > -17.5f) // below: e^x < 2.6e-8 and the series is already exact to fp32
+            w = fsc_step (w, -(w + log1pf (sig)));
+        return w; // one quartic step from <= 4e-4 is far below fp32 round-off
+    }
+    else if (x <= 4.141592653589793f)
+    { // series about x = 1
+        const float p = x - 1.0f;
+        const float s = fma_ (p, fma_ (p, fma_ (p, 2.1158854166666667e-4f, -3.2552083333333333e-4f), -5.2083333333333333e-3f), 0.0625f);
+        w = fma_ (p * p, s, fma_ (0.5f, x, 0.5f));
+        w = fsc_step (w, (x - w) - logf (w));
+    }
+    else
+    { // asymptotic series in ln(x)
+        const float l = logf (x);
+        const float it = 1.0f / x;
+        const float li = l * it;
+        w = (x - l) + li * (1.0f + it * (fma_ (0.5f, l, -1.0f) + it * fma_ (l, fma_ (l, 0.33333333333333333f, -1.5f), 1.0f)));
+        w = fsc_step (w, (x - w) - logf (w));
+    }
+    for (int k = 1; k < n_iter; ++k)
+    {
+        const float r = (x - w) - logf (w);
+        if (fabsf (r) <= tol)
+            break;
+        w = fsc_step (w, r);
+    }
+    return w;
+}
+
+// ---- diode-pair root ---------------------------------------------------------------------------
+enum : int
+{
+    kModeApprox = 0,
+    kModeExact = 1,
+    kModeApproxGood = 2
+};
+
+// Constants of one root at one port impedance: wdf_t.h:875-882 (setDiodeParameters) and :928-933
+// (calcImpedanceInternal); Toms917DiodePair.h:28-42 is identical. The general law adds the
+// per-branch logs of diode_pretraining.py:49-50.
+struct PairConst
+{
+    float V, twoV, invV; // V = nDiodes * Vt
+    float L; // ln(Rp * Is / V)
+    float RIs, RIs_overV; // "Good" law only
+    float n_up, n_dn, L_up, L_dn, inv_up, inv_dn; // general law: mu, ln(Rp Is / (V mu)), 1 / (mu V)
+    int n_iter;
+    float tol;
+};
+
+DWDF_HD void pair_setup (PairConst& c, float Rp, float Is, float Vt, float nabla, float n_up, float n_down, int n_iter, float tol)
+{
+    c.V = nabla * Vt;
+    c.twoV = 2.0f * c.V;
+    c.invV = 1.0f / c.V;
+    c.RIs = Rp * Is;
+    c.RIs_overV = c.RIs * c.invV;
+    c.L = logf (c.RIs_overV);
+    c.n_up = n_up;
+    c.n_dn = n_down;
+    c.L_up = logf (c.RIs_overV / n_up);
+    c.L_dn = logf (c.RIs_overV / n_down);
+    c.inv_up = 1.0f / (n_up * c.V);
+    c.inv_dn = 1.0f / (n_down * c.V);
+    c.n_iter = n_iter <= 0 ? 2 : n_iter;
+    c.tol = tol;
+}
+
+template <int MODE>
+DWDF_HD float root_omega (const PairConst& c, float u)
+{
+    if (MODE == kModeExact)
+        return omega_exact (u, c.n_iter, c.tol);
+    return omega4_approx (u);
+}
+
+// Derivative pieces of b = f(a; ell, V) with ell = ln(Rp Is), omega' = omega / (1 + omega):
+//   S1 = w0' + w1'                       df/da      = 1 - 2 S1
+//   M1 = lambda (mu0 w0' - mu1 w1')      df/d ell   = -2 V M1
+//   dV = (b - a)/V + 2 M1 + 2 (a/V) S1   df/dV at fixed ell
+struct PairDeriv
+{
+    float S1, M1, dV;
+};
+
+// b = f(a).  Symmetric (eq. 39): wdf_t.h:917-924 == Toms917DiodePair.h:51-59.
+//            General   (eq. 45): diode_pretraining.py:39-60 with N_up / N_down.
+//            Good      (eq. 18): wdf_t.h:907-913.
+// LSMALL: the caller guarantees L < kOmega3Zero (true for every physical diode: Rp*Is << V), so
+// the reverse-branch omega4(L - |a|/V) is exactly exp_approx(L - |a|/V) (omega3 == 0 there) and the
+// cubic / log / Newton work is skipped. Approx + symmetric only.
+template <int MODE, bool GENERAL, bool DERIV, bool LSMALL>
+DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
+{
+    const float aa = fabsf (a);
+    float w0, w1, mu0 = 1.0f, mu1 = 1.0f, s; // s = 2 V lambda, lambda = signum(a) (signum.h:5-9; 0 at a == 0)
+    if (MODE == kModeApproxGood)
+    {
+        w0 = omega4_approx (c.L + aa * c.invV + c.RIs_overV);
+        const float lam = (0.0f < a) - (a < 0.0f);
+        return a + 2.0f * lam * (c.RIs - c.V * w0);
+    }
+    if (GENERAL)
+    {
+        const bool pos = a >= 0.0f; // diode_pretraining.py:46-47
+        mu0 = pos ? c.n_dn : c.n_up;
+        mu1 = pos ? c.n_up : c.n_dn;
+        const float l0 = pos ? c.L_dn : c.L_up, l1 = pos ? c.L_up : c.L_dn;
+        const float q0 = aa * (pos ? c.inv_dn : c.inv_up), q1 = aa * (pos ? c.inv_up : c.inv_dn);
+        w0 = root_omega<MODE> (c, l0 + q0);
+        w1 = root_omega<MODE> (c, l1 - q1);
+    }
+    else
+    {
+        const float q = aa * c.invV;
+        w0 = root_omega<MODE> (c, c.L + q);
+        if (MODE == kModeApprox && LSMALL)
+            w1 = exp_approx (c.L - q);
+        else
+            w1 = root_omega<MODE> (c, c.L - q);
+    }
+    s = a == 0.0f ? 0.0f : copysignf (c.twoV, a);
+    const float diff = GENERAL ? fma_ (mu0, w0, -(mu1 * w1)) : (w0 - w1);
+    const float b = fma_ (-s, diff, a);
+    if (DERIV)
+    {
+        const float wp0 = w0 * rcp (1.0f + w0), wp1 = w1 * rcp (1.0f + w1);
+        const float lam = a == 0.0f ? 0.0f : copysignf (1.0f, a);
+        d->S1 = wp0 + wp1;
+        d->M1 = lam * (GENERAL ? fma_ (mu0, wp0, -(mu1 * wp1)) : (wp0 - wp1));
+        d->dV = fma_ (2.0f * a * c.invV, d->S1, fma_ (b - a, c.invV, 2.0f * d->M1));
+    }
+    return b;
+}
+
+// ---- the diode clipper: Parallel(ResistiveVoltageSource, Capacitor) closed by a DiodePair ------
+// Constants of tf_wdf.py:168-177 / wdf_t.h:465-470 with P1 = Vs, P2 = C; Capacitor tf_wdf.py:114-115.
+struct ClipConst
+{
+    float gamma; // p1R = Gv / G
+    float Rp; // port resistance seen by the root
+    PairConst pair;
+};
+
+struct ClipDesc // by-value kernel argument: everything that is not a trainable parameter
+{
+    float fs, Vt, n_up, n_down, tol;
+    int n_iter;
+    int slot_R, slot_C, slot_Is, slot_nabla; // positions in the parameter vector
+};
+
+DWDF_HD void clip_setup (ClipConst& c, const ClipDesc& d, float R, float C, float Is, float nabla)
+{
+    const float Gv = 1.0f / R;
+    const float Rc = 1.0f / (2.0f * C * d.fs);
+    const float Gc = 1.0f / Rc;
+    const float G = Gv + Gc;
+    c.Rp = 1.0f / G;
+    c.gamma = Gv / G;
+    pair_setup (c.pair, c.Rp, Is, d.Vt, nabla, d.n_up, d.n_down, d.n_iter, d.tol);
+}
+
+// One sample of clipper_pot.py:113-124 / DiodeClipperWDF.cpp:24-29:
+//   up-sweep   b_diff = z - x; b_temp = -p1R b_diff; a = z + b_temp        (tf_wdf.py:185-192)
+//   root       b = f(a)
+//   down-sweep z' = b + b_temp  (Capacitor.incident, tf_wdf.py:120-122,179-183)
+//   probe      voltage(C): python ordering (z' + z)/2, plugin ordering z
+template <int MODE, bool GENERAL, bool LSMALL, bool PYORDER>
+DWDF_HD float clip_step (const ClipConst& c, float x, float& z)
+{
+    const float t = -c.gamma * (z - x);
+    const float a = z + t;
+    const float b = pair_reflect<MODE, GENERAL, false, LSMALL> (c.pair, a, nullptr);
+    const float zn = b + t;
+    const float y = PYORDER ? 0.5f * (zn + z) : z;
+    z = zn;
+    return y;
+}
+
+// Same step, also returning what the adjoint sweep needs:
+//   A  = dz'/dz     = f'(a)(1 - gamma) - gamma
+//   cg = dz'/dgamma = (x - z)(f'(a) + 1)
+//   cl = dz'/d ell  = -2 V M1
+//   cv = dz'/dV     (at fixed ell)
+struct StepTape
+{
+    float A, cg, cl, cv;
+};
+template <int MODE, bool GENERAL, bool LSMALL, bool PYORDER>
+DWDF_HD float clip_step_tape (const ClipConst& c, float x, float& z, StepTape& tp)
+{
+    const float xz = x - z;
+    const float t = c.gamma * xz;
+    const float a = z + t;
+    PairDeriv d;
+    const float b = pair_reflect<MODE, GENERAL, true, LSMALL> (c.pair, a, &d);
+    const float zn = b + t;
+    const float y = PYORDER ? 0.5f * (zn + z) : z;
+    const float fp1 = fma_ (-2.0f, d.S1, 2.0f); // f'(a) + 1
+    tp.A = fma_ (fp1, 1.0f - c.gamma, -1.0f); // (fp1 - 1)(1 - gamma) - gamma = fp1 (1 - gamma) - 1
+    tp.cg = xz * fp1;
+    tp.cl = -c.pair.twoV * d.M1;
+    tp.cv = d.dV;
+    z = zn;
+    return y;
+}
+
+} // namespace dwdf

@@ -1,0 +1,589 @@
+"""The wdf_py element/adaptor API (wdf_py/lib/tf_wdf.py) over the B200 engine.
+
+Same class names, constructor signatures, attributes (``a``, ``b``, ``R``, ``P1``, ``P2``, ``Vs``,
+``z``, ``C``, ``FS``, ``p1R``) and methods (``incident``, ``reflected``, ``calc_impedance``,
+``set_voltage``, ``set_resistance``, ``reset``) as the reference, plus the analytic ``DiodePair``
+root the north-star adds (semantics: wdf_t.h:859-985, Toms917DiodePair.h, diode_pretraining.py:39-60)
+and ``PolarityInverter`` as the C++ name of ``Inverter`` (wdf_t.h:558).
+
+Two ways to run a circuit built from these objects:
+
+* **imperative**, exactly like the reference scripts — ``root.incident(tree.reflected());
+  tree.incident(root.reflected())`` once per sample in a Python loop. The element methods are the
+  reference's own one-line wave equations on torch tensors; this is the API surface the scripts are
+  written against (config 1, RC low-pass plumbing) and is as slow as the reference's eager loop.
+* **compiled** — ``compile_circuit(root, tree, probe)`` lowers the object graph to the flat
+  post-order program of ``include/dwdf.h`` and returns a :class:`CompiledCircuit` whose
+  ``forward`` / ``backward`` / ``train_pass`` run whole (B, T) batches in the fused sm_100a kernels.
+  That path is CUDA-only and raises if the extension or the GPU is missing — it never falls back
+  to the imperative code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def voltage(wdf):
+    """tf_wdf.py:8-10"""
+    return (wdf.a + wdf.b) * 0.5
+
+
+def _scalar(v, trainable=False):
+    t = torch.tensor(float(v), dtype=torch.float32)
+    t.requires_grad_(bool(trainable))
+    return t
+
+
+class _Element:
+    trainable = False
+
+    def __init__(self):
+        self.a = torch.zeros(1)
+        self.b = torch.zeros(1)
+
+
+class IdealVoltageSource(_Element):
+    """tf_wdf.py:13-28 (root): b = -a + 2 Vs"""
+
+    def __init__(self):
+        super().__init__()
+        self.Vs = torch.zeros(1)
+
+    def set_voltage(self, voltage):
+        self.Vs = voltage
+
+    def incident(self, x):
+        self.a = x
+
+    def reflected(self):
+        self.b = -self.a + 2.0 * self.Vs
+        return self.b
+
+
+class ResistiveVoltageSource(_Element):
+    """tf_wdf.py:31-59: b = Vs, port resistance R (settable per sample, clipper_pot.py:116)"""
+
+    def __init__(self, initial_R=1.0e-9, trainable=False):
+        super().__init__()
+        self.trainable = trainable
+        self.R = _scalar(initial_R, trainable)
+        self.Vs = torch.zeros(1)
+
+    def calc_impedance(self):
+        pass
+
+    def reset(self):
+        self.a = torch.zeros(1)
+
+    def set_voltage(self, voltage):
+        self.Vs = voltage
+
+    def set_resistance(self, resistance):
+        self.R = resistance
+
+    def incident(self, x):
+        self.a = x
+
+    def reflected(self):
+        self.b = self.Vs * torch.ones_like(self.a) if torch.is_tensor(self.Vs) else torch.full_like(self.a, float(self.Vs))
+        return self.b
+
+
+class Resistor(_Element):
+    """tf_wdf.py:62-88: b = 0; R trainable, clipped to [180, 1e6] after each optimizer step (:74)"""
+
+    clip = (180.0, 1.0e6)
+
+    def __init__(self, initial_R, trainable=False):
+        super().__init__()
+        self.trainable = trainable
+        self.R = _scalar(initial_R, trainable)
+
+    def calc_impedance(self):
+        pass
+
+    def set_resistance(self, resistance):
+        self.R = resistance
+
+    def incident(self, x):
+        self.a = x
+
+    def reflected(self):
+        self.b = torch.zeros_like(self.a)
+        return self.b
+
+
+class Capacitor(_Element):
+    """tf_wdf.py:91-126: b = z, z <- a; R = 1/(2 C FS); C trainable, clipped to [1e-13, 1] (:104)"""
+
+    clip = (1.0e-13, 1.0)
+
+    def __init__(self, initial_C, FS, trainable=False):
+        super().__init__()
+        self.trainable = trainable
+        self.FS = FS
+        self.C = _scalar(initial_C, trainable)
+        self.R = torch.tensor(1.0 / (2.0 * float(initial_C) * FS), dtype=torch.float32)
+        self.z = torch.zeros(1)
+
+    def calc_impedance(self):
+        self.R = torch.reciprocal(self.C * (2.0 * self.FS))
+
+    def reset(self):
+        self.z = torch.zeros(1)
+
+    def incident(self, x):
+        self.a = x
+        self.z = self.a
+
+    def reflected(self):
+        self.b = self.z
+        return self.b
+
+
+class Series(_Element):
+    """tf_wdf.py:129-155"""
+
+    def __init__(self, P1, P2):
+        super().__init__()
+        self.P1 = P1
+        self.P2 = P2
+
+    def calc_impedance(self):
+        self.P1.calc_impedance()
+        self.P2.calc_impedance()
+        self.R = self.P1.R + self.P2.R
+        self.p1R = self.P1.R / self.R
+        self.p2R = self.P2.R / self.R
+
+    def incident(self, x):
+        b1 = self.P1.b - self.p1R * (x + self.P1.b + self.P2.b)
+        self.P1.incident(b1)
+        self.P2.incident(-(x + b1))
+        self.a = x
+
+    def reflected(self):
+        self.b = -(self.P1.reflected() + self.P2.reflected())
+        return self.b
+
+
+class Parallel(_Element):
+    """tf_wdf.py:158-192 (``incident`` uses the b_temp / b_diff left by the preceding ``reflected``)"""
+
+    def __init__(self, P1, P2):
+        super().__init__()
+        self.P1 = P1
+        self.P2 = P2
+
+    def calc_impedance(self):
+        self.P1.calc_impedance()
+        self.P2.calc_impedance()
+        G1 = 1.0 / self.P1.R
+        G2 = 1.0 / self.P2.R
+        G = G1 + G2
+        self.R = 1.0 / G
+        self.p1R = G1 / G
+
+    def incident(self, x):
+        b2 = x + self.b_temp
+        self.P1.incident(self.b_diff + b2)
+        self.P2.incident(b2)
+        self.a = x
+
+    def reflected(self):
+        b1 = self.P1.reflected()
+        b2 = self.P2.reflected()
+        self.b_diff = b2 - b1
+        self.b_temp = -self.p1R * self.b_diff
+        self.b = b2 + self.b_temp
+        return self.b
+
+
+class Inverter(_Element):
+    """tf_wdf.py:195-214"""
+
+    def __init__(self, P1):
+        super().__init__()
+        self.P1 = P1
+
+    def calc_impedance(self):
+        self.P1.calc_impedance()
+        self.R = self.P1.R
+
+    def incident(self, x):
+        self.P1.incident(-x)
+        self.a = x
+
+    def reflected(self):
+        self.b = -self.P1.reflected()
+        return self.b
+
+
+PolarityInverter = Inverter  # wdf_t.h:558
+
+
+def wright_omega(x: torch.Tensor, iters: int = 3) -> torch.Tensor:
+    """Wright omega on the real axis for the imperative API: start from the branches of
+    omega.h:159-169, then Halley iterations on w + ln w = x (converges to round-off in 3)."""
+    w = torch.where(x < -3.341459552768620, torch.exp(x), torch.where(x < 8.0, 0.6313183464296682 + x * (0.3631952663804445 + x * (0.04775931364975583 - x * 0.0013142931498778)),
+                                                                     x - torch.log(torch.clamp(x, min=1.0))))
+    w = torch.clamp(w, min=1e-30)
+    for _ in range(iters):
+        r = x - w - torch.log(w)
+        wp1 = w + 1.0
+        q = 2.0 * wp1 * (wp1 + (2.0 / 3.0) * r)
+        w = w * (1.0 + (r / wp1) * (q - r) / (q - 2.0 * r))
+    return w
+
+
+class DiodePair(_Element):
+    """Analytic antiparallel diode-pair root (new Python surface).
+
+    Law: Werner eq. 45 as in diode_pretraining.py:39-60 (``N_up``/``N_down`` diodes per branch); with
+    ``N_up == N_down == 1`` it is eq. 39 = wdf_t.h:917-924 / Toms917DiodePair.h:51-59. Constructor
+    modelled on ``DiodePairT(next, Is, Vt, nDiodes)`` (wdf_t.h:868-872) and ``DiodeConfig``
+    (diode_config.py:5-9: ``nabla`` multiplies Vt). ``mode``: 'approx' (omega4, omega.h:172-177),
+    'exact' (Wright omega to fp32 round-off) or 'approx_good' (eq. 18, wdf_t.h:907-913) — the mode
+    selects the fused kernels' root; the imperative ``reflected()`` below always evaluates the exact law.
+    """
+
+    def __init__(self, next, Is, Vt=25.85e-3, nabla=1.0, N_up=1, N_down=1, trainable=False, mode="approx", newton_max_iter=2, newton_tol=0.0):
+        super().__init__()
+        if mode not in ("approx", "exact", "approx_good"):
+            raise ValueError(f"unknown DiodePair mode {mode!r}")
+        self.next = next
+        self.trainable = trainable
+        self.Is = _scalar(Is, trainable)
+        self.nabla = _scalar(nabla, trainable)
+        self.Vt = float(Vt)
+        self.N_up = float(N_up)
+        self.N_down = float(N_down)
+        self.mode = mode
+        self.newton_max_iter = int(newton_max_iter)
+        self.newton_tol = float(newton_tol)
+
+    def incident(self, x):
+        self.a = x
+
+    def reflected(self):
+        a = self.a
+        V = self.Vt * self.nabla
+        k = self.Is * self.next.R / V
+        pos = a >= 0
+        mu0 = torch.where(pos, torch.full_like(a, self.N_down), torch.full_like(a, self.N_up))
+        mu1 = torch.where(pos, torch.full_like(a, self.N_up), torch.full_like(a, self.N_down))
+        lam = torch.sign(a)
+        w0 = wright_omega(torch.log(k / mu0) + lam * a / (mu0 * V))
+        w1 = wright_omega(torch.log(k / mu1) - lam * a / (mu1 * V))
+        self.b = a - 2 * V * lam * (mu0 * w0 - mu1 * w1)
+        return self.b
+
+
+# ==================================================================================================
+# compiled path
+# ==================================================================================================
+_KIND = {Resistor: L.RESISTOR, Capacitor: L.CAPACITOR, ResistiveVoltageSource: L.RESISTIVE_VS, Series: L.SERIES, Parallel: L.PARALLEL, Inverter: L.INVERTER}
+_MODE = {"approx": L.MODE_APPROX, "exact": L.MODE_EXACT, "approx_good": L.MODE_APPROX_GOOD}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class CompiledCircuit:
+    """A circuit lowered to the flat program of include/dwdf.h, bound to one CUDA device.
+
+    ``params`` (float32, on the device) is the parameter vector the kernels read: one slot per leaf
+    in post-order, then ``Is`` and ``nabla`` for a DiodePair root. ``slots`` maps (element, attribute)
+    to the slot; ``trainable`` lists the slots whose elements were built with ``trainable=True``.
+    """
+
+    def __init__(self, root, tree=None, probe=None, ordering="python", r_element=None, device=None, fs=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("differentiable-wdfs_b200: the compiled path is CUDA-only and no CUDA device is visible (there is no CPU fallback)")
+        self.lib = L.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.root = root
+        self.tree = tree if tree is not None else getattr(root, "next", None)
+        if self.tree is None:
+            raise ValueError("compile_circuit needs the tree the root closes (tree=...)")
+        if ordering not in ("python", "plugin"):
+            raise ValueError("ordering is 'python' (probe after tree.incident) or 'plugin' (probe between the sweeps)")
+        self.ordering = ordering
+        nodes, self.elements, self.slots, values = [], [], {}, []
+        fs_seen = []
+
+        def visit(e):
+            kind = _KIND.get(type(e))
+            if kind is None:
+                raise TypeError(f"{type(e).__name__} is not a WDF tree element")
+            c1 = c2 = -1
+            if kind in (L.SERIES, L.PARALLEL):
+                c1, c2 = visit(e.P1), visit(e.P2)
+            elif kind == L.INVERTER:
+                c1 = visit(e.P1)
+            slot = -1
+            if kind in (L.RESISTOR, L.RESISTIVE_VS):
+                slot = len(values)
+                values.append(float(e.R))
+                self.slots[(id(e), "R")] = slot
+            elif kind == L.CAPACITOR:
+                slot = len(values)
+                values.append(float(e.C))
+                self.slots[(id(e), "C")] = slot
+                fs_seen.append(float(e.FS))
+            nodes.append(L.Node(kind, c1, c2, slot))
+            self.elements.append(e)
+            return len(nodes) - 1
+
+        visit(self.tree)
+        if len(nodes) > L.MAX_NODES:
+            raise ValueError(f"circuit has {len(nodes)} nodes; the engine handles up to {L.MAX_NODES}")
+        index = {id(e): i for i, e in enumerate(self.elements)}
+        if probe is None or id(probe) not in index:
+            raise ValueError("probe must be an element of the tree (the node whose voltage is the output)")
+        d = L.CircuitDesc()
+        d.probe = index[id(probe)]
+        d.ordering = L.ORDER_PYTHON if ordering == "python" else L.ORDER_PLUGIN
+        d.source = -1
+        d.r_node = index[id(r_element)] if r_element is not None else -1
+        d.param_Is = d.param_nabla = -1
+        d.Vt, d.n_up, d.n_down = 25.85e-3, 1.0, 1.0
+        if isinstance(root, DiodePair):
+            d.root_kind = L.ROOT_DIODE_PAIR
+            d.root_mode = _MODE[root.mode]
+            sources = [i for i, e in enumerate(self.elements) if isinstance(e, ResistiveVoltageSource)]
+            if len(sources) != 1:
+                raise ValueError("a DiodePair circuit is driven through exactly one ResistiveVoltageSource")
+            d.source = sources[0]
+            d.param_Is = len(values)
+            values.append(float(root.Is))
+            self.slots[(id(root), "Is")] = d.param_Is
+            d.param_nabla = len(values)
+            values.append(float(root.nabla))
+            self.slots[(id(root), "nabla")] = d.param_nabla
+            d.Vt, d.n_up, d.n_down = root.Vt, root.N_up, root.N_down
+            d.newton_max_iter, d.newton_tol = root.newton_max_iter, root.newton_tol
+        elif isinstance(root, IdealVoltageSource):
+            d.root_kind = L.ROOT_IDEAL_VS
+        else:
+            raise TypeError("root must be an IdealVoltageSource or a DiodePair")
+        if fs is None:
+            if not fs_seen:
+                fs = 48000.0
+            elif len(set(fs_seen)) != 1:
+                raise ValueError("capacitors disagree on the sample rate")
+            else:
+                fs = fs_seen[0]
+        d.fs = float(fs)
+        d.n_params = len(values)
+        self.desc = d
+        self.n_params = len(values)
+        arr = (L.Node * len(nodes))(*nodes)
+        handle = C.c_void_p()
+        L.check(self.lib.dwdf_program_create(arr, len(nodes), C.byref(d), C.byref(handle)))
+        self.handle = handle
+        self.is_clipper = bool(self.lib.dwdf_program_is_clipper(handle))
+        self.n_states = int(self.lib.dwdf_program_n_states(handle))
+        self.params = torch.tensor(values, dtype=torch.float32, device=self.device)
+        self.trainable = sorted(s for (eid, _), s in self.slots.items() if getattr(self._owner(eid), "trainable", False))
+        lo = [-float("inf")] * self.n_params
+        hi = [float("inf")] * self.n_params
+        for (eid, attr), s in self.slots.items():
+            e = self._owner(eid)
+            if attr in ("R", "C") and hasattr(e, "clip"):
+                lo[s], hi[s] = e.clip
+        self.clip_lo = torch.tensor(lo, dtype=torch.float32, device=self.device)
+        self.clip_hi = torch.tensor(hi, dtype=torch.float32, device=self.device)
+        self.out = torch.zeros(L.OUT_LEN, dtype=torch.float64, device=self.device)
+        self._ckpt = None
+        self._work = None
+        self._last = None
+
+    def _owner(self, eid):
+        if id(self.root) == eid:
+            return self.root
+        for e in self.elements:
+            if id(e) == eid:
+                return e
+        raise KeyError(eid)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.dwdf_program_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def slot(self, element, attr) -> int:
+        return self.slots[(id(element), attr)]
+
+    # ---- buffers -------------------------------------------------------------------------------
+    def _check_xy(self, x, name="x"):
+        if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()):
+            raise ValueError(f"{name} must be a contiguous float32 CUDA tensor of shape (B, T)")
+        if x.device != self.device:
+            raise ValueError(f"{name} lives on {x.device}, the circuit on {self.device}")
+        return x.shape
+
+    def _scratch(self, attr, nbytes):
+        buf = getattr(self, attr)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
+            setattr(self, attr, buf)
+        return buf
+
+    # ---- forward / backward ----------------------------------------------------------------------
+    def forward(self, x, r=None, out=None, keep_for_backward=True):
+        """y = circuit(x): (B, T) float32 CUDA tensors, every sequence from reset state."""
+        B, T = self._check_xy(x)
+        if r is not None:
+            self._check_xy(r, "r")
+        y = torch.empty_like(x) if out is None else out
+        self._check_xy(y, "out")
+        ck = None
+        if keep_for_backward and self.is_clipper and B * T > 0:
+            ck = self._scratch("_ckpt", self.lib.dwdf_ckpt_bytes(self.handle, B, T))
+        L.check(self.lib.dwdf_forward(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), B, T, _stream_ptr(self.device)))
+        self._last = (x, r, B, T) if keep_for_backward else None
+        return y
+
+    def forward_time_major(self, x, r=None):
+        """The reference's output convention: (T, B, 1) as stacked by TensorArray (lpf.py:48, clipper_pot.py:126)."""
+        return self.forward(x, r).t().unsqueeze(-1)
+
+    def backward(self, gy=None, target=None, loss="mse", skip=0, want_gx=False, raw=False):
+        """Gradients of the last ``forward``: upstream ``gy = dL/dy`` or a fused loss against ``target``.
+
+        Returns a dict with ``grads`` (float64 tensor, one per parameter slot, on the device), ``loss``,
+        ``mse``, ``esr`` (0-d device tensors; target mode) and ``gx`` if requested.
+        """
+        if self._last is None:
+            raise RuntimeError("backward() needs a preceding forward(keep_for_backward=True)")
+        if (gy is None) == (target is None):
+            raise ValueError("give exactly one of gy (upstream gradient) or target (fused loss)")
+        x, r, B, T = self._last
+        g = gy if gy is not None else target
+        self._check_xy(g, "gy/target")
+        if tuple(g.shape) != (B, T):
+            raise ValueError("gy/target must have the shape of x")
+        gx = torch.empty_like(x) if want_gx else None
+        nbytes = self.lib.dwdf_workspace_bytes(self.handle, B, T)
+        work = self._scratch("_work", nbytes)
+        ck = self._ckpt if self.is_clipper else None
+        mode = L.GRAD_UPSTREAM if gy is not None else L.GRAD_TARGET
+        if raw:
+            L.check(self.lib.dwdf_backward_raw(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(ck), _ptr(g), mode, int(skip), _ptr(gx), _ptr(self.out), _ptr(work), work.numel(), B, T,
+                                               _stream_ptr(self.device)))
+        else:
+            L.check(self.lib.dwdf_backward(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(ck), _ptr(g), mode, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(gx),
+                                           _ptr(self.out), _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
+        return self._result(gx)
+
+    def finalize(self, target=True, loss="mse"):
+        """Turns the (all-reduced) raw sums in ``self.out`` into gradients and loss, in place."""
+        L.check(self.lib.dwdf_finalize(self.handle, _ptr(self.params), L.GRAD_TARGET if target else L.GRAD_UPSTREAM, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, _ptr(self.out),
+                                       _stream_ptr(self.device)))
+        return self._result(None)
+
+    def train_pass(self, x, target, loss="mse", skip=0, y=None, raw=False):
+        """Fused forward + loss + parameter gradients in one sweep (diode clipper only)."""
+        B, T = self._check_xy(x)
+        self._check_xy(target, "target")
+        if y is not None:
+            self._check_xy(y, "y")
+        work = self._scratch("_work", self.lib.dwdf_workspace_bytes(self.handle, B, T))
+        if raw:
+            L.check(self.lib.dwdf_train_pass_raw(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), int(skip), _ptr(y), _ptr(self.out), _ptr(work), work.numel(), B, T,
+                                                 _stream_ptr(self.device)))
+        else:
+            L.check(self.lib.dwdf_train_pass(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(y), _ptr(self.out),
+                                             _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
+        return self._result(None)
+
+    def _result(self, gx):
+        o = self.out
+        return {"grads": o[: self.n_params], "loss": o[L.OUT_LOSS], "mse": o[L.OUT_MSE], "esr": o[L.OUT_ESR], "gx": gx, "out": o}
+
+    def process_block(self, x, state, r=None, out=None):
+        """Streaming twin of DiodeClipperWDF::process: continues from ``state`` ((n_states, B) float32) and updates it."""
+        B, T = self._check_xy(x)
+        if not (torch.is_tensor(state) and state.is_cuda and state.dtype == torch.float32 and state.numel() == self.n_states * B and state.is_contiguous()):
+            raise ValueError(f"state must be a contiguous float32 CUDA tensor with {self.n_states} x B elements")
+        y = torch.empty_like(x) if out is None else out
+        L.check(self.lib.dwdf_process_block(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(state), B, T, _stream_ptr(self.device)))
+        return y
+
+    def new_state(self, B):
+        return torch.zeros(self.n_states, B, dtype=torch.float32, device=self.device)
+
+    # ---- end-to-end with host (numpy / pinned torch) buffers ------------------------------------------
+    def forward_host(self, x_host: torch.Tensor, y_host: torch.Tensor, params_host: Optional[torch.Tensor] = None):
+        B, T = x_host.shape
+        p = self.params.cpu() if params_host is None else params_host
+        L.check(self.lib.dwdf_forward_host(self.handle, _ptr(p), _ptr(x_host), None, _ptr(y_host), B, T))
+        return y_host
+
+    def grad_host(self, x_host, g_host, out_host, y_host=None, params_host=None, target=True, loss="mse", skip=0):
+        B, T = x_host.shape
+        p = self.params.cpu() if params_host is None else params_host
+        L.check(self.lib.dwdf_grad_host(self.handle, _ptr(p), _ptr(x_host), None, _ptr(g_host), L.GRAD_TARGET if target else L.GRAD_UPSTREAM, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE,
+                                        int(skip), _ptr(y_host), _ptr(out_host), B, T))
+        return out_host
+
+    # ---- parameters ------------------------------------------------------------------------------------
+    def sync_from_elements(self):
+        """Re-reads every element's current value into the device parameter vector."""
+        vals = [0.0] * self.n_params
+        for (eid, attr), s in self.slots.items():
+            vals[s] = float(getattr(self._owner(eid), attr))
+        self.params.copy_(torch.tensor(vals, dtype=torch.float32))
+
+    def sync_to_elements(self):
+        """Writes the device parameter vector back into the element objects (R, C, Is, nabla)."""
+        vals = self.params.detach().cpu()
+        for (eid, attr), s in self.slots.items():
+            e = self._owner(eid)
+            setattr(e, attr, _scalar(float(vals[s]), getattr(e, "trainable", False)))
+
+
+def compile_circuit(root, tree=None, probe=None, ordering="python", r_element=None, device=None, fs=None) -> CompiledCircuit:
+    return CompiledCircuit(root, tree, probe, ordering, r_element, device, fs)
+
+
+class Adam:
+    """tf.keras.optimizers.Adam for a CompiledCircuit (clipper_pot.py:180,269). ``lr`` is one rate for
+    every trainable slot or a dict slot -> rate (lpf.py:79-80 trains R and C with different rates);
+    slots that are not trainable get rate 0. One device kernel per step, moments and step counter on
+    the device, then the reference's clip constraints (tf_wdf.py:74,104)."""
+
+    def __init__(self, circuit: CompiledCircuit, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, slots=None):
+        self.c = circuit
+        dev = circuit.device
+        self.m = torch.zeros(circuit.n_params, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(circuit.n_params, dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
+        rates = [0.0] * circuit.n_params
+        if isinstance(lr, dict):
+            for s, v in lr.items():
+                rates[int(s)] = float(v)
+        else:
+            for s in (circuit.trainable if slots is None else slots):
+                rates[int(s)] = float(lr)
+        self.lr = torch.tensor(rates, dtype=torch.float32, device=dev)
+
+    def apply(self, grad_scale=1.0):
+        c = self.c
+        L.check(c.lib.dwdf_adam_step(_ptr(c.params), _ptr(c.out), _ptr(self.m), _ptr(self.v), _ptr(self.step_count), c.n_params, 0.0, _ptr(self.lr), float(self.beta_1), float(self.beta_2),
+                                     float(self.epsilon), float(grad_scale), _ptr(c.clip_lo), _ptr(c.clip_hi), _stream_ptr(c.device)))

@@ -1,0 +1,220 @@
+/* dwdf.h — C ABI of libdwdf.so, the B200-native differentiable wave-digital-filter engine.
+ *
+ * The reference (jatinchowdhury18/differentiable-wdfs) has no FFI: its Python half calls
+ * TensorFlow eager ops sample by sample and its C++ half is header-only templates. The boundary
+ * this library sits behind is therefore the reference's *element protocol* and the script-level
+ * forward()/GradientTape contract. Each entry point below cites the reference
+ * interface it replaces. Plain pointers and sizes only; no torch / C++ types cross this boundary;
+ * every function returns a status (0 = ok) and never throws.
+ *
+ * Buffers are caller-owned. `x`, `y`, `r`, `gy_or_target`, `gx`, `params`, `workspace`, `out` are
+ * DEVICE pointers in the dwdf_forward / dwdf_backward / dwdf_train_* calls and HOST pointers in
+ * the *_host calls (which stage through library-owned device memory and pinned bounce buffers).
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). Launches are
+ * asynchronous on that stream.
+ *
+ * Tensors: x, y, r, gy_or_target, gx are (B, T) fp32, batch-major, contiguous — the layout of the
+ * reference's training batches (clipper_pot.py:61-80; channel 0 = x, channel 1 = r).
+ */
+#ifndef DWDF_H
+#define DWDF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DWDF_VERSION 1
+#if defined(__GNUC__)
+#define DWDF_API __attribute__ ((visibility ("default")))
+#else
+#define DWDF_API
+#endif
+
+/* ---- status codes -------------------------------------------------------------------------- */
+enum dwdf_status
+{
+    DWDF_OK = 0,
+    DWDF_ERR_INVALID = 1, /* bad argument / malformed tree                     */
+    DWDF_ERR_UNSUPPORTED = 2, /* valid, but not implemented for this combination   */
+    DWDF_ERR_CUDA = 3, /* a CUDA runtime / driver call failed               */
+    DWDF_ERR_NO_DEVICE = 4, /* no CUDA device: there is NO CPU fallback          */
+    DWDF_ERR_WORKSPACE = 5 /* workspace too small                               */
+};
+
+/* ---- circuit description ------------------------------------------------------------------- */
+/* One-port leaves and adaptors. Same set as wdf_py/lib/tf_wdf.py:31-214 and, on the C++ side,
+ * wdf_t.h ResistorT:69, CapacitorT:118, ResistiveVoltageSourceT:693, WDFSeriesT:508,
+ * WDFParallelT:448, PolarityInverterT:558. */
+enum dwdf_node_kind
+{
+    DWDF_RESISTOR = 0, /* tf_wdf.py:62-88   value = R [ohm]                                      */
+    DWDF_CAPACITOR = 1, /* tf_wdf.py:91-126  value = C [farad]; port resistance 1/(2 C fs)        */
+    DWDF_RESISTIVE_VS = 2, /* tf_wdf.py:31-59   value = R [ohm]; reflected wave = source voltage     */
+    DWDF_SERIES = 3, /* tf_wdf.py:129-155 child1 = P1, child2 = P2                             */
+    DWDF_PARALLEL = 4, /* tf_wdf.py:158-192 child1 = P1, child2 = P2                             */
+    DWDF_INVERTER = 5 /* tf_wdf.py:195-214 child1 = P1                                          */
+};
+
+/* Non-adaptable root closing the tree. */
+enum dwdf_root_kind
+{
+    DWDF_ROOT_IDEAL_VS = 0, /* tf_wdf.py:13-28 / wdf_t.h:658-689: b = -a + 2 Vs, Vs = x[n]            */
+    DWDF_ROOT_DIODE_PAIR = 1 /* analytic antiparallel diode pair (see dwdf_root_mode)                 */
+};
+
+/* How the diode-pair root evaluates the Wright-omega function. */
+enum dwdf_root_mode
+{
+    DWDF_MODE_APPROX = 0, /* wdft::DiodePairT<Best>, wdf_t.h:917-924 with omega4 of omega.h:172-177  */
+    DWDF_MODE_EXACT = 1, /* Toms917DiodePair.h:51-67 / diode_pretraining.py:39-60: omega to fp32
+                            round-off (series start + Fritsch-Shafer-Crowley/Newton iterations)   */
+    DWDF_MODE_APPROX_GOOD = 2 /* wdft::DiodePairT<Good>, wdf_t.h:907-913 (forward only)               */
+};
+
+/* Where the voltage probe sits inside one sample. */
+enum dwdf_ordering
+{
+    DWDF_ORDER_PLUGIN = 0, /* between root.incident and tree.incident (DiodeClipperWDF.cpp:26-28)    */
+    DWDF_ORDER_PYTHON = 1 /* after tree.incident (lpf.py:42-45, clipper_pot.py:121-123)             */
+};
+
+/* One node of the element tree, listed in post-order (children before parents, top adaptor last).
+ * `param` is the index into the parameter vector of this leaf's value (R or C), or -1 for
+ * adaptors. */
+typedef struct dwdf_node
+{
+    int32_t kind; /* dwdf_node_kind */
+    int32_t child1; /* node index or -1 */
+    int32_t child2; /* node index or -1 */
+    int32_t param; /* parameter slot or -1 */
+} dwdf_node;
+
+typedef struct dwdf_circuit_desc
+{
+    int32_t root_kind; /* dwdf_root_kind */
+    int32_t root_mode; /* dwdf_root_mode (diode pair only) */
+    int32_t ordering; /* dwdf_ordering */
+    int32_t probe; /* node whose voltage (a+b)/2 is the output (tf_wdf.py:8-10) */
+    int32_t source; /* node driven by x[n] (a DWDF_RESISTIVE_VS; ignored for DWDF_ROOT_IDEAL_VS) */
+    int32_t r_node; /* leaf whose resistance is the per-sample channel `r` (clipper_pot.py:116), or -1 */
+    int32_t param_Is; /* parameter slot of the diode saturation current, diode pair only */
+    int32_t param_nabla; /* parameter slot of the ideality factor / nDiodes (wdf_t.h:875-882) */
+    int32_t n_params; /* length of the parameter vector */
+    int32_t newton_max_iter; /* exact mode: omega refinement iterations (<=0: default 2, toms917.cpp:345-364) */
+    float fs; /* sample rate [Hz] */
+    float Vt; /* thermal voltage, 25.85e-3 in the reference */
+    float n_up; /* diodes in series, "up" branch (diode_config.py:5-9); 1 = symmetric */
+    float n_down;
+    float newton_tol; /* exact mode: stop refining when |residual| <= tol (0: run all iterations) */
+} dwdf_circuit_desc;
+
+typedef struct dwdf_program dwdf_program; /* opaque, immutable after creation, thread-shareable */
+
+/* ---- loss / gradient ------------------------------------------------------------------------ */
+enum dwdf_grad_mode
+{
+    DWDF_GRAD_UPSTREAM = 0, /* gy_or_target holds dL/dy (what tape.gradient feeds back)               */
+    DWDF_GRAD_TARGET = 1 /* gy_or_target holds the target; loss fused (clipper_pot.py:141-177)     */
+};
+enum dwdf_loss_kind
+{
+    DWDF_LOSS_MSE = 0, /* tf.keras.losses.MeanSquaredError, clipper_pot.py:176                   */
+    DWDF_LOSS_MSE_ESR = 1 /* MSE + error-to-signal ratio, clipper_pot.py:148-156,177               */
+};
+
+/* Result block written by dwdf_backward / dwdf_train_step: doubles, device (or host in *_host).
+ *   [0 .. n_params)   dL/dparam, same slot order as the parameter vector
+ *   [DWDF_OUT_LOSS]   loss     [DWDF_OUT_MSE] mse     [DWDF_OUT_ESR] esr   (target mode; else 0)
+ * n_params <= DWDF_MAX_PARAMS. */
+#define DWDF_MAX_PARAMS 16
+#define DWDF_MAX_NODES 16
+#define DWDF_OUT_LOSS 16
+#define DWDF_OUT_MSE 17
+#define DWDF_OUT_ESR 18
+#define DWDF_OUT_LEN 24
+
+/* ---- API ------------------------------------------------------------------------------------ */
+
+/* Replaces: building the element object graph (lpf.py:23-28, clipper_pot.py:97-101,
+ * DiodeClipperWDF.h:18-25). Validates the tree, recognises topologies that have a specialised
+ * kernel (Parallel(ResistiveVs, Capacitor) + DiodePair = the diode clipper) and stores the flat
+ * post-order program every kernel consumes. */
+DWDF_API int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_circuit_desc* desc, dwdf_program** out);
+DWDF_API int dwdf_program_destroy (dwdf_program* prog);
+/* 1 if the program runs on the specialised diode-clipper kernels, 0 if on the tree interpreter. */
+DWDF_API int dwdf_program_is_clipper (const dwdf_program* prog);
+
+/* Floats of streaming state per sequence for dwdf_process_block: 1 for the diode-clipper program
+ * (its capacitor), number of capacitors + 1 (the probe's last incident wave) for other trees. */
+DWDF_API int dwdf_program_n_states (const dwdf_program* prog);
+
+/* Bytes of device scratch dwdf_forward(z_ckpt)/dwdf_backward need for a (B, T) batch. */
+DWDF_API size_t dwdf_ckpt_bytes (const dwdf_program* prog, int64_t B, int64_t T);
+DWDF_API size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T);
+
+/* Replaces: Model.forward / ClipperModel.forward (lpf.py:30-49, clipper_pot.py:103-127) and
+ * processDiodeClipper (DiodeClipperWDF.cpp:18-30): T samples of
+ *     root.incident(tree.reflected()); tree.incident(root.reflected()); y[n] = voltage(probe)
+ * for B independent sequences, each from reset state. `params` (device, n_params floats) holds the
+ * trainable values; `r` is NULL or the per-sample resistance channel; `z_ckpt` is NULL or receives
+ * the capacitor-state checkpoints the adjoint replays from (dwdf_ckpt_bytes). */
+DWDF_API int dwdf_forward (const dwdf_program* prog, const float* params, const float* x, const float* r, float* y, float* z_ckpt, int64_t B, int64_t T, void* stream);
+
+/* Replaces: tape.gradient(loss, trainable_variables) (lpf.py:87-90, clipper_pot.py:246-269).
+ * Hand-written adjoint: walks the checkpoints written by dwdf_forward in reverse, replays each
+ * segment of the recurrence and sweeps it backwards; no tape, no autodiff framework. `skip`
+ * leading samples are excluded from the fused loss (clipper_pot.py:232,248). `gx` is NULL or
+ * receives dL/dx. `out` receives the DWDF_OUT_LEN doubles described above, already reduced over
+ * the batch in a fixed order (bit-reproducible). */
+DWDF_API int dwdf_backward (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+
+/* Fused training pass (forward + loss + parameter gradients in ONE sweep, by propagating the
+ * parameter sensitivities with the recurrence): same `out` as dwdf_forward followed by
+ * dwdf_backward in DWDF_GRAD_TARGET mode; y may be NULL. Diode clipper only. */
+DWDF_API int dwdf_train_pass (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+
+/* Multi-GPU split of the two calls above. The *_raw variants stop after the fixed-order batch
+ * reduction and write the RAW sums (before the chain rule and the loss normalisation; raw[23] = number
+ * of samples in the loss) so that ranks can all-reduce them (one ncclAllReduce of DWDF_OUT_LEN doubles);
+ * dwdf_finalize then turns the summed block, in place, into the `out` block described above. The
+ * result is independent of how the batch was sharded. */
+DWDF_API int dwdf_backward_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int64_t skip, float* gx, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+DWDF_API int dwdf_train_pass_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* target, int64_t skip, float* y, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+DWDF_API int dwdf_finalize (const dwdf_program* prog, const float* params, int32_t grad_mode, int32_t loss_kind, double* raw_inout, void* stream);
+
+/* Replaces: tf.keras.optimizers.Adam.apply_gradients + the Keras clip constraints
+ * (clipper_pot.py:180,269; tf_wdf.py:74,104). One tiny kernel; state m, v (n_params floats each)
+ * and the step counter live on the device so a whole training step is capturable in a CUDA
+ * graph. `grad_scale` multiplies the gradients first (1/world_size after an all-reduce).
+ * lr_per_slot: NULL, or n_params device floats overriding `lr` per slot (0 freezes a slot; lpf.py:79-80
+ * trains R and C with different rates). lo/hi: per-slot clip bounds (device, n_params floats each) or NULL. */
+DWDF_API int dwdf_adam_step (float* params, const double* out, float* m, float* v, int32_t* step, int32_t n_params, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, double grad_scale, const float* lo, const float* hi, void* stream);
+
+/* End-to-end variants with HOST buffers (what a training script holding numpy batches calls):
+ * host->device copies of x / r / target, the kernels, device->host copy of y / out, all on one
+ * internal stream, synchronous on return. */
+DWDF_API int dwdf_forward_host (const dwdf_program* prog, const float* params_host, const float* x_host, const float* r_host, float* y_host, int64_t B, int64_t T);
+DWDF_API int dwdf_grad_host (const dwdf_program* prog, const float* params_host, const float* x_host, const float* r_host, const float* gy_or_target_host, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* y_host, double* out_host, int64_t B, int64_t T);
+
+/* Streaming twin of DiodeClipperWDF::{prepare, process} (DiodeClipperWDF.cpp:3-30): like
+ * dwdf_forward, but the capacitor states are read from and written back to `state`
+ * (dwdf_program_n_states() * B floats, device, state-major) so consecutive blocks continue the same signal. */
+DWDF_API int dwdf_process_block (const dwdf_program* prog, const float* params, const float* x, const float* r, float* y, float* state, int64_t B, int64_t T, void* stream);
+
+/* Last error message of the calling thread ("" if none). */
+DWDF_API const char* dwdf_last_error (void);
+/* Compile-time facts for the drop-in check: "sm_100a", version, feature flags. */
+DWDF_API const char* dwdf_build_info (void);
+/* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
+DWDF_API int64_t dwdf_launch_count (void);
+/* Selects the data-movement path of the clipper kernels: 1 = TMA tiles (default when usable),
+ * 0 = direct global loads. Returns the previous value. For tests and A/B timing. */
+DWDF_API int dwdf_set_tma (int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWDF_H */

@@ -64,3 +64,23 @@ def make_inputs(B, T, fs=48000.0, seed=1234, amp=(0.1, 2.0)):
     f = np.exp(rng.uniform(np.log(50.0), np.log(5000.0), B))
     x = A[:, None] * np.sin(2 * np.pi * f[:, None] * n[None, :] / fs) + 0.05 * rng.standard_normal((B, T))
     return x.astype(np.float32)
+
+
+def load_pkg():
+    """The product package (its directory name carries the reference's hyphen)."""
+    import importlib
+
+    return importlib.import_module("differentiable-wdfs_b200")
+
+
+@pytest.fixture(scope="session")
+def dwdf():
+    return load_pkg()
+
+
+def seq_rel_err(y, y_ref):
+    """Parity metric of SURVEY.md §7-4: max|y - y_ref| / max|y_ref| per sequence, worst sequence."""
+    y = np.asarray(y, np.float64)
+    y_ref = np.asarray(y_ref, np.float64)
+    den = np.maximum(np.max(np.abs(y_ref), axis=-1), 1e-30)
+    return float(np.max(np.max(np.abs(y - y_ref), axis=-1) / den))

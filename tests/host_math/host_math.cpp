@@ -1,0 +1,118 @@
+// TEST INFRASTRUCTURE ONLY. Compiles the product's device math header (csrc/dwdf_math.cuh) with
+// g++ for the HOST so that `-m "not gpu"` tests can check its logic against the oracle on a
+// machine without a GPU (MUFU/round-down intrinsics are replaced by their IEEE host equivalents,
+// see the #if blocks in the header). Never shipped, never loaded by the product.
+#include "dwdf_math.cuh"
+#include <vector>
+
+using namespace dwdf;
+
+// kind: 0 omega3, 1 omega4, 2 exp_approx, 3 log_approx (x > 0), 4 omega_exact(2 iterations), 5 omega_exact(1 iteration)
+extern "C" void hm_scalar (int kind, const float* x, float* out, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i)
+    {
+        switch (kind)
+        {
+            case 0: out[i] = omega3_approx (x[i]); break;
+            case 1: out[i] = omega4_approx (x[i]); break;
+            case 2: out[i] = exp_approx (x[i]); break;
+            case 3: out[i] = log_approx_pos (x[i]); break;
+            case 4: out[i] = omega_exact (x[i], 2, 0.0f); break;
+            default: out[i] = omega_exact (x[i], 1, 0.0f); break;
+        }
+    }
+}
+
+template <int MODE, bool GENERAL, bool LSMALL>
+static void pair_run (const PairConst& c, const float* a, float* b, float* dv, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i)
+    {
+        PairDeriv d;
+        b[i] = pair_reflect<MODE, GENERAL, true, LSMALL> (c, a[i], &d);
+        if (dv)
+        {
+            dv[3 * i] = d.S1;
+            dv[3 * i + 1] = d.M1;
+            dv[3 * i + 2] = d.dV;
+        }
+    }
+}
+
+// root law at a fixed port impedance; dv (optional) receives (S1, M1, dV) per sample
+extern "C" void hm_pair (int mode, int general, int lsmall, float Rp, float Is, float Vt, float nabla, float n_up, float n_down, const float* a, float* b, float* dv, int64_t n)
+{
+    PairConst c;
+    pair_setup (c, Rp, Is, Vt, nabla, n_up, n_down, 2, 0.0f);
+    if (mode == kModeApproxGood)
+    {
+        for (int64_t i = 0; i < n; ++i)
+            b[i] = pair_reflect<kModeApproxGood, false, false, false> (c, a[i], nullptr);
+        return;
+    }
+    if (mode == kModeApprox)
+    {
+        if (general) pair_run<kModeApprox, true, false> (c, a, b, dv, n);
+        else if (lsmall) pair_run<kModeApprox, false, true> (c, a, b, dv, n);
+        else pair_run<kModeApprox, false, false> (c, a, b, dv, n);
+    }
+    else
+    {
+        if (general) pair_run<kModeExact, true, false> (c, a, b, dv, n);
+        else pair_run<kModeExact, false, false> (c, a, b, dv, n);
+    }
+}
+
+template <int MODE, bool GENERAL, bool LSMALL, bool PY>
+static void clip_run (const ClipConst& c, const float* x, const float* g, float* y, double* acc, int64_t B, int64_t T)
+{
+    std::vector<StepTape> tape ((size_t) T);
+    for (int64_t s = 0; s < B; ++s)
+    {
+        float z = 0.0f;
+        for (int64_t n = 0; n < T; ++n)
+        {
+            if (g)
+                y[s * T + n] = clip_step_tape<MODE, GENERAL, LSMALL, PY> (c, x[s * T + n], z, tape[(size_t) n]);
+            else
+                y[s * T + n] = clip_step<MODE, GENERAL, LSMALL, PY> (c, x[s * T + n], z);
+        }
+        if (! g)
+            continue;
+        double G = 0.0; // adjoint of z[n+1]
+        for (int64_t n = T - 1; n >= 0; --n)
+        {
+            const StepTape& tp = tape[(size_t) n];
+            const double gy = g[s * T + n];
+            if (PY) G += 0.5 * gy;
+            acc[0] += G * tp.cg;
+            acc[1] += G * tp.cl;
+            acc[2] += G * tp.cv;
+            G = (PY ? 0.5 * gy : gy) + G * tp.A;
+        }
+    }
+}
+
+// the clipper recurrence on the host; g == NULL: forward only, else also the raw adjoint sums
+// acc[0..2] = sum G dz'/d{gamma, ell, V} for upstream gradient g
+extern "C" void hm_clipper (int mode, int general, int pyorder, float fs, float R, float C, float Is, float Vt, float nabla, float n_up, float n_down, const float* x, const float* g, float* y, double* acc, int64_t B, int64_t T)
+{
+    ClipDesc d { fs, Vt, n_up, n_down, 0.0f, 2, 0, 1, 2, 3 };
+    ClipConst c;
+    clip_setup (c, d, R, C, Is, nabla);
+    const bool lsmall = mode == kModeApprox && ! general && c.pair.L < kOmega3Zero;
+#define RUN(M, G, L) (pyorder ? clip_run<M, G, L, true> (c, x, g, y, acc, B, T) : clip_run<M, G, L, false> (c, x, g, y, acc, B, T))
+    if (mode == kModeApprox)
+    {
+        if (general) RUN (kModeApprox, true, false);
+        else if (lsmall) RUN (kModeApprox, false, true);
+        else RUN (kModeApprox, false, false);
+    }
+    else
+    {
+        if (general) RUN (kModeExact, true, false);
+        else RUN (kModeExact, false, false);
+    }
+#undef RUN
+}

@@ -1,0 +1,407 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI (ctypes over
+libdwdf.so), checked against the CPU oracle, the committed golden vectors produced by the
+reference itself, and size-independent properties at the benchmark's full sizes.
+
+Tolerances (BASELINE.json north_star: "output within 1e-5 relative of the reference"):
+  forward   max|y - y_ref| / max|y_ref| per sequence <= 1e-5, per root mode
+  gradients relative 2e-4 per parameter against the fp64 oracle (the reference pins no gradient;
+            fp32 recurrences over 4096 samples), loss relative 1e-5
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_inputs, seq_rel_err
+from oracle.cpu import (CAPACITOR, INVERTER, ORDER_PLUGIN, ORDER_PYTHON, PARALLEL, RESISTOR, RESVS, ROOT_DIODE_PAIR, ROOT_IDEAL_VS, SERIES, ClipperParams)
+
+pytestmark = pytest.mark.gpu
+FWD_TOL = 1e-5
+GRAD_TOL = 2e-4
+
+
+def make_clipper(dwdf, p=ClipperParams(), mode="approx", ordering="python", trainable=True, **kw):
+    Vs = dwdf.ResistiveVoltageSource(p.R, trainable)
+    C = dwdf.Capacitor(p.C, p.fs, trainable)
+    P1 = dwdf.Parallel(Vs, C)
+    dp = dwdf.DiodePair(P1, p.Is, p.Vt, p.nabla, p.n_up, p.n_down, trainable=trainable, mode=mode, **kw)
+    circ = dwdf.compile_circuit(dp, probe=C, ordering=ordering)
+    assert circ.is_clipper
+    order = [circ.slot(dp, "Is"), circ.slot(dp, "nabla"), circ.slot(Vs, "R"), circ.slot(C, "C")]
+    return circ, order
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(params=[True, False], ids=["tma", "direct"])
+def tma(request, dwdf):
+    prev = dwdf.set_tma(request.param)
+    yield request.param
+    dwdf.set_tma(prev)
+
+
+# ---- forward ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("circuit", ["plugin", "training"])
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+@pytest.mark.parametrize("ordering", ["plugin", "python"])
+def test_forward_golden(dwdf, golden, tma, circuit, mode, ordering):
+    """Against the reference's own C++ (fixtures written by tests/golden/make_golden.py)."""
+    p = ClipperParams() if circuit == "plugin" else ClipperParams(R=45000.0, C=4.7e-9)
+    circ, _ = make_clipper(dwdf, p, mode, ordering)
+    y = circ.forward(dev(golden["clip_x"])).cpu().numpy()
+    for prec, tol in (("f32", FWD_TOL), ("f64", FWD_TOL)):
+        ref = golden[f"clip_{circuit}_{mode}_{ordering}_{prec}"]
+        assert seq_rel_err(y, ref) < tol, (circuit, mode, ordering, prec, seq_rel_err(y, ref))
+
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+def test_forward_golden_loud(dwdf, golden, mode):
+    """Inputs up to +-10 V: omega arguments far into the log branch of omega3 / the asymptotic region."""
+    circ, _ = make_clipper(dwdf, ClipperParams(), mode, "python")
+    y = circ.forward(dev(golden["clip_loud_x"])).cpu().numpy()
+    assert seq_rel_err(y, golden[f"clip_loud_{mode}_python_f32"]) < FWD_TOL
+
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+@pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
+@pytest.mark.parametrize("B,T", [(1, 4), (1, 1), (3, 7), (33, 20), (32, 32), (31, 36), (64, 4096), (5, 37), (257, 1000)])
+def test_forward_vs_oracle_shapes(dwdf, oracle, tma, mode, ordering, oord, B, T):
+    """Ragged shapes: B not a multiple of 32, T not a multiple of 4 / 16 / 32 (direct path), tiny T."""
+    x = make_inputs(B, T, seed=B * 1000 + T)
+    circ, _ = make_clipper(dwdf, ClipperParams(), mode, ordering)
+    y = circ.forward(dev(x)).cpu().numpy()
+    ref = oracle.clipper_forward(x, ClipperParams(), exact=(mode == "exact"), ordering=oord)
+    assert seq_rel_err(y, ref) < FWD_TOL
+
+
+def test_forward_empty(dwdf):
+    circ, _ = make_clipper(dwdf)
+    for shape in ((0, 64), (4, 0)):
+        y = circ.forward(torch.empty(shape, dtype=torch.float32, device="cuda"))
+        assert tuple(y.shape) == shape
+
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+@pytest.mark.parametrize("n_up,n_down", [(1, 2), (2, 1), (2, 2), (3, 3), (1, 3)])
+def test_forward_asymmetric(dwdf, oracle, tma, mode, n_up, n_down):
+    """N_up != N_down: Werner eq. 45 (diode_pretraining.py:39-60); config 4's 'OA1154' stand-in among them."""
+    for p in (ClipperParams(n_up=n_up, n_down=n_down), ClipperParams(Is=1e-6, nabla=1.3, n_up=n_up, n_down=n_down)):
+        x = make_inputs(48, 512, seed=11)
+        circ, _ = make_clipper(dwdf, p, mode, "python")
+        y = circ.forward(dev(x)).cpu().numpy()
+        ref = oracle.clipper_forward(x, p, exact=(mode == "exact"))
+        assert seq_rel_err(y, ref) < FWD_TOL
+
+
+def test_forward_special_inputs(dwdf, oracle, known):
+    """Zero input -> exactly zero (signum(0) = 0, signum.h:5-9); the plugin impulse response."""
+    circ, _ = make_clipper(dwdf, ClipperParams(), "exact", "plugin")
+    z = circ.forward(torch.zeros(40, 64, device="cuda")).cpu().numpy()
+    assert np.all(z == 0.0)
+    imp = np.zeros((1, 16), np.float32)
+    imp[0, 0] = 1.0
+    y = circ.forward(dev(imp)).cpu().numpy()[0]
+    np.testing.assert_allclose(y[:4], known["plugin_impulse_response_toms"][:4], rtol=0, atol=2e-7)
+
+
+def test_newton_iterations(dwdf, oracle):
+    """Exact mode: one Fritsch-Shafer-Crowley iteration already meets the tolerance; a residual
+    tolerance stops the refinement early without changing the result beyond it (config 4)."""
+    x = make_inputs(64, 1024, seed=3)
+    ref = oracle.clipper_forward(x, ClipperParams(Is=1e-6, nabla=1.3, n_up=1, n_down=2), exact=True)
+    for kw in (dict(newton_max_iter=1), dict(newton_max_iter=4, newton_tol=1e-9), dict(newton_max_iter=3, newton_tol=1e-3)):
+        circ, _ = make_clipper(dwdf, ClipperParams(Is=1e-6, nabla=1.3, n_up=1, n_down=2), "exact", "python", **kw)
+        assert seq_rel_err(circ.forward(dev(x)).cpu().numpy(), ref) < FWD_TOL
+
+
+# ---- gradients ---------------------------------------------------------------------------------------
+
+def perturbed(p):
+    return ClipperParams(fs=p.fs, R=p.R * 1.1, C=p.C * 0.9, Is=p.Is * 2, Vt=p.Vt, nabla=p.nabla * 1.05, n_up=p.n_up, n_down=p.n_down)
+
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+@pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
+@pytest.mark.parametrize("loss,skip", [("mse", 0), ("mse+esr", 50)])
+@pytest.mark.parametrize("B,T", [(64, 2048), (33, 100), (7, 37)])
+def test_backward_target(dwdf, oracle, tma, mode, ordering, oord, loss, skip, B, T):
+    """Config 3: MSE (+ESR, clipper_pot.py:141-177) against the output of a perturbed parameter set."""
+    p = ClipperParams()
+    x = make_inputs(B, T, seed=1235)
+    target = oracle.clipper_forward(x, perturbed(p), exact=True, ordering=oord)
+    circ, order = make_clipper(dwdf, p, mode, ordering)
+    circ.forward(dev(x))
+    res = circ.backward(target=dev(target), loss=loss, skip=min(skip, T // 2))
+    ref = oracle.clipper_grad(x, target, p, exact=(mode == "exact"), ordering=oord, mode="target", loss=loss, skip=min(skip, T // 2), dtype=np.float64)
+    g = res["grads"].cpu().numpy()[order]
+    assert np.max(np.abs(g / ref["grads"] - 1.0)) < GRAD_TOL, (g, ref["grads"])
+    assert abs(float(res["loss"]) / ref["loss"] - 1.0) < 1e-4
+    assert abs(float(res["mse"]) / ref["mse"] - 1.0) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+@pytest.mark.parametrize("n_up,n_down", [(1, 1), (1, 2)])
+def test_backward_upstream_and_gx(dwdf, oracle, mode, n_up, n_down):
+    """Arbitrary upstream dL/dy (what tape.gradient feeds back) and dL/dx."""
+    p = ClipperParams(n_up=n_up, n_down=n_down)
+    x = make_inputs(40, 512, seed=5)
+    gy = np.random.default_rng(9).standard_normal(x.shape).astype(np.float32)
+    circ, order = make_clipper(dwdf, p, mode, "python")
+    circ.forward(dev(x))
+    ref = oracle.clipper_grad(x, gy, p, exact=(mode == "exact"), mode="upstream", dtype=np.float64, want_gx=True)
+    res = circ.backward(gy=dev(gy), want_gx=True)
+    g = res["grads"].cpu().numpy()[order]
+    assert np.max(np.abs(g / ref["grads"] - 1.0)) < GRAD_TOL
+    gx = res["gx"].cpu().numpy()
+    assert np.max(np.abs(gx - ref["gx"])) / np.max(np.abs(ref["gx"])) < 1e-4
+    res2 = circ.backward(gy=dev(gy))  # TMA adjoint, no gx
+    assert np.max(np.abs(res2["grads"].cpu().numpy()[order] / ref["grads"] - 1.0)) < GRAD_TOL
+
+
+def test_gradient_finite_differences(dwdf):
+    """fp64-free check of the adjoint against central differences of the GPU forward itself (loss in fp64)."""
+    p = ClipperParams()
+    x = make_inputs(256, 512, seed=21)
+    xd = dev(x)
+    circ, order = make_clipper(dwdf, p, "exact", "python")
+    target = torch.zeros_like(xd)
+    circ.forward(xd)
+    g = circ.backward(target=target, loss="mse")["grads"].cpu().numpy().copy()
+    base = circ.params.clone()
+    for s in range(circ.n_params):
+        h = float(base[s]) * 2e-3
+        vals = []
+        for sign in (+1, -1):
+            circ.params.copy_(base)
+            circ.params[s] += sign * h
+            vals.append(float((circ.forward(xd, keep_for_backward=False).double() ** 2).mean()))
+        fd = (vals[0] - vals[1]) / (2 * h)
+        assert abs(g[s] / fd - 1.0) < 5e-3, (s, g[s], fd)
+    circ.params.copy_(base)
+
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+@pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
+@pytest.mark.parametrize("want_y", [False, True])
+def test_train_pass_equals_forward_backward(dwdf, oracle, tma, mode, ordering, oord, want_y):
+    """The one-sweep fused training pass gives the same loss and gradients as forward + adjoint."""
+    p = ClipperParams(n_up=1, n_down=2) if mode == "exact" else ClipperParams()
+    x = make_inputs(70, 1000, seed=77)
+    target = oracle.clipper_forward(x, perturbed(p), exact=True, ordering=oord)
+    circ, order = make_clipper(dwdf, p, mode, ordering)
+    y1 = circ.forward(dev(x))
+    a = {k: v.clone() for k, v in circ.backward(target=dev(target), loss="mse+esr", skip=50).items() if k in ("grads", "loss")}
+    y2 = torch.zeros_like(y1) if want_y else None
+    b = circ.train_pass(dev(x), dev(target), loss="mse+esr", skip=50, y=y2)
+    assert torch.allclose(a["grads"], b["grads"], rtol=2e-5, atol=0)
+    assert abs(float(a["loss"]) / float(b["loss"]) - 1) < 1e-6
+    if want_y:
+        assert torch.equal(y1, y2)
+
+
+# ---- properties at the benchmark's sizes ----------------------------------------------------------------
+
+@pytest.mark.parametrize("B,T", [(1024, 4096), (8192, 4096)])
+def test_full_size_properties(dwdf, oracle, B, T):
+    """Configs 3 / 5 (per-GPU shard) sizes: the oracle checks a sample of rows; everything else through
+    properties — TMA path == direct path bit for bit, run-to-run determinism (outputs AND reduced
+    gradients), batch-permutation equivariance, odd symmetry of the symmetric clipper, streaming
+    continuation == one long block."""
+    p = ClipperParams()
+    x = make_inputs(B, T, seed=1237)
+    xd = dev(x)
+    circ, order = make_clipper(dwdf, p, "approx", "python")
+    y = circ.forward(xd)
+    rows = np.random.default_rng(0).choice(B, 48, replace=False)
+    assert seq_rel_err(y[rows].cpu().numpy(), oracle.clipper_forward(x[rows], p)) < FWD_TOL
+    target = torch.roll(y, 1, 0).contiguous()
+    g1 = circ.backward(target=target, loss="mse+esr", skip=50)["out"].clone()
+    y_again = circ.forward(xd)
+    g2 = circ.backward(target=target, loss="mse+esr", skip=50)["out"].clone()
+    assert torch.equal(y, y_again) and torch.equal(g1, g2)
+    prev = dwdf.set_tma(False)
+    try:
+        y_direct = circ.forward(xd)
+        g3 = circ.backward(target=target, loss="mse+esr", skip=50)["out"].clone()
+    finally:
+        dwdf.set_tma(prev)
+    assert torch.equal(y, y_direct)
+    assert torch.allclose(g1, g3, rtol=1e-12, atol=0)
+    perm = torch.randperm(B, device="cuda")
+    assert torch.equal(circ.forward(xd[perm].contiguous(), keep_for_backward=False), y[perm])
+    assert torch.equal(circ.forward((-xd).contiguous(), keep_for_backward=False), -y)
+    circ_pl, _ = make_clipper(dwdf, p, "approx", "plugin")
+    whole = circ_pl.forward(xd, keep_for_backward=False)
+    st = circ_pl.new_state(B)
+    parts = [circ_pl.process_block(xd[:, a:b].contiguous(), st) for a, b in ((0, 1000), (1000, 1004), (1004, T))]
+    assert torch.equal(torch.cat(parts, 1), whole)
+
+
+# ---- generic tree interpreter ------------------------------------------------------------------------------
+
+def test_tree_rc_lowpass(dwdf, golden):
+    """Config 1's circuit (lpf.py:23-28) on the GPU interpreter, against the reference C++ run of the same tree."""
+    fs = 48000.0
+    Vs = dwdf.IdealVoltageSource()
+    R1 = dwdf.Resistor(1000.0, True)
+    C1 = dwdf.Capacitor(1.0e-6, fs, True)
+    S1 = dwdf.Series(R1, C1)
+    I1 = dwdf.Inverter(S1)
+    x = dev(golden["lpf_x"][None, :])
+    circ = dwdf.compile_circuit(Vs, tree=I1, probe=C1)
+    assert not circ.is_clipper
+    y = circ.forward(x).cpu().numpy()[0]
+    assert seq_rel_err(y, golden["lpf_y_f64"]) < FWD_TOL
+    circ_r = dwdf.compile_circuit(Vs, tree=I1, probe=R1)
+    assert seq_rel_err(circ_r.forward(x).cpu().numpy()[0], golden["lpf_vr_f64"]) < FWD_TOL
+    assert tuple(circ.forward_time_major(x).shape) == (1024, 1, 1)  # the reference's (T, B, 1)
+
+
+def test_tree_known_answers(dwdf, known):
+    """wdf_standalone_test.cpp:16-36 (4.77 +- 0.1), the divider (CommonWDFTests.h:6-23), StaticWDFTest.cpp:216-271."""
+    R1 = dwdf.Resistor(1000.0)
+    Vs = dwdf.ResistiveVoltageSource(1000.0)
+    S = dwdf.Series(R1, dwdf.PolarityInverter(Vs))
+    dp = dwdf.DiodePair(S, 1.0e-10, mode="approx")
+    y = dwdf.compile_circuit(dp, probe=R1).forward(torch.full((1, 1), 10.0, device="cuda"))
+    assert abs(float(y[0, 0]) - known["standalone_test"]["expected"]) < known["standalone_test"]["tol"]
+    assert abs(float(y[0, 0]) - known["standalone_test"]["value"]) < 1e-5
+    Ra, Rb = dwdf.Resistor(10000.0), dwdf.Resistor(10000.0)
+    top = dwdf.Inverter(dwdf.Series(Ra, Rb))
+    y = dwdf.compile_circuit(dwdf.IdealVoltageSource(), tree=top, probe=Ra).forward(torch.full((1, 1), 10.0, device="cuda"))
+    assert float(y[0, 0]) == known["divider"]["expected"]
+    k = known["static_wdf_test"]
+    for mode, key in (("approx", "best"), ("approx_good", "good")):
+        Vs = dwdf.ResistiveVoltageSource(1.0e-9)
+        Rr = dwdf.Resistor(k["R"])
+        Cc = dwdf.Capacitor(k["C"], k["fs"])
+        P = dwdf.Parallel(dwdf.Series(Vs, Rr), Cc)
+        dp = dwdf.DiodePair(P, k["Is"], mode=mode)
+        y = dwdf.compile_circuit(dp, probe=Cc, ordering="plugin").forward(dev(np.array([k["inputs"]], np.float32))).cpu().numpy()[0]
+        np.testing.assert_allclose(y, k[key], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+@pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
+def test_tree_clipper_with_resistance_channel(dwdf, oracle, mode, ordering, oord):
+    """clipper_pot.py's (B, T, 2) input: channel 1 sets the source resistance every sample (:114-117)."""
+    p = ClipperParams(R=45000.0, C=4.7e-9)
+    x = make_inputs(37, 300, seed=4)
+    r = (np.random.default_rng(1).uniform(1e4, 1e5, (37, 1)) * np.ones((1, 300))).astype(np.float32)
+    r[:, 150:] *= 1.5
+    Vs = dwdf.ResistiveVoltageSource(p.R)
+    C = dwdf.Capacitor(p.C, p.fs)
+    P1 = dwdf.Parallel(Vs, C)
+    dp = dwdf.DiodePair(P1, p.Is, p.Vt, p.nabla, mode=mode)
+    circ = dwdf.compile_circuit(dp, probe=C, ordering=ordering, r_element=Vs)
+    assert not circ.is_clipper
+    y = circ.forward(dev(x), r=dev(r)).cpu().numpy()
+    nodes = [(RESVS, -1, -1, p.R), (CAPACITOR, -1, -1, p.C), (PARALLEL, 0, 1, 0.0)]
+    ref = oracle.tree_run(nodes, p.fs, ROOT_DIODE_PAIR, x, probe=1, source=0, root_par=[float(mode == "exact"), 0, p.Is, p.Vt, p.nabla, 1, 1], ordering=oord, r_in=r, r_node=0)
+    assert seq_rel_err(y, ref) < FWD_TOL
+
+
+def test_tree_adjoint_rc_lowpass(dwdf):
+    """tape.gradient of lpf.py:87-90 (grads w.r.t. C1.C and R1.R): interpreter adjoint against
+    torch.autograd over the per-sample restatement of tf_wdf.py (oracle/torch_wdf.py), fp64."""
+    from oracle import torch_wdf as tw
+
+    fs, T = 48000.0, 600
+    x = make_inputs(5, T, seed=8)
+    target = (0.5 * np.roll(x, 3, axis=1)).astype(np.float32)
+    y_ref, leaves = tw.lpf_forward(x, 1000.0, 1.0e-6, fs)
+    loss = torch.mean((y_ref[..., 0].t() - torch.from_numpy(target).double()) ** 2)
+    gR, gC = torch.autograd.grad(loss, [leaves["R"], leaves["C"]])
+    R1 = dwdf.Resistor(1000.0, True)
+    C1 = dwdf.Capacitor(1.0e-6, fs, True)
+    top = dwdf.Inverter(dwdf.Series(R1, C1))
+    circ = dwdf.compile_circuit(dwdf.IdealVoltageSource(), tree=top, probe=C1)
+    y = circ.forward(dev(x))
+    assert seq_rel_err(y.cpu().numpy(), y_ref[..., 0].t().numpy()) < FWD_TOL
+    res = circ.backward(target=dev(target), loss="mse")
+    g = res["grads"].cpu().numpy()
+    assert abs(g[circ.slot(R1, "R")] / float(gR) - 1) < GRAD_TOL
+    assert abs(g[circ.slot(C1, "C")] / float(gC) - 1) < GRAD_TOL
+    assert abs(float(res["loss"]) / float(loss) - 1) < 1e-5
+
+
+@pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
+def test_tree_adjoint_matches_clipper_adjoint(dwdf, oracle, ordering, oord):
+    """The interpreter's reverse mode on a diode circuit: same tree as the clipper but with the ports
+    swapped (Parallel(C, Vs)), so it runs on the interpreter; gradients against the clipper oracle."""
+    p = ClipperParams()
+    x = make_inputs(40, 400, seed=31)
+    target = oracle.clipper_forward(x, perturbed(p), exact=True, ordering=oord)
+    Vs = dwdf.ResistiveVoltageSource(p.R, True)
+    C = dwdf.Capacitor(p.C, p.fs, True)
+    dp = dwdf.DiodePair(dwdf.Parallel(C, Vs), p.Is, p.Vt, p.nabla, trainable=True, mode="exact")
+    circ = dwdf.compile_circuit(dp, probe=C, ordering=ordering)
+    assert not circ.is_clipper
+    circ.forward(dev(x))
+    res = circ.backward(target=dev(target), loss="mse+esr", skip=20)
+    ref = oracle.clipper_grad(x, target, p, exact=True, ordering=oord, mode="target", loss="mse+esr", skip=20, dtype=np.float64)
+    g = res["grads"].cpu().numpy()[[circ.slot(dp, "Is"), circ.slot(dp, "nabla"), circ.slot(Vs, "R"), circ.slot(C, "C")]]
+    assert np.max(np.abs(g / ref["grads"] - 1.0)) < 5e-4, (g, ref["grads"])
+    assert abs(float(res["loss"]) / ref["loss"] - 1.0) < 1e-4
+
+
+# ---- optimizer, host entry points ---------------------------------------------------------------------------
+
+def test_adam_matches_keras_formula(dwdf, oracle):
+    """Adam(1e-4, beta_1=0.5) of clipper_pot.py:180 + the clip constraints of tf_wdf.py:74,104."""
+    p = ClipperParams()
+    x = make_inputs(64, 512, seed=2)
+    target = oracle.clipper_forward(x, perturbed(p), exact=True)
+    circ, _ = make_clipper(dwdf, p, "approx", "python")
+    opt = dwdf.Adam(circ, lr=1e-4, beta_1=0.5)
+    p0 = circ.params.double().cpu().numpy().copy()
+    m = np.zeros_like(p0)
+    v = np.zeros_like(p0)
+    for t in range(1, 4):
+        circ.forward(dev(x))
+        g = circ.backward(target=dev(target))["grads"].cpu().numpy().copy()
+        before = circ.params.double().cpu().numpy().copy()
+        opt.apply()
+        g32 = g.astype(np.float32).astype(np.float64)
+        m = 0.5 * m + 0.5 * g32
+        v = 0.999 * v + 0.001 * g32 * g32
+        lr_t = 1e-4 * np.sqrt(1 - 0.999 ** t) / (1 - 0.5 ** t)
+        want = np.clip(before - lr_t * m / (np.sqrt(v) + 1e-7), circ.clip_lo.cpu().numpy(), circ.clip_hi.cpu().numpy())
+        np.testing.assert_allclose(circ.params.cpu().numpy(), want, rtol=2e-6)
+    assert int(opt.step_count) == 3
+
+
+@pytest.mark.parametrize("B", [100, 9000])
+def test_host_entry_points(dwdf, oracle, B):
+    """dwdf_forward_host / dwdf_grad_host (pinned host buffers in, host buffers out, chunk-pipelined
+    copies) give the device path's results."""
+    p = ClipperParams()
+    T = 256
+    x = make_inputs(B, T, seed=6)
+    circ, order = make_clipper(dwdf, p, "approx", "python")
+    yd = circ.forward(dev(x))
+    target = torch.roll(yd, 1, 0).contiguous()
+    gd = circ.backward(target=target, loss="mse+esr", skip=10)["out"].clone()
+    xh = torch.from_numpy(x).pin_memory()
+    th = target.cpu().pin_memory()
+    yh = torch.empty_like(xh).pin_memory()
+    circ.forward_host(xh, yh)
+    assert torch.equal(yh, yd.cpu())
+    outh = torch.zeros(24, dtype=torch.float64).pin_memory()
+    yh2 = torch.empty_like(xh).pin_memory()
+    circ.grad_host(xh, th, outh, y_host=yh2, loss="mse+esr", skip=10)
+    assert torch.equal(yh2, yd.cpu())
+    assert torch.allclose(outh, gd.cpu(), rtol=1e-10, atol=0)
+
+
+def test_errors_are_loud(dwdf):
+    circ, _ = make_clipper(dwdf)
+    with pytest.raises(ValueError):
+        circ.forward(torch.zeros(4, 8))  # host tensor: never silently computed on the CPU
+    with pytest.raises(RuntimeError):
+        circ.backward(target=torch.zeros(4, 8, device="cuda"))  # no forward yet
+    circ.forward(torch.zeros(4, 8, device="cuda"))
+    with pytest.raises(ValueError):
+        circ.backward()

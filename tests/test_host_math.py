@@ -1,0 +1,112 @@
+"""CPU-side checks of the product's device math (csrc/dwdf_math.cuh compiled for the host by
+tests/host_math/host_math.cpp): same source the kernels inline, with the MUFU / round-down
+intrinsics replaced by IEEE host equivalents. Catches logic errors without a GPU; the GPU parity
+tests (-m gpu) are the ones that count."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_inputs, seq_rel_err
+from oracle.cpu import ORDER_PLUGIN, ORDER_PYTHON, ClipperParams
+
+SRC = os.path.join(ROOT, "tests", "host_math", "host_math.cpp")
+OUT = os.path.join(ROOT, "tests", "host_math", "_build", "libhostmath.so")
+INC = os.path.join(ROOT, "differentiable-wdfs_b200", "csrc")
+
+
+@pytest.fixture(scope="session")
+def hm():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", "-I", INC, SRC, "-o", OUT], check=True)
+    return C.CDLL(OUT)
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def scalar(hm, kind, x):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    hm.hm_scalar(C.c_int(kind), P(x), P(out), C.c_int64(x.size))
+    return out
+
+
+def clip(hm, mode, py, p, x, g=None):
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.empty_like(x)
+    acc = np.zeros(3)
+    g = None if g is None else np.ascontiguousarray(g, np.float32)
+    general = int(not (p.n_up == 1 and p.n_down == 1))
+    hm.hm_clipper(C.c_int(mode), C.c_int(general), C.c_int(py), C.c_float(p.fs), C.c_float(p.R), C.c_float(p.C), C.c_float(p.Is), C.c_float(p.Vt), C.c_float(p.nabla), C.c_float(p.n_up),
+                  C.c_float(p.n_down), P(x), None if g is None else P(g), P(y), P(acc), C.c_int64(x.shape[0]), C.c_int64(x.shape[1]))
+    return y, acc
+
+
+def test_omega_against_reference_vectors(hm, golden, known):
+    """The throughput-oriented omega3/omega4/exp/log of dwdf_math.cuh against the reference's own
+    outputs (golden) and the OmegaTest.cpp table."""
+    x = golden["omega_x"]
+    assert np.max(np.abs(scalar(hm, 0, x) - golden["omega3_f32"])) < 4e-6
+    w4, r4 = scalar(hm, 1, x), golden["omega4_f32"]
+    assert np.max(np.abs(w4 - r4) / np.maximum(np.abs(r4), 1e-30)) < 2e-6
+    e, re_ = scalar(hm, 2, x), golden["exp_approx_f32"]
+    integer = (np.round(x * 1.442695) == x * 1.442695)  # the reference's truncation quirk at negative integers
+    assert np.max((np.abs(e - re_) / np.maximum(np.abs(re_), 1e-37))[~integer]) < 2e-6
+    assert np.max(np.abs(scalar(hm, 3, golden["log_x"]) - golden["log_approx_f32"])) < 4e-6
+    tab = np.array(known["omega_table"])
+    assert np.max(np.abs(scalar(hm, 1, tab[:, 0]) - tab[:, 1])) < known["omega_tolerances"]["omega4"]
+    for kind in (4, 5):  # exact omega, 2 and 1 refinement iterations
+        assert np.max(np.abs(scalar(hm, kind, tab[:, 0]) / tab[:, 1] - 1)) < 5e-7
+        assert np.max(np.abs(scalar(hm, kind, x) / golden["toms917_f64"] - 1)) < 5e-7
+
+
+@pytest.mark.parametrize("mode,name", [(0, "best"), (1, "toms"), (2, "good")])
+def test_pair_law_against_reference_vectors(hm, golden, mode, name):
+    a = golden["pair_a"]
+    p = ClipperParams()
+    for Rp in ("4301.51", "100", "1e+06"):
+        b = np.empty_like(a)
+        hm.hm_pair(C.c_int(mode), C.c_int(0), C.c_int(0), C.c_float(float(Rp)), C.c_float(p.Is), C.c_float(p.Vt), C.c_float(p.nabla), C.c_float(1), C.c_float(1), P(a), P(b), None, C.c_int64(a.size))
+        ref = golden[f"pair_{name}_f32_Rp{Rp}"]
+        assert np.max(np.abs(b - ref)) / np.max(np.abs(ref)) < 2e-6, (name, Rp)
+
+
+def test_general_pair_law_eq45(hm, golden, diode_configs):
+    """N_up / N_down law against diode_pretraining.py:39-60 executed as is (golden eq45_*)."""
+    a = golden["eq45_a"].astype(np.float32)
+    for name, cfg in diode_configs.items():
+        if f"eq45_{name}" not in golden.files:
+            continue
+        for i, R in enumerate(golden["eq45_R"]):
+            b = np.empty_like(a)
+            hm.hm_pair(C.c_int(1), C.c_int(1), C.c_int(0), C.c_float(R), C.c_float(cfg["Is"]), C.c_float(cfg["Vt"]), C.c_float(cfg["nabla"]), C.c_float(cfg["N_up"]), C.c_float(cfg["N_down"]), P(a), P(b),
+                       None, C.c_int64(a.size))
+            ref = golden[f"eq45_{name}"][i]
+            assert np.max(np.abs(b - ref)) / np.max(np.abs(ref)) < 5e-6, (name, R)
+
+
+@pytest.mark.parametrize("circuit", ["plugin", "training"])
+@pytest.mark.parametrize("mode,mname", [(0, "approx"), (1, "exact")])
+@pytest.mark.parametrize("py,oname", [(0, "plugin"), (1, "python")])
+def test_clipper_recurrence_against_reference_vectors(hm, golden, circuit, mode, mname, py, oname):
+    p = ClipperParams() if circuit == "plugin" else ClipperParams(R=45000.0, C=4.7e-9)
+    y, _ = clip(hm, mode, py, p, golden["clip_x"])
+    assert seq_rel_err(y, golden[f"clip_{circuit}_{mname}_{oname}_f32"]) < 1e-5
+    assert seq_rel_err(y, golden[f"clip_{circuit}_{mname}_{oname}_f64"]) < 1e-5
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("py,oord", [(0, ORDER_PLUGIN), (1, ORDER_PYTHON)])
+@pytest.mark.parametrize("n_up,n_down", [(1, 1), (1, 2)])
+def test_step_tape_adjoint_sums(hm, oracle, mode, py, oord, n_up, n_down):
+    """clip_step_tape's (A, cg, cl, cv) swept backwards reproduce the oracle's raw adjoint sums."""
+    p = ClipperParams(n_up=n_up, n_down=n_down)
+    x = make_inputs(8, 1024, seed=5)
+    g = np.random.default_rng(5).standard_normal(x.shape).astype(np.float32)
+    _, acc = clip(hm, mode, py, p, x, g)
+    ref = oracle.clipper_grad(x, g, p, exact=bool(mode), ordering=oord, mode="upstream", dtype=np.float64)
+    assert np.max(np.abs(acc / ref["raw"][:3] - 1)) < 2e-5
