@@ -102,10 +102,11 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(sample_rows, threads):
+def cpu_baseline(sample_rows, threads, budget_s=12.0, passes=None, warmup=1):
     """The CPU implementation of the same step (forward + reverse sweep + loss) timed on the host.
     kind "port": oracle/wdf_oracle.c (the reference's arithmetic restated in C; the reference's C++
-    half has no backward pass and its TensorFlow half cannot be installed here)."""
+    half has no backward pass and its TensorFlow half cannot be installed here). Repeats passes over
+    one bounded sample until ~budget_s of CPU work is done; returns (median samples/s, seconds, passes)."""
     from oracle.cpu import ClipperParams, Oracle
 
     rng = np.random.default_rng(0)
@@ -114,11 +115,15 @@ def cpu_baseline(sample_rows, threads):
     target = np.roll(x, 1, 0) * 0.3
     orc = Oracle()
     p = ClipperParams()
-    orc.clipper_grad(x[:64], target[:64], p, exact=False, mode="target", dtype=np.float32, threads=threads)  # warm
-    t0 = time.perf_counter()
-    orc.clipper_grad(x, target, p, exact=False, mode="target", dtype=np.float32, threads=threads)
-    dt = time.perf_counter() - t0
-    return x.size / dt, dt
+    for _ in range(warmup):
+        orc.clipper_grad(x, target, p, exact=False, mode="target", dtype=np.float32, threads=threads)
+    times = []
+    t_all = time.perf_counter()
+    while (len(times) < passes) if passes is not None else (time.perf_counter() - t_all < budget_s and len(times) < 200):
+        t0 = time.perf_counter()
+        orc.clipper_grad(x, target, p, exact=False, mode="target", dtype=np.float32, threads=threads)
+        times.append(time.perf_counter() - t0)
+    return x.size / float(np.median(times)), float(np.sum(times)), len(times)
 
 
 def reference_forward(sample_rows, threads):
@@ -148,15 +153,9 @@ def reference_arm(args):
         return
     threads = os.cpu_count() or 1
     rows = 4096  # bounded sample: 4096 x 4096 samples per step
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, dt = cpu_baseline(rows, threads)
-        if i >= args.warmup:
-            vals.append((v, dt))
-        if sum(d for _, d in vals) > 150:
-            break
-    value = float(np.median([v for v, _ in vals]))
-    ms = float(np.median([d for _, d in vals])) * 1e3
+    value, secs, passes = cpu_baseline(rows, threads, passes=args.steps, warmup=args.warmup)  # exactly W untimed + K timed steps
+    ms = rows * T / value * 1e3
+    vals = [None] * passes
     fwd = reference_forward(rows, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms,
@@ -207,7 +206,8 @@ def main():
     P1 = dwdf.Parallel(Vs, Cc)
     dpair = dwdf.DiodePair(P1, 4.352e-9, 25.85e-3, 1.906, trainable=True, mode=args.mode)
     circ = dwdf.compile_circuit(dpair, probe=Cc, ordering="python", device=device)
-    opt = dwdf.Adam(circ, lr=1e-4, beta_1=0.5)  # clipper_pot.py:180
+    # Adam(beta_1=0.5) of clipper_pot.py:180; one rate per slot, 1e-4 of the value (R, C, Is, nF span 13 decades)
+    opt = dwdf.Adam(circ, lr={s: 1e-4 * float(circ.params[s]) for s in range(circ.n_params)}, beta_1=0.5)
 
     x = synth_inputs(torch, B, 1237 + rank, device)
     y = torch.empty_like(x)
@@ -307,13 +307,10 @@ def main():
         }
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            rows = 4096
-            v, dt = cpu_baseline(rows, threads)
-            if dt < 5.0:  # scale the sample towards ~10 s of CPU work
-                rows = int(min(32768, rows * max(1.0, 8.0 / max(dt, 1e-3)))) // 64 * 64
-                v, dt = cpu_baseline(rows, threads)
+            rows = 8192
+            v, dt, passes = cpu_baseline(rows, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
-                                    "sample": f"{rows} sequences x {T} samples, forward + reverse sweep + MSE (oracle/wdf_oracle.c, fp32), {threads} threads"}
+                                    "sample": f"{rows} sequences x {T} samples x {passes} passes (median), forward + reverse sweep + MSE (oracle/wdf_oracle.c, fp32), {threads} threads"}
             line["cpu_reference_forward"] = {"value": reference_forward(min(rows, 8192), threads), "unit": UNIT, "cores": threads, "kind": "reference",
                                              "what": "unmodified chowdsp_wdf DiodePairT forward only (oracle/_ref)"}
         print(json.dumps(line), flush=True)

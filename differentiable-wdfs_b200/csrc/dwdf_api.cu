@@ -259,10 +259,10 @@ size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
 
 static int check_batch (const dwdf_program* prog, const void* params, const void* x, int64_t B, int64_t T)
 {
-    if (prog == nullptr || params == nullptr || x == nullptr)
-        return fail (DWDF_ERR_INVALID, "null argument");
     if (B < 0 || T < 0 || T > (int64_t) 1 << 30 || B > (int64_t) 1 << 36)
         return fail (DWDF_ERR_INVALID, "bad batch shape (%lld, %lld)", (long long) B, (long long) T);
+    if (prog == nullptr || params == nullptr || (x == nullptr && B * T > 0))
+        return fail (DWDF_ERR_INVALID, "null argument");
     return DWDF_OK;
 }
 
@@ -270,10 +270,10 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
 {
     if (int rc = check_batch (prog, params, x, B, T))
         return rc;
+    if (B == 0 || T == 0)
+        return DWDF_OK; // empty batch: nothing to do (and the pointers may be null)
     if (y == nullptr)
         return fail (DWDF_ERR_INVALID, "null output");
-    if (B == 0 || T == 0)
-        return DWDF_OK;
     if ((prog->desc.r_node >= 0) != (r != nullptr))
         return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
     if (prog->is_clipper)

@@ -71,6 +71,9 @@ __device__ __forceinline__ void tree_impedance (const TreeProgram& p, const floa
 __device__ __forceinline__ float tree_root_pair (const TreeProgram& p, const PairConst& pc, float a, PairDeriv* d)
 {
     const bool general = ! (p.n_up == 1.0f && p.n_down == 1.0f);
+    PairDeriv unused;
+    if (d == nullptr)
+        d = &unused;
     if (p.root_mode == DWDF_MODE_APPROX_GOOD)
         return pair_reflect<kModeApproxGood, false, false, false> (pc, a, nullptr);
     if (p.root_mode == DWDF_MODE_EXACT)

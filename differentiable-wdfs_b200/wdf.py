@@ -334,11 +334,11 @@ class CompiledCircuit:
             slot = -1
             if kind in (L.RESISTOR, L.RESISTIVE_VS):
                 slot = len(values)
-                values.append(float(e.R))
+                values.append(float(e.R.detach()) if torch.is_tensor(e.R) else float(e.R))
                 self.slots[(id(e), "R")] = slot
             elif kind == L.CAPACITOR:
                 slot = len(values)
-                values.append(float(e.C))
+                values.append(float(e.C.detach()) if torch.is_tensor(e.C) else float(e.C))
                 self.slots[(id(e), "C")] = slot
                 fs_seen.append(float(e.FS))
             nodes.append(L.Node(kind, c1, c2, slot))
@@ -366,10 +366,10 @@ class CompiledCircuit:
                 raise ValueError("a DiodePair circuit is driven through exactly one ResistiveVoltageSource")
             d.source = sources[0]
             d.param_Is = len(values)
-            values.append(float(root.Is))
+            values.append(float(root.Is.detach()))
             self.slots[(id(root), "Is")] = d.param_Is
             d.param_nabla = len(values)
-            values.append(float(root.nabla))
+            values.append(float(root.nabla.detach()))
             self.slots[(id(root), "nabla")] = d.param_nabla
             d.Vt, d.n_up, d.n_down = root.Vt, root.N_up, root.N_down
             d.newton_max_iter, d.newton_tol = root.newton_max_iter, root.newton_tol
@@ -451,6 +451,9 @@ class CompiledCircuit:
             self._check_xy(r, "r")
         y = torch.empty_like(x) if out is None else out
         self._check_xy(y, "out")
+        if B * T == 0:
+            self._last = None
+            return y
         ck = None
         if keep_for_backward and self.is_clipper and B * T > 0:
             ck = self._scratch("_ckpt", self.lib.dwdf_ckpt_bytes(self.handle, B, T))
@@ -546,7 +549,7 @@ class CompiledCircuit:
         """Re-reads every element's current value into the device parameter vector."""
         vals = [0.0] * self.n_params
         for (eid, attr), s in self.slots.items():
-            vals[s] = float(getattr(self._owner(eid), attr))
+            vals[s] = float(torch.as_tensor(getattr(self._owner(eid), attr)).detach())
         self.params.copy_(torch.tensor(vals, dtype=torch.float32))
 
     def sync_to_elements(self):
