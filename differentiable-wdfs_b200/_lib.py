@@ -72,9 +72,9 @@ def lib() -> C.CDLL:
     L.dwdf_workspace_bytes.argtypes = [vp, i64, i64]
     L.dwdf_workspace_bytes.restype = sz
     L.dwdf_forward.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, vp]
-    L.dwdf_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, vp, sz, i64, i64, vp]
+    L.dwdf_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, vp, sz, i64, i64, vp]
     L.dwdf_train_pass.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, sz, i64, i64, vp]
-    L.dwdf_backward_raw.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, sz, i64, i64, vp]
+    L.dwdf_backward_raw.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, sz, i64, i64, vp]
     L.dwdf_train_pass_raw.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, sz, i64, i64, vp]
     L.dwdf_finalize.argtypes = [vp, vp, i32, i32, vp, vp]
     L.dwdf_adam_step.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, vp, C.c_float, C.c_float, C.c_float, C.c_double, vp, vp, vp]

@@ -302,7 +302,7 @@ int dwdf_process_block (const dwdf_program* prog, const float* params, const flo
     return forward_impl (prog, params, x, r, y, nullptr, state, B, T, (cudaStream_t) stream);
 }
 
-static int backward_impl (bool raw_only, const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream_)
+static int backward_impl (bool raw_only, const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t) stream_;
     if (int rc = check_batch (prog, params, x, B, T))
@@ -325,11 +325,11 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
     double* partials = (double*) workspace;
     if (prog->is_clipper)
     {
-        if (z_ckpt == nullptr)
-            return fail (DWDF_ERR_INVALID, "the clipper adjoint replays from the checkpoints dwdf_forward wrote: z_ckpt is null");
+        if (z_ckpt == nullptr || y == nullptr)
+            return fail (DWDF_ERR_INVALID, "the clipper adjoint reads the output y and the checkpoints z_ckpt that dwdf_forward wrote: %s is null", y == nullptr ? "y" : "z_ckpt");
         ClipTmaMaps maps;
-        const bool tma = gx == nullptr && tma_usable (x, gy_or_target, nullptr, B, T) && make_map (&maps.x, x, B, T, kSeg) && make_map (&maps.y, gy_or_target, B, T, kSeg);
-        DWDF_CUDA (launch_clipper_adjoint (prog->variant, tma, &maps, prog->clip, params, x, z_ckpt, gy_or_target, target, sk, gx, partials, B, T, stream));
+        const bool tma = gx == nullptr && tma_usable (x, gy_or_target, y, B, T) && make_map (&maps.x, x, B, T, kSeg) && make_map (&maps.y, y, B, T, kSeg) && make_map (&maps.g, gy_or_target, B, T, kSeg);
+        DWDF_CUDA (launch_clipper_adjoint (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, gy_or_target, target, sk, gx, partials, B, T, stream));
         DWDF_CUDA (launch_clipper_finalize (prog->clip, params, partials, n_groups (B), nullptr, raw_only, target, loss_kind, count, out, stream));
     }
     else
@@ -346,14 +346,14 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
     return DWDF_OK;
 }
 
-int dwdf_backward (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
+int dwdf_backward (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
 {
-    return backward_impl (false, prog, params, x, r, z_ckpt, gy_or_target, grad_mode, loss_kind, skip, gx, out, workspace, workspace_bytes, B, T, stream);
+    return backward_impl (false, prog, params, x, r, y, z_ckpt, gy_or_target, grad_mode, loss_kind, skip, gx, out, workspace, workspace_bytes, B, T, stream);
 }
 
-int dwdf_backward_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int64_t skip, float* gx, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
+int dwdf_backward_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int64_t skip, float* gx, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
 {
-    return backward_impl (true, prog, params, x, r, z_ckpt, gy_or_target, grad_mode, DWDF_LOSS_MSE, skip, gx, raw, workspace, workspace_bytes, B, T, stream);
+    return backward_impl (true, prog, params, x, r, y, z_ckpt, gy_or_target, grad_mode, DWDF_LOSS_MSE, skip, gx, raw, workspace, workspace_bytes, B, T, stream);
 }
 
 int dwdf_finalize (const dwdf_program* prog, const float* params, int32_t grad_mode, int32_t loss_kind, double* raw_inout, void* stream)
@@ -537,8 +537,8 @@ int dwdf_grad_host (const dwdf_program* prog, const float* params_host, const fl
         if (y_host != nullptr)
             DWDF_CUDA (cudaMemcpyAsync (y_host + b0 * T, d_y + b0 * T, (size_t) nb * row, cudaMemcpyDeviceToHost, s));
         ClipTmaMaps maps;
-        const bool tma = tma_usable (d_x + b0 * T, d_g + b0 * T, nullptr, nb, T) && make_map (&maps.x, d_x + b0 * T, nb, T, kSeg) && make_map (&maps.y, d_g + b0 * T, nb, T, kSeg);
-        DWDF_CUDA (launch_clipper_adjoint (prog->variant, tma, &maps, prog->clip, d_params, d_x + b0 * T, ckc, d_g + b0 * T, target, sk, nullptr, d_part + group0 * kPartialStride, nb, T, s));
+        const bool tma = tma_usable (d_x + b0 * T, d_g + b0 * T, d_y + b0 * T, nb, T) && make_map (&maps.x, d_x + b0 * T, nb, T, kSeg) && make_map (&maps.y, d_y + b0 * T, nb, T, kSeg) && make_map (&maps.g, d_g + b0 * T, nb, T, kSeg);
+        DWDF_CUDA (launch_clipper_adjoint (prog->variant, tma, &maps, prog->clip, d_params, d_x + b0 * T, d_y + b0 * T, ckc, d_g + b0 * T, target, sk, nullptr, d_part + group0 * kPartialStride, nb, T, s));
         g_launches.fetch_add (1);
         group0 += n_groups (nb);
         DWDF_CUDA (cudaEventRecord (g_arena.done[k % 3], s));

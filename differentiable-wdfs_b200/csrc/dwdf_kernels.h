@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 
 #include "dwdf_math.cuh"
 
@@ -33,13 +34,21 @@ struct ClipVariant
 // TMA descriptors of one launch (valid only when use_tma)
 struct ClipTmaMaps
 {
-    CUtensorMap x, y; // forward: 32 x 32 tiles, 128-byte swizzle; adjoint: 16 x 32 tiles, 64-byte swizzle
+    CUtensorMap x, y, g; // forward (x, y): 32 x 32 tiles, 128-byte swizzle; adjoint (x, y, g): 16 x 32 tiles, 64-byte swizzle
 };
+
+// per-(root mode, law) launchers, each specialised in its own translation unit (clipper_kernels.cu, 4 parts)
+template <int MODE, bool GENERAL>
+cudaError_t clipper_forward_part (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, float* y, float* ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream);
+template <int MODE, bool GENERAL>
+cudaError_t clipper_adjoint_part (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* y, const float* ckpt, const float* g, bool target, int skip, float* gx, double* partials, int64_t B, int64_t T, cudaStream_t stream);
+template <int MODE, bool GENERAL>
+cudaError_t clipper_train_part (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* target, int skip, float* y, double* partials, int64_t B, int64_t T, cudaStream_t stream);
 
 cudaError_t launch_clipper_forward (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, float* y, float* ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream);
 
-// adjoint: raw sums per group of 32 sequences into partials[(group0 + group) * kPartialStride + k]
-cudaError_t launch_clipper_adjoint (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* ckpt, const float* g, bool target, int64_t skip, float* gx, double* partials, int64_t B, int64_t T, cudaStream_t stream);
+// adjoint (reverse sweep over x, the forward output y and g = dL/dy or the target): raw sums per group of 32 sequences into partials[(group0 + group) * kPartialStride + k]
+cudaError_t launch_clipper_adjoint (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* y, const float* ckpt, const float* g, bool target, int64_t skip, float* gx, double* partials, int64_t B, int64_t T, cudaStream_t stream);
 
 // fused training pass: forward + loss + parameter sensitivities in one sweep
 cudaError_t launch_clipper_train (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* target, int64_t skip, float* y, double* partials, int64_t B, int64_t T, cudaStream_t stream);

@@ -84,17 +84,22 @@ DWDF_HD float fma_ (float a, float b, float c)
 //          shift out).
 // Differs from the reference only at negative integer x', where omega.h's truncation quirk picks
 // (l = x'-1, f = 1) and this picks (l = x', f = 0): both are 2^x' to 1.3e-5 (cubic end-point error).
-DWDF_HD float exp_approx_scaled (float xp) // takes x' = x * log2(e)
+template <bool CLAMP = true>
+DWDF_HD float exp_approx_scaled (float xp) // takes x' = x * log2(e); CLAMP = false: the caller guarantees x' >= -126
 {
     const float kMagic = 12582912.0f; // 1.5 * 2^23
-    xp = fmaxf (xp, -126.0f);
+    if (CLAMP)
+        xp = fmaxf (xp, -126.0f);
     const float t = add_rd (xp, kMagic);
     const float l = t - kMagic;
     const float f = xp - l;
     const float p = fma_ (f, fma_ (f, fma_ (f, 0.07944154167983575f, 0.2274112777602189f), 0.6931471805599453f), 1.0f);
     return i2f (f2i (p) + (int32_t) ((uint32_t) f2i (t) << 23));
 }
-DWDF_HD float exp_approx (float x) { return exp_approx_scaled (1.442695040888963f * x); }
+DWDF_HD float exp_approx (float x) { return exp_approx_scaled<true> (1.442695040888963f * x); }
+
+// a with the sign bit of s XOR-ed in: a * sign(s) for s != 0 (one LOP3)
+DWDF_HD float xor_sign (float a, float s) { return i2f (f2i (a) ^ (f2i (s) & (int32_t) 0x80000000)); }
 
 // log_approx, omega.h:49-63 (with log2_approx :33-42), for x > 0: ln2 * (exponent + cubic(mantissa)).
 //   exponent as float without I2F: (bits >> 23) OR'ed into the mantissa of 2^23, minus (2^23 + 127).
@@ -107,25 +112,38 @@ DWDF_HD float log_approx_pos (float x)
     return 0.693147180559945f * (e + p);
 }
 
-// omega3, omega.h:159-169
+// omega3, omega.h:159-169.
+// WARP (device only): the caller guarantees that all 32 lanes of the warp are converged here; the
+// x >= 8 branch (x - log_approx(x), ~11 instructions) is then skipped when no lane needs it — one
+// vote instead of computing both sides of the select for every sample. Same value either way.
+template <bool WARP = false>
 DWDF_HD float omega3_approx (float x)
 {
-    const float cub = fma_ (x, fma_ (x, fma_ (x, -1.314293149877800e-3f, 4.775931364975583e-2f), 3.631952663804445e-1f), 6.313183464296682e-1f);
-    const float lg = x - log_approx_pos (x);
-    float y = x < 8.0f ? cub : lg;
+    float y = fma_ (x, fma_ (x, fma_ (x, -1.314293149877800e-3f, 4.775931364975583e-2f), 3.631952663804445e-1f), 6.313183464296682e-1f);
+#if defined(__CUDA_ARCH__)
+    if (! WARP || __any_sync (0xffffffffu, x >= 8.0f))
+#endif
+        y = x < 8.0f ? y : x - log_approx_pos (x);
     y = x < -3.341459552768620f ? 0.0f : y;
     return y;
 }
 
-// omega4, omega.h:172-177: omega3 + one Newton step on  w - exp(x - w)
+// omega4, omega.h:172-177: omega3 + one Newton step on  w - exp(x - w).
+// FAST: WARP as above, and the caller guarantees x * log2(e) >= -126 (no clamp in exp_approx).
+template <bool FAST = false>
 DWDF_HD float omega4_approx (float x)
 {
-    const float y = omega3_approx (x);
-    const float e = exp_approx (x - y);
+    const float y = omega3_approx<FAST> (x);
+    const float e = exp_approx_scaled<! FAST> (1.442695040888963f * (x - y));
     return y - (y - e) * rcp (y + 1.0f);
 }
 
 constexpr float kOmega3Zero = -3.341459552768620f; // below this omega3 == 0 and omega4(x) == exp_approx(x)
+constexpr float kLog2e = 1.442695040888963f;
+// The clipper kernels' fast path ("LSMALL") applies when  -87 < L < kOmega3Zero  (every physical
+// diode: Rp*Is << V, and Rp*Is/V a normal float): the reverse-biased omega4(L - |a|/V) is exactly
+// exp_approx(L - |a|/V), and the forward-biased argument never needs exp_approx's -126 clamp.
+DWDF_HD bool lsmall_ok (float L) { return L < kOmega3Zero && L > -87.0f; }
 
 // ---- "exact" Wright-omega in fp32 ---------------------------------------------------------------
 // Replaces Toms917DiodePair.h:64-67 (float -> complex<double> TOMS-917 -> float) and
@@ -197,8 +215,11 @@ struct PairConst
 {
     float V, twoV, invV; // V = nDiodes * Vt
     float L; // ln(Rp * Is / V)
+    float Ll2e, invVl2e; // L * log2(e), log2(e) / V: the reverse-biased exp_approx argument in one FMA
+    float inv2V; // 1 / (2 V)
     float RIs, RIs_overV; // "Good" law only
     float n_up, n_dn, L_up, L_dn, inv_up, inv_dn; // general law: mu, ln(Rp Is / (V mu)), 1 / (mu V)
+    float rn_up, rn_dn; // 1 / mu
     int n_iter;
     float tol;
 };
@@ -211,22 +232,27 @@ DWDF_HD void pair_setup (PairConst& c, float Rp, float Is, float Vt, float nabla
     c.RIs = Rp * Is;
     c.RIs_overV = c.RIs * c.invV;
     c.L = logf (c.RIs_overV);
+    c.Ll2e = kLog2e * c.L;
+    c.invVl2e = kLog2e * c.invV;
+    c.inv2V = 0.5f * c.invV;
     c.n_up = n_up;
     c.n_dn = n_down;
     c.L_up = logf (c.RIs_overV / n_up);
     c.L_dn = logf (c.RIs_overV / n_down);
     c.inv_up = 1.0f / (n_up * c.V);
     c.inv_dn = 1.0f / (n_down * c.V);
+    c.rn_up = 1.0f / n_up;
+    c.rn_dn = 1.0f / n_down;
     c.n_iter = n_iter <= 0 ? 2 : n_iter;
     c.tol = tol;
 }
 
-template <int MODE>
+template <int MODE, bool FAST = false>
 DWDF_HD float root_omega (const PairConst& c, float u)
 {
     if (MODE == kModeExact)
         return omega_exact (u, c.n_iter, c.tol);
-    return omega4_approx (u);
+    return omega4_approx<FAST> (u);
 }
 
 // Derivative pieces of b = f(a; ell, V) with ell = ln(Rp Is), omega' = omega / (1 + omega):
@@ -238,17 +264,31 @@ struct PairDeriv
     float S1, M1, dV;
 };
 
+// (S1, M1, dV) from the two omegas of one sample
+template <bool GENERAL>
+DWDF_HD void pair_deriv (const PairConst& c, float a, float b, float w0, float w1, float mu0, float mu1, PairDeriv* d)
+{
+    const float wp0 = w0 * rcp (1.0f + w0), wp1 = w1 * rcp (1.0f + w1);
+    d->S1 = wp0 + wp1;
+    if (GENERAL)
+    {
+        const float lam = a == 0.0f ? 0.0f : copysignf (1.0f, a);
+        d->M1 = lam * fma_ (mu0, wp0, -(mu1 * wp1));
+    }
+    else
+        d->M1 = xor_sign (wp0 - wp1, a); // wp0 == wp1 at a == 0
+    d->dV = fma_ (2.0f * a * c.invV, d->S1, fma_ (b - a, c.invV, 2.0f * d->M1));
+}
+
 // b = f(a).  Symmetric (eq. 39): wdf_t.h:917-924 == Toms917DiodePair.h:51-59.
 //            General   (eq. 45): diode_pretraining.py:39-60 with N_up / N_down.
 //            Good      (eq. 18): wdf_t.h:907-913.
-// LSMALL: the caller guarantees L < kOmega3Zero (true for every physical diode: Rp*Is << V), so
-// the reverse-branch omega4(L - |a|/V) is exactly exp_approx(L - |a|/V) (omega3 == 0 there) and the
-// cubic / log / Newton work is skipped. Approx + symmetric only.
+// LSMALL: the caller guarantees lsmall_ok(L) and (on the device) a converged warp. Approx + symmetric only.
 template <int MODE, bool GENERAL, bool DERIV, bool LSMALL>
 DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
 {
     const float aa = fabsf (a);
-    float w0, w1, mu0 = 1.0f, mu1 = 1.0f, s; // s = 2 V lambda, lambda = signum(a) (signum.h:5-9; 0 at a == 0)
+    float w0, w1, mu0 = 1.0f, mu1 = 1.0f, b;
     if (MODE == kModeApproxGood)
     {
         w0 = omega4_approx (c.L + aa * c.invV + c.RIs_overV);
@@ -264,27 +304,27 @@ DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
         const float q0 = aa * (pos ? c.inv_dn : c.inv_up), q1 = aa * (pos ? c.inv_up : c.inv_dn);
         w0 = root_omega<MODE> (c, l0 + q0);
         w1 = root_omega<MODE> (c, l1 - q1);
+        const float s = a == 0.0f ? 0.0f : copysignf (c.twoV, a); // 2 V lambda, lambda = signum(a) (signum.h:5-9; 0 at a == 0)
+        b = fma_ (-s, fma_ (mu0, w0, -(mu1 * w1)), a);
     }
     else
     {
-        const float q = aa * c.invV;
-        w0 = root_omega<MODE> (c, c.L + q);
         if (MODE == kModeApprox && LSMALL)
-            w1 = exp_approx (c.L - q);
+        {
+            w0 = omega4_approx<true> (fma_ (aa, c.invV, c.L));
+            w1 = exp_approx_scaled<true> (fma_ (aa, -c.invVl2e, c.Ll2e));
+        }
         else
+        {
+            const float q = aa * c.invV;
+            w0 = root_omega<MODE> (c, c.L + q);
             w1 = root_omega<MODE> (c, c.L - q);
+        }
+        // a == 0 makes both branches the same computation, w0 - w1 == 0 and b == a: signum's zero needs no select
+        b = fma_ (-c.twoV, xor_sign (w0 - w1, a), a);
     }
-    s = a == 0.0f ? 0.0f : copysignf (c.twoV, a);
-    const float diff = GENERAL ? fma_ (mu0, w0, -(mu1 * w1)) : (w0 - w1);
-    const float b = fma_ (-s, diff, a);
     if (DERIV)
-    {
-        const float wp0 = w0 * rcp (1.0f + w0), wp1 = w1 * rcp (1.0f + w1);
-        const float lam = a == 0.0f ? 0.0f : copysignf (1.0f, a);
-        d->S1 = wp0 + wp1;
-        d->M1 = lam * (GENERAL ? fma_ (mu0, wp0, -(mu1 * wp1)) : (wp0 - wp1));
-        d->dV = fma_ (2.0f * a * c.invV, d->S1, fma_ (b - a, c.invV, 2.0f * d->M1));
-    }
+        pair_deriv<GENERAL> (c, a, b, w0, w1, mu0, mu1, d);
     return b;
 }
 
@@ -293,6 +333,7 @@ DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
 struct ClipConst
 {
     float gamma; // p1R = Gv / G
+    float one_m_gamma;
     float Rp; // port resistance seen by the root
     PairConst pair;
 };
@@ -312,6 +353,7 @@ DWDF_HD void clip_setup (ClipConst& c, const ClipDesc& d, float R, float C, floa
     const float G = Gv + Gc;
     c.Rp = 1.0f / G;
     c.gamma = Gv / G;
+    c.one_m_gamma = 1.0f - c.gamma;
     pair_setup (c.pair, c.Rp, Is, d.Vt, nabla, d.n_up, d.n_down, d.n_iter, d.tol);
 }
 
@@ -352,12 +394,55 @@ DWDF_HD float clip_step_tape (const ClipConst& c, float x, float& z, StepTape& t
     const float zn = b + t;
     const float y = PYORDER ? 0.5f * (zn + z) : z;
     const float fp1 = fma_ (-2.0f, d.S1, 2.0f); // f'(a) + 1
-    tp.A = fma_ (fp1, 1.0f - c.gamma, -1.0f); // (fp1 - 1)(1 - gamma) - gamma = fp1 (1 - gamma) - 1
+    tp.A = fma_ (fp1, c.one_m_gamma, -1.0f); // (fp1 - 1)(1 - gamma) - gamma = fp1 (1 - gamma) - 1
     tp.cg = xz * fp1;
     tp.cl = -c.pair.twoV * d.M1;
     tp.cv = d.dV;
     z = zn;
     return y;
+}
+
+// The same linearisation recovered from BOTH end points of a step — the adjoint's way: it knows the
+// state before (z) and after (zn) each sample from the forward pass's output, so nothing is replayed.
+//   a = z + gamma (x - z),  b = zn - gamma (x - z)            (the step's own equations, solved for b)
+//   b = a - 2 V lambda (mu0 w0 - mu1 w1)  =>  mu0 w0 = mu1 w1 + lambda (a - b) / (2 V)
+// Only the reverse-biased omega w1 is evaluated (argument <= L: the cheap branch; under LSMALL one
+// exp_approx); the forward-biased w0 — the expensive one, and the one whose value fixes f'(a) — is
+// read off the reflected wave the forward pass produced. (x, z, zn) -> (A, cg, cl, cv).
+template <int MODE, bool GENERAL, bool LSMALL>
+DWDF_HD void clip_step_recover (const ClipConst& c, float x, float z, float zn, StepTape& tp)
+{
+    const float xz = x - z;
+    const float a = fma_ (c.gamma, xz, z);
+    const float b = fma_ (-c.gamma, xz, zn);
+    const float aa = fabsf (a);
+    const float dl = xor_sign (a - b, a); // lambda (a - b) >= 0
+    float w0, w1, mu0 = 1.0f, mu1 = 1.0f;
+    if (GENERAL)
+    {
+        const bool pos = a >= 0.0f;
+        mu0 = pos ? c.pair.n_dn : c.pair.n_up;
+        mu1 = pos ? c.pair.n_up : c.pair.n_dn;
+        w1 = root_omega<MODE> (c.pair, (pos ? c.pair.L_up : c.pair.L_dn) - aa * (pos ? c.pair.inv_up : c.pair.inv_dn));
+        w0 = fma_ (dl, c.pair.inv2V, mu1 * w1) * (pos ? c.pair.rn_dn : c.pair.rn_up);
+        if (a == 0.0f) // lambda = 0 hides w0 from b; rare, evaluate it
+            w0 = root_omega<MODE> (c.pair, c.pair.L_dn);
+    }
+    else
+    {
+        if (MODE == kModeApprox && LSMALL)
+            w1 = exp_approx_scaled<true> (fma_ (aa, -c.pair.invVl2e, c.pair.Ll2e));
+        else
+            w1 = root_omega<MODE> (c.pair, c.pair.L - aa * c.pair.invV);
+        w0 = fma_ (dl, c.pair.inv2V, w1);
+    }
+    PairDeriv d;
+    pair_deriv<GENERAL> (c.pair, a, b, w0, w1, mu0, mu1, &d);
+    const float fp1 = fma_ (-2.0f, d.S1, 2.0f); // f'(a) + 1
+    tp.A = fma_ (fp1, c.one_m_gamma, -1.0f);
+    tp.cg = xz * fp1;
+    tp.cl = -c.pair.twoV * d.M1;
+    tp.cv = d.dV;
 }
 
 } // namespace dwdf

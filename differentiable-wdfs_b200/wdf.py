@@ -458,7 +458,7 @@ class CompiledCircuit:
         if keep_for_backward and self.is_clipper and B * T > 0:
             ck = self._scratch("_ckpt", self.lib.dwdf_ckpt_bytes(self.handle, B, T))
         L.check(self.lib.dwdf_forward(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), B, T, _stream_ptr(self.device)))
-        self._last = (x, r, B, T) if keep_for_backward else None
+        self._last = (x, r, y, B, T) if keep_for_backward else None
         return y
 
     def forward_time_major(self, x, r=None):
@@ -467,6 +467,7 @@ class CompiledCircuit:
 
     def backward(self, gy=None, target=None, loss="mse", skip=0, want_gx=False, raw=False):
         """Gradients of the last ``forward``: upstream ``gy = dL/dy`` or a fused loss against ``target``.
+        The adjoint kernel reads the output tensor that ``forward`` returned; do not modify it in between.
 
         Returns a dict with ``grads`` (float64 tensor, one per parameter slot, on the device), ``loss``,
         ``mse``, ``esr`` (0-d device tensors; target mode) and ``gx`` if requested.
@@ -475,7 +476,7 @@ class CompiledCircuit:
             raise RuntimeError("backward() needs a preceding forward(keep_for_backward=True)")
         if (gy is None) == (target is None):
             raise ValueError("give exactly one of gy (upstream gradient) or target (fused loss)")
-        x, r, B, T = self._last
+        x, r, y, B, T = self._last
         g = gy if gy is not None else target
         self._check_xy(g, "gy/target")
         if tuple(g.shape) != (B, T):
@@ -486,10 +487,10 @@ class CompiledCircuit:
         ck = self._ckpt if self.is_clipper else None
         mode = L.GRAD_UPSTREAM if gy is not None else L.GRAD_TARGET
         if raw:
-            L.check(self.lib.dwdf_backward_raw(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(ck), _ptr(g), mode, int(skip), _ptr(gx), _ptr(self.out), _ptr(work), work.numel(), B, T,
+            L.check(self.lib.dwdf_backward_raw(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), _ptr(g), mode, int(skip), _ptr(gx), _ptr(self.out), _ptr(work), work.numel(), B, T,
                                                _stream_ptr(self.device)))
         else:
-            L.check(self.lib.dwdf_backward(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(ck), _ptr(g), mode, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(gx),
+            L.check(self.lib.dwdf_backward(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), _ptr(g), mode, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(gx),
                                            _ptr(self.out), _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
         return self._result(gx)
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DWDF_VERSION 1
+#define DWDF_VERSION 2
 #if defined(__GNUC__)
 #define DWDF_API __attribute__ ((visibility ("default")))
 #else
@@ -164,12 +164,14 @@ DWDF_API size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64
 DWDF_API int dwdf_forward (const dwdf_program* prog, const float* params, const float* x, const float* r, float* y, float* z_ckpt, int64_t B, int64_t T, void* stream);
 
 /* Replaces: tape.gradient(loss, trainable_variables) (lpf.py:87-90, clipper_pot.py:246-269).
- * Hand-written adjoint: walks the checkpoints written by dwdf_forward in reverse, replays each
- * segment of the recurrence and sweeps it backwards; no tape, no autodiff framework. `skip`
- * leading samples are excluded from the fused loss (clipper_pot.py:232,248). `gx` is NULL or
- * receives dL/dx. `out` receives the DWDF_OUT_LEN doubles described above, already reduced over
- * the batch in a fixed order (bit-reproducible). */
-DWDF_API int dwdf_backward (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+ * Hand-written adjoint, no tape, no autodiff framework: one reverse sweep over (x, y, g) that
+ * re-derives every step of the recurrence from its two end states — recovered from the forward
+ * output `y` (the (B, T) buffer dwdf_forward wrote, unchanged) and re-anchored at the checkpoints
+ * `z_ckpt` — and carries the adjoint of the capacitor state backwards. `skip` leading samples are
+ * excluded from the fused loss (clipper_pot.py:232,248). `gx` is NULL or receives dL/dx. `out`
+ * receives the DWDF_OUT_LEN doubles described above, already reduced over the batch in a fixed
+ * order (bit-reproducible). Programs on the tree interpreter ignore `y` and `z_ckpt` (may be NULL). */
+DWDF_API int dwdf_backward (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
 
 /* Fused training pass (forward + loss + parameter gradients in ONE sweep, by propagating the
  * parameter sensitivities with the recurrence): same `out` as dwdf_forward followed by
@@ -181,7 +183,7 @@ DWDF_API int dwdf_train_pass (const dwdf_program* prog, const float* params, con
  * of samples in the loss) so that ranks can all-reduce them (one ncclAllReduce of DWDF_OUT_LEN doubles);
  * dwdf_finalize then turns the summed block, in place, into the `out` block described above. The
  * result is independent of how the batch was sharded. */
-DWDF_API int dwdf_backward_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int64_t skip, float* gx, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+DWDF_API int dwdf_backward_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int64_t skip, float* gx, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
 DWDF_API int dwdf_train_pass_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* target, int64_t skip, float* y, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
 DWDF_API int dwdf_finalize (const dwdf_program* prog, const float* params, int32_t grad_mode, int32_t loss_kind, double* raw_inout, void* stream);
 

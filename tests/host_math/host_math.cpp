@@ -101,8 +101,80 @@ extern "C" void hm_clipper (int mode, int general, int pyorder, float fs, float 
     ClipDesc d { fs, Vt, n_up, n_down, 0.0f, 2, 0, 1, 2, 3 };
     ClipConst c;
     clip_setup (c, d, R, C, Is, nabla);
-    const bool lsmall = mode == kModeApprox && ! general && c.pair.L < kOmega3Zero;
+    const bool lsmall = mode == kModeApprox && ! general && lsmall_ok (c.pair.L);
 #define RUN(M, G, L) (pyorder ? clip_run<M, G, L, true> (c, x, g, y, acc, B, T) : clip_run<M, G, L, false> (c, x, g, y, acc, B, T))
+    if (mode == kModeApprox)
+    {
+        if (general) RUN (kModeApprox, true, false);
+        else if (lsmall) RUN (kModeApprox, false, true);
+        else RUN (kModeApprox, false, false);
+    }
+    else
+    {
+        if (general) RUN (kModeExact, true, false);
+        else RUN (kModeExact, false, false);
+    }
+#undef RUN
+}
+
+// The adjoint's way (clipper_kernels.cu adjoint_segment): forward once for y, then a reverse sweep that
+// recovers the states from y (re-anchored every 16 samples at a checkpoint) and each step's
+// linearisation with clip_step_recover. acc as in hm_clipper.
+template <int MODE, bool GENERAL, bool LSMALL, bool PY>
+static void recover_run (const ClipConst& c, const float* x, const float* g, float* y, double* acc, int64_t B, int64_t T)
+{
+    constexpr int SEG = 16;
+    std::vector<float> ck ((size_t) ((T + SEG - 1) / SEG)), zs ((size_t) T + 1);
+    for (int64_t s = 0; s < B; ++s)
+    {
+        float z = 0.0f;
+        for (int64_t n = 0; n < T; ++n)
+        {
+            if (n % SEG == 0)
+                ck[(size_t) (n / SEG)] = z;
+            y[s * T + n] = clip_step<MODE, GENERAL, LSMALL, PY> (c, x[s * T + n], z);
+        }
+        for (int64_t n = 0; n < T; ++n) // states from the output only
+        {
+            if (n % SEG == 0)
+                zs[(size_t) n] = ck[(size_t) (n / SEG)];
+            if (PY)
+                zs[(size_t) n + 1] = std::fmaf (2.0f, y[s * T + n], -zs[(size_t) n]);
+            else
+                zs[(size_t) n] = y[s * T + n];
+        }
+        // python ordering: the segment's last z[n+1] is overwritten by the next checkpoint in the loop above
+        // (n % SEG == 0), exactly like the kernel, which starts every segment from its checkpoint
+        double G = 0.0;
+        for (int64_t n = T - 1; n >= 0; --n)
+        {
+            const double gy = g[s * T + n];
+            if (! PY && n == T - 1)
+            {
+                G = gy;
+                continue;
+            }
+            float zn = zs[(size_t) n + 1];
+            if (PY && (n + 1) % SEG == 0)
+                zn = std::fmaf (2.0f, y[s * T + n], -zs[(size_t) n]); // within-segment reconstruction, not the next checkpoint
+            StepTape tp;
+            clip_step_recover<MODE, GENERAL, LSMALL> (c, x[s * T + n], zs[(size_t) n], zn, tp);
+            if (PY) G += 0.5 * gy;
+            acc[0] += G * tp.cg;
+            acc[1] += G * tp.cl;
+            acc[2] += G * tp.cv;
+            G = (PY ? 0.5 * gy : gy) + G * tp.A;
+        }
+    }
+}
+
+extern "C" void hm_clipper_recover (int mode, int general, int pyorder, float fs, float R, float C, float Is, float Vt, float nabla, float n_up, float n_down, const float* x, const float* g, float* y, double* acc, int64_t B, int64_t T)
+{
+    ClipDesc d { fs, Vt, n_up, n_down, 0.0f, 2, 0, 1, 2, 3 };
+    ClipConst c;
+    clip_setup (c, d, R, C, Is, nabla);
+    const bool lsmall = mode == kModeApprox && ! general && lsmall_ok (c.pair.L);
+#define RUN(M, G, L) (pyorder ? recover_run<M, G, L, true> (c, x, g, y, acc, B, T) : recover_run<M, G, L, false> (c, x, g, y, acc, B, T))
     if (mode == kModeApprox)
     {
         if (general) RUN (kModeApprox, true, false);
