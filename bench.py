@@ -236,9 +236,6 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -246,6 +243,9 @@ def main():
     launches0 = dwdf.launch_count()
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()  # every rank enters the timed region together (rank 0 has just started the clock sampler)
+        torch.cuda.synchronize()
     t_beg.record()
     for i in range(args.steps):
         step(i)

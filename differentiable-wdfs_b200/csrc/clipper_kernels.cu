@@ -192,8 +192,10 @@ struct AdjAcc
 // With the trajectory known up front the only serial chain left is the two-FMA recurrence of the
 // running adjoint G of z[n+1]; everything else is independent work per sample.
 //   IO::x4 / y4 / g4 (cc): 4 samples of x / forward output / (dL/dy or target); IO::put_gx: dL/dx.
-template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, class IO>
-__device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, float z0, float zend, float& G, AdjAcc& acc, int n0, int nvalid, int skip, int last)
+//   FULL: all kSeg samples are valid, none is skipped by the loss and (plugin ordering) none is the
+//   sequence's last — the common case, free of per-sample predicates.
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, bool FULL, class IO>
+__device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io, float z0, float zend, float& G, AdjAcc& acc, int n0, int nvalid, int skip, int last)
 {
     float zs[kSeg + 1];
     zs[0] = z0;
@@ -218,7 +220,7 @@ __device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, flo
 #pragma unroll
     for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
     {
-        if (cc * 4 < nvalid)
+        if (FULL || cc * 4 < nvalid)
         {
             const float4 xv = io.x4 (cc), gv = io.g4 (cc);
             const float xs[4] = { xv.x, xv.y, xv.z, xv.w };
@@ -228,18 +230,18 @@ __device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, flo
             for (int k = 3; k >= 0; --k)
             {
                 const int idx = cc * 4 + k;
-                if (idx < nvalid)
+                if (FULL || idx < nvalid)
                 {
                     float gy = gs[k];
                     if (TARGET)
                     {
-                        const bool on = n0 + idx >= skip;
+                        const bool on = FULL || n0 + idx >= skip;
                         const float yk = PY ? 0.5f * (zs[idx + 1] + zs[idx]) : zs[idx];
                         gy = on ? yk - gs[k] : 0.0f;
                         sse = fma_ (gy, gy, sse);
                         st2 = on ? fma_ (gs[k], gs[k], st2) : st2;
                     }
-                    if (! PY && idx == last)
+                    if (! FULL && ! PY && idx == last)
                         G = gy; // plugin ordering never observes z[T]: the final step has nothing to recover and feeds nothing back
                     else
                     {
@@ -268,6 +270,15 @@ __device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, flo
         acc.sse += (double) sse;
         acc.st2 += (double) st2;
     }
+}
+
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, class IO>
+__device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, float z0, float zend, float& G, AdjAcc& acc, int n0, int nvalid, int skip, int last)
+{
+    if (nvalid == kSeg && n0 >= skip && (PY || last >= kSeg))
+        adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, true> (c, io, z0, zend, G, acc, n0, nvalid, skip, last);
+    else
+        adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, false> (c, io, z0, zend, G, acc, n0, nvalid, skip, last);
 }
 
 __device__ __forceinline__ void write_partials (AdjAcc& acc, double* __restrict__ partials, int group, int lane)
