@@ -5,6 +5,8 @@
 
 namespace dwdf
 {
+int g_clip_opts = 0;
+
 namespace
 {
 // =================================================================================================

@@ -56,7 +56,58 @@ __device__ __forceinline__ double warp_sum (double v)
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int MODE, bool GENERAL, bool LSMALL, bool PY>
+// One 4-sample chunk of one sequence (V = f1) or of two (V = f2) the forward kernels' way: fast step, and
+// the instances that crossed omega3's log branch redone the general way (a per-lane branch: rare, and it
+// keeps every sequence's result independent of its neighbours in the warp).
+template <bool PY>
+__device__ __forceinline__ float4 forward_chunk (const ClipConst& c, float4 v, float& z)
+{
+    const f1 x[4] = { { v.x }, { v.y }, { v.z }, { v.w } };
+    f1 o[4], zz { z }, um { -1.0e30f };
+    clip_chunk_fastv<f1, PY> (c, x, zz, o, um);
+    float4 r = make_float4 (o[0].x, o[1].x, o[2].x, o[3].x);
+    if (um.x >= kFastLoud)
+    {
+        const float xs[4] = { v.x, v.y, v.z, v.w };
+        float os[4];
+        clip_chunk_general<PY> (c, xs, z, os);
+        return make_float4 (os[0], os[1], os[2], os[3]);
+    }
+    z = zz.x;
+    return r;
+}
+template <bool PY>
+__device__ __forceinline__ void forward_chunk2 (const ClipConst& c, float4 va, float4 vb, f2& z, float4& oa, float4& ob)
+{
+    const f2 x[4] = { { va.x, vb.x }, { va.y, vb.y }, { va.z, vb.z }, { va.w, vb.w } };
+    f2 o[4], zz = z, um { -1.0e30f, -1.0e30f };
+    clip_chunk_fastv<f2, PY> (c, x, zz, o, um);
+    oa = make_float4 (o[0].x, o[1].x, o[2].x, o[3].x);
+    ob = make_float4 (o[0].y, o[1].y, o[2].y, o[3].y);
+    if (fmaxf (um.x, um.y) >= kFastLoud)
+    {
+        float os[4];
+        if (um.x >= kFastLoud)
+        {
+            const float xs[4] = { va.x, va.y, va.z, va.w };
+            float za = z.x;
+            clip_chunk_general<PY> (c, xs, za, os);
+            oa = make_float4 (os[0], os[1], os[2], os[3]);
+            zz.x = za;
+        }
+        if (um.y >= kFastLoud)
+        {
+            const float xs[4] = { vb.x, vb.y, vb.z, vb.w };
+            float zb = z.y;
+            clip_chunk_general<PY> (c, xs, zb, os);
+            ob = make_float4 (os[0], os[1], os[2], os[3]);
+            zz.y = zb;
+        }
+    }
+    z = zz;
+}
+
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool FAST = true>
 __device__ __forceinline__ void forward_tma_body (const ClipConst& c, const CUtensorMap* tmx, const CUtensorMap* tmy, uint32_t tiles, uint32_t bars, float* __restrict__ ckpt, float& z, int64_t B, int T, int lane, int b0)
 {
     const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
@@ -75,7 +126,7 @@ __device__ __forceinline__ void forward_tma_body (const ClipConst& c, const CUte
         const uint32_t tile = tiles + s * kFwdTileBytes;
         mbar_wait (bars + 8 * s, (i / kFwdStages) & 1);
         const int nch = min (8, (T - i * kFwdTileT) >> 2);
-#pragma unroll
+#pragma unroll 2 // the hot loop stays well inside the 32 KB instruction cache
         for (int cc = 0; cc < 8; ++cc)
         {
             if (cc < nch)
@@ -85,10 +136,15 @@ __device__ __forceinline__ void forward_tma_body (const ClipConst& c, const CUte
                 const uint32_t addr = chunk128 (tile, lane, cc);
                 const float4 v = lds128 (addr);
                 float4 o;
-                o.x = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.x, z);
-                o.y = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.y, z);
-                o.z = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.z, z);
-                o.w = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.w, z);
+                if (MODE == kModeApprox && ! GENERAL && LSMALL && FAST)
+                    o = forward_chunk<PY> (c, v, z);
+                else
+                {
+                    o.x = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.x, z);
+                    o.y = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.y, z);
+                    o.z = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.z, z);
+                    o.w = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.w, z);
+                }
                 sts128 (addr, o);
             }
         }
@@ -113,7 +169,7 @@ __device__ __forceinline__ void forward_tma_body (const ClipConst& c, const CUte
 }
 
 template <int MODE, bool GENERAL, bool PY>
-__global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T)
+__global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T, int opts)
 {
     __shared__ __align__ (1024) uint8_t smem[kFwdStages * kFwdTileBytes];
     __shared__ __align__ (8) uint64_t bar_mem[kFwdStages];
@@ -133,12 +189,121 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_con
     load_consts (c, desc, params);
     const bool valid = (int64_t) b0 + lane < B;
     float z = (state != nullptr && valid) ? state[b0 + lane] : 0.0f;
-    if (MODE == kModeApprox && ! GENERAL && lsmall_ok (c.pair.L))
-        forward_tma_body<MODE, GENERAL, true, PY> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
+    if (MODE == kModeApprox && ! GENERAL && fast_ok (c.pair.L))
+    {
+        if (opts & kOptNoFastStep) // A/B switch (dwdf_set_option): per-sample vote instead of the latency-arranged chunk
+            forward_tma_body<MODE, GENERAL, true, PY, false> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
+        else
+            forward_tma_body<MODE, GENERAL, true, PY, true> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
+    }
     else
         forward_tma_body<MODE, GENERAL, false, PY> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
     if (state != nullptr && valid)
         state[b0 + lane] = z;
+}
+
+// ---- two sequences per lane: the packed-fp32x2 forward (approx root, symmetric pair) -----------------
+// One warp owns 64 sequences (lane l: rows b0 + l and b0 + 32 + l) and moves [64 x 32] tiles. Half the
+// issue slots per sample (clip_step_fastv<f2>); with one or two such warps per scheduler the kernel runs at
+// the latency of one sample chain and the HBM stream, not the issue port, sets the pace.
+constexpr int kPairRows = 2 * kLanes;
+constexpr int kPairTileBytes = kPairRows * kFwdTileT * 4; // 8 KB
+constexpr int kPairStages = 3;
+
+template <bool PY>
+__global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T)
+{
+    __shared__ __align__ (1024) uint8_t smem[kPairStages * kPairTileBytes];
+    __shared__ __align__ (8) uint64_t bar_mem[kPairStages];
+    const int lane = threadIdx.x;
+    const int b0 = blockIdx.x * kPairRows;
+    const uint32_t tiles = smem_u32 (smem), bars = smem_u32 (bar_mem);
+    if (lane == 0)
+    {
+        tma_prefetch_desc (&tmx);
+        tma_prefetch_desc (&tmy);
+        for (int s = 0; s < kPairStages; ++s)
+            mbar_init (bars + 8 * s, 1);
+        fence_mbar_init ();
+    }
+    __syncwarp ();
+    ClipConst c;
+    load_consts (c, desc, params);
+    const int64_t rowA = (int64_t) b0 + lane, rowB = rowA + kLanes;
+    const bool validA = rowA < B, validB = rowB < B;
+    f2 z { (state != nullptr && validA) ? state[rowA] : 0.0f, (state != nullptr && validB) ? state[rowB] : 0.0f };
+    const bool fast = fast_ok (c.pair.L); // warp-uniform (same parameters for every lane)
+    const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
+    if (lane == 0)
+    {
+        for (int s = 0; s < kPairStages - 1 && s < ntiles; ++s)
+        {
+            mbar_expect_tx (bars + 8 * s, kPairTileBytes);
+            tma_load_2d (tiles + s * kPairTileBytes, &tmx, s * kFwdTileT, b0, bars + 8 * s);
+        }
+    }
+    for (int i = 0; i < ntiles; ++i)
+    {
+        const int s = i % kPairStages;
+        const uint32_t tile = tiles + s * kPairTileBytes;
+        mbar_wait (bars + 8 * s, (i / kPairStages) & 1);
+        const int nch = min (8, (T - i * kFwdTileT) >> 2);
+#pragma unroll 2
+        for (int cc = 0; cc < 8; ++cc)
+        {
+            if (cc < nch)
+            {
+                if ((cc & 3) == 0 && ckpt != nullptr)
+                {
+                    float* ck = ckpt + (int64_t) (i * 2 + (cc >> 2)) * B;
+                    if (validA)
+                        ck[rowA] = z.x;
+                    if (validB)
+                        ck[rowB] = z.y;
+                }
+                const uint32_t addrA = chunk128 (tile, lane, cc), addrB = addrA + kLanes * 128; // row + 32: same swizzle phase
+                const float4 va = lds128 (addrA), vb = lds128 (addrB);
+                float4 oa, ob;
+                if (fast)
+                    forward_chunk2<PY> (c, va, vb, z, oa, ob);
+                else
+                { // parameters outside the fast path's range: the general step, one instance after the other
+                    const float xa[4] = { va.x, va.y, va.z, va.w }, xb[4] = { vb.x, vb.y, vb.z, vb.w };
+                    float os[4];
+                    clip_chunk_general<PY> (c, xa, z.x, os);
+                    oa = make_float4 (os[0], os[1], os[2], os[3]);
+                    clip_chunk_general<PY> (c, xb, z.y, os);
+                    ob = make_float4 (os[0], os[1], os[2], os[3]);
+                }
+                sts128 (addrA, oa);
+                sts128 (addrB, ob);
+            }
+        }
+        fence_proxy_async ();
+        __syncwarp ();
+        if (lane == 0)
+        {
+            tma_store_2d (&tmy, i * kFwdTileT, b0, tile);
+            tma_commit ();
+            const int j = i + kPairStages - 1;
+            if (j < ntiles)
+            {
+                tma_wait_read<1> ();
+                const int sj = j % kPairStages;
+                mbar_expect_tx (bars + 8 * sj, kPairTileBytes);
+                tma_load_2d (tiles + sj * kPairTileBytes, &tmx, j * kFwdTileT, b0, bars + 8 * sj);
+            }
+        }
+    }
+    if (lane == 0)
+        tma_wait_all<0> ();
+    if (state != nullptr)
+    {
+        if (validA)
+            state[rowA] = z.x;
+        if (validB)
+            state[rowB] = z.y;
+    }
 }
 
 // Same recurrence with plain global accesses: any T, any alignment (the TMA path needs T % 4 == 0
@@ -146,12 +311,24 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_con
 template <int MODE, bool GENERAL, bool LSMALL, bool PY>
 __device__ __forceinline__ void forward_direct_body (const ClipConst& c, const float* __restrict__ xr, float* __restrict__ yr, float* __restrict__ ckpt, float& z, int64_t B, int64_t b, int T, bool valid)
 {
+    int n = 0;
+    if (MODE == kModeApprox && ! GENERAL && LSMALL)
+    { // same arithmetic as the TMA kernels (bit-identical per sequence): fast chunks of 4 samples
+        for (; n + 4 <= T; n += 4)
+        {
+            if ((n & (kSeg - 1)) == 0 && ckpt != nullptr && valid)
+                ckpt[(int64_t) (n / kSeg) * B + b] = z;
+            const float4 o = forward_chunk<PY> (c, make_float4 (__ldg (xr + n), __ldg (xr + n + 1), __ldg (xr + n + 2), __ldg (xr + n + 3)), z);
+            if (valid)
+                yr[n] = o.x, yr[n + 1] = o.y, yr[n + 2] = o.z, yr[n + 3] = o.w;
+        }
+    }
 #pragma unroll 4
-    for (int n = 0; n < T; ++n)
+    for (; n < T; ++n)
     {
         if ((n & (kSeg - 1)) == 0 && ckpt != nullptr && valid)
             ckpt[(int64_t) (n / kSeg) * B + b] = z;
-        const float y = clip_step<MODE, GENERAL, LSMALL, PY> (c, __ldg (xr + n), z);
+        const float y = clip_step<MODE, GENERAL, false, PY> (c, __ldg (xr + n), z);
         if (valid)
             yr[n] = y;
     }
@@ -168,7 +345,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_direct (const float* 
     ClipConst c;
     load_consts (c, desc, params);
     float z = state != nullptr ? state[b] : 0.0f;
-    if (MODE == kModeApprox && ! GENERAL && lsmall_ok (c.pair.L))
+    if (MODE == kModeApprox && ! GENERAL && fast_ok (c.pair.L))
         forward_direct_body<MODE, GENERAL, true, PY> (c, x + b * T, y + b * T, ckpt, z, B, b, T, valid);
     else
         forward_direct_body<MODE, GENERAL, false, PY> (c, x + b * T, y + b * T, ckpt, z, B, b, T, valid);
@@ -620,8 +797,16 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
     const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
     auto go = [&] (auto P) {
         constexpr bool p = decltype (P)::value;
+        if constexpr (kM == kModeApprox && ! kG)
+        {
+            if (use_tma && maps->pair)
+            {
+                clipper_forward_pair_tma<p><<<(unsigned) ((B + kPairRows - 1) / kPairRows), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, B, (int) T);
+                return;
+            }
+        }
         if (use_tma)
-            clipper_forward_tma<kM, kG, p><<<grid, kLanes, 0, stream>>> (maps->x, maps->y, params, desc, ckpt, state, B, (int) T);
+            clipper_forward_tma<kM, kG, p><<<grid, kLanes, 0, stream>>> (maps->x, maps->y, params, desc, ckpt, state, B, (int) T, g_clip_opts);
         else
             clipper_forward_direct<kM, kG, p><<<grid, kLanes, 0, stream>>> (x, y, params, desc, ckpt, state, B, (int) T);
     };

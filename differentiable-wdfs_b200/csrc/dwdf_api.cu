@@ -73,14 +73,14 @@ PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder ()
 // (B, T) fp32 batch-major tensor, tiles of [32 sequences x tile_t samples]; rows of a tile are
 // tile_t*4 = 128 or 64 bytes and use the matching swizzle so that 32 lanes reading the same
 // 16-byte chunk index of their own rows hit 32 distinct banks.
-bool make_map (CUtensorMap* m, const float* base, int64_t B, int64_t T, int tile_t)
+bool make_map (CUtensorMap* m, const float* base, int64_t B, int64_t T, int tile_t, int rows = 32)
 {
     auto enc = tensor_map_encoder ();
     if (enc == nullptr)
         return false;
     const cuuint64_t dims[2] = { (cuuint64_t) T, (cuuint64_t) B };
     const cuuint64_t strides[1] = { (cuuint64_t) T * 4 };
-    const cuuint32_t box[2] = { (cuuint32_t) tile_t, 32 };
+    const cuuint32_t box[2] = { (cuuint32_t) tile_t, (cuuint32_t) rows };
     const cuuint32_t estr[2] = { 1, 1 };
     const CUtensorMapSwizzle sw = tile_t == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     return enc (m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*> (base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -109,6 +109,12 @@ const char* dwdf_last_error (void) { return g_err; }
 const char* dwdf_build_info (void) { return "libdwdf " "v1 sm_100a cuda-12.9 tma+mbarrier fp32 no-cpu-fallback"; }
 int64_t dwdf_launch_count (void) { return g_launches.load (); }
 int dwdf_set_tma (int enable) { return g_use_tma.exchange (enable ? 1 : 0); }
+int dwdf_set_option (int bits)
+{
+    const int prev = g_clip_opts;
+    g_clip_opts = bits;
+    return prev;
+}
 
 int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_circuit_desc* d, dwdf_program** out)
 {
@@ -280,6 +286,8 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
     {
         ClipTmaMaps maps;
         const bool tma = tma_usable (x, y, nullptr, B, T) && make_map (&maps.x, x, B, T, 32) && make_map (&maps.y, y, B, T, 32);
+        // approx root, symmetric pair, more than one warp's worth of sequences: two sequences per lane (packed fp32x2)
+        maps.pair = tma && prog->variant.mode == kModeApprox && ! prog->variant.general && B > 32 && ! (g_clip_opts & kOptNoPair) && make_map (&maps.x2, x, B, T, 32, 64) && make_map (&maps.y2, y, B, T, 32, 64);
         DWDF_CUDA (launch_clipper_forward (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, state, B, T, stream));
     }
     else

@@ -24,6 +24,14 @@ enum : int
     kAccSt2 = 4 // sum target^2
 };
 
+// tuning / A-B switches of the clipper kernels (dwdf_set_option); 0 = shipped behaviour
+enum : int
+{
+    kOptNoFastStep = 1, // forward, approx: per-sample warp vote (clip_step) instead of clip_step_fast chunks
+    kOptNoPair = 2 // forward, approx: one sequence per lane instead of the packed-fp32x2 pair kernel
+};
+extern int g_clip_opts;
+
 struct ClipVariant
 {
     int mode; // kModeApprox / kModeExact
@@ -35,6 +43,8 @@ struct ClipVariant
 struct ClipTmaMaps
 {
     CUtensorMap x, y, g; // forward (x, y): 32 x 32 tiles, 128-byte swizzle; adjoint (x, y, g): 16 x 32 tiles, 64-byte swizzle
+    CUtensorMap x2, y2; // paired forward: [64 sequences x 32 samples] tiles
+    bool pair = false; // x2 / y2 are valid and the paired kernel is wanted
 };
 
 // per-(root mode, law) launchers, each specialised in its own translation unit (clipper_kernels.cu, 4 parts)

@@ -374,6 +374,132 @@ DWDF_HD float clip_step (const ClipConst& c, float x, float& z)
     return y;
 }
 
+// ---- the forward kernel's sample: approx root, symmetric pair, fast-path parameters ---------------------
+// ncu on the first version of the forward kernel (one lane per sequence, omega4 evaluated as omega.h
+// writes it): ~47 issue slots per sample, issue ports ~80 % busy on the schedulers that hold 4 warps,
+// fma pipe ~40 %, DRAM ~45 %: bound by instruction ISSUE. The sample below is the same arithmetic
+// arranged for this machine:
+//   * two circuit instances per lane in packed fp32x2 registers: every add / mul / fma is ONE FFMA2 /
+//     FADD2 / FMUL2 issue for both (sm_100a). Only the sign/exponent bit operations, the selects, the
+//     reciprocal (MUFU) and min/max stay per element. Inputs enter through a per-element multiply
+//     (gamma x) and outputs leave through a per-element add, so no register-pairing moves are needed;
+//   * fewer operations: the cubic of omega3 is evaluated in the log2(e)-scaled argument the exp needs
+//     anyway, z' = b + gamma (x - z) is taken as  -2V lambda (w0 - w1) + (2a - z),  and the Newton step
+//     y - (y - e)/(y + 1)  as  e r + y (1 - r),  r = 1/(y + 1);
+//   * omega3's x >= 8 branch (x - log_approx(x), ~11 instructions) is not evaluated: max(u0) is tracked
+//     per instance and the caller redoes a loud 4-sample chunk of THAT instance with the general
+//     clip_step (|a| > ~0.78 V for the 1N4148 clipper) — per instance, so a sequence's result never
+//     depends on which other sequences share its warp.
+// ~23 issue slots and ~14 fma-pipe cycles per sample instead of ~47 and ~17.
+// V = f2 (two instances, packed) or f1 (one instance; same operations in the same order, hence
+// bit-identical per sequence — the direct-access kernel and sub-warp batches use it).
+// Preconditions (fast_ok): lsmall_ok(L) and L > -39, so that wherever a chunk is accepted (u0 < 8)
+// the reverse-biased argument (2L - u0) log2(e) stays above exp_approx's -126 clamp.
+struct f1
+{
+    float x;
+};
+struct f2
+{
+    float x, y;
+};
+DWDF_HD f1 bc (f1, float a) { return f1 { a }; }
+DWDF_HD f2 bc (f2, float a) { return f2 { a, a }; }
+DWDF_HD f1 fmav (f1 a, f1 b, f1 c) { return f1 { fma_ (a.x, b.x, c.x) }; }
+DWDF_HD f1 addv (f1 a, f1 b) { return f1 { a.x + b.x }; }
+DWDF_HD f1 mulv (f1 a, f1 b) { return f1 { a.x * b.x }; }
+DWDF_HD f1 addv_rd (f1 a, f1 b) { return f1 { add_rd (a.x, b.x) }; }
+#if defined(__CUDA_ARCH__)
+DWDF_HD float2 as_float2 (f2 a) { return make_float2 (a.x, a.y); }
+DWDF_HD f2 from_float2 (float2 a) { return f2 { a.x, a.y }; }
+DWDF_HD f2 fmav (f2 a, f2 b, f2 c) { return from_float2 (__ffma2_rn (as_float2 (a), as_float2 (b), as_float2 (c))); }
+DWDF_HD f2 addv (f2 a, f2 b) { return from_float2 (__fadd2_rn (as_float2 (a), as_float2 (b))); }
+DWDF_HD f2 mulv (f2 a, f2 b) { return from_float2 (__fmul2_rn (as_float2 (a), as_float2 (b))); }
+DWDF_HD f2 addv_rd (f2 a, f2 b) { return from_float2 (__fadd2_rd (as_float2 (a), as_float2 (b))); }
+#else
+DWDF_HD f2 fmav (f2 a, f2 b, f2 c) { return f2 { fma_ (a.x, b.x, c.x), fma_ (a.y, b.y, c.y) }; }
+DWDF_HD f2 addv (f2 a, f2 b) { return f2 { a.x + b.x, a.y + b.y }; }
+DWDF_HD f2 mulv (f2 a, f2 b) { return f2 { a.x * b.x, a.y * b.y }; }
+DWDF_HD f2 addv_rd (f2 a, f2 b) { return f2 { add_rd (a.x, b.x), add_rd (a.y, b.y) }; }
+#endif
+// per-element helpers (negation and |.| fold into the consumer's operand modifiers)
+DWDF_HD f1 negv (f1 a) { return f1 { -a.x }; }
+DWDF_HD f2 negv (f2 a) { return f2 { -a.x, -a.y }; }
+DWDF_HD f1 absv (f1 a) { return f1 { fabsf (a.x) }; }
+DWDF_HD f2 absv (f2 a) { return f2 { fabsf (a.x), fabsf (a.y) }; }
+DWDF_HD f1 maxv (f1 a, f1 b) { return f1 { fmaxf (a.x, b.x) }; }
+DWDF_HD f2 maxv (f2 a, f2 b) { return f2 { fmaxf (a.x, b.x), fmaxf (a.y, b.y) }; }
+DWDF_HD f1 rcpv (f1 a) { return f1 { rcp (a.x) }; }
+DWDF_HD f2 rcpv (f2 a) { return f2 { rcp (a.x), rcp (a.y) }; }
+DWDF_HD f1 ldexp_bits (f1 p, f1 t) { return f1 { i2f (f2i (p.x) + (int32_t) ((uint32_t) f2i (t.x) << 23)) }; }
+DWDF_HD f2 ldexp_bits (f2 p, f2 t) { return f2 { i2f (f2i (p.x) + (int32_t) ((uint32_t) f2i (t.x) << 23)), i2f (f2i (p.y) + (int32_t) ((uint32_t) f2i (t.y) << 23)) }; }
+DWDF_HD f1 xor_signv (f1 a, f1 s) { return f1 { xor_sign (a.x, s.x) }; }
+DWDF_HD f2 xor_signv (f2 a, f2 s) { return f2 { xor_sign (a.x, s.x), xor_sign (a.y, s.y) }; }
+DWDF_HD f1 zero_below (f1 y, f1 u, float thr) { return f1 { u.x < thr ? 0.0f : y.x }; }
+DWDF_HD f2 zero_below (f2 y, f2 u, float thr) { return f2 { u.x < thr ? 0.0f : y.x, u.y < thr ? 0.0f : y.y }; }
+// element-wise, deliberately NOT packed: the way data enters and leaves the packed registers
+DWDF_HD f1 scale_in (float g, f1 x) { return f1 { g * x.x }; }
+DWDF_HD f2 scale_in (float g, f2 x) { return f2 { g * x.x, g * x.y }; }
+DWDF_HD f1 add_out (f1 a, f1 b) { return f1 { a.x + b.x }; }
+DWDF_HD f2 add_out (f2 a, f2 b) { return f2 { a.x + b.x, a.y + b.y }; }
+
+DWDF_HD bool fast_ok (float L) { return lsmall_ok (L) && L > -39.0f; }
+constexpr float kFastLoud = 8.0f * kLog2e; // omega3's log branch starts at u0 = 8, i.e. here in the scaled argument
+
+// 2^floor(x') * cubic(frac(x')) of exp_approx (omega.h:83-116), x' already scaled by log2(e) and >= -126
+template <class V>
+DWDF_HD V exp_approx_scaledv (V xp)
+{
+    const V kMagic = bc (V {}, 12582912.0f);
+    const V t = addv_rd (xp, kMagic);
+    const V f = addv (xp, negv (addv (t, negv (kMagic))));
+    const V p = fmav (f, fmav (f, fmav (f, bc (V {}, 0.07944154167983575f), bc (V {}, 0.2274112777602189f)), bc (V {}, 0.6931471805599453f)), bc (V {}, 1.0f));
+    return ldexp_bits (p, t);
+}
+
+// One sample. State: z = z[n] and hz = z[n]/2 (python ordering's output is hz[n+1] + hz[n]).
+// umax = max(umax, u0 log2(e)). Returns y[n].
+template <class V, bool PY>
+DWDF_HD V clip_step_fastv (const ClipConst& c, V x, V& z, V& hz, V& umax)
+{
+    const PairConst& p = c.pair;
+    const V gx = scale_in (c.gamma, x);
+    const V a = fmav (bc (V {}, c.one_m_gamma), z, gx); // z + gamma (x - z)
+    const V a2z = fmav (bc (V {}, 2.0f), a, negv (z)); // a + gamma (x - z)
+    const V aa = absv (a);
+    const V us = fmav (aa, bc (V {}, p.invVl2e), bc (V {}, p.Ll2e)); // u0 log2(e), u0 = L + |a| / V
+    const V w1 = exp_approx_scaledv (fmav (aa, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e))); // omega4(L - |a|/V) = exp_approx
+    umax = maxv (umax, us);
+    // omega3 below 8 (omega.h:160-167) in the scaled argument; exact 0 below the cubic's root (silence in, silence out)
+    constexpr float i1 = 1.0f / kLog2e, i2 = i1 * i1, i3 = i2 * i1;
+    V y = fmav (us, fmav (us, fmav (us, bc (V {}, -1.314293149877800e-3f * i3), bc (V {}, 4.775931364975583e-2f * i2)), bc (V {}, 3.631952663804445e-1f * i1)), bc (V {}, 6.313183464296682e-1f));
+    y = zero_below (y, us, kOmega3Zero * kLog2e);
+    const V r = rcpv (addv (y, bc (V {}, 1.0f)));
+    const V q = fmav (negv (y), r, y); // y (1 - r)
+    const V e = exp_approx_scaledv (fmav (y, bc (V {}, -kLog2e), us));
+    const V w0 = fmav (e, r, q); // omega4 = y - (y - e) / (y + 1)
+    const V ds = xor_signv (addv (w0, negv (w1)), a); // lambda (w0 - w1); w0 == w1 bit for bit at a == 0
+    const V zn = fmav (bc (V {}, -p.twoV), ds, a2z); // b + gamma (x - z),  b = a - 2 V lambda (w0 - w1)
+    const V hzn = mulv (bc (V {}, 0.5f), zn);
+    const V yo = PY ? add_out (hzn, hz) : z;
+    z = zn;
+    hz = hzn;
+    return yo;
+}
+
+// Four consecutive samples (one 16-byte chunk of a row) through the fast step.
+template <class V, bool PY>
+DWDF_HD void clip_chunk_fastv (const ClipConst& c, const V (&x)[4], V& z, V (&o)[4], V& umax)
+{
+    V hz = mulv (bc (V {}, 0.5f), z);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        o[k] = clip_step_fastv<V, PY> (c, x[k], z, hz, umax);
+}
+// ... and the general way (omega3's log branch included), one instance: the redo of a loud chunk
+template <bool PY>
+DWDF_HD void clip_chunk_general (const ClipConst& c, const float (&x)[4], float& z, float (&o)[4]);
+
 // Same step, also returning what the adjoint sweep needs:
 //   A  = dz'/dz     = f'(a)(1 - gamma) - gamma
 //   cg = dz'/dgamma = (x - z)(f'(a) + 1)
@@ -443,6 +569,15 @@ DWDF_HD void clip_step_recover (const ClipConst& c, float x, float z, float zn, 
     tp.cg = xz * fp1;
     tp.cl = -c.pair.twoV * d.M1;
     tp.cv = d.dV;
+}
+
+template <bool PY>
+DWDF_HD void clip_chunk_general (const ClipConst& c, const float (&x)[4], float& z, float (&o)[4])
+{
+    o[0] = clip_step<kModeApprox, false, false, PY> (c, x[0], z);
+    o[1] = clip_step<kModeApprox, false, false, PY> (c, x[1], z);
+    o[2] = clip_step<kModeApprox, false, false, PY> (c, x[2], z);
+    o[3] = clip_step<kModeApprox, false, false, PY> (c, x[3], z);
 }
 
 } // namespace dwdf

@@ -215,6 +215,9 @@ DWDF_API int64_t dwdf_launch_count (void);
 /* Selects the data-movement path of the clipper kernels: 1 = TMA tiles (default when usable),
  * 0 = direct global loads. Returns the previous value. For tests and A/B timing. */
 DWDF_API int dwdf_set_tma (int enable);
+/* Kernel-variant switches for A/B timing (bit 0: forward approx root without the latency-arranged
+ * fast step). 0 = shipped behaviour. Returns the previous bits. */
+DWDF_API int dwdf_set_option (int bits);
 
 #ifdef __cplusplus
 }

@@ -188,3 +188,71 @@ extern "C" void hm_clipper_recover (int mode, int general, int pyorder, float fs
     }
 #undef RUN
 }
+
+// The forward kernels' fast path exactly as clipper_kernels.cu arranges it: clip_chunk_fastv on 4-sample
+// chunks, V = f1 (one sequence) or f2 (two per lane: rows s, s + 1), the instances that crossed omega3's
+// log branch redone with the general step; a tail of T % 4 samples the general way (direct kernel).
+// fallbacks (optional) counts the redone chunk-instances.
+template <class V, bool PY>
+static void fastv_run (const ClipConst& c, const float* x, float* y, int64_t* fallbacks, int64_t B, int64_t T)
+{
+    constexpr int W = sizeof (V) / sizeof (float);
+    for (int64_t s = 0; s < B; s += W)
+    {
+        int64_t row[2] = { s, s + 1 < B ? s + 1 : s };
+        float z[2] = { 0.0f, 0.0f };
+        int64_t n = 0;
+        for (; n + 4 <= T; n += 4)
+        {
+            V xv[4], ov[4], zz, um;
+            float* zp = (float*) &zz;
+            float* up = (float*) &um;
+            for (int w = 0; w < W; ++w)
+                zp[w] = z[w], up[w] = -1.0e30f;
+            for (int k = 0; k < 4; ++k)
+                for (int w = 0; w < W; ++w)
+                    ((float*) &xv[k])[w] = x[row[w] * T + n + k];
+            clip_chunk_fastv<V, PY> (c, xv, zz, ov, um);
+            for (int w = 0; w < W; ++w)
+            {
+                if (up[w] >= kFastLoud)
+                {
+                    float xs[4], os[4];
+                    for (int k = 0; k < 4; ++k)
+                        xs[k] = x[row[w] * T + n + k];
+                    clip_chunk_general<PY> (c, xs, z[w], os);
+                    for (int k = 0; k < 4; ++k)
+                        y[row[w] * T + n + k] = os[k];
+                    if (fallbacks)
+                        ++*fallbacks;
+                }
+                else
+                {
+                    z[w] = zp[w];
+                    for (int k = 0; k < 4; ++k)
+                        y[row[w] * T + n + k] = ((float*) &ov[k])[w];
+                }
+            }
+        }
+        for (; n < T; ++n)
+            for (int w = 0; w < W; ++w)
+                y[row[w] * T + n] = clip_step<kModeApprox, false, false, PY> (c, x[row[w] * T + n], z[w]);
+    }
+}
+
+// pairs = 0: one sequence per lane (f1), 1: two (f2, packed fp32x2 on the device)
+extern "C" int hm_clipper_fast (int pairs, int pyorder, float fs, float R, float C, float Is, float Vt, float nabla, const float* x, float* y, int64_t* fallbacks, int64_t B, int64_t T)
+{
+    ClipDesc d { fs, Vt, 1.0f, 1.0f, 0.0f, 2, 0, 1, 2, 3 };
+    ClipConst c;
+    clip_setup (c, d, R, C, Is, nabla);
+    if (! fast_ok (c.pair.L))
+        return 1;
+    if (fallbacks)
+        *fallbacks = 0;
+    if (pairs)
+        pyorder ? fastv_run<f2, true> (c, x, y, fallbacks, B, T) : fastv_run<f2, false> (c, x, y, fallbacks, B, T);
+    else
+        pyorder ? fastv_run<f1, true> (c, x, y, fallbacks, B, T) : fastv_run<f1, false> (c, x, y, fallbacks, B, T);
+    return 0;
+}

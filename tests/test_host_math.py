@@ -131,3 +131,37 @@ def test_step_recover_adjoint_sums(hm, oracle, mode, py, oord, n_up, n_down, amp
         # (loud inputs cross the seams of omega4's piecewise approximation, where the fp32 and fp64 trajectories part: no oracle there)
         ref = oracle.clipper_grad(x, g, p, exact=bool(mode), ordering=oord, mode="upstream", dtype=np.float64)
         assert np.max(np.abs(acc / ref["raw"][:3] - 1)) < 5e-5, (acc / ref["raw"][:3] - 1, acc0 / ref["raw"][:3] - 1)
+
+
+def fast(hm, pairs, py, p, x):
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.empty_like(x)
+    nfb = C.c_int64(0)
+    rc = hm.hm_clipper_fast(C.c_int(pairs), C.c_int(py), C.c_float(p.fs), C.c_float(p.R), C.c_float(p.C), C.c_float(p.Is), C.c_float(p.Vt), C.c_float(p.nabla), P(x), P(y), C.byref(nfb),
+                            C.c_int64(x.shape[0]), C.c_int64(x.shape[1]))
+    assert rc == 0
+    return y, nfb.value
+
+
+@pytest.mark.parametrize("circuit", ["plugin", "training"])
+@pytest.mark.parametrize("py,oname", [(0, "plugin"), (1, "python")])
+def test_fast_forward_step_against_reference_vectors(hm, golden, circuit, py, oname):
+    """clip_step_fastv — the forward kernels' sample (packed pairs f2 and its one-sequence twin f1) with
+    the per-instance loud-chunk fallback — against the reference's own outputs, quiet and loud
+    (+-10 V: nearly every chunk falls back); f1 and f2 agree bit for bit; silence stays exact silence."""
+    p = ClipperParams() if circuit == "plugin" else ClipperParams(R=45000.0, C=4.7e-9)
+    for xname, refname, expect_fallbacks in (("clip_x", f"clip_{circuit}_approx_{oname}_f32", False), ("clip_loud_x", "clip_loud_approx_python_f32", True)):
+        if xname == "clip_loud_x" and (circuit != "plugin" or not py):
+            continue
+        y1, n1 = fast(hm, 0, py, p, golden[xname])
+        y2, n2 = fast(hm, 1, py, p, golden[xname])
+        assert np.array_equal(y1, y2) and n1 == n2
+        assert seq_rel_err(y2, golden[refname]) < 1e-5
+        assert (n2 > 0) == expect_fallbacks, n2
+    x = make_inputs(5, 1003, seed=3)  # odd row count, T % 4 != 0
+    y1, _ = fast(hm, 0, py, p, x)
+    y2, _ = fast(hm, 1, py, p, x)
+    assert np.array_equal(y1, y2)
+    assert seq_rel_err(y2, clip(hm, 0, py, p, x)[0]) < 2e-6
+    ys, _ = fast(hm, 1, py, p, np.zeros((3, 64), np.float32))
+    assert not ys.any()
