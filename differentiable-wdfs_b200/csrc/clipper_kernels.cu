@@ -449,11 +449,109 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
     }
 }
 
+// The common segment (all kSeg samples valid, inside the loss, not the sequence's end) of the hot variant
+// (approx root, symmetric pair, fast-path parameters) on pairs of consecutive samples in packed fp32x2:
+// 8 pair-steps of clip_step_recoverv<f2> instead of 16 scalar ones; only the state reconstruction
+// (one FMA per sample) and the adjoint recurrence (two FMAs per sample) run per element.
+template <bool PY, bool TARGET, class IO>
+__device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& io, float z0, float zend, float& G, AdjAcc& acc)
+{
+    constexpr int NP = kSeg / 2;
+    f2 z2[NP], zn2[NP]; // (z[2p], z[2p+1]) and (z[2p+1], z[2p+2])
+    float zc = z0;
+#pragma unroll
+    for (int cc = 0; cc < kSeg / 4; ++cc)
+    {
+        const float4 yv = io.y4 (cc);
+        const float ys[4] = { yv.x, yv.y, yv.z, yv.w };
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+        {
+            const int p = cc * 2 + h;
+            if (PY)
+            { // z[n+1] = 2 y[n] - z[n]
+                z2[p].x = zc;
+                zn2[p].x = fma_ (2.0f, ys[2 * h], -zc);
+                z2[p].y = zn2[p].x;
+                zn2[p].y = fma_ (2.0f, ys[2 * h + 1], -z2[p].y);
+                zc = zn2[p].y;
+            }
+            else
+            { // y[n] = z[n]
+                z2[p] = f2 { ys[2 * h], ys[2 * h + 1] };
+                zn2[p].x = ys[2 * h + 1];
+                if (p > 0)
+                    zn2[p - 1].y = ys[2 * h];
+            }
+        }
+    }
+    if (! PY)
+        zn2[NP - 1].y = zend;
+    f2 ag { 0.0f, 0.0f }, al { 0.0f, 0.0f }, av { 0.0f, 0.0f }, sse { 0.0f, 0.0f }, st2 { 0.0f, 0.0f };
+#pragma unroll
+    for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
+    {
+        const float4 xv = io.x4 (cc), gv = io.g4 (cc);
+        float4 yv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+        if (TARGET)
+            yv = io.y4 (cc);
+#pragma unroll
+        for (int h = 1; h >= 0; --h)
+        {
+            const int p = cc * 2 + h;
+            const f2 x2 = h ? f2 { xv.z, xv.w } : f2 { xv.x, xv.y };
+            const f2 g2 = h ? f2 { gv.z, gv.w } : f2 { gv.x, gv.y };
+            StepTapeV<f2> tp;
+            clip_step_recoverv<f2> (c, x2, z2[p], zn2[p], tp);
+            f2 gy = g2;
+            if (TARGET)
+            {
+                const f2 y2 = h ? f2 { yv.z, yv.w } : f2 { yv.x, yv.y };
+                gy = addv (y2, negv (g2));
+                sse = fmav (gy, gy, sse);
+                st2 = fmav (g2, g2, st2);
+            }
+            const f2 he = PY ? mulv (bc (f2 {}, 0.5f), gy) : gy;
+            f2 Gm; // the adjoint of z[n+1] each sample's parameter terms are weighted with
+            if (PY)
+            {
+                Gm.y = G + he.y;
+                G = fma_ (Gm.y, tp.A.y, he.y);
+                Gm.x = G + he.x;
+                G = fma_ (Gm.x, tp.A.x, he.x);
+            }
+            else
+            {
+                Gm.y = G;
+                G = fma_ (G, tp.A.y, he.y);
+                Gm.x = G;
+                G = fma_ (G, tp.A.x, he.x);
+            }
+            ag = fmav (Gm, tp.cg, ag);
+            al = fmav (Gm, tp.cl, al);
+            av = fmav (Gm, tp.cv, av);
+        }
+    }
+    acc.g += (double) (ag.x + ag.y);
+    acc.l += (double) (al.x + al.y);
+    acc.v += (double) (av.x + av.y);
+    if (TARGET)
+    {
+        acc.sse += (double) (sse.x + sse.y);
+        acc.st2 += (double) (st2.x + st2.y);
+    }
+}
+
 template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, class IO>
 __device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, float z0, float zend, float& G, AdjAcc& acc, int n0, int nvalid, int skip, int last)
 {
     if (nvalid == kSeg && n0 >= skip && (PY || last >= kSeg))
-        adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, true> (c, io, z0, zend, G, acc, n0, nvalid, skip, last);
+    {
+        if (MODE == kModeApprox && ! GENERAL && LSMALL && ! WANT_GX)
+            adjoint_segment_pairs<PY, TARGET> (c, io, z0, zend, G, acc);
+        else
+            adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, true> (c, io, z0, zend, G, acc, n0, nvalid, skip, last);
+    }
     else
         adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, false> (c, io, z0, zend, G, acc, n0, nvalid, skip, last);
 }

@@ -571,6 +571,40 @@ DWDF_HD void clip_step_recover (const ClipConst& c, float x, float z, float zn, 
     tp.cv = d.dV;
 }
 
+// clip_step_recover for the fast-path parameters (approx root, symmetric pair, lsmall_ok(L)), written
+// over V so that the adjoint kernel can run it on PAIRS OF CONSECUTIVE SAMPLES of one sequence in packed
+// fp32x2 registers: with the trajectory known, neighbouring samples are independent work (only the
+// two-FMA recurrence of the running adjoint stays serial), and a 16-byte shared-memory read delivers them
+// as aligned register pairs. (x, z, z') -> (A, cg, cl, cv) as in clip_step_recover.
+template <class V>
+struct StepTapeV
+{
+    V A, cg, cl, cv;
+};
+DWDF_HD f1 clamp_exp_arg (f1 a) { return f1 { fmaxf (a.x, -126.0f) }; }
+DWDF_HD f2 clamp_exp_arg (f2 a) { return f2 { fmaxf (a.x, -126.0f), fmaxf (a.y, -126.0f) }; }
+template <class V>
+DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V>& tp)
+{
+    const PairConst& p = c.pair;
+    const V xz = addv (x, negv (z));
+    const V a = fmav (bc (V {}, c.gamma), xz, z);
+    const V b = fmav (bc (V {}, -c.gamma), xz, zn);
+    const V aa = absv (a);
+    const V w1 = exp_approx_scaledv (clamp_exp_arg (fmav (aa, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e))));
+    const V d = addv (a, negv (b));
+    const V w0 = fmav (xor_signv (d, a), bc (V {}, p.inv2V), w1); // mu0 w0 = mu1 w1 + lambda (a - b) / (2 V)
+    const V wp0 = mulv (w0, rcpv (addv (w0, bc (V {}, 1.0f))));
+    const V wp1 = mulv (w1, rcpv (addv (w1, bc (V {}, 1.0f))));
+    const V S1 = addv (wp0, wp1);
+    const V M1 = xor_signv (addv (wp0, negv (wp1)), a);
+    const V fp1 = fmav (bc (V {}, -2.0f), S1, bc (V {}, 2.0f)); // f'(a) + 1
+    tp.A = fmav (fp1, bc (V {}, c.one_m_gamma), bc (V {}, -1.0f));
+    tp.cg = mulv (xz, fp1);
+    tp.cl = mulv (bc (V {}, -p.twoV), M1);
+    tp.cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, fmav (d, bc (V {}, -p.invV), addv (M1, M1)));
+}
+
 template <bool PY>
 DWDF_HD void clip_chunk_general (const ClipConst& c, const float (&x)[4], float& z, float (&o)[4])
 {

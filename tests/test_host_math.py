@@ -165,3 +165,18 @@ def test_fast_forward_step_against_reference_vectors(hm, golden, circuit, py, on
     assert seq_rel_err(y2, clip(hm, 0, py, p, x)[0]) < 2e-6
     ys, _ = fast(hm, 1, py, p, np.zeros((3, 64), np.float32))
     assert not ys.any()
+
+
+def test_recover_pairs_equal_scalar(hm):
+    """The adjoint kernel's packed pair step gives the scalar step's linearisation (same formulas)."""
+    p = ClipperParams()
+    x = make_inputs(4, 1000, seed=11, amp=(0.1, 6.0))
+    y, _ = clip(hm, 0, 0, p, x)  # plugin ordering: y[n] = z[n]
+    xs, z, zn = x[:, :-1].ravel(), y[:, :-1].ravel(), y[:, 1:].ravel()
+    n = xs.size - xs.size % 2
+    out = np.zeros((n, 8), np.float32)
+    rc = hm.hm_recover_pairs(C.c_float(p.fs), C.c_float(p.R), C.c_float(p.C), C.c_float(p.Is), C.c_float(p.Vt), C.c_float(p.nabla), P(np.ascontiguousarray(xs[:n])), P(np.ascontiguousarray(z[:n])),
+                             P(np.ascontiguousarray(zn[:n])), P(out), C.c_int64(n))
+    assert rc == 0
+    scale = np.max(np.abs(out[:, 4:]), axis=0)
+    assert np.all(np.max(np.abs(out[:, :4] - out[:, 4:]), axis=0) <= 2e-6 * scale)
