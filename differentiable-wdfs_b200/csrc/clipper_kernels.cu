@@ -35,6 +35,7 @@ constexpr int kFwdStages = 3;
 constexpr int kAdjTileT = kSeg; // samples per adjoint tile = one checkpoint segment (64-byte rows)
 constexpr int kAdjTileBytes = kLanes * kAdjTileT * 4; // 2 KB
 constexpr int kAdjStages = 2;
+constexpr int kAdjL2Ahead = 4; // segments the L2 prefetch runs ahead of the shared-memory ring
 
 // 16-byte chunk `c` (4 samples) of row `lane` inside a swizzled tile
 __device__ __forceinline__ uint32_t chunk128 (uint32_t tile, int lane, int c) { return tile + lane * 128 + ((c ^ (lane & 7)) << 4); } // CU_TENSOR_MAP_SWIZZLE_128B
@@ -209,9 +210,10 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_con
 constexpr int kPairRows = 2 * kLanes;
 constexpr int kPairTileBytes = kPairRows * kFwdTileT * 4; // 8 KB
 constexpr int kPairStages = 3;
+constexpr int kFwdL2Ahead = 3; // tiles the L2 prefetch runs ahead of the shared-memory ring
 
 template <bool PY>
-__global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T)
+__global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T, int opts)
 {
     __shared__ __align__ (1024) uint8_t smem[kPairStages * kPairTileBytes];
     __shared__ __align__ (8) uint64_t bar_mem[kPairStages];
@@ -286,6 +288,8 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __gri
             tma_store_2d (&tmy, i * kFwdTileT, b0, tile);
             tma_commit ();
             const int j = i + kPairStages - 1;
+            if (j + kFwdL2Ahead < ntiles && (opts & kOptL2Prefetch) != 0)
+                tma_prefetch_l2_2d (&tmx, (j + kFwdL2Ahead) * kFwdTileT, b0);
             if (j < ntiles)
             {
                 tma_wait_read<1> ();
@@ -582,12 +586,20 @@ struct TileIO
 };
 
 template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET>
-__device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUtensorMap* tmx, const CUtensorMap* tmy, const CUtensorMap* tmg, uint32_t tiles, uint32_t bars, const float* __restrict__ ckpt, AdjAcc& acc, int64_t B, int T, int skip, int lane, int b0)
+__device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUtensorMap* tmx, const CUtensorMap* tmy, const CUtensorMap* tmg, uint32_t tiles, uint32_t bars, const float* __restrict__ ckpt, AdjAcc& acc, int64_t B, int T, int skip, int lane, int b0, bool l2_ahead)
 {
     const int nseg = (T + kSeg - 1) / kSeg;
     const bool valid = (int64_t) b0 + lane < B;
     constexpr int kStageBytes = 3 * kAdjTileBytes;
+    auto prefetch = [&] (int k) { // HBM -> L2, kAdjL2Ahead segments ahead of the ring
+        const int i = nseg - 1 - k;
+        tma_prefetch_l2_2d (tmx, i * kSeg, b0);
+        tma_prefetch_l2_2d (tmy, i * kSeg, b0);
+        tma_prefetch_l2_2d (tmg, i * kSeg, b0);
+    };
     auto fetch = [&] (int k) { // the k-th processed segment is i = nseg - 1 - k
+        if (k + kAdjL2Ahead < nseg && l2_ahead)
+            prefetch (k + kAdjL2Ahead);
         const int i = nseg - 1 - k, s = k % kAdjStages;
         const uint32_t dst = tiles + s * kStageBytes, bar = bars + 8 * s;
         mbar_expect_tx (bar, kStageBytes);
@@ -596,8 +608,13 @@ __device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUte
         tma_load_2d (dst + 2 * kAdjTileBytes, tmg, i * kSeg, b0, bar);
     };
     if (lane == 0)
+    {
+        if (l2_ahead)
+            for (int k = 1; k < kAdjL2Ahead && k < nseg; ++k)
+                prefetch (k);
         for (int k = 0; k < kAdjStages - 1 && k < nseg; ++k)
             fetch (k);
+    }
     float G = 0.0f;
     float zend = 0.0f; // plugin ordering: state after the segment = checkpoint of the next one (nothing depends on it past the end)
     float znext = valid ? __ldg (ckpt + (int64_t) (nseg - 1) * B + b0 + lane) : 0.0f;
@@ -623,7 +640,7 @@ __device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUte
 }
 
 template <int MODE, bool GENERAL, bool PY, bool TARGET>
-__global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg, const float* __restrict__ params, const ClipDesc desc, const float* __restrict__ ckpt, double* __restrict__ partials, int64_t B, int T, int skip)
+__global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg, const float* __restrict__ params, const ClipDesc desc, const float* __restrict__ ckpt, double* __restrict__ partials, int64_t B, int T, int skip, int opts)
 {
     __shared__ __align__ (1024) uint8_t smem[kAdjStages * 3 * kAdjTileBytes];
     __shared__ __align__ (8) uint64_t bar_mem[kAdjStages];
@@ -644,9 +661,9 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid
     load_consts (c, desc, params);
     AdjAcc acc;
     if (MODE == kModeApprox && ! GENERAL && lsmall_ok (c.pair.L))
-        adjoint_tma_body<MODE, GENERAL, true, PY, TARGET> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, B, T, skip, lane, b0);
+        adjoint_tma_body<MODE, GENERAL, true, PY, TARGET> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, B, T, skip, lane, b0, (opts & kOptL2Prefetch) != 0);
     else
-        adjoint_tma_body<MODE, GENERAL, false, PY, TARGET> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, B, T, skip, lane, b0);
+        adjoint_tma_body<MODE, GENERAL, false, PY, TARGET> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, B, T, skip, lane, b0, (opts & kOptL2Prefetch) != 0);
     write_partials (acc, partials, blockIdx.x, lane);
 }
 
@@ -899,7 +916,7 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
         {
             if (use_tma && maps->pair)
             {
-                clipper_forward_pair_tma<p><<<(unsigned) ((B + kPairRows - 1) / kPairRows), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, B, (int) T);
+                clipper_forward_pair_tma<p><<<(unsigned) ((B + kPairRows - 1) / kPairRows), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, B, (int) T, g_clip_opts);
                 return;
             }
         }
@@ -919,7 +936,7 @@ cudaError_t clipper_adjoint_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
     auto go = [&] (auto P, auto TG) {
         constexpr bool p = decltype (P)::value, tg = decltype (TG)::value;
         if (use_tma && gx == nullptr)
-            clipper_adjoint_tma<kM, kG, p, tg><<<grid, kLanes, 0, stream>>> (maps->x, maps->y, maps->g, params, desc, ckpt, partials, B, (int) T, skip);
+            clipper_adjoint_tma<kM, kG, p, tg><<<grid, kLanes, 0, stream>>> (maps->x, maps->y, maps->g, params, desc, ckpt, partials, B, (int) T, skip, g_clip_opts);
         else if (gx != nullptr)
             clipper_adjoint_direct<kM, kG, p, tg, true><<<grid, kLanes, 0, stream>>> (x, y, g, gx, params, desc, ckpt, partials, B, (int) T, skip);
         else

@@ -148,56 +148,89 @@ DWDF_HD bool lsmall_ok (float L) { return L < kOmega3Zero && L > -87.0f; }
 // ---- "exact" Wright-omega in fp32 ---------------------------------------------------------------
 // Replaces Toms917DiodePair.h:64-67 (float -> complex<double> TOMS-917 -> float) and
 // scipy.special.wrightomega (diode_pretraining.py:57-58). Same published algorithm (Lawrence,
-// Corless & Jeffrey, ACM TOMS 917) restricted to the real axis, where only three of its regions
-// are reachable (toms917.cpp:240-261,290-296): a series start, then Fritsch-Shafer-Crowley
-// iterations (toms917.cpp:345-364). Evaluated in fp32: one FSC iteration already reaches fp32
-// round-off (measured <= 3e-7 relative on x in [-60, 300]); n_iter (default 2, like TOMS-917)
-// and tol bound the refinement ("Newton tolerance").
-//   For x <= -2 the residual x - w - ln(w) cancels catastrophically in fp32; there w = e^x * s and
-//   ln(w) = x + log1p(s - 1) exactly, so r = -(w + log1p(s - 1)) has no cancellation.
+// Corless & Jeffrey, ACM TOMS 917) restricted to the real axis, where only three of its regions are
+// reachable (toms917.cpp:240-261,290-296): a series start, then Fritsch-Shafer-Crowley iterations
+// (toms917.cpp:345-364). Arranged for a SIMT machine whose lanes sit in different regions at the same
+// time: all three starts are evaluated branch-free (MUFU.EX2 / MUFU.LG2 / MUFU.RCP instead of libm
+// calls) and selected, then one common FSC iteration.
+//   x <= -2      w = e^x s with s the root of  s = exp(-e^x s)  — the same equation divided by e^x, all
+//                terms O(1): the residual x - w - ln(w) of the original form cancels catastrophically in
+//                fp32 here. Series in e^x (toms917.cpp:240-248) + one Newton step; no FSC needed.
+//   -2 < x <= 1+pi  series about x = 1 (toms917.cpp:253-261), one FSC iteration
+//   else            asymptotic series in ln(x) (toms917.cpp:290-296), one FSC iteration
+// Measured against scipy.special.wrightomega on [-60, 300]: <= 3.5e-7 relative after ONE iteration
+// (fp32 round-off), so n_iter defaults to 1; TOMS-917's second iteration is conditional on a
+// double-precision residual test that cannot fire at this accuracy. n_iter > 1 and tol ("Newton
+// tolerance": stop when |residual| <= tol) bound further refinement.
+DWDF_HD float ex2_ (float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return exp2f (x);
+#endif
+}
+DWDF_HD float lg2_ (float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return log2f (x);
+#endif
+}
+// e^x for x <= 0 to fp32 round-off: x log2(e) as a compensated product (the rounding of a single product
+// alone costs |x| * 4e-8 relative)
+DWDF_HD float exp_nonpos (float x)
+{
+    const float kHi = 1.44269502162933349609375f, kLo = 1.925963033500011e-8f; // log2(e) = kHi + kLo
+    const float t = x * kHi;
+    const float lo = fma_ (x, kLo, fma_ (x, kHi, -t));
+    const float e0 = ex2_ (t);
+    return fma_ (e0, 0.693147180559945f * lo, e0);
+}
+DWDF_HD float ln_ (float x) { return 0.693147180559945f * lg2_ (x); }
+
 DWDF_HD float fsc_step (float w, float r)
 {
     const float wp1 = w + 1.0f;
     const float q = 2.0f * wp1 * fma_ (0.66666666666666667f, r, wp1);
-    const float e = (r * (q - r)) / (wp1 * fma_ (-2.0f, r, q));
+    const float e = (r * (q - r)) * rcp (wp1 * fma_ (-2.0f, r, q));
     return fma_ (w, e, w);
 }
 
 DWDF_HD float omega_exact (float x, int n_iter, float tol)
 {
-    float w;
-    if (x <= -2.0f)
-    { // series in e^x
-        const float e = expf (x);
-        const float sig = e * fma_ (e, fma_ (e, fma_ (e, 5.2083333333333333f, -2.6666666666666667f), 1.5f), -1.0f);
-        w = fma_ (e, sig, e);
-        if (x > -17.5f) // below: e^x < 2.6e-8 and the series is already exact to fp32
-            w = fsc_step (w, -(w + log1pf (sig)));
-        return w; // one quartic step from <= 4e-4 is far below fp32 round-off
-    }
-    else if (x <= 4.141592653589793f)
-    { // series about x = 1
-        const float p = x - 1.0f;
-        const float s = fma_ (p, fma_ (p, fma_ (p, 2.1158854166666667e-4f, -3.2552083333333333e-4f), -5.2083333333333333e-3f), 0.0625f);
-        w = fma_ (p * p, s, fma_ (0.5f, x, 0.5f));
-        w = fsc_step (w, (x - w) - logf (w));
-    }
-    else
-    { // asymptotic series in ln(x)
-        const float l = logf (x);
-        const float it = 1.0f / x;
-        const float li = l * it;
-        w = (x - l) + li * (1.0f + it * (fma_ (0.5f, l, -1.0f) + it * fma_ (l, fma_ (l, 0.33333333333333333f, -1.5f), 1.0f)));
-        w = fsc_step (w, (x - w) - logf (w));
-    }
+    // x <= -2
+    const float E = exp_nonpos (fminf (x, 0.0f));
+    const float Ec = fminf (E, 0.1353352832f);
+    const float sig = Ec * fma_ (Ec, fma_ (Ec, fma_ (Ec, 5.2083333333333333f, -2.6666666666666667f), 1.5f), -1.0f);
+    const float s = 1.0f + sig;
+    const float ex = ex2_ (-1.442695040888963f * (Ec * s));
+    const float w_lo = E * (s - (s - ex) * rcp (fma_ (Ec, ex, 1.0f)));
+    // -2 < x <= 1 + pi
+    const float p = x - 1.0f;
+    const float ser = fma_ (p, fma_ (p, fma_ (p, 2.1158854166666667e-4f, -3.2552083333333333e-4f), -5.2083333333333333e-3f), 0.0625f);
+    const float w_mid = fma_ (p * p, ser, fma_ (0.5f, x, 0.5f));
+    // x > 1 + pi
+    const float xc = fmaxf (x, 1.0f);
+    const float l = ln_ (xc);
+    const float it = rcp (xc);
+    const float li = l * it;
+    const float w_hi = (xc - l) + li * (1.0f + it * (fma_ (0.5f, l, -1.0f) + it * fma_ (l, fma_ (l, 0.33333333333333333f, -1.5f), 1.0f)));
+    float w = fmaxf (x <= 4.141592653589793f ? w_mid : w_hi, 0.05f); // (the floor only ever acts on lanes that end up taking w_lo)
+    w = fsc_step (w, (x - w) - ln_ (w));
     for (int k = 1; k < n_iter; ++k)
     {
-        const float r = (x - w) - logf (w);
+        const float r = (x - w) - ln_ (w);
         if (fabsf (r) <= tol)
             break;
         w = fsc_step (w, r);
     }
-    return w;
+    return x <= -2.0f ? w_lo : w;
 }
 
 // ---- diode-pair root ---------------------------------------------------------------------------
@@ -243,7 +276,7 @@ DWDF_HD void pair_setup (PairConst& c, float Rp, float Is, float Vt, float nabla
     c.inv_dn = 1.0f / (n_down * c.V);
     c.rn_up = 1.0f / n_up;
     c.rn_dn = 1.0f / n_down;
-    c.n_iter = n_iter <= 0 ? 2 : n_iter;
+    c.n_iter = n_iter <= 0 ? 1 : n_iter;
     c.tol = tol;
 }
 

@@ -45,6 +45,12 @@ __device__ __forceinline__ void tma_load_2d (uint32_t dst, const CUtensorMap* tm
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
 }
+// global tile -> L2 only (no shared-memory destination, no completion to wait for): run a few tiles ahead
+// of the shared-memory ring so that the ring's own loads find their data in L2 instead of paying HBM latency
+__device__ __forceinline__ void tma_prefetch_l2_2d (const CUtensorMap* tm, int32_t c0, int32_t c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
 // shared tile -> global; out-of-bounds rows / columns are clipped by the TMA unit
 __device__ __forceinline__ void tma_store_2d (const CUtensorMap* tm, int32_t c0, int32_t c1, uint32_t src)
 {

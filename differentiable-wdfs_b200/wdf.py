@@ -252,7 +252,7 @@ class DiodePair(_Element):
     selects the fused kernels' root; the imperative ``reflected()`` below always evaluates the exact law.
     """
 
-    def __init__(self, next, Is, Vt=25.85e-3, nabla=1.0, N_up=1, N_down=1, trainable=False, mode="approx", newton_max_iter=2, newton_tol=0.0):
+    def __init__(self, next, Is, Vt=25.85e-3, nabla=1.0, N_up=1, N_down=1, trainable=False, mode="approx", newton_max_iter=0, newton_tol=0.0):
         super().__init__()
         if mode not in ("approx", "exact", "approx_good"):
             raise ValueError(f"unknown DiodePair mode {mode!r}")

@@ -103,7 +103,7 @@ typedef struct dwdf_circuit_desc
     int32_t param_Is; /* parameter slot of the diode saturation current, diode pair only */
     int32_t param_nabla; /* parameter slot of the ideality factor / nDiodes (wdf_t.h:875-882) */
     int32_t n_params; /* length of the parameter vector */
-    int32_t newton_max_iter; /* exact mode: omega refinement iterations (<=0: default 2, toms917.cpp:345-364) */
+    int32_t newton_max_iter; /* exact mode: Fritsch-Shafer-Crowley refinement iterations of omega (toms917.cpp:345-364); <=0: 1, which already reaches fp32 round-off */
     float fs; /* sample rate [Hz] */
     float Vt; /* thermal voltage, 25.85e-3 in the reference */
     float n_up; /* diodes in series, "up" branch (diode_config.py:5-9); 1 = symmetric */
@@ -215,8 +215,9 @@ DWDF_API int64_t dwdf_launch_count (void);
 /* Selects the data-movement path of the clipper kernels: 1 = TMA tiles (default when usable),
  * 0 = direct global loads. Returns the previous value. For tests and A/B timing. */
 DWDF_API int dwdf_set_tma (int enable);
-/* Kernel-variant switches for A/B timing (bit 0: forward approx root without the latency-arranged
- * fast step). 0 = shipped behaviour. Returns the previous bits. */
+/* Kernel-variant switches for A/B timing. bit 0: forward approx root evaluated sample by sample
+ * (no packed fast step); bit 1: one sequence per lane instead of the packed-fp32x2 pair kernel;
+ * bit 2: TMA L2 prefetch run-ahead. 0 = shipped behaviour. Returns the previous bits. */
 DWDF_API int dwdf_set_option (int bits);
 
 #ifdef __cplusplus
