@@ -197,6 +197,8 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_con
         else
             forward_tma_body<MODE, GENERAL, true, PY, true> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
     }
+    else if ((MODE != kModeApprox || GENERAL) && rev_small_ok (c.pair)) // exact root / N_up != N_down law: cheap reverse-biased branch
+        forward_tma_body<MODE, GENERAL, true, PY, false> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
     else
         forward_tma_body<MODE, GENERAL, false, PY> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
     if (state != nullptr && valid)
@@ -332,7 +334,7 @@ __device__ __forceinline__ void forward_direct_body (const ClipConst& c, const f
     {
         if ((n & (kSeg - 1)) == 0 && ckpt != nullptr && valid)
             ckpt[(int64_t) (n / kSeg) * B + b] = z;
-        const float y = clip_step<MODE, GENERAL, false, PY> (c, __ldg (xr + n), z);
+        const float y = clip_step<MODE, GENERAL, (MODE != kModeApprox || GENERAL) && LSMALL, PY> (c, __ldg (xr + n), z);
         if (valid)
             yr[n] = y;
     }
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_direct (const float* 
     ClipConst c;
     load_consts (c, desc, params);
     float z = state != nullptr ? state[b] : 0.0f;
-    if (MODE == kModeApprox && ! GENERAL && fast_ok (c.pair.L))
+    if (MODE == kModeApprox && ! GENERAL ? fast_ok (c.pair.L) : rev_small_ok (c.pair))
         forward_direct_body<MODE, GENERAL, true, PY> (c, x + b * T, y + b * T, ckpt, z, B, b, T, valid);
     else
         forward_direct_body<MODE, GENERAL, false, PY> (c, x + b * T, y + b * T, ckpt, z, B, b, T, valid);
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid
     ClipConst c;
     load_consts (c, desc, params);
     AdjAcc acc;
-    if (MODE == kModeApprox && ! GENERAL && lsmall_ok (c.pair.L))
+    if (rev_small_ok (c.pair))
         adjoint_tma_body<MODE, GENERAL, true, PY, TARGET> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, B, T, skip, lane, b0, (opts & kOptL2Prefetch) != 0);
     else
         adjoint_tma_body<MODE, GENERAL, false, PY, TARGET> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, B, T, skip, lane, b0, (opts & kOptL2Prefetch) != 0);
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__ (kLanes, 12) clipper_adjoint_direct (const flo
     AdjAcc acc;
     if (b < B)
     {
-        if (MODE == kModeApprox && ! GENERAL && lsmall_ok (c.pair.L))
+        if (rev_small_ok (c.pair))
             adjoint_direct_body<MODE, GENERAL, true, PY, TARGET, WANT_GX> (c, x, y, g, gx, ckpt, acc, B, b, T, skip);
         else
             adjoint_direct_body<MODE, GENERAL, false, PY, TARGET, WANT_GX> (c, x, y, g, gx, ckpt, acc, B, b, T, skip);
@@ -854,7 +856,7 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_train_tma (const __grid_c
     ClipConst c;
     load_consts (c, desc, params);
     AdjAcc acc;
-    if (MODE == kModeApprox && ! GENERAL && lsmall_ok (c.pair.L))
+    if (rev_small_ok (c.pair))
         train_tma_body<MODE, GENERAL, true, PY> (c, &tmx, &tmt, &tmy, want_y != 0, tiles, bars, acc, T, skip, lane, b0);
     else
         train_tma_body<MODE, GENERAL, false, PY> (c, &tmx, &tmt, &tmy, want_y != 0, tiles, bars, acc, T, skip, lane, b0);
@@ -875,7 +877,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_train_direct (const float* __
         const float* xr = x + b * T;
         const float* tr = target + b * T;
         float* yr = (y != nullptr && valid) ? y + b * T : nullptr;
-        const bool lsmall = MODE == kModeApprox && ! GENERAL && lsmall_ok (c.pair.L);
+        const bool lsmall = rev_small_ok (c.pair);
         TrainState<MODE, GENERAL, true, PY> sa;
         TrainState<MODE, GENERAL, false, PY> sb;
         for (int n = 0; n < T; ++n)

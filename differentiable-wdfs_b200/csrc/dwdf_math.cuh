@@ -67,6 +67,24 @@ DWDF_HD float add_rd (float x, float y)
     return f;
 #endif
 }
+// products / sums the compiler must not contract into a neighbouring FMA (where two evaluations of the
+// same function have to agree bit for bit whatever code surrounds them)
+DWDF_HD float mul_ (float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn (a, b);
+#else
+    return a * b;
+#endif
+}
+DWDF_HD float add_ (float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn (a, b);
+#else
+    return a + b;
+#endif
+}
 DWDF_HD float fma_ (float a, float b, float c)
 {
 #if defined(__CUDA_ARCH__)
@@ -187,10 +205,10 @@ DWDF_HD float lg2_ (float x)
 DWDF_HD float exp_nonpos (float x)
 {
     const float kHi = 1.44269502162933349609375f, kLo = 1.925963033500011e-8f; // log2(e) = kHi + kLo
-    const float t = x * kHi;
+    const float t = mul_ (x, kHi);
     const float lo = fma_ (x, kLo, fma_ (x, kHi, -t));
     const float e0 = ex2_ (t);
-    return fma_ (e0, 0.693147180559945f * lo, e0);
+    return fma_ (e0, mul_ (0.693147180559945f, lo), e0);
 }
 DWDF_HD float ln_ (float x) { return 0.693147180559945f * lg2_ (x); }
 
@@ -202,15 +220,22 @@ DWDF_HD float fsc_step (float w, float r)
     return fma_ (w, e, w);
 }
 
-DWDF_HD float omega_exact (float x, int n_iter, float tol)
+// omega(x) for x <= -2 (any x: the value is only meaningful there)
+DWDF_HD float omega_exact_low (float x)
 {
-    // x <= -2
+    // (explicit mul_/add_/fma_: the forward-biased and the reverse-biased branch evaluate this at the same
+    //  argument when a == 0 and must then cancel exactly — silence in, silence out)
     const float E = exp_nonpos (fminf (x, 0.0f));
     const float Ec = fminf (E, 0.1353352832f);
-    const float sig = Ec * fma_ (Ec, fma_ (Ec, fma_ (Ec, 5.2083333333333333f, -2.6666666666666667f), 1.5f), -1.0f);
-    const float s = 1.0f + sig;
-    const float ex = ex2_ (-1.442695040888963f * (Ec * s));
-    const float w_lo = E * (s - (s - ex) * rcp (fma_ (Ec, ex, 1.0f)));
+    const float sig = mul_ (Ec, fma_ (Ec, fma_ (Ec, fma_ (Ec, 5.2083333333333333f, -2.6666666666666667f), 1.5f), -1.0f));
+    const float s = add_ (1.0f, sig);
+    const float ex = ex2_ (mul_ (-1.442695040888963f, mul_ (Ec, s)));
+    return mul_ (E, fma_ (-add_ (s, -ex), rcp (fma_ (Ec, ex, 1.0f)), s));
+}
+
+DWDF_HD float omega_exact (float x, int n_iter, float tol)
+{
+    const float w_lo = omega_exact_low (x);
     // -2 < x <= 1 + pi
     const float p = x - 1.0f;
     const float ser = fma_ (p, fma_ (p, fma_ (p, 2.1158854166666667e-4f, -3.2552083333333333e-4f), -5.2083333333333333e-3f), 0.0625f);
@@ -288,6 +313,18 @@ DWDF_HD float root_omega (const PairConst& c, float u)
     return omega4_approx<FAST> (u);
 }
 
+// The reverse-biased branch, omega(ln(Rp Is / (mu V)) - |a| / (mu V)). REVSMALL: the caller guarantees that
+// every such argument stays below kOmega3Zero (rev_small_ok: true for every physical diode, Rp*Is << V);
+// then omega4 is exactly exp_approx (omega3 == 0 there) and the exact omega needs only its x <= -2 region.
+template <int MODE, bool REVSMALL>
+DWDF_HD float root_omega_rev (const PairConst& c, float u)
+{
+    if (REVSMALL)
+        return MODE == kModeExact ? omega_exact_low (u) : exp_approx (u);
+    return root_omega<MODE> (c, u);
+}
+DWDF_HD bool rev_small_ok (const PairConst& c) { return lsmall_ok (c.L) && lsmall_ok (c.L_up) && lsmall_ok (c.L_dn); }
+
 // Derivative pieces of b = f(a; ell, V) with ell = ln(Rp Is), omega' = omega / (1 + omega):
 //   S1 = w0' + w1'                       df/da      = 1 - 2 S1
 //   M1 = lambda (mu0 w0' - mu1 w1')      df/d ell   = -2 V M1
@@ -316,7 +353,8 @@ DWDF_HD void pair_deriv (const PairConst& c, float a, float b, float w0, float w
 // b = f(a).  Symmetric (eq. 39): wdf_t.h:917-924 == Toms917DiodePair.h:51-59.
 //            General   (eq. 45): diode_pretraining.py:39-60 with N_up / N_down.
 //            Good      (eq. 18): wdf_t.h:907-913.
-// LSMALL: the caller guarantees lsmall_ok(L) and (on the device) a converged warp. Approx + symmetric only.
+// LSMALL: the caller guarantees rev_small_ok (reverse-biased arguments below kOmega3Zero) and, for the
+// approx symmetric law, a converged warp on the device (omega3's log branch is skipped by a warp vote).
 template <int MODE, bool GENERAL, bool DERIV, bool LSMALL>
 DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
 {
@@ -336,7 +374,7 @@ DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
         const float l0 = pos ? c.L_dn : c.L_up, l1 = pos ? c.L_up : c.L_dn;
         const float q0 = aa * (pos ? c.inv_dn : c.inv_up), q1 = aa * (pos ? c.inv_up : c.inv_dn);
         w0 = root_omega<MODE> (c, l0 + q0);
-        w1 = root_omega<MODE> (c, l1 - q1);
+        w1 = root_omega_rev<MODE, LSMALL> (c, l1 - q1);
         const float s = a == 0.0f ? 0.0f : copysignf (c.twoV, a); // 2 V lambda, lambda = signum(a) (signum.h:5-9; 0 at a == 0)
         b = fma_ (-s, fma_ (mu0, w0, -(mu1 * w1)), a);
     }
@@ -351,7 +389,7 @@ DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
         {
             const float q = aa * c.invV;
             w0 = root_omega<MODE> (c, c.L + q);
-            w1 = root_omega<MODE> (c, c.L - q);
+            w1 = root_omega_rev<MODE, LSMALL> (c, c.L - q);
         }
         // a == 0 makes both branches the same computation, w0 - w1 == 0 and b == a: signum's zero needs no select
         b = fma_ (-c.twoV, xor_sign (w0 - w1, a), a);
@@ -582,7 +620,7 @@ DWDF_HD void clip_step_recover (const ClipConst& c, float x, float z, float zn, 
         const bool pos = a >= 0.0f;
         mu0 = pos ? c.pair.n_dn : c.pair.n_up;
         mu1 = pos ? c.pair.n_up : c.pair.n_dn;
-        w1 = root_omega<MODE> (c.pair, (pos ? c.pair.L_up : c.pair.L_dn) - aa * (pos ? c.pair.inv_up : c.pair.inv_dn));
+        w1 = root_omega_rev<MODE, LSMALL> (c.pair, (pos ? c.pair.L_up : c.pair.L_dn) - aa * (pos ? c.pair.inv_up : c.pair.inv_dn));
         w0 = fma_ (dl, c.pair.inv2V, mu1 * w1) * (pos ? c.pair.rn_dn : c.pair.rn_up);
         if (a == 0.0f) // lambda = 0 hides w0 from b; rare, evaluate it
             w0 = root_omega<MODE> (c.pair, c.pair.L_dn);
@@ -592,7 +630,7 @@ DWDF_HD void clip_step_recover (const ClipConst& c, float x, float z, float zn, 
         if (MODE == kModeApprox && LSMALL)
             w1 = exp_approx_scaled<true> (fma_ (aa, -c.pair.invVl2e, c.pair.Ll2e));
         else
-            w1 = root_omega<MODE> (c.pair, c.pair.L - aa * c.pair.invV);
+            w1 = root_omega_rev<MODE, LSMALL> (c.pair, c.pair.L - aa * c.pair.invV);
         w0 = fma_ (dl, c.pair.inv2V, w1);
     }
     PairDeriv d;
