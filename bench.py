@@ -38,6 +38,10 @@ METRIC = "diode-clipper samples/sec fwd+bwd"
 UNIT = "samples/s"
 # algorithmic bytes per sample: forward reads x, writes y; adjoint re-reads x, reads target
 BYTES_FWD, BYTES_ADJ = 8, 8
+# measured DRAM traffic per sample (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at
+# B = 65536, T = 4096: profiles/r01_b_ncu_full_summary.txt). The adjoint also reads the forward output y (4 B/sample):
+# that read replaces the replay of the forward recurrence.
+TRAFFIC_FWD, TRAFFIC_ADJ = 2.166901e9 / (65536 * 4096), 3.293523e9 / (65536 * 4096)
 
 
 def measured_peak_gbs():
@@ -290,8 +294,8 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         # dominant kernel = the adjoint (replay + reverse sweep); its algorithmic traffic is x + target
-        dom = "clipper_adjoint_tma" if adj_ms >= fwd_ms else "clipper_forward_tma"
-        dom_ms, dom_bytes = (adj_ms, BYTES_ADJ) if adj_ms >= fwd_ms else (fwd_ms, BYTES_FWD)
+        dom = "clipper_adjoint_tma" if adj_ms >= fwd_ms else ("clipper_forward_pair_tma" if args.mode == "approx" else "clipper_forward_tma")
+        dom_ms, dom_bytes, dom_traffic = (adj_ms, BYTES_ADJ, TRAFFIC_ADJ) if adj_ms >= fwd_ms else (fwd_ms, BYTES_FWD, TRAFFIC_FWD)
         achieved = B * T * dom_bytes / (dom_ms * 1e-3) / 1e9
         step_bytes = B * T * (BYTES_FWD + BYTES_ADJ)
         line = {
@@ -299,7 +303,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[4]: 1N4148 diode clipper fwd+bwd (grads Is,nF,R,C; MSE; Adam), {args.mode} root, B={B} seqs/GPU x T={T} @48kHz, sharded by sequence", "batch_per_gpu": B, "T": T,
                        "root_mode": args.mode, "l2": "inputs larger than L2 (3 GiB working set per GPU, no flush needed)", "parallelism": f"dp{world} (one all-reduce of 24 doubles per step)"},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": dom_traffic * B * T if args.mode == "approx" else None,
+                         "traffic_source": "ncu --set full, profiles/r01_b_ncu_full_summary.txt (bytes per sample x samples per launch)", "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": dom_bytes, "kernel_ms": dom_ms,
                          "step": {"forward_ms": fwd_ms, "adjoint_ms": adj_ms, "bytes_per_sample": BYTES_FWD + BYTES_ADJ, "achieved_GBs": step_bytes / ((fwd_ms + adj_ms) * 1e-3) / 1e9,
                                   "frac": step_bytes / ((fwd_ms + adj_ms) * 1e-3) / 1e9 / peak}},
