@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdwdf.so")
 
 # enums of include/dwdf.h
 RESISTOR, CAPACITOR, RESISTIVE_VS, SERIES, PARALLEL, INVERTER = range(6)
-ROOT_IDEAL_VS, ROOT_DIODE_PAIR = 0, 1
+ROOT_IDEAL_VS, ROOT_DIODE_PAIR, ROOT_NEURAL = 0, 1, 2
 MODE_APPROX, MODE_EXACT, MODE_APPROX_GOOD = 0, 1, 2
 ORDER_PLUGIN, ORDER_PYTHON = 0, 1
 GRAD_UPSTREAM, GRAD_TARGET = 0, 1
@@ -28,7 +28,7 @@ STATUS = {0: "ok", 1: "invalid argument", 2: "unsupported", 3: "CUDA error", 4: 
 SYMBOLS = (
     "dwdf_program_create", "dwdf_program_destroy", "dwdf_program_is_clipper", "dwdf_program_n_states", "dwdf_ckpt_bytes", "dwdf_workspace_bytes",
     "dwdf_forward", "dwdf_backward", "dwdf_train_pass", "dwdf_adam_step", "dwdf_forward_host", "dwdf_grad_host", "dwdf_process_block",
-    "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_last_error", "dwdf_build_info", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option",
+    "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_last_error", "dwdf_build_info", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option",
 )
 
 
@@ -42,6 +42,10 @@ class CircuitDesc(C.Structure):
         ("param_Is", C.c_int32), ("param_nabla", C.c_int32), ("n_params", C.c_int32), ("newton_max_iter", C.c_int32),
         ("fs", C.c_float), ("Vt", C.c_float), ("n_up", C.c_float), ("n_down", C.c_float), ("newton_tol", C.c_float),
     ]
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [("n_hidden", C.c_int32), ("hidden", C.c_int32)]
 
 
 class DwdfError(RuntimeError):
@@ -81,6 +85,10 @@ def lib() -> C.CDLL:
     L.dwdf_forward_host.argtypes = [vp, vp, vp, vp, vp, i64, i64]
     L.dwdf_grad_host.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, i64, i64]
     L.dwdf_process_block.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.dwdf_mlp_weight_count.argtypes = [C.POINTER(MlpDesc)]
+    L.dwdf_mlp_weight_count.restype = sz
+    L.dwdf_program_create_neural.argtypes = [C.POINTER(Node), i32, C.POINTER(CircuitDesc), C.POINTER(MlpDesc), C.POINTER(vp)]
+    L.dwdf_forward_neural.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
     L.dwdf_last_error.restype = C.c_char_p
     L.dwdf_build_info.restype = C.c_char_p
     L.dwdf_launch_count.restype = i64

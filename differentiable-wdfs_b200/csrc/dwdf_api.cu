@@ -21,6 +21,8 @@ struct dwdf_program
     std::vector<dwdf_node> nodes;
     dwdf_circuit_desc desc;
     bool is_clipper = false;
+    bool is_neural = false;
+    dwdf_mlp_desc mlp {};
     ClipDesc clip {};
     ClipVariant variant {};
     TreeProgram tree {};
@@ -104,9 +106,10 @@ int64_t n_segments (int64_t T) { return (T + kSeg - 1) / kSeg; }
 } // namespace
 
 extern "C" {
+static int check_batch (const dwdf_program* prog, const void* params, const void* x, int64_t B, int64_t T);
 
 const char* dwdf_last_error (void) { return g_err; }
-const char* dwdf_build_info (void) { return "libdwdf " "v1 sm_100a cuda-12.9 tma+mbarrier fp32 no-cpu-fallback"; }
+const char* dwdf_build_info (void) { return "libdwdf v3 sm_100a cuda-12.9 tma+mbarrier fp32x2 no-cpu-fallback"; }
 int64_t dwdf_launch_count (void) { return g_launches.load (); }
 int dwdf_set_tma (int enable) { return g_use_tma.exchange (enable ? 1 : 0); }
 int dwdf_set_option (int bits)
@@ -175,6 +178,13 @@ int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_cir
         if (d->root_mode == DWDF_MODE_APPROX_GOOD && (d->n_up != 1.0f || d->n_down != 1.0f))
             return fail (DWDF_ERR_UNSUPPORTED, "the eq.18 'Good' law is defined for a symmetric pair only");
     }
+    else if (d->root_kind == DWDF_ROOT_NEURAL)
+    {
+        const bool shape = n_nodes == 3 && nodes[0].kind == DWDF_RESISTIVE_VS && nodes[1].kind == DWDF_CAPACITOR && nodes[2].kind == DWDF_PARALLEL && nodes[2].child1 == 0 && nodes[2].child2 == 1
+                           && d->source == 0 && d->probe == 1 && (d->r_node == -1 || d->r_node == 0) && nodes[0].param != nodes[1].param;
+        if (! shape)
+            return fail (DWDF_ERR_UNSUPPORTED, "the neural root closes the clipper tree Parallel(ResistiveVoltageSource, Capacitor) with the probe on the capacitor");
+    }
     else if (d->root_kind != DWDF_ROOT_IDEAL_VS)
         return fail (DWDF_ERR_INVALID, "unknown root kind %d", d->root_kind);
 
@@ -235,6 +245,49 @@ int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_cir
     return DWDF_OK;
 }
 
+size_t dwdf_mlp_weight_count (const dwdf_mlp_desc* m)
+{
+    if (m == nullptr || m->hidden <= 0 || m->n_hidden < 0)
+        return 0;
+    const size_t H = (size_t) m->hidden;
+    return 3 * H + (size_t) m->n_hidden * (H * H + H) + H + 1;
+}
+
+int dwdf_program_create_neural (const dwdf_node* nodes, int32_t n_nodes, const dwdf_circuit_desc* d, const dwdf_mlp_desc* mlp, dwdf_program** out)
+{
+    if (mlp == nullptr || d == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if (d->root_kind != DWDF_ROOT_NEURAL)
+        return fail (DWDF_ERR_INVALID, "dwdf_program_create_neural needs root_kind = DWDF_ROOT_NEURAL");
+    if (mlp->hidden != 4 && mlp->hidden != 8 && mlp->hidden != 16)
+        return fail (DWDF_ERR_UNSUPPORTED, "hidden width %d: the kernels are built for 4, 8 and 16 (the reference's model sizes)", mlp->hidden);
+    if (mlp->n_hidden < 1 || mlp->n_hidden > 6)
+        return fail (DWDF_ERR_UNSUPPORTED, "%d hidden layers outside [1, 6]", mlp->n_hidden);
+    if (int rc = dwdf_program_create (nodes, n_nodes, d, out))
+        return rc;
+    (*out)->is_neural = true;
+    (*out)->mlp = *mlp;
+    return DWDF_OK;
+}
+
+int dwdf_forward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, float* y, float* state, int64_t B, int64_t T, void* stream)
+{
+    if (int rc = check_batch (prog, params, x, B, T))
+        return rc;
+    if (! prog->is_neural)
+        return fail (DWDF_ERR_INVALID, "not a neural-root program (dwdf_program_create_neural)");
+    if (B == 0 || T == 0)
+        return DWDF_OK;
+    if (y == nullptr || weights == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if ((prog->desc.r_node >= 0) != (r != nullptr))
+        return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
+    DWDF_CUDA (launch_nn_forward (prog->mlp.hidden, prog->mlp.n_hidden, prog->desc.ordering == DWDF_ORDER_PYTHON, x, r, y, params, prog->nodes[0].param, prog->nodes[1].param, prog->desc.fs, weights,
+                                  (int) dwdf_mlp_weight_count (&prog->mlp), state, B, T, (cudaStream_t) stream));
+    g_launches.fetch_add (1);
+    return DWDF_OK;
+}
+
 int dwdf_program_destroy (dwdf_program* prog)
 {
     delete prog;
@@ -242,7 +295,7 @@ int dwdf_program_destroy (dwdf_program* prog)
 }
 
 int dwdf_program_is_clipper (const dwdf_program* prog) { return prog != nullptr && prog->is_clipper ? 1 : 0; }
-int dwdf_program_n_states (const dwdf_program* prog) { return prog == nullptr ? 0 : (prog->is_clipper ? 1 : prog->n_states + 1); }
+int dwdf_program_n_states (const dwdf_program* prog) { return prog == nullptr ? 0 : ((prog->is_clipper || prog->is_neural) ? 1 : prog->n_states + 1); }
 
 size_t dwdf_ckpt_bytes (const dwdf_program* prog, int64_t B, int64_t T)
 {
@@ -280,6 +333,8 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
         return DWDF_OK; // empty batch: nothing to do (and the pointers may be null)
     if (y == nullptr)
         return fail (DWDF_ERR_INVALID, "null output");
+    if (prog->is_neural)
+        return fail (DWDF_ERR_INVALID, "neural-root programs run through dwdf_forward_neural (they carry a weight vector)");
     if ((prog->desc.r_node >= 0) != (r != nullptr))
         return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
     if (prog->is_clipper)
@@ -325,6 +380,8 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
         return fail (DWDF_ERR_WORKSPACE, "workspace of %zu bytes, need %zu", workspace_bytes, dwdf_workspace_bytes (prog, B, T));
     if (B == 0 || T == 0)
         return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
+    if (prog->is_neural)
+        return fail (DWDF_ERR_UNSUPPORTED, "the neural root is inference-only in this version (no adjoint kernel yet)");
     if (prog->desc.root_kind == DWDF_ROOT_DIODE_PAIR && prog->desc.root_mode == DWDF_MODE_APPROX_GOOD)
         return fail (DWDF_ERR_UNSUPPORTED, "the 'Good' diode law is forward only");
     const bool target = grad_mode == DWDF_GRAD_TARGET;

@@ -69,6 +69,10 @@ cudaError_t launch_clipper_finalize (const ClipDesc& desc, const float* params, 
 
 cudaError_t launch_adam (float* params, const double* out, float* m, float* v, int32_t* step, int n_params, float lr, const float* lr_vec, float beta1, float beta2, float eps, double grad_scale, const float* lo, const float* hi, cudaStream_t stream);
 
+// ---- neural diode-pair root (inference): clipper tree + b = -MLP(a, ln Rp), hidden width 4 / 8 / 16 ----------
+cudaError_t launch_nn_forward (int hidden, int n_hidden, bool pyorder, const float* x, const float* r, float* y, const float* params, int slot_R, int slot_C, float fs, const float* weights,
+                               int n_weights, float* state, int64_t B, int64_t T, cudaStream_t stream);
+
 // ---- generic tree interpreter -----------------------------------------------------------------
 struct TreeProgram // by-value kernel argument (fits the 4 KB parameter space comfortably)
 {

@@ -26,6 +26,7 @@ from typing import Optional
 import torch
 
 from . import _lib as L
+from . import model_io
 
 
 def voltage(wdf):
@@ -284,6 +285,60 @@ class DiodePair(_Element):
         return self.b
 
 
+class DenseLayer:
+    """layers.py:7-39: ``input @ kernel + bias`` (kernel (in, out), bias (out,))."""
+
+    def __init__(self, in_size, out_size):
+        self.kernel = torch.zeros(in_size, out_size)
+        self.bias = torch.zeros(out_size)
+
+    def set_weights(self, json_weights):
+        W, b = json_weights
+        self.kernel = torch.as_tensor(model_io._squeeze_to(W, 2))
+        self.bias = torch.as_tensor(model_io._squeeze_to(b, 1))
+
+    def __call__(self, input):
+        return input @ self.kernel + self.bias
+
+
+class DenseRootModel(_Element):
+    """layers.py:42-82: the neural WDF root. Built from the RTNeural-style JSON dict (dense layers, tanh
+    between them); ``incident(x)`` takes the (..., 2) tensor [a, log R] the scripts assemble
+    (clipper_pot.py:119-120), ``reflected()`` returns the network output b_nn (the scripts feed
+    ``-b_nn`` to the tree, :121). In a compiled circuit the same weights run in the fused kernel."""
+
+    def __init__(self, json):
+        super().__init__()
+        self.json = json
+        parsed, self.sizes = model_io.layers_from_json(json)
+        self.layers = []
+        self.activations = []
+        for W, b, act in parsed:
+            layer = DenseLayer(*W.shape)
+            layer.set_weights([W, b])
+            self.layers.append(layer)
+            self.activations.append(act)
+        self.model_in = None
+
+    def weight_vector(self):
+        return model_io.flatten_weights([(l.kernel.numpy(), l.bias.numpy(), a) for l, a in zip(self.layers, self.activations)])
+
+    def incident(self, x):
+        self.a = x[..., 0]
+        self.model_in = x
+
+    def reflected(self):
+        x = self.model_in
+        for layer, act in zip(self.layers, self.activations):
+            x = layer(x)
+            if act == "tanh":
+                x = torch.tanh(x)
+            elif act == "relu":
+                x = torch.relu(x)
+        self.b = x
+        return self.b
+
+
 # ==================================================================================================
 # compiled path
 # ==================================================================================================
@@ -375,8 +430,18 @@ class CompiledCircuit:
             d.newton_max_iter, d.newton_tol = root.newton_max_iter, root.newton_tol
         elif isinstance(root, IdealVoltageSource):
             d.root_kind = L.ROOT_IDEAL_VS
+        elif isinstance(root, DenseRootModel):
+            d.root_kind = L.ROOT_NEURAL
+            sources = [i for i, e in enumerate(self.elements) if isinstance(e, ResistiveVoltageSource)]
+            if len(sources) != 1:
+                raise ValueError("a neural-root circuit is driven through exactly one ResistiveVoltageSource")
+            d.source = sources[0]
+            hidden = root.sizes[1:-1]
+            if root.sizes[0] != 2 or root.sizes[-1] != 1 or len(set(hidden)) != 1 or any(a != "tanh" for a in root.activations[:-1]) or root.activations[-1] not in ("", None):
+                raise ValueError(f"network {root.sizes} / {root.activations}: the fused kernel runs the reference's shapes, 2 -> H (tanh) x (n+1) -> 1")
+            self.mlp = L.MlpDesc(len(hidden) - 1, hidden[0])
         else:
-            raise TypeError("root must be an IdealVoltageSource or a DiodePair")
+            raise TypeError("root must be an IdealVoltageSource, a DiodePair or a DenseRootModel")
         if fs is None:
             if not fs_seen:
                 fs = 48000.0
@@ -390,7 +455,14 @@ class CompiledCircuit:
         self.n_params = len(values)
         arr = (L.Node * len(nodes))(*nodes)
         handle = C.c_void_p()
-        L.check(self.lib.dwdf_program_create(arr, len(nodes), C.byref(d), C.byref(handle)))
+        self.is_neural = isinstance(root, DenseRootModel)
+        if self.is_neural:
+            L.check(self.lib.dwdf_program_create_neural(arr, len(nodes), C.byref(d), C.byref(self.mlp), C.byref(handle)))
+            w = root.weight_vector()
+            assert w.size == self.lib.dwdf_mlp_weight_count(C.byref(self.mlp))
+            self.weights = torch.from_numpy(w).to(self.device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        else:
+            L.check(self.lib.dwdf_program_create(arr, len(nodes), C.byref(d), C.byref(handle)))
         self.handle = handle
         self.is_clipper = bool(self.lib.dwdf_program_is_clipper(handle))
         self.n_states = int(self.lib.dwdf_program_n_states(handle))
@@ -452,6 +524,10 @@ class CompiledCircuit:
         y = torch.empty_like(x) if out is None else out
         self._check_xy(y, "out")
         if B * T == 0:
+            self._last = None
+            return y
+        if self.is_neural:
+            L.check(self.lib.dwdf_forward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), None, B, T, _stream_ptr(self.device)))
             self._last = None
             return y
         ck = None
@@ -525,6 +601,9 @@ class CompiledCircuit:
         if not (torch.is_tensor(state) and state.is_cuda and state.dtype == torch.float32 and state.numel() == self.n_states * B and state.is_contiguous()):
             raise ValueError(f"state must be a contiguous float32 CUDA tensor with {self.n_states} x B elements")
         y = torch.empty_like(x) if out is None else out
+        if self.is_neural:
+            L.check(self.lib.dwdf_forward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), _ptr(state), B, T, _stream_ptr(self.device)))
+            return y
         L.check(self.lib.dwdf_process_block(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(state), B, T, _stream_ptr(self.device)))
         return y
 

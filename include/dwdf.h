@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DWDF_VERSION 2
+#define DWDF_VERSION 3
 #if defined(__GNUC__)
 #define DWDF_API __attribute__ ((visibility ("default")))
 #else
@@ -62,7 +62,9 @@ enum dwdf_node_kind
 enum dwdf_root_kind
 {
     DWDF_ROOT_IDEAL_VS = 0, /* tf_wdf.py:13-28 / wdf_t.h:658-689: b = -a + 2 Vs, Vs = x[n]            */
-    DWDF_ROOT_DIODE_PAIR = 1 /* analytic antiparallel diode pair (see dwdf_root_mode)                 */
+    DWDF_ROOT_DIODE_PAIR = 1, /* analytic antiparallel diode pair (see dwdf_root_mode)                 */
+    DWDF_ROOT_NEURAL = 2 /* b = -MLP(a, ln Rp): layers.py:42-82 (DenseRootModel), DiodePairNeuralModel.h:62-75;
+                            programs of this kind are created by dwdf_program_create_neural                */
 };
 
 /* How the diode-pair root evaluates the Wright-omega function. */
@@ -112,6 +114,16 @@ typedef struct dwdf_circuit_desc
 } dwdf_circuit_desc;
 
 typedef struct dwdf_program dwdf_program; /* opaque, immutable after creation, thread-shareable */
+
+/* The reference's network shapes (DiodePairNeuralModel.h:5-41, diode_pretraining.py:114-126): dense 2 -> H
+ * (tanh), n_hidden x dense H -> H (tanh), dense H -> 1. "2x16" is n_hidden = 2, hidden = 16.
+ * Weight vector (device floats): per layer the kernel, (in x out) row-major as in the RTNeural JSON files
+ * (model_utils.py:17-85), then the bias; layers in order. */
+typedef struct dwdf_mlp_desc
+{
+    int32_t n_hidden; /* 1 .. 6 */
+    int32_t hidden; /* H: 4, 8 or 16 */
+} dwdf_mlp_desc;
 
 /* ---- loss / gradient ------------------------------------------------------------------------ */
 enum dwdf_grad_mode
@@ -200,6 +212,16 @@ DWDF_API int dwdf_adam_step (float* params, const double* out, float* m, float* 
  * internal stream, synchronous on return. */
 DWDF_API int dwdf_forward_host (const dwdf_program* prog, const float* params_host, const float* x_host, const float* r_host, float* y_host, int64_t B, int64_t T);
 DWDF_API int dwdf_grad_host (const dwdf_program* prog, const float* params_host, const float* x_host, const float* r_host, const float* gy_or_target_host, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* y_host, double* out_host, int64_t B, int64_t T);
+
+/* Neural diode-pair root (inference). dwdf_program_create_neural: like dwdf_program_create with
+ * desc->root_kind = DWDF_ROOT_NEURAL; the tree must be the clipper's Parallel(ResistiveVoltageSource,
+ * Capacitor) with the probe on the capacitor; desc->r_node may name the source (per-sample resistance,
+ * clipper_pot.py:114-117). dwdf_forward_neural replaces ClipperModel.forward (clipper_pot.py:103-127) and
+ * DiodeClipperWDF::process for plugin models 2-11 (DiodeClipperWDF.cpp:32-166): `weights` =
+ * dwdf_mlp_weight_count() device floats, `state` NULL (reset state) or B capacitor states (streaming). */
+DWDF_API size_t dwdf_mlp_weight_count (const dwdf_mlp_desc* mlp);
+DWDF_API int dwdf_program_create_neural (const dwdf_node* nodes, int32_t n_nodes, const dwdf_circuit_desc* desc, const dwdf_mlp_desc* mlp, dwdf_program** out);
+DWDF_API int dwdf_forward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, float* y, float* state, int64_t B, int64_t T, void* stream);
 
 /* Streaming twin of DiodeClipperWDF::{prepare, process} (DiodeClipperWDF.cpp:3-30): like
  * dwdf_forward, but the capacitor states are read from and written back to `state`

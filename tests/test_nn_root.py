@@ -1,0 +1,130 @@
+"""The neural diode-pair root (inference): host-side pieces on CPU, the fused kernel on
+the GPU against golden vectors produced by the reference's own RTNeural + chowdsp_wdf code
+(tests/golden/make_golden_nn.py) and against the numpy oracle (oracle/nn.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, make_inputs, seq_rel_err
+from oracle import nn
+
+MODELS = ["2x4", "2x8", "2x16", "4x4", "4x8"]
+CLIP_TOL = 5e-5  # see tests/test_oracle_nn.py
+
+
+@pytest.fixture(scope="module")
+def nnv():
+    return np.load(os.path.join(GOLDEN, "nn_vectors.npz"))
+
+
+def model_json(dwdf, nnv, name):
+    return dwdf.model_io.json_from_weights(nnv[f"{name}_weights"], [int(v) for v in nnv[f"{name}_sizes"]])
+
+
+# ---- CPU: JSON format, imperative element, dataset loader -----------------------------------------------
+
+@pytest.mark.parametrize("name", MODELS)
+def test_json_roundtrip_and_imperative_root(dwdf, nnv, name, tmp_path):
+    mj = model_json(dwdf, nnv, name)
+    path = tmp_path / "model.json"
+    dwdf.model_io.save_model_json(mj, str(path))
+    back = dwdf.model_io.load_model_json(str(path))
+    layers, sizes = dwdf.model_io.layers_from_json(back)
+    assert sizes == [int(v) for v in nnv[f"{name}_sizes"]]
+    assert [a for _, _, a in layers] == ["tanh"] * (len(layers) - 1) + [""]
+    assert np.array_equal(dwdf.model_io.flatten_weights(layers), nnv[f"{name}_weights"])
+    # Keras-style nesting (layers.py:29-35: kernel = [weights]) is accepted too
+    nested = json.loads(json.dumps(back))
+    for layer in nested["layers"]:
+        layer["weights"] = [[layer["weights"][0]], [layer["weights"][1]]]
+    assert np.array_equal(dwdf.model_io.flatten_weights(dwdf.model_io.layers_from_json(nested)[0]), nnv[f"{name}_weights"])
+    # imperative element = layers.py:72-82
+    root = dwdf.DenseRootModel(back)
+    x = torch.from_numpy(np.stack([nnv["grid_a"], nnv["grid_logR"]], -1))
+    root.incident(x)
+    out = root.reflected()[..., 0].numpy()
+    assert np.max(np.abs(out - nnv[f"{name}_grid_out"])) < 5e-6
+
+
+def test_dataset_loader(dwdf, tmp_path):
+    """A synthetic Digilent CSV pair (same header layout as diode_dataset/1N4148/1up1down/10.0k_4.7nF.csv:1-12)."""
+    fs, n = 1000.0, 20000
+    d = tmp_path / "diode_dataset" / "1N4148" / "1up1down"
+    d.mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    data = {}
+    for fname in ("10.0k_4.7nF.csv", "47.0k_4.7nF.csv"):
+        a = rng.standard_normal((n, 2))
+        data[fname] = a
+        with open(d / fname, "w") as f:
+            f.write("#Digilent WaveForms Oscilloscope Acquisition\n#Device Name: Discovery2\n#Serial Number: SN:0\n#Date Time: 2022-01-12 19:41:59.543\n")
+            f.write(f"#Sample rate: {fs:g}Hz\n#Samples: {n}\n#Trigger: x\n#Channel 1: x\n#Channel 2: x\n\nChannel 1 (V),Channel 2 (V)\n")
+            for row in a:
+                f.write(f"{float(row[0])!r},{float(row[1])!r}\n")
+    path = dwdf.dataimport.data_path_for_diode(1, 1, str(tmp_path))
+    tr, ntr, va, nva, FS = dwdf.dataimport.load_diode_data(path)
+    lo, hi = 2500, 16800  # 2.5 s .. 16.8 s (dataimport.py:35-48)
+    assert FS == fs and ntr == hi - lo and nva == hi - lo
+    assert np.allclose(tr[0], data["10.0k_4.7nF.csv"][lo:hi, 0].astype(np.float32)) and np.all(tr[1] == 10000.0)  # R < 36 k: training
+    assert np.allclose(va[2], data["47.0k_4.7nF.csv"][lo:hi, 1].astype(np.float32)) and np.all(va[1] == 47000.0)  # 36 k..73 k: validation
+    X, Y = dwdf.dataimport.batch_data(tr, 2048)
+    assert X.shape == (6, 2048, 2) and Y.shape == (6, 2048, 1) and np.array_equal(X[1, :, 0], tr[0, 2048:4096])
+
+
+# ---- GPU: the fused kernel -------------------------------------------------------------------------------
+
+def make_circuit(dwdf, mj, ordering, with_r=False, R=47000.0, C=2.2e-9, fs=48000.0):
+    Vs = dwdf.ResistiveVoltageSource(R)
+    Cc = dwdf.Capacitor(C, fs)
+    P1 = dwdf.Parallel(Vs, Cc)
+    root = dwdf.DenseRootModel(mj)
+    return dwdf.compile_circuit(root, tree=P1, probe=Cc, ordering=ordering, r_element=Vs if with_r else None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", MODELS)
+@pytest.mark.parametrize("ordering,order", [("plugin", nn.ORDER_PLUGIN), ("python", nn.ORDER_PYTHON)])
+def test_forward_against_reference_vectors(dwdf, nnv, name, ordering, order):
+    circ = make_circuit(dwdf, model_json(dwdf, nnv, name), ordering)
+    assert circ.is_neural
+    y = circ.forward(torch.from_numpy(nnv["x"]).cuda()).cpu().numpy()
+    assert seq_rel_err(y, nnv[f"{name}_clip_{ordering}"]) < CLIP_TOL
+    ref64 = nn.nn_clipper_forward(nnv["x"], nnv[f"{name}_weights"], nnv[f"{name}_sizes"], 48000.0, 47000.0, 2.2e-9, order, dtype=np.float64)
+    assert seq_rel_err(y, ref64) < CLIP_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["2x8", "4x8", "2x16"])
+@pytest.mark.parametrize("B,T", [(1, 5), (7, 333), (64, 256)])
+def test_forward_resistance_channel_and_shapes(dwdf, nnv, name, B, T):
+    """clipper_pot.py's (B, T, 2) layout: channel 1 sets the source resistance every sample; odd batches, ragged T."""
+    x = make_inputs(B, T, seed=B + T)
+    r = (np.random.default_rng(2).uniform(1e4, 1e5, (B, 1)) * np.ones((1, T))).astype(np.float32)
+    r[:, T // 2:] *= 1.7
+    mj = model_json(dwdf, nnv, name)
+    circ = make_circuit(dwdf, mj, "python", with_r=True, R=45000.0, C=4.7e-9, fs=50000.0)
+    y = circ.forward(torch.from_numpy(x).cuda(), r=torch.from_numpy(r).cuda()).cpu().numpy()
+    ref = nn.nn_clipper_forward(x, nnv[f"{name}_weights"], nnv[f"{name}_sizes"], 50000.0, 45000.0, 4.7e-9, nn.ORDER_PYTHON, r=r, dtype=np.float64)
+    assert seq_rel_err(y, ref) < CLIP_TOL
+    circ0 = make_circuit(dwdf, mj, "python", R=45000.0, C=4.7e-9, fs=50000.0)
+    y0 = circ0.forward(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert seq_rel_err(y0, nn.nn_clipper_forward(x, nnv[f"{name}_weights"], nnv[f"{name}_sizes"], 50000.0, 45000.0, 4.7e-9, nn.ORDER_PYTHON, dtype=np.float64)) < CLIP_TOL
+
+
+@pytest.mark.gpu
+def test_streaming_and_errors(dwdf, nnv):
+    mj = model_json(dwdf, nnv, "2x8")
+    circ = make_circuit(dwdf, mj, "plugin")
+    x = torch.from_numpy(make_inputs(9, 600, seed=8)).cuda()
+    whole = circ.forward(x)
+    st = circ.new_state(9)
+    parts = [circ.process_block(x[:, a:b].contiguous(), st) for a, b in ((0, 100), (100, 101), (101, 600))]
+    assert torch.equal(torch.cat(parts, 1), whole)
+    with pytest.raises(RuntimeError):
+        circ.backward(target=x)  # inference only: no adjoint kernel for the neural root yet
+    bad = dwdf.model_io.json_from_weights(np.zeros(2 * 5 + 5 + 5 + 1, np.float32), [2, 5, 1])
+    with pytest.raises(Exception):
+        make_circuit(dwdf, bad, "plugin")
