@@ -28,7 +28,7 @@ STATUS = {0: "ok", 1: "invalid argument", 2: "unsupported", 3: "CUDA error", 4: 
 SYMBOLS = (
     "dwdf_program_create", "dwdf_program_destroy", "dwdf_program_is_clipper", "dwdf_program_n_states", "dwdf_ckpt_bytes", "dwdf_workspace_bytes",
     "dwdf_forward", "dwdf_backward", "dwdf_train_pass", "dwdf_adam_step", "dwdf_forward_host", "dwdf_grad_host", "dwdf_process_block",
-    "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_last_error", "dwdf_build_info", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option",
+    "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_backward_neural", "dwdf_neural_ckpt_bytes", "dwdf_neural_workspace_bytes", "dwdf_adam_step_vec", "dwdf_last_error", "dwdf_build_info", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option",
 )
 
 
@@ -88,7 +88,13 @@ def lib() -> C.CDLL:
     L.dwdf_mlp_weight_count.argtypes = [C.POINTER(MlpDesc)]
     L.dwdf_mlp_weight_count.restype = sz
     L.dwdf_program_create_neural.argtypes = [C.POINTER(Node), i32, C.POINTER(CircuitDesc), C.POINTER(MlpDesc), C.POINTER(vp)]
-    L.dwdf_forward_neural.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.dwdf_forward_neural.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.dwdf_backward_neural.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, vp, sz, i64, i64, vp]
+    L.dwdf_neural_ckpt_bytes.argtypes = [vp, i64, i64]
+    L.dwdf_neural_ckpt_bytes.restype = sz
+    L.dwdf_neural_workspace_bytes.argtypes = [vp, i64, i64]
+    L.dwdf_neural_workspace_bytes.restype = sz
+    L.dwdf_adam_step_vec.argtypes = [vp, vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double, vp]
     L.dwdf_last_error.restype = C.c_char_p
     L.dwdf_build_info.restype = C.c_char_p
     L.dwdf_launch_count.restype = i64

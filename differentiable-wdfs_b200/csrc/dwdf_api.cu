@@ -270,7 +270,16 @@ int dwdf_program_create_neural (const dwdf_node* nodes, int32_t n_nodes, const d
     return DWDF_OK;
 }
 
-int dwdf_forward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, float* y, float* state, int64_t B, int64_t T, void* stream)
+size_t dwdf_neural_ckpt_bytes (const dwdf_program* prog, int64_t B, int64_t T)
+{
+    return (prog == nullptr || ! prog->is_neural || B <= 0 || T <= 0) ? 0 : (size_t) nn_ckpt_floats (B, T) * sizeof (float);
+}
+size_t dwdf_neural_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
+{
+    return (prog == nullptr || ! prog->is_neural || B <= 0 || T <= 0) ? 0 : (size_t) nn_groups (B) * (dwdf_mlp_weight_count (&prog->mlp) + 8) * sizeof (double);
+}
+
+int dwdf_forward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, float* y, float* state, float* z_ckpt, int64_t B, int64_t T, void* stream)
 {
     if (int rc = check_batch (prog, params, x, B, T))
         return rc;
@@ -283,7 +292,49 @@ int dwdf_forward_neural (const dwdf_program* prog, const float* params, const fl
     if ((prog->desc.r_node >= 0) != (r != nullptr))
         return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
     DWDF_CUDA (launch_nn_forward (prog->mlp.hidden, prog->mlp.n_hidden, prog->desc.ordering == DWDF_ORDER_PYTHON, x, r, y, params, prog->nodes[0].param, prog->nodes[1].param, prog->desc.fs, weights,
-                                  (int) dwdf_mlp_weight_count (&prog->mlp), state, B, T, (cudaStream_t) stream));
+                                  (int) dwdf_mlp_weight_count (&prog->mlp), state, z_ckpt, B, T, (cudaStream_t) stream));
+    g_launches.fetch_add (1);
+    return DWDF_OK;
+}
+
+int dwdf_backward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode,
+                          int32_t loss_kind, int64_t skip, double* grad_w, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t) stream_;
+    if (int rc = check_batch (prog, params, x, B, T))
+        return rc;
+    if (! prog->is_neural)
+        return fail (DWDF_ERR_INVALID, "not a neural-root program (dwdf_program_create_neural)");
+    if (weights == nullptr || y == nullptr || z_ckpt == nullptr || gy_or_target == nullptr || grad_w == nullptr || out == nullptr || workspace == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if (grad_mode != DWDF_GRAD_UPSTREAM && grad_mode != DWDF_GRAD_TARGET)
+        return fail (DWDF_ERR_INVALID, "unknown grad mode %d", grad_mode);
+    if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
+        return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
+    if (B == 0 || T == 0)
+        return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
+    if (workspace_bytes < dwdf_neural_workspace_bytes (prog, B, T))
+        return fail (DWDF_ERR_WORKSPACE, "workspace of %zu bytes, need %zu", workspace_bytes, dwdf_neural_workspace_bytes (prog, B, T));
+    if ((prog->desc.r_node >= 0) != (r != nullptr))
+        return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
+    const bool shape_ok = (prog->mlp.n_hidden == 2 && (prog->mlp.hidden == 4 || prog->mlp.hidden == 8 || prog->mlp.hidden == 16)) || (prog->mlp.n_hidden == 4 && (prog->mlp.hidden == 4 || prog->mlp.hidden == 8));
+    if (! shape_ok)
+        return fail (DWDF_ERR_UNSUPPORTED, "the adjoint kernel is built for the reference's shapes 2x4, 2x8, 2x16, 4x4, 4x8 (got %dx%d)", prog->mlp.n_hidden, prog->mlp.hidden);
+    const bool target = grad_mode == DWDF_GRAD_TARGET;
+    const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
+    const int nw = (int) dwdf_mlp_weight_count (&prog->mlp);
+    DWDF_CUDA (launch_nn_adjoint (prog->mlp.hidden, prog->mlp.n_hidden, prog->desc.ordering == DWDF_ORDER_PYTHON, target, x, r, y, gy_or_target, z_ckpt, params, prog->nodes[0].param, prog->nodes[1].param,
+                                  prog->desc.fs, weights, nw, (double*) workspace, (int) sk, B, T, stream));
+    DWDF_CUDA (launch_nn_finalize ((const double*) workspace, nn_groups (B), nw, target, loss_kind, (double) B * (double) (T - sk), grad_w, out, stream));
+    g_launches.fetch_add (2);
+    return DWDF_OK;
+}
+
+int dwdf_adam_step_vec (float* w, const double* grad, float* m, float* v, int32_t* step, int64_t n, float lr, float beta1, float beta2, float eps, double grad_scale, void* stream)
+{
+    if (w == nullptr || grad == nullptr || m == nullptr || v == nullptr || step == nullptr || n < 1)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    DWDF_CUDA (launch_adam_vec (w, grad, m, v, step, n, lr, beta1, beta2, eps, grad_scale, (cudaStream_t) stream));
     g_launches.fetch_add (1);
     return DWDF_OK;
 }
@@ -381,7 +432,7 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
     if (B == 0 || T == 0)
         return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
     if (prog->is_neural)
-        return fail (DWDF_ERR_UNSUPPORTED, "the neural root is inference-only in this version (no adjoint kernel yet)");
+        return fail (DWDF_ERR_INVALID, "neural-root programs differentiate through dwdf_backward_neural (the gradient is a weight vector)");
     if (prog->desc.root_kind == DWDF_ROOT_DIODE_PAIR && prog->desc.root_mode == DWDF_MODE_APPROX_GOOD)
         return fail (DWDF_ERR_UNSUPPORTED, "the 'Good' diode law is forward only");
     const bool target = grad_mode == DWDF_GRAD_TARGET;

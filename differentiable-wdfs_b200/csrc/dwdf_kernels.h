@@ -71,7 +71,14 @@ cudaError_t launch_adam (float* params, const double* out, float* m, float* v, i
 
 // ---- neural diode-pair root (inference): clipper tree + b = -MLP(a, ln Rp), hidden width 4 / 8 / 16 ----------
 cudaError_t launch_nn_forward (int hidden, int n_hidden, bool pyorder, const float* x, const float* r, float* y, const float* params, int slot_R, int slot_C, float fs, const float* weights,
-                               int n_weights, float* state, int64_t B, int64_t T, cudaStream_t stream);
+                               int n_weights, float* state, float* ckpt, int64_t B, int64_t T, cudaStream_t stream);
+// reverse sweep: dL/d(weights) partials per warp (64 sequences): [n_groups][n_weights + 8] doubles (then sse, st2)
+int64_t nn_ckpt_floats (int64_t B, int64_t T);
+int64_t nn_groups (int64_t B);
+cudaError_t launch_nn_adjoint (int hidden, int n_hidden, bool pyorder, bool target, const float* x, const float* r, const float* y, const float* g, const float* ckpt, const float* params, int slot_R, int slot_C,
+                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, cudaStream_t stream);
+cudaError_t launch_nn_finalize (const double* partials, int64_t n_groups, int n_weights, bool target, int loss_kind, double count, double* grad_w, double* out, cudaStream_t stream);
+cudaError_t launch_adam_vec (float* w, const double* gw, float* m, float* v, int32_t* step, int64_t n, float lr, float beta1, float beta2, float eps, double grad_scale, cudaStream_t stream);
 
 // ---- generic tree interpreter -----------------------------------------------------------------
 struct TreeProgram // by-value kernel argument (fits the 4 KB parameter space comfortably)

@@ -18,6 +18,8 @@ namespace dwdf
 {
 namespace
 {
+constexpr int kNnSeg = 64; // checkpoint spacing of the neural-root kernels [samples]
+
 __device__ __forceinline__ float tanh_acc (float x)
 {
     const float e = ex2_ (2.885390081777927f * x); // e^(2x)
@@ -92,7 +94,7 @@ __device__ __forceinline__ f2 mlp (const float* __restrict__ sw, int n_hidden, f
 
 template <int H, bool PY>
 __global__ void __launch_bounds__ (128) nn_clipper_forward (const float* __restrict__ x, const float* __restrict__ r, float* __restrict__ y, const float* __restrict__ params, int slot_R, int slot_C, float fs,
-                                                           const float* __restrict__ weights, int n_weights, int n_hidden, float* __restrict__ state, int64_t B, int T)
+                                                           const float* __restrict__ weights, int n_weights, int n_hidden, float* __restrict__ state, float* __restrict__ ckpt, int64_t B, int T)
 {
     extern __shared__ __align__ (16) float sw[];
     for (int i = threadIdx.x; i < n_weights; i += blockDim.x)
@@ -117,6 +119,12 @@ __global__ void __launch_bounds__ (128) nn_clipper_forward (const float* __restr
     f2 z { state != nullptr ? state[rowA] : 0.0f, (state != nullptr && validB) ? state[rowB] : 0.0f };
     for (int n = 0; n < T; ++n)
     {
+        if (ckpt != nullptr && (n & (kNnSeg - 1)) == 0)
+        { // state at the start of every kNnSeg-sample block: the adjoint re-anchors its reconstruction there
+            ckpt[(int64_t) (n / kNnSeg) * B + rowA] = z.x;
+            if (validB)
+                ckpt[(int64_t) (n / kNnSeg) * B + rowB] = z.y;
+        }
         const f2 xv { __ldg (xa + n), __ldg (xb + n) };
         if (ra != nullptr)
         { // clipper_pot.py:116-117: set_resistance + calc_impedance every sample
@@ -135,6 +143,13 @@ __global__ void __launch_bounds__ (128) nn_clipper_forward (const float* __restr
             yb[n] = yo.y;
         z = zn;
     }
+    if (ckpt != nullptr)
+    { // ... and the state after the last sample
+        const int64_t last = (int64_t) ((T + kNnSeg - 1) / kNnSeg) * B;
+        ckpt[last + rowA] = z.x;
+        if (validB)
+            ckpt[last + rowB] = z.y;
+    }
     if (state != nullptr)
     {
         state[rowA] = z.x;
@@ -142,10 +157,258 @@ __global__ void __launch_bounds__ (128) nn_clipper_forward (const float* __restr
             state[rowB] = z.y;
     }
 }
+
+// =================================================================================================
+// adjoint: dL/d(weights) and the loss, no tape
+// =================================================================================================
+// One reverse sweep per pair of sequences. As in the analytic-root adjoint nothing of the forward pass is
+// replayed across samples: z[n] comes back from the forward OUTPUT (python ordering z[n] = 2 y[n] - z[n+1],
+// re-anchored at a checkpoint every kNnSeg samples; plugin ordering z[n] = y[n]). Per sample the network is
+// evaluated once forwards (keeping the H activations of every layer in registers) and once backwards with
+// seed 1: that gives f'(a) = -dN/da for the state recurrence  G <- G ((1 - gamma) f' - gamma) + dL/dy  and,
+// scaled by -G, every weight's gradient term. The terms are accumulated per lane in shared memory
+// (acc[weight][lane], conflict-free, no atomics), reduced over the warp at the end in a fixed order and
+// written as one fp64 partial vector per warp; nn_finalize sums the partials in order (bit-reproducible).
+template <int H, int NH, bool PY, bool TARGET>
+__global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ ckpt,
+                                                          const float* __restrict__ params, int slot_R, int slot_C, float fs, const float* __restrict__ weights, int n_weights, double* __restrict__ partials,
+                                                          int skip, int64_t B, int T)
+{
+    extern __shared__ __align__ (16) float smem[];
+    const int nw4 = (n_weights + 3) / 4 * 4;
+    float* sw = smem; // weights
+    float* acc = smem + nw4; // [n_weights][32]
+    const int lane = threadIdx.x;
+    for (int i = lane; i < n_weights; i += 32)
+        sw[i] = __ldg (weights + i);
+    for (int i = lane; i < n_weights * 32; i += 32)
+        acc[i] = 0.0f;
+    __syncwarp ();
+    const int64_t pair = (int64_t) blockIdx.x * 32 + lane;
+    const int64_t rowA = 2 * pair, rowB = rowA + 1;
+    const bool validA = rowA < B, validB = rowB < B;
+    const int64_t ra_ = validA ? rowA : B - 1, rb_ = validB ? rowB : ra_;
+    const float *xa = x + ra_ * T, *xb = x + rb_ * T, *ya = y + ra_ * T, *yb = y + rb_ * T, *ga = g + ra_ * T, *gb = g + rb_ * T;
+    const float* rpa = r != nullptr ? r + ra_ * T : nullptr;
+    const float* rpb = r != nullptr ? r + rb_ * T : nullptr;
+    const float Gc = 2.0f * __ldg (params + slot_C) * fs;
+    const float Gv0 = 1.0f / __ldg (params + slot_R);
+    const float Rp0 = 1.0f / (Gv0 + Gc);
+    f2 gamma = bc (f2 {}, Gv0 * Rp0), lr = bc (f2 {}, logf (Rp0));
+    const float* wout = sw + 3 * H + NH * (H * H + H);
+    const int nblk = (T + kNnSeg - 1) / kNnSeg;
+    f2 zn { __ldg (ckpt + (int64_t) nblk * B + ra_), __ldg (ckpt + (int64_t) nblk * B + rb_) }; // z[T]
+    f2 G { 0.0f, 0.0f };
+    double sse = 0.0, st2 = 0.0;
+    float sse_f = 0.0f, st2_f = 0.0f;
+    for (int n = T - 1; n >= 0; --n)
+    {
+        const f2 yv { __ldg (ya + n), __ldg (yb + n) };
+        f2 z = PY ? fmav (bc (f2 {}, 2.0f), yv, negv (zn)) : yv;
+        if ((n & (kNnSeg - 1)) == 0)
+            z = f2 { __ldg (ckpt + (int64_t) (n / kNnSeg) * B + ra_), __ldg (ckpt + (int64_t) (n / kNnSeg) * B + rb_) };
+        if (rpa != nullptr)
+        {
+            const float GvA = 1.0f / __ldg (rpa + n), GvB = 1.0f / __ldg (rpb + n);
+            const float RpA = 1.0f / (GvA + Gc), RpB = 1.0f / (GvB + Gc);
+            gamma = f2 { GvA * RpA, GvB * RpB };
+            lr = f2 { logf (RpA), logf (RpB) };
+        }
+        const f2 xv { __ldg (xa + n), __ldg (xb + n) };
+        const f2 a = fmav (gamma, addv (xv, negv (z)), z);
+        // dL/dy[n]
+        f2 gy { __ldg (ga + n), __ldg (gb + n) };
+        if (TARGET)
+        {
+            const bool on = n >= skip;
+            const f2 yk = PY ? mulv (bc (f2 {}, 0.5f), addv (zn, z)) : z;
+            const f2 tv = gy;
+            gy = f2 { (on && validA) ? yk.x - tv.x : 0.0f, (on && validB) ? yk.y - tv.y : 0.0f };
+            sse_f += gy.x * gy.x + gy.y * gy.y;
+            st2_f += ((on && validA) ? tv.x * tv.x : 0.0f) + ((on && validB) ? tv.y * tv.y : 0.0f);
+        }
+        else
+            gy = f2 { validA ? gy.x : 0.0f, validB ? gy.y : 0.0f };
+        const bool last_plugin = ! PY && n == T - 1; // plugin ordering never observes z[T]
+        if (PY)
+            G = fmav (bc (f2 {}, 0.5f), gy, G);
+        // ---- network forwards, activations kept ---------------------------------------------------
+        f2 in[2] = { a, lr };
+        f2 hs[NH + 1][H];
+        dense<2, H, true> (sw, sw + 2 * H, in, hs[0]);
+#pragma unroll
+        for (int l = 0; l < NH; ++l)
+            dense<H, H, true> (sw + 3 * H + l * (H * H + H), sw + 3 * H + l * (H * H + H) + H * H, hs[l], hs[l + 1]);
+        // ---- network backwards with seed 1; every weight's term scaled by s = -G (b = -N) -----------
+        const f2 s = last_plugin ? f2 { 0.0f, 0.0f } : negv (G);
+        f2 d[H]; // dN/d(pre-activation) of the layer being visited
+        int wofs = 3 * H + NH * (H * H + H);
+        // output layer H -> 1
+#pragma unroll
+        for (int i = 0; i < H; ++i)
+        {
+            acc[(wofs + i) * 32 + lane] += s.x * hs[NH][i].x + s.y * hs[NH][i].y;
+            const f2 hh = hs[NH][i];
+            d[i] = mulv (bc (f2 {}, wout[i]), fmav (negv (hh), hh, bc (f2 {}, 1.0f)));
+        }
+        acc[(wofs + H) * 32 + lane] += s.x + s.y;
+        // hidden layers, last to first
+#pragma unroll
+        for (int l = NH - 1; l >= 0; --l)
+        {
+            wofs = 3 * H + l * (H * H + H);
+            f2 sd[H], dp[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j)
+            {
+                sd[j] = mulv (s, d[j]);
+                acc[(wofs + H * H + j) * 32 + lane] += sd[j].x + sd[j].y; // bias
+            }
+#pragma unroll
+            for (int i = 0; i < H; ++i)
+            {
+                f2 sum = bc (f2 {}, 0.0f);
+#pragma unroll
+                for (int j = 0; j < H; j += 4)
+                {
+                    const float4 w4 = *reinterpret_cast<const float4*> (sw + wofs + i * H + j);
+                    const float ws[4] = { w4.x, w4.y, w4.z, w4.w };
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                    {
+                        sum = fmav (bc (f2 {}, ws[q]), d[j + q], sum);
+                        acc[(wofs + i * H + j + q) * 32 + lane] += hs[l][i].x * sd[j + q].x + hs[l][i].y * sd[j + q].y;
+                    }
+                }
+                const f2 hh = hs[l][i];
+                dp[i] = mulv (sum, fmav (negv (hh), hh, bc (f2 {}, 1.0f)));
+            }
+#pragma unroll
+            for (int i = 0; i < H; ++i)
+                d[i] = dp[i];
+        }
+        // input layer 2 -> H
+        f2 dNda = bc (f2 {}, 0.0f);
+#pragma unroll
+        for (int j = 0; j < H; ++j)
+        {
+            const f2 sd = mulv (s, d[j]);
+            acc[j * 32 + lane] += a.x * sd.x + a.y * sd.y;
+            acc[(H + j) * 32 + lane] += lr.x * sd.x + lr.y * sd.y;
+            acc[(2 * H + j) * 32 + lane] += sd.x + sd.y;
+            dNda = fmav (bc (f2 {}, sw[j]), d[j], dNda);
+        }
+        // ---- state recurrence: A = (1 - gamma) f'(a) - gamma, f' = -dN/da ---------------------------
+        const f2 omg = addv (bc (f2 {}, 1.0f), negv (gamma));
+        const f2 A = addv (mulv (omg, negv (dNda)), negv (gamma));
+        G = last_plugin ? gy : fmav (G, A, PY ? mulv (bc (f2 {}, 0.5f), gy) : gy);
+        zn = z;
+        if ((n & 63) == 0)
+        {
+            sse += (double) sse_f, st2 += (double) st2_f;
+            sse_f = st2_f = 0.0f;
+        }
+    }
+    __syncwarp ();
+    // ---- per-warp reduction in a fixed order, one fp64 partial vector per warp ----------------------
+    double* out = partials + (int64_t) blockIdx.x * (n_weights + 8);
+    for (int w = lane; w < n_weights; w += 32)
+    {
+        double sum = 0.0;
+        for (int k = 0; k < 32; ++k)
+            sum += (double) acc[w * 32 + ((k + lane) & 31)]; // skewed: conflict-free; the order is fixed per (w, lane)
+        out[w] = sum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        sse += __shfl_xor_sync (0xffffffffu, sse, o);
+        st2 += __shfl_xor_sync (0xffffffffu, st2, o);
+    }
+    if (lane == 0)
+    {
+        out[n_weights] = sse;
+        out[n_weights + 1] = st2;
+    }
+}
+
+// fixed-order reduction over the warps' partials, loss, and the loss's scale on the gradients
+// (MSE: 2/N; + ESR: clipper_pot.py:148-156 with eps = float64 eps, :145); upstream mode: scale 1.
+__global__ void __launch_bounds__ (256) nn_finalize (const double* __restrict__ partials, int64_t n_groups, int n_weights, int target, int loss_kind, double count, double* __restrict__ grad_w, double* __restrict__ out)
+{
+    __shared__ double sm[2][256];
+    __shared__ double alpha_s;
+    const int tid = threadIdx.x;
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t gidx = tid; gidx < n_groups; gidx += 256)
+    {
+        a0 += partials[gidx * (n_weights + 8) + n_weights];
+        a1 += partials[gidx * (n_weights + 8) + n_weights + 1];
+    }
+    sm[0][tid] = a0, sm[1][tid] = a1;
+    __syncthreads ();
+    for (int o = 128; o > 0; o >>= 1)
+    {
+        if (tid < o)
+            sm[0][tid] += sm[0][tid + o], sm[1][tid] += sm[1][tid + o];
+        __syncthreads ();
+    }
+    if (tid == 0)
+    {
+        double alpha = 1.0, loss = 0.0, mse = 0.0, esr = 0.0;
+        if (target)
+        {
+            const double sse = sm[0][0], st2 = sm[1][0], N = count > 0.0 ? count : 1.0;
+            mse = sse / N;
+            alpha = 2.0 / N;
+            loss = mse;
+            if (loss_kind == 1)
+            {
+                const double energy = st2 + 2.220446049250313e-16;
+                esr = sqrt (sse / energy / N);
+                loss += esr;
+                if (esr > 0.0)
+                    alpha += 1.0 / (esr * energy * N);
+            }
+        }
+        for (int k = 0; k < 24; ++k)
+            out[k] = 0.0;
+        out[16] = loss, out[17] = mse, out[18] = esr;
+        alpha_s = alpha;
+    }
+    __syncthreads ();
+    const double alpha = alpha_s;
+    for (int w = tid; w < n_weights; w += 256)
+    {
+        double sum = 0.0;
+        for (int64_t gidx = 0; gidx < n_groups; ++gidx)
+            sum += partials[gidx * (n_weights + 8) + w];
+        grad_w[w] = alpha * sum;
+    }
+}
+
+// Adam on a weight vector of any length (clipper_pot.py:180,269: Adam(1e-4, beta_1 = 0.5) on the network)
+__global__ void adam_vec_kernel (float* __restrict__ w, const double* __restrict__ gw, float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ step, int64_t n, float lr, float beta1, float beta2,
+                                 float eps, double grad_scale)
+{
+    const int t = *step + 1;
+    const float lr_t = lr * sqrtf (1.0f - powf (beta2, (float) t)) / (1.0f - powf (beta1, (float) t));
+    for (int64_t k = threadIdx.x; k < n; k += blockDim.x)
+    {
+        const float gk = (float) (gw[k] * grad_scale);
+        const float mk = beta1 * m[k] + (1.0f - beta1) * gk;
+        const float vk = beta2 * v[k] + (1.0f - beta2) * gk * gk;
+        m[k] = mk, v[k] = vk;
+        w[k] -= lr_t * mk / (sqrtf (vk) + eps);
+    }
+    __syncthreads ();
+    if (threadIdx.x == 0)
+        *step = t;
+}
 } // namespace
 
 cudaError_t launch_nn_forward (int hidden, int n_hidden, bool pyorder, const float* x, const float* r, float* y, const float* params, int slot_R, int slot_C, float fs, const float* weights,
-                               int n_weights, float* state, int64_t B, int64_t T, cudaStream_t stream)
+                               int n_weights, float* state, float* ckpt, int64_t B, int64_t T, cudaStream_t stream)
 {
     const int64_t pairs = (B + 1) / 2;
     const unsigned grid = (unsigned) ((pairs + 127) / 128);
@@ -154,9 +417,9 @@ cudaError_t launch_nn_forward (int hidden, int n_hidden, bool pyorder, const flo
     if (hidden == HH) \
     { \
         if (pyorder) \
-            nn_clipper_forward<HH, true><<<grid, 128, smem, stream>>> (x, r, y, params, slot_R, slot_C, fs, weights, n_weights, n_hidden, state, B, (int) T); \
+            nn_clipper_forward<HH, true><<<grid, 128, smem, stream>>> (x, r, y, params, slot_R, slot_C, fs, weights, n_weights, n_hidden, state, ckpt, B, (int) T); \
         else \
-            nn_clipper_forward<HH, false><<<grid, 128, smem, stream>>> (x, r, y, params, slot_R, slot_C, fs, weights, n_weights, n_hidden, state, B, (int) T); \
+            nn_clipper_forward<HH, false><<<grid, 128, smem, stream>>> (x, r, y, params, slot_R, slot_C, fs, weights, n_weights, n_hidden, state, ckpt, B, (int) T); \
         return cudaGetLastError (); \
     }
     DWDF_NN (4)
@@ -164,6 +427,49 @@ cudaError_t launch_nn_forward (int hidden, int n_hidden, bool pyorder, const flo
     DWDF_NN (16)
 #undef DWDF_NN
     return cudaErrorInvalidValue;
+}
+
+int64_t nn_ckpt_floats (int64_t B, int64_t T) { return ((T + kNnSeg - 1) / kNnSeg + 1) * B; }
+int64_t nn_groups (int64_t B) { return ((B + 1) / 2 + 31) / 32; }
+
+cudaError_t launch_nn_adjoint (int hidden, int n_hidden, bool pyorder, bool target, const float* x, const float* r, const float* y, const float* g, const float* ckpt, const float* params, int slot_R, int slot_C,
+                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, cudaStream_t stream)
+{
+    const unsigned grid = (unsigned) nn_groups (B);
+    const size_t smem = (size_t) ((n_weights + 3) / 4 * 4 + (size_t) n_weights * 32) * sizeof (float);
+    auto go = [&] (auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess)
+            return e;
+        kern<<<grid, 32, smem, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T);
+        return cudaGetLastError ();
+    };
+#define DWDF_NNA(HH, NN) \
+    if (hidden == HH && n_hidden == NN) \
+    { \
+        if (pyorder) \
+            return target ? go (nn_clipper_adjoint<HH, NN, true, true>) : go (nn_clipper_adjoint<HH, NN, true, false>); \
+        return target ? go (nn_clipper_adjoint<HH, NN, false, true>) : go (nn_clipper_adjoint<HH, NN, false, false>); \
+    }
+    DWDF_NNA (4, 2)
+    DWDF_NNA (8, 2)
+    DWDF_NNA (16, 2)
+    DWDF_NNA (4, 4)
+    DWDF_NNA (8, 4)
+#undef DWDF_NNA
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_nn_finalize (const double* partials, int64_t n_groups, int n_weights, bool target, int loss_kind, double count, double* grad_w, double* out, cudaStream_t stream)
+{
+    nn_finalize<<<1, 256, 0, stream>>> (partials, n_groups, n_weights, target ? 1 : 0, loss_kind, count, grad_w, out);
+    return cudaGetLastError ();
+}
+
+cudaError_t launch_adam_vec (float* w, const double* gw, float* m, float* v, int32_t* step, int64_t n, float lr, float beta1, float beta2, float eps, double grad_scale, cudaStream_t stream)
+{
+    adam_vec_kernel<<<1, 256, 0, stream>>> (w, gw, m, v, step, n, lr, beta1, beta2, eps, grad_scale);
+    return cudaGetLastError ();
 }
 
 } // namespace dwdf

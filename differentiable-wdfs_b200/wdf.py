@@ -527,8 +527,9 @@ class CompiledCircuit:
             self._last = None
             return y
         if self.is_neural:
-            L.check(self.lib.dwdf_forward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), None, B, T, _stream_ptr(self.device)))
-            self._last = None
+            ck = self._scratch("_ckpt", self.lib.dwdf_neural_ckpt_bytes(self.handle, B, T)) if keep_for_backward else None
+            L.check(self.lib.dwdf_forward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), None, _ptr(ck), B, T, _stream_ptr(self.device)))
+            self._last = (x, r, y, B, T) if keep_for_backward else None
             return y
         ck = None
         if keep_for_backward and self.is_clipper and B * T > 0:
@@ -557,6 +558,17 @@ class CompiledCircuit:
         self._check_xy(g, "gy/target")
         if tuple(g.shape) != (B, T):
             raise ValueError("gy/target must have the shape of x")
+        if self.is_neural:
+            if want_gx or raw:
+                raise NotImplementedError("neural root: dL/dx and raw (pre-all-reduce) sums are not implemented")
+            work = self._scratch("_work", self.lib.dwdf_neural_workspace_bytes(self.handle, B, T))
+            if getattr(self, "grad_w", None) is None:
+                self.grad_w = torch.zeros(self.weights.numel(), dtype=torch.float64, device=self.device)
+            L.check(self.lib.dwdf_backward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), _ptr(self._ckpt), _ptr(g), L.GRAD_UPSTREAM if gy is not None else L.GRAD_TARGET,
+                                                  L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(self.grad_w), _ptr(self.out), _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
+            res = self._result(None)
+            res["grads"] = self.grad_w
+            return res
         gx = torch.empty_like(x) if want_gx else None
         nbytes = self.lib.dwdf_workspace_bytes(self.handle, B, T)
         work = self._scratch("_work", nbytes)
@@ -602,7 +614,7 @@ class CompiledCircuit:
             raise ValueError(f"state must be a contiguous float32 CUDA tensor with {self.n_states} x B elements")
         y = torch.empty_like(x) if out is None else out
         if self.is_neural:
-            L.check(self.lib.dwdf_forward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), _ptr(state), B, T, _stream_ptr(self.device)))
+            L.check(self.lib.dwdf_forward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), _ptr(state), None, B, T, _stream_ptr(self.device)))
             return y
         L.check(self.lib.dwdf_process_block(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(state), B, T, _stream_ptr(self.device)))
         return y
@@ -642,6 +654,23 @@ class CompiledCircuit:
 
 def compile_circuit(root, tree=None, probe=None, ordering="python", r_element=None, device=None, fs=None) -> CompiledCircuit:
     return CompiledCircuit(root, tree, probe, ordering, r_element, device, fs)
+
+
+class AdamWeights:
+    """tf.keras.optimizers.Adam on the weight vector of a neural-root circuit (clipper_pot.py:180,269)."""
+
+    def __init__(self, circuit: "CompiledCircuit", lr=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.c = circuit
+        n = circuit.weights.numel()
+        self.m = torch.zeros(n, dtype=torch.float32, device=circuit.device)
+        self.v = torch.zeros(n, dtype=torch.float32, device=circuit.device)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=circuit.device)
+        self.lr, self.beta_1, self.beta_2, self.epsilon = float(lr), float(beta_1), float(beta_2), float(epsilon)
+
+    def apply(self, grad_scale=1.0):
+        c = self.c
+        L.check(c.lib.dwdf_adam_step_vec(_ptr(c.weights), _ptr(c.grad_w), _ptr(self.m), _ptr(self.v), _ptr(self.step_count), c.weights.numel(), self.lr, self.beta_1, self.beta_2, self.epsilon,
+                                         float(grad_scale), _stream_ptr(c.device)))
 
 
 class Adam:

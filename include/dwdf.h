@@ -213,15 +213,25 @@ DWDF_API int dwdf_adam_step (float* params, const double* out, float* m, float* 
 DWDF_API int dwdf_forward_host (const dwdf_program* prog, const float* params_host, const float* x_host, const float* r_host, float* y_host, int64_t B, int64_t T);
 DWDF_API int dwdf_grad_host (const dwdf_program* prog, const float* params_host, const float* x_host, const float* r_host, const float* gy_or_target_host, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* y_host, double* out_host, int64_t B, int64_t T);
 
-/* Neural diode-pair root (inference). dwdf_program_create_neural: like dwdf_program_create with
- * desc->root_kind = DWDF_ROOT_NEURAL; the tree must be the clipper's Parallel(ResistiveVoltageSource,
- * Capacitor) with the probe on the capacitor; desc->r_node may name the source (per-sample resistance,
- * clipper_pot.py:114-117). dwdf_forward_neural replaces ClipperModel.forward (clipper_pot.py:103-127) and
- * DiodeClipperWDF::process for plugin models 2-11 (DiodeClipperWDF.cpp:32-166): `weights` =
- * dwdf_mlp_weight_count() device floats, `state` NULL (reset state) or B capacitor states (streaming). */
+/* Neural diode-pair root. dwdf_program_create_neural: like dwdf_program_create with desc->root_kind =
+ * DWDF_ROOT_NEURAL; the tree must be the clipper's Parallel(ResistiveVoltageSource, Capacitor) with the
+ * probe on the capacitor; desc->r_node may name the source (per-sample resistance, clipper_pot.py:114-117).
+ * dwdf_forward_neural replaces ClipperModel.forward (clipper_pot.py:103-127) and DiodeClipperWDF::process
+ * for plugin models 2-11 (DiodeClipperWDF.cpp:32-166): `weights` = dwdf_mlp_weight_count() device floats,
+ * `state` NULL (reset state) or B capacitor states (streaming), `z_ckpt` NULL or dwdf_neural_ckpt_bytes()
+ * of device scratch for dwdf_backward_neural.
+ * dwdf_backward_neural replaces tape.gradient(loss, model.trainable_variables) (clipper_pot.py:246-269;
+ * the trainable variables are the network's kernels and biases): one reverse sweep over (x, y, g), the
+ * network differentiated by hand per sample; grad_w receives dL/d(weights) (n_weights doubles, same layout
+ * as `weights`), out[DWDF_OUT_LOSS / _MSE / _ESR] the fused loss. Implemented for the reference's shapes
+ * 2xH (H = 4, 8, 16) and 4xH (H = 4, 8). dwdf_adam_step_vec: Adam on a vector of any length. */
 DWDF_API size_t dwdf_mlp_weight_count (const dwdf_mlp_desc* mlp);
 DWDF_API int dwdf_program_create_neural (const dwdf_node* nodes, int32_t n_nodes, const dwdf_circuit_desc* desc, const dwdf_mlp_desc* mlp, dwdf_program** out);
-DWDF_API int dwdf_forward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, float* y, float* state, int64_t B, int64_t T, void* stream);
+DWDF_API size_t dwdf_neural_ckpt_bytes (const dwdf_program* prog, int64_t B, int64_t T);
+DWDF_API size_t dwdf_neural_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T);
+DWDF_API int dwdf_forward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, float* y, float* state, float* z_ckpt, int64_t B, int64_t T, void* stream);
+DWDF_API int dwdf_backward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, double* grad_w, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+DWDF_API int dwdf_adam_step_vec (float* w, const double* grad, float* m, float* v, int32_t* step, int64_t n, float lr, float beta1, float beta2, float eps, double grad_scale, void* stream);
 
 /* Streaming twin of DiodeClipperWDF::{prepare, process} (DiodeClipperWDF.cpp:3-30): like
  * dwdf_forward, but the capacitor states are read from and written back to `state`

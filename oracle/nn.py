@@ -64,3 +64,62 @@ def nn_clipper_forward(x, weights, sizes, fs, R, C, ordering=ORDER_PYTHON, r=Non
         y[:, n] = z if ordering == ORDER_PLUGIN else dtype(0.5) * (zn + z)
         z = zn
     return y
+
+
+def nn_clipper_grad_torch(x, target, weights, sizes, fs, R, C, ordering=ORDER_PYTHON, r=None, loss="mse", skip=0, gy=None):
+    """Gradient oracle: the same recurrence in fp64 PyTorch, differentiated by autograd (what tf.GradientTape
+    does for clipper_pot.py:246-269; trainable variables = the network's kernels and biases, :268).
+    Loss: MSE [+ ESR, clipper_pot.py:148-156,177] on samples >= skip (:232,248), or sum(gy * y) when gy is given.
+    Returns dict(y, loss, mse, esr, grad_w (flat, same layout as weights))."""
+    import torch
+
+    dt = torch.float64
+    xt = torch.as_tensor(np.asarray(x), dtype=dt)
+    B, T = xt.shape
+    w = torch.tensor(np.asarray(weights, np.float64), dtype=dt, requires_grad=True)
+    layers, k = [], 0
+    for i, o in zip(sizes[:-1], sizes[1:]):
+        W = w[k:k + i * o].reshape(int(i), int(o))
+        k += i * o
+        b = w[k:k + o]
+        k += o
+        layers.append((W, b))
+    Gc = 2.0 * C * fs
+    z = torch.zeros(B, dtype=dt)
+    ys = []
+    rt = None if r is None else torch.as_tensor(np.asarray(r), dtype=dt)
+    for n in range(T):
+        Rv = torch.full((B,), float(R), dtype=dt) if rt is None else rt[:, n]
+        Gv = 1.0 / Rv
+        G = Gv + Gc
+        Rp = 1.0 / G
+        gamma = Gv / G
+        t = gamma * (xt[:, n] - z)
+        a = z + t
+        h = torch.stack([a, torch.log(Rp)], dim=-1)
+        for li, (W, b) in enumerate(layers):
+            h = h @ W + b
+            if li + 1 < len(layers):
+                h = torch.tanh(h)
+        zn = -h[:, 0] + t
+        ys.append(z if ordering == ORDER_PLUGIN else 0.5 * (zn + z))
+        z = zn
+    y = torch.stack(ys, dim=1)
+    out = {"y": y.detach().numpy()}
+    if gy is not None:
+        L = (torch.as_tensor(np.asarray(gy), dtype=dt) * y).sum()
+        out.update(loss=float(L.detach()), mse=0.0, esr=0.0)
+    else:
+        tt = torch.as_tensor(np.asarray(target), dtype=dt)[:, skip:]
+        e = y[:, skip:] - tt
+        N = e.numel()
+        mse = (e * e).sum() / N
+        L = mse
+        esr = torch.zeros((), dtype=dt)
+        if loss == "mse+esr":
+            esr = torch.sqrt((e * e).sum() / ((tt * tt).sum() + 2.220446049250313e-16) / N)  # clipper_pot.py:145,148-156
+            L = mse + esr
+        out.update(loss=float(L.detach()), mse=float(mse.detach()), esr=float(esr.detach()))
+    L.backward()
+    out["grad_w"] = w.grad.numpy().copy()
+    return out

@@ -123,8 +123,65 @@ def test_streaming_and_errors(dwdf, nnv):
     st = circ.new_state(9)
     parts = [circ.process_block(x[:, a:b].contiguous(), st) for a, b in ((0, 100), (100, 101), (101, 600))]
     assert torch.equal(torch.cat(parts, 1), whole)
-    with pytest.raises(RuntimeError):
-        circ.backward(target=x)  # inference only: no adjoint kernel for the neural root yet
     bad = dwdf.model_io.json_from_weights(np.zeros(2 * 5 + 5 + 5 + 1, np.float32), [2, 5, 1])
     with pytest.raises(Exception):
         make_circuit(dwdf, bad, "plugin")
+
+
+NN_GRAD_TOL = 2e-3  # relative to the largest gradient entry (fp32 network + fp32 per-lane accumulation vs fp64 autograd)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", MODELS)
+@pytest.mark.parametrize("ordering,order", [("plugin", nn.ORDER_PLUGIN), ("python", nn.ORDER_PYTHON)])
+@pytest.mark.parametrize("loss,skip", [("mse", 0), ("mse+esr", 50)])
+def test_weight_gradients_against_autograd(dwdf, nnv, name, ordering, order, loss, skip):
+    """dL/d(weights) of the hand-written adjoint against fp64 autograd through the same recurrence
+    (what tape.gradient computes for clipper_pot.py:246-269)."""
+    B, T = 9, 200
+    x = make_inputs(B, T, seed=21)
+    w, sizes = nnv[f"{name}_weights"], [int(v) for v in nnv[f"{name}_sizes"]]
+    target = 0.8 * nn.nn_clipper_forward(x, w, sizes, 48000.0, 47000.0, 2.2e-9, order, dtype=np.float64) + 0.01
+    circ = make_circuit(dwdf, model_json(dwdf, nnv, name), ordering)
+    circ.forward(torch.from_numpy(x).cuda())
+    res = circ.backward(target=torch.from_numpy(target.astype(np.float32)).cuda(), loss=loss, skip=skip)
+    ref = nn.nn_clipper_grad_torch(x, target.astype(np.float32), w, sizes, 48000.0, 47000.0, 2.2e-9, order, loss=loss, skip=skip)
+    g = res["grads"].cpu().numpy()
+    assert g.shape == ref["grad_w"].shape
+    assert np.max(np.abs(g - ref["grad_w"])) < NN_GRAD_TOL * np.max(np.abs(ref["grad_w"]))
+    assert abs(float(res["loss"]) / ref["loss"] - 1) < 1e-4
+
+
+@pytest.mark.gpu
+def test_weight_gradients_upstream_and_resistance_channel(dwdf, nnv):
+    B, T = 5, 150
+    x = make_inputs(B, T, seed=22)
+    r = (np.random.default_rng(3).uniform(1e4, 1e5, (B, 1)) * np.ones((1, T))).astype(np.float32)
+    gy = np.random.default_rng(4).standard_normal((B, T)).astype(np.float32)
+    w, sizes = nnv["2x8_weights"], [int(v) for v in nnv["2x8_sizes"]]
+    circ = make_circuit(dwdf, model_json(dwdf, nnv, "2x8"), "python", with_r=True, R=45000.0, C=4.7e-9, fs=50000.0)
+    circ.forward(torch.from_numpy(x).cuda(), r=torch.from_numpy(r).cuda())
+    g = circ.backward(gy=torch.from_numpy(gy).cuda())["grads"].cpu().numpy()
+    ref = nn.nn_clipper_grad_torch(x, None, w, sizes, 50000.0, 45000.0, 4.7e-9, nn.ORDER_PYTHON, r=r, gy=gy)
+    assert np.max(np.abs(g - ref["grad_w"])) < NN_GRAD_TOL * np.max(np.abs(ref["grad_w"]))
+
+
+@pytest.mark.gpu
+def test_training_reduces_the_loss(dwdf, nnv):
+    """A few Adam steps on the network (clipper_pot.py:180: Adam(1e-4, beta_1=0.5)) towards the output of another
+    trained model: the loss goes down, run to run identically (fixed-order reductions)."""
+    x = torch.from_numpy(make_inputs(64, 512, seed=23)).cuda()
+    teacher = make_circuit(dwdf, model_json(dwdf, nnv, "2x16"), "python")
+    target = teacher.forward(x, keep_for_backward=False).clone()
+    losses = []
+    for run in range(2):
+        circ = make_circuit(dwdf, model_json(dwdf, nnv, "2x8"), "python")
+        opt = dwdf.AdamWeights(circ, lr=1e-3, beta_1=0.5)
+        ls = []
+        for _ in range(15):
+            circ.forward(x)
+            ls.append(float(circ.backward(target=target, loss="mse+esr", skip=50)["loss"]))
+            opt.apply()
+        losses.append(ls)
+    assert losses[0] == losses[1]
+    assert losses[0][-1] < 0.7 * losses[0][0]
