@@ -128,7 +128,7 @@ def test_streaming_and_errors(dwdf, nnv):
         make_circuit(dwdf, bad, "plugin")
 
 
-NN_GRAD_TOL = 2e-3  # relative to the largest gradient entry (fp32 network + fp32 per-lane accumulation vs fp64 autograd)
+NN_GRAD_TOL = 1e-4  # relative to the largest gradient entry (fp32 network + fp32 per-lane accumulation vs fp64 autograd; measured 1e-6 .. 2e-5)
 
 
 @pytest.mark.gpu

@@ -39,3 +39,9 @@ for name in a.models.split(","):
     # CPU: oracle (numpy) is not a fair baseline; the reference's own RTNeural path lives in oracle/_ref (not on the GPU box unless built here)
     ref = os.path.join(ROOT, "oracle", "_ref", "libdwdf_ref_nn.so")
     print(line, flush=True)
+    tgt = (0.9 * y).clone()
+    circ.forward(x, r=r)
+    for _ in range(1): circ.backward(target=tgt)
+    torch.cuda.synchronize(); e0.record(); circ.backward(target=tgt); e1.record(); torch.cuda.synchronize()
+    msb = e0.elapsed_time(e1)
+    print(f"            adjoint {msb:.3f} ms  fwd+bwd {a.B*a.T/(ms+msb)/1e6:.2f} Gsamples/s", flush=True)
