@@ -5,7 +5,7 @@ reference's hyphen). The element API mirrors ``wdf_py/lib/tf_wdf.py``; the compi
 fused sm_100a kernels of ``csrc/`` through the C ABI of ``include/dwdf.h`` (``libdwdf.so``).
 """
 from . import _lib
-from ._lib import DwdfError, build_info, launch_count, set_option, set_tma
+from ._lib import DwdfError, build_info, launch_count, set_option, set_tma, time_parallel_redone
 from . import dataimport, model_io
 from .wdf import (Adam, AdamWeights, Capacitor, CompiledCircuit, DenseLayer, DenseRootModel, DiodePair, IdealVoltageSource, Inverter, Parallel, PolarityInverter, ResistiveVoltageSource, Resistor, Series, compile_circuit, voltage,
                   wright_omega)

@@ -28,7 +28,7 @@ STATUS = {0: "ok", 1: "invalid argument", 2: "unsupported", 3: "CUDA error", 4: 
 SYMBOLS = (
     "dwdf_program_create", "dwdf_program_destroy", "dwdf_program_is_clipper", "dwdf_program_n_states", "dwdf_ckpt_bytes", "dwdf_workspace_bytes",
     "dwdf_forward", "dwdf_backward", "dwdf_train_pass", "dwdf_adam_step", "dwdf_forward_host", "dwdf_grad_host", "dwdf_process_block",
-    "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_backward_neural", "dwdf_neural_ckpt_bytes", "dwdf_neural_workspace_bytes", "dwdf_adam_step_vec", "dwdf_last_error", "dwdf_build_info", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option",
+    "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_backward_neural", "dwdf_neural_ckpt_bytes", "dwdf_neural_workspace_bytes", "dwdf_adam_step_vec", "dwdf_last_error", "dwdf_build_info", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option", "dwdf_time_parallel_redone",
 )
 
 
@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
     L.dwdf_launch_count.restype = i64
     L.dwdf_set_tma.argtypes = [C.c_int]
     L.dwdf_set_option.argtypes = [C.c_int]
+    L.dwdf_time_parallel_redone.restype = i64
     _lib = L
     return L
 
@@ -123,3 +124,7 @@ def set_tma(enable: bool) -> bool:
 
 def set_option(bits: int) -> int:
     return int(lib().dwdf_set_option(int(bits)))
+
+
+def time_parallel_redone() -> int:
+    return int(lib().dwdf_time_parallel_redone())

@@ -731,6 +731,237 @@ __global__ void __launch_bounds__ (kLanes, 12) clipper_adjoint_direct (const flo
 }
 
 // =================================================================================================
+// time-parallel kernels for small batches
+// =================================================================================================
+// With one lane per sequence a batch of B sequences gives B / 32 warps however long the sequences are:
+// 8 warps for config 2 (256 x 4096), 32 for config 3 — a B200 has 592 schedulers. The recurrence is
+// strictly serial in time, but it is CONTRACTIVE (|dz'/dz| = |f'(a)(1 - gamma) - gamma| < 1; with the
+// diodes off it forgets its state like the RC time constant, faster when they conduct), so a sequence is
+// cut into chunks of kChunk samples that run concurrently, one lane per (sequence, chunk):
+//   forward  chunk k > 0 starts W samples early from z = 0 and discards that warm-up; W is chosen in the
+//            kernel from gamma so that the off-state decay (1 - 2 gamma)^W is below 1e-13. It records the
+//            state it assumed at its first sample and the state it ended with. A second, tiny kernel walks
+//            each sequence's chunks in order and ACCEPTS chunk k only if its assumed start equals the
+//            true end of chunk k-1 BIT FOR BIT (a contractive map in fp32 merges two trajectories exactly
+//            once they are within an ulp or so); otherwise that chunk is recomputed from the true state
+//            (hard-driven inputs, where the contraction is slow). The output is therefore identical to the
+//            serial kernels' whatever the chunking: the result never rests on the speculation being right.
+//   adjoint  needs no speculation: given the trajectory (recovered from y), the running adjoint is a
+//            LINEAR recurrence G <- A[n] G + q[n], so a chunk returns the affine map of its incoming G
+//            (P, Q) and of its parameter sums (S0 + G_in S1); a second kernel composes the chunks of each
+//            sequence in reverse order. Exact up to fp32 summation order.
+constexpr int kChunk = kTimeChunk; // samples per chunk (a multiple of kSeg)
+
+__device__ __forceinline__ int warmup_samples (const ClipConst& c, int n0)
+{
+    // off-state contraction per sample: dz'/dz = 1 - 2 gamma (f' = 1). (1 - 2 gamma)^W <= 1e-13: far enough below
+    // one ulp of a quiet signal that the speculated and the true trajectory have merged bit for bit
+    const float rho = fmaxf (fabsf (1.0f - 2.0f * c.gamma), 0.5f);
+    const float w = -29.9f / logf (fminf (rho, 0.99f));
+    int W = (int) fminf (w, 1.0e6f);
+    W = (W + 3) & ~3;
+    return W < n0 ? W : n0;
+}
+
+// 4 samples of one sequence, any variant
+template <int MODE, bool GENERAL, bool LSMALL, bool PY>
+__device__ __forceinline__ float4 chunk4 (const ClipConst& c, float4 v, float& z)
+{
+    if (MODE == kModeApprox && ! GENERAL && LSMALL)
+        return forward_chunk<PY> (c, v, z);
+    float4 o;
+    o.x = clip_step<MODE, GENERAL, (MODE != kModeApprox || GENERAL) && LSMALL, PY> (c, v.x, z);
+    o.y = clip_step<MODE, GENERAL, (MODE != kModeApprox || GENERAL) && LSMALL, PY> (c, v.y, z);
+    o.z = clip_step<MODE, GENERAL, (MODE != kModeApprox || GENERAL) && LSMALL, PY> (c, v.z, z);
+    o.w = clip_step<MODE, GENERAL, (MODE != kModeApprox || GENERAL) && LSMALL, PY> (c, v.w, z);
+    return o;
+}
+
+// samples [n0, n1) of row b from state z: outputs, checkpoints; returns the end state in z. T % 4 == 0, 16-byte aligned rows.
+template <int MODE, bool GENERAL, bool LSMALL, bool PY>
+__device__ __forceinline__ void run_span (const ClipConst& c, const float* __restrict__ xr, float* __restrict__ yr, float* __restrict__ ckpt, int64_t B, int64_t b, int n0, int n1, float& z)
+{
+    for (int n = n0; n < n1; n += 4)
+    {
+        if ((n & (kSeg - 1)) == 0 && ckpt != nullptr)
+            ckpt[(int64_t) (n / kSeg) * B + b] = z;
+        const float4 v = __ldg (reinterpret_cast<const float4*> (xr + n));
+        *reinterpret_cast<float4*> (yr + n) = chunk4<MODE, GENERAL, LSMALL, PY> (c, v, z);
+    }
+}
+
+template <int MODE, bool GENERAL, bool PY>
+__global__ void __launch_bounds__ (128) clipper_forward_chunked (const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, const float* __restrict__ state,
+                                                                float* __restrict__ zs, float* __restrict__ ze, int64_t B, int T, int K)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * K)
+        return;
+    const int64_t b = i / K;
+    const int k = (int) (i % K);
+    ClipConst c;
+    load_consts (c, desc, params);
+    const bool ls = (MODE == kModeApprox && ! GENERAL) ? fast_ok (c.pair.L) : rev_small_ok (c.pair);
+    const int n0 = k * kChunk, n1 = min (n0 + kChunk, T);
+    const int W = warmup_samples (c, n0);
+    const float* xr = x + b * T;
+    // warm-up from z = 0, or — when it reaches back to the first sample — from the true initial state (then nothing is assumed)
+    float z = (n0 - W == 0 && state != nullptr) ? state[b] : 0.0f;
+    for (int n = n0 - W; n < n0; n += 4)
+    {
+        const float4 v = __ldg (reinterpret_cast<const float4*> (xr + n));
+        if (ls)
+            (void) chunk4<MODE, GENERAL, true, PY> (c, v, z);
+        else
+            (void) chunk4<MODE, GENERAL, false, PY> (c, v, z);
+    }
+    zs[i] = z; // the state this chunk assumes at its first sample
+    if (ls)
+        run_span<MODE, GENERAL, true, PY> (c, xr, y + b * T, ckpt, B, b, n0, n1, z);
+    else
+        run_span<MODE, GENERAL, false, PY> (c, xr, y + b * T, ckpt, B, b, n0, n1, z);
+    ze[i] = z;
+}
+
+// one lane per sequence: accept or redo each chunk in order; writes the final state
+template <int MODE, bool GENERAL, bool PY>
+__global__ void __launch_bounds__ (128) clipper_forward_stitch (const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state,
+                                                               const float* __restrict__ zs, const float* __restrict__ ze, int64_t B, int T, int K, int* __restrict__ redone)
+{
+    const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B)
+        return;
+    ClipConst c;
+    load_consts (c, desc, params);
+    const bool ls = (MODE == kModeApprox && ! GENERAL) ? fast_ok (c.pair.L) : rev_small_ok (c.pair);
+    float zend = ze[b * K];
+    for (int k = 1; k < K; ++k)
+    {
+        const float assumed = zs[b * K + k];
+        if (assumed == zend) // bit for bit: an accepted chunk is exactly what the serial recurrence computes
+        {
+            zend = ze[b * K + k];
+            continue;
+        }
+        float z = zend; // the speculation missed: this chunk again, from the true state
+        const int n0 = k * kChunk, n1 = min (n0 + kChunk, T);
+        if (ls)
+            run_span<MODE, GENERAL, true, PY> (c, x + b * T, y + b * T, ckpt, B, b, n0, n1, z);
+        else
+            run_span<MODE, GENERAL, false, PY> (c, x + b * T, y + b * T, ckpt, B, b, n0, n1, z);
+        zend = z;
+        if (redone != nullptr)
+            atomicAdd (redone, 1);
+    }
+    if (state != nullptr)
+        state[b] = zend;
+}
+
+// ---- adjoint ---------------------------------------------------------------------------------------
+constexpr int kChunkOut = 12; // floats per (sequence, chunk): P, Q, S0[3], S1[3], sse, st2, pad
+
+template <int MODE, bool GENERAL, bool PY, bool TARGET>
+__global__ void __launch_bounds__ (128) clipper_adjoint_chunked (const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ params, const ClipDesc desc,
+                                                                const float* __restrict__ ckpt, float* __restrict__ cout, int64_t B, int T, int K, int skip)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * K)
+        return;
+    const int64_t b = i / K;
+    const int k = (int) (i % K);
+    ClipConst c;
+    load_consts (c, desc, params);
+    const bool ls = rev_small_ok (c.pair);
+    const int n0 = k * kChunk, n1 = min (n0 + kChunk, T);
+    const float *xr = x + b * T, *yr = y + b * T, *gr = g + b * T;
+    float Gp = 0.0f, Gh = 1.0f; // particular (sources, G_in = 0) and homogeneous (no sources, G_in = 1) solutions
+    float s0[3] = { 0.0f, 0.0f, 0.0f }, s1[3] = { 0.0f, 0.0f, 0.0f }, sse = 0.0f, st2 = 0.0f;
+    for (int seg0 = ((n1 - 1) / kSeg) * kSeg; seg0 >= n0; seg0 -= kSeg)
+    {
+        const int nv = min (kSeg, n1 - seg0);
+        float zs[kSeg + 1];
+        zs[0] = __ldg (ckpt + (int64_t) (seg0 / kSeg) * B + b);
+        float ys[kSeg];
+#pragma unroll
+        for (int q = 0; q < kSeg; ++q)
+        {
+            ys[q] = q < nv ? __ldg (yr + seg0 + q) : 0.0f;
+            if (PY)
+                zs[q + 1] = fma_ (2.0f, ys[q], -zs[q]);
+            else
+                zs[q] = ys[q];
+        }
+        if (! PY)
+            zs[nv] = seg0 + nv < T ? __ldg (ckpt + (int64_t) ((seg0 + nv) / kSeg) * B + b) : 0.0f; // nv == kSeg whenever another segment follows
+#pragma unroll
+        for (int q = kSeg - 1; q >= 0; --q)
+        {
+            if (q < nv)
+            {
+                const int n = seg0 + q;
+                float gy = __ldg (gr + n);
+                if (TARGET)
+                {
+                    const bool on = n >= skip;
+                    const float yk = PY ? 0.5f * (zs[q + 1] + zs[q]) : zs[q];
+                    const float tv = gy;
+                    gy = on ? yk - tv : 0.0f;
+                    sse = fma_ (gy, gy, sse);
+                    st2 = on ? fma_ (tv, tv, st2) : st2;
+                }
+                if (! PY && n == T - 1)
+                { // plugin ordering never observes z[T]
+                    Gp = gy;
+                    Gh = 0.0f;
+                }
+                else
+                {
+                    StepTape tp;
+                    if (ls)
+                        clip_step_recover<MODE, GENERAL, true> (c, __ldg (xr + n), zs[q], zs[q + 1], tp);
+                    else
+                        clip_step_recover<MODE, GENERAL, false> (c, __ldg (xr + n), zs[q], zs[q + 1], tp);
+                    if (PY)
+                        Gp = fma_ (0.5f, gy, Gp);
+                    s0[0] = fma_ (Gp, tp.cg, s0[0]), s0[1] = fma_ (Gp, tp.cl, s0[1]), s0[2] = fma_ (Gp, tp.cv, s0[2]);
+                    s1[0] = fma_ (Gh, tp.cg, s1[0]), s1[1] = fma_ (Gh, tp.cl, s1[1]), s1[2] = fma_ (Gh, tp.cv, s1[2]);
+                    Gp = fma_ (Gp, tp.A, PY ? 0.5f * gy : gy);
+                    Gh *= tp.A;
+                }
+            }
+        }
+    }
+    float* o = cout + i * kChunkOut;
+    o[0] = Gh, o[1] = Gp;
+    o[2] = s0[0], o[3] = s0[1], o[4] = s0[2];
+    o[5] = s1[0], o[6] = s1[1], o[7] = s1[2];
+    o[8] = sse, o[9] = st2;
+}
+
+// one lane per sequence: compose the chunks' affine maps last to first; one partial per group of 32 sequences
+__global__ void __launch_bounds__ (kLanes) clipper_adjoint_stitch (const float* __restrict__ cout, double* __restrict__ partials, int64_t B, int K)
+{
+    const int lane = threadIdx.x;
+    const int64_t b = (int64_t) blockIdx.x * kLanes + lane;
+    AdjAcc acc;
+    if (b < B)
+    {
+        double G = 0.0;
+        for (int k = K - 1; k >= 0; --k)
+        {
+            const float* o = cout + (b * K + k) * kChunkOut;
+            acc.g += (double) o[2] + G * (double) o[5];
+            acc.l += (double) o[3] + G * (double) o[6];
+            acc.v += (double) o[4] + G * (double) o[7];
+            acc.sse += (double) o[8];
+            acc.st2 += (double) o[9];
+            G = (double) o[0] * G + (double) o[1];
+        }
+    }
+    write_partials (acc, partials, blockIdx.x, lane);
+}
+
+// =================================================================================================
 // fused training pass: forward + loss + parameter sensitivities in one sweep
 // =================================================================================================
 // With only three raw parameters (gamma, ell, V) the tangents s_k[n] = dz[n]/dk ride along the
@@ -914,6 +1145,13 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
     const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
     auto go = [&] (auto P) {
         constexpr bool p = decltype (P)::value;
+        if (maps != nullptr && maps->chunks > 1)
+        { // small batch, long sequences: time-parallel
+            const int K = maps->chunks;
+            clipper_forward_chunked<kM, kG, p><<<(unsigned) ((B * K + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, K);
+            clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, K, maps->redone);
+            return;
+        }
         if constexpr (kM == kModeApprox && ! kG)
         {
             if (use_tma && maps->pair)
@@ -937,6 +1175,13 @@ cudaError_t clipper_adjoint_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
     const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
     auto go = [&] (auto P, auto TG) {
         constexpr bool p = decltype (P)::value, tg = decltype (TG)::value;
+        if (maps != nullptr && maps->chunks > 1 && gx == nullptr)
+        {
+            const int K = maps->chunks;
+            clipper_adjoint_chunked<kM, kG, p, tg><<<(unsigned) ((B * K + 127) / 128), 128, 0, stream>>> (x, y, g, params, desc, ckpt, maps->cout, B, (int) T, K, skip);
+            clipper_adjoint_stitch<<<grid, kLanes, 0, stream>>> (maps->cout, partials, B, K);
+            return;
+        }
         if (use_tma && gx == nullptr)
             clipper_adjoint_tma<kM, kG, p, tg><<<grid, kLanes, 0, stream>>> (maps->x, maps->y, maps->g, params, desc, ckpt, partials, B, (int) T, skip, g_clip_opts);
         else if (gx != nullptr)

@@ -34,6 +34,7 @@ namespace
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches { 0 };
 std::atomic<int> g_use_tma { 1 };
+int* g_redone = nullptr; // device counter: chunks the time-parallel forward had to recompute (diagnostics)
 
 int fail (int code, const char* fmt, ...)
 {
@@ -102,6 +103,11 @@ bool tma_usable (const void* a, const void* b, const void* c, int64_t B, int64_t
 bool is_leaf (int k) { return k == DWDF_RESISTOR || k == DWDF_CAPACITOR || k == DWDF_RESISTIVE_VS; }
 
 int64_t n_groups (int64_t B) { return (B + 31) / 32; }
+// time-parallel kernels: few sequences, long ones (fewer than ~1 warp per scheduler otherwise)
+// (measured crossovers at T = 4096: forward 0.15 vs 0.32 ms at B = 4096, 0.40 vs 0.32 at 8192; adjoint 0.13 vs 0.21 ms at 2048, 0.24 vs 0.21 at 4096)
+int time_chunks (int64_t B, int64_t T, int64_t max_B) { return (! (g_clip_opts & kOptNoChunks) && B <= max_B && T >= 2 * kTimeChunk) ? (int) ((T + kTimeChunk - 1) / kTimeChunk) : 0; }
+constexpr int64_t kChunkedForwardMaxB = 4096, kChunkedAdjointMaxB = 2048;
+size_t partials_bytes (int64_t B) { return ((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256 * 256 + 256; }
 int64_t n_segments (int64_t T) { return (T + kSeg - 1) / kSeg; }
 } // namespace
 
@@ -112,6 +118,13 @@ const char* dwdf_last_error (void) { return g_err; }
 const char* dwdf_build_info (void) { return "libdwdf v3 sm_100a cuda-12.9 tma+mbarrier fp32x2 no-cpu-fallback"; }
 int64_t dwdf_launch_count (void) { return g_launches.load (); }
 int dwdf_set_tma (int enable) { return g_use_tma.exchange (enable ? 1 : 0); }
+int64_t dwdf_time_parallel_redone (void)
+{
+    int v = 0;
+    if (g_redone != nullptr && cudaMemcpy (&v, g_redone, sizeof (int), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    return v;
+}
 int dwdf_set_option (int bits)
 {
     const int prev = g_clip_opts;
@@ -361,7 +374,9 @@ size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
 {
     if (prog == nullptr || B <= 0 || T <= 0)
         return 0;
-    size_t bytes = ((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256 * 256 + 256;
+    size_t bytes = partials_bytes (B);
+    if (prog->is_clipper)
+        bytes += (size_t) B * (size_t) ((T + kTimeChunk - 1) / kTimeChunk) * kChunkOutFloats * sizeof (float); // time-parallel adjoint (small batches)
     if (! prog->is_clipper) // per-sample tape of the interpreter adjoint: (n_states + 1) floats per sample
         bytes += (size_t) B * (size_t) T * (size_t) (prog->n_states + 1) * sizeof (float);
     return bytes;
@@ -393,8 +408,25 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
         ClipTmaMaps maps;
         const bool tma = tma_usable (x, y, nullptr, B, T) && make_map (&maps.x, x, B, T, 32) && make_map (&maps.y, y, B, T, 32);
         // approx root, symmetric pair, more than one warp's worth of sequences: two sequences per lane (packed fp32x2)
+        float* scratch = nullptr;
+        const int K = (T % 4 == 0 && ((uintptr_t) x & 15u) == 0 && ((uintptr_t) y & 15u) == 0) ? time_chunks (B, T, kChunkedForwardMaxB) : 0;
+        if (K > 1)
+        {
+            DWDF_CUDA (cudaMallocAsync ((void**) &scratch, (size_t) 2 * B * K * sizeof (float), stream));
+            if (g_redone == nullptr && cudaMalloc ((void**) &g_redone, sizeof (int)) == cudaSuccess)
+                cudaMemset (g_redone, 0, sizeof (int));
+            maps.redone = g_redone;
+            maps.chunks = K;
+            maps.zs = scratch;
+            maps.ze = scratch + (size_t) B * K;
+        }
         maps.pair = tma && prog->variant.mode == kModeApprox && ! prog->variant.general && B > 32 && ! (g_clip_opts & kOptNoPair) && make_map (&maps.x2, x, B, T, 32, 64) && make_map (&maps.y2, y, B, T, 32, 64);
         DWDF_CUDA (launch_clipper_forward (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, state, B, T, stream));
+        if (scratch != nullptr)
+        {
+            DWDF_CUDA (cudaFreeAsync (scratch, stream));
+            g_launches.fetch_add (1);
+        }
     }
     else
     {
@@ -445,6 +477,12 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
             return fail (DWDF_ERR_INVALID, "the clipper adjoint reads the output y and the checkpoints z_ckpt that dwdf_forward wrote: %s is null", y == nullptr ? "y" : "z_ckpt");
         ClipTmaMaps maps;
         const bool tma = gx == nullptr && tma_usable (x, gy_or_target, y, B, T) && make_map (&maps.x, x, B, T, kSeg) && make_map (&maps.y, y, B, T, kSeg) && make_map (&maps.g, gy_or_target, B, T, kSeg);
+        if (gx == nullptr && time_chunks (B, T, kChunkedAdjointMaxB) > 1)
+        {
+            maps.chunks = time_chunks (B, T, kChunkedAdjointMaxB);
+            maps.cout = (float*) ((char*) workspace + partials_bytes (B));
+            g_launches.fetch_add (1);
+        }
         DWDF_CUDA (launch_clipper_adjoint (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, gy_or_target, target, sk, gx, partials, B, T, stream));
         DWDF_CUDA (launch_clipper_finalize (prog->clip, params, partials, n_groups (B), nullptr, raw_only, target, loss_kind, count, out, stream));
     }

@@ -12,6 +12,8 @@ namespace dwdf
 {
 
 constexpr int kSeg = 16; // capacitor-state checkpoint spacing [samples]; also the adjoint's segment
+constexpr int kTimeChunk = 256; // samples per chunk of the time-parallel (small-batch) kernels
+constexpr int kChunkOutFloats = 12; // adjoint: floats per (sequence, chunk)
 constexpr int kPartialStride = 8; // doubles per sequence-group in the clipper partials buffer
 constexpr int kTreePartialStride = 24; // ... in the tree interpreter partials buffer
 // partial sums one warp (32 sequences) hands to the finalize kernel
@@ -29,6 +31,7 @@ enum : int
 {
     kOptNoFastStep = 1, // forward, approx: per-sample warp vote (clip_step) instead of clip_step_fast chunks
     kOptNoPair = 2, // forward, approx: one sequence per lane instead of the packed-fp32x2 pair kernel
+    kOptNoChunks = 8, // never use the time-parallel kernels
     kOptL2Prefetch = 4 // cp.async.bulk.prefetch.tensor L2 run-ahead (measured: slower — forward 0.47 -> 0.58 ms, adjoint 0.63 -> 0.94 ms; off)
 };
 extern int g_clip_opts;
@@ -46,6 +49,10 @@ struct ClipTmaMaps
     CUtensorMap x, y, g; // forward (x, y): 32 x 32 tiles, 128-byte swizzle; adjoint (x, y, g): 16 x 32 tiles, 64-byte swizzle
     CUtensorMap x2, y2; // paired forward: [64 sequences x 32 samples] tiles
     bool pair = false; // x2 / y2 are valid and the paired kernel is wanted
+    // time-parallel path (small batches): chunks > 1 selects it; scratch of B * chunks floats each (forward) / B * chunks * 12 (adjoint)
+    int chunks = 0;
+    float *zs = nullptr, *ze = nullptr, *cout = nullptr;
+    int* redone = nullptr; // optional counter of chunks the forward had to recompute
 };
 
 // per-(root mode, law) launchers, each specialised in its own translation unit (clipper_kernels.cu, 4 parts)

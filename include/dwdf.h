@@ -249,8 +249,12 @@ DWDF_API int64_t dwdf_launch_count (void);
 DWDF_API int dwdf_set_tma (int enable);
 /* Kernel-variant switches for A/B timing. bit 0: forward approx root evaluated sample by sample
  * (no packed fast step); bit 1: one sequence per lane instead of the packed-fp32x2 pair kernel;
- * bit 2: TMA L2 prefetch run-ahead. 0 = shipped behaviour. Returns the previous bits. */
+ * bit 2: TMA L2 prefetch run-ahead; bit 3: never use the time-parallel (small-batch) kernels.
+ * 0 = shipped behaviour. Returns the previous bits. */
 DWDF_API int dwdf_set_option (int bits);
+/* Diagnostics: chunks the time-parallel forward kernels (small batches) had to recompute so far because
+ * the speculated start state did not match bit for bit (synchronises the device). */
+DWDF_API int64_t dwdf_time_parallel_redone (void);
 
 #ifdef __cplusplus
 }

@@ -410,3 +410,33 @@ def test_errors_are_loud(dwdf):
     circ.forward(torch.zeros(4, 8, device="cuda"))
     with pytest.raises(ValueError):
         circ.backward()
+
+
+# ---- time-parallel kernels (small batches) ---------------------------------------------------------------
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+@pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
+@pytest.mark.parametrize("amp", [(0.1, 2.0), (2.0, 10.0)])
+def test_time_parallel_equals_serial(dwdf, oracle, mode, ordering, oord, amp):
+    """Configs 2-3 (few long sequences) run one lane per (sequence, 256-sample chunk): speculative warm-up +
+    verification in the forward pass, affine composition in the adjoint. Same outputs and gradients as the
+    one-lane-per-sequence kernels (and the oracle), also for loud inputs whose slow contraction defeats the
+    speculation (those chunks are recomputed), for the training constants (longer RC memory) and ragged T."""
+    for p, B, T in ((ClipperParams(), 256, 4096), (ClipperParams(R=45000.0, C=4.7e-9), 70, 1000 if mode == "approx" else 2052)):
+        x = make_inputs(B, T, seed=31, amp=amp)
+        target = oracle.clipper_forward(x, perturbed(p), exact=True, ordering=oord)
+        outs = []
+        for opts in (0, 8):  # 8 = kOptNoChunks
+            prev = dwdf.set_option(opts)
+            try:
+                circ, order = make_clipper(dwdf, p, mode, ordering)
+                y = circ.forward(dev(x))
+                res = circ.backward(target=dev(target), loss="mse+esr", skip=50)
+                outs.append((y.cpu().numpy(), res["grads"].cpu().numpy()[order], float(res["loss"])))
+            finally:
+                dwdf.set_option(prev)
+        (y_tp, g_tp, l_tp), (y_se, g_se, l_se) = outs
+        assert np.array_equal(y_tp, y_se)  # accepted chunks are bit-identical to the serial recurrence, missed ones are recomputed
+        assert np.max(np.abs(g_tp / g_se - 1)) < 2e-5 and abs(l_tp / l_se - 1) < 1e-6
+        if amp[1] <= 2.0 or mode == "exact":
+            assert seq_rel_err(y_tp, oracle.clipper_forward(x, p, exact=(mode == "exact"), ordering=oord)) < FWD_TOL

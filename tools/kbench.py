@@ -43,4 +43,5 @@ for o in [int(v) for v in a.opts.split(",")]:
     circ.forward(x, out=y)
     b = timed(lambda: circ.backward(target=target, loss="mse", raw=True))
     t = timed(lambda: circ.train_pass(x, target, raw=True))
+    print(f"[redone chunks so far: {dwdf.time_parallel_redone()}] ", end="")
     print(f"B={a.B} T={a.T} {a.mode} amp={a.amp} opts={o}: forward {f:.4f} ms ({n*8/f/1e6:.0f} GB/s)  adjoint {b:.4f} ms ({n*8/b/1e6:.0f} GB/s alg)  train_pass {t:.4f} ms  fwd+adj {n/(f+b)/1e6:.1f} Gsamples/s", flush=True)
