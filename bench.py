@@ -172,6 +172,56 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def other_paths(torch, dwdf, device, x, target):
+    """samples/s (forward + adjoint kernels, CUDA events, 3 repetitions after 2 warm-ups) of the rows of the hot
+    path that `value` does not cover: the exact (TOMS-917) root, BASELINE configs 2-3 (small batches: the
+    time-parallel kernels) and the neural root (forward and training) on the reference's own 2x8 / 2x16 weights."""
+    out = {}
+
+    def timed(fn, reps=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    def clipper(mode):
+        Vs = dwdf.ResistiveVoltageSource(47000.0, True)
+        Cc = dwdf.Capacitor(2.2e-9, FS, True)
+        dp = dwdf.DiodePair(dwdf.Parallel(Vs, Cc), 4.352e-9, 25.85e-3, 1.906, trainable=True, mode=mode)
+        return dwdf.compile_circuit(dp, probe=Cc, ordering="python", device=device)
+
+    def fwd_bwd(circ, xs, ts):
+        circ.forward(xs)
+        circ.backward(target=ts, loss="mse")
+
+    try:
+        ce = clipper("exact")
+        out["exact_root_fwd_bwd"] = {"value": x.numel() / timed(lambda: fwd_bwd(ce, x, target)), "unit": UNIT, "B": x.shape[0], "T": T}
+        ca = clipper("approx")
+        for name, b in (("config2_B256_fwd_bwd", 256), ("config3_B1024_fwd_bwd", 1024)):
+            xs, ts = x[:b].contiguous(), target[:b].contiguous()
+            out[name] = {"value": xs.numel() / timed(lambda: fwd_bwd(ca, xs, ts)), "unit": UNIT, "B": b, "T": T, "kernels": "time-parallel (256-sample chunks)"}
+        nn_path = os.path.join(ROOT, "tests", "golden", "nn_vectors.npz")
+        if os.path.exists(nn_path):
+            nnv = np.load(nn_path)
+            for name, b in (("2x8", 8192), ("2x16", 4096)):
+                mj = dwdf.model_io.json_from_weights(nnv[f"{name}_weights"], [int(v) for v in nnv[f"{name}_sizes"]])
+                Vs, Cc = dwdf.ResistiveVoltageSource(47000.0), dwdf.Capacitor(2.2e-9, FS)
+                cn = dwdf.compile_circuit(dwdf.DenseRootModel(mj), tree=dwdf.Parallel(Vs, Cc), probe=Cc, ordering="python", device=device)
+                xs, ts = x[:b].contiguous(), target[:b].contiguous()
+                out[f"neural_root_{name}_forward"] = {"value": xs.numel() / timed(lambda: cn.forward(xs, keep_for_backward=False)), "unit": UNIT, "B": b, "T": T}
+                out[f"neural_root_{name}_fwd_bwd"] = {"value": xs.numel() / timed(lambda: fwd_bwd(cn, xs, ts), reps=2), "unit": UNIT, "B": b, "T": T}
+    except Exception as e:  # the headline line must not depend on these
+        out["error"] = repr(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +232,7 @@ def main():
     ap.add_argument("--mode", default="approx", choices=["approx", "exact"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the brief timings of the other paths (exact root, small batches, neural root)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -291,6 +342,11 @@ def main():
                "api": "dwdf_grad_host (forward + adjoint + finalize, chunk-pipelined copies)", "loss": float(outh[dwdf._lib.OUT_LOSS])}
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the other rows of the hot path, timed briefly on rank 0 (not part of `value`) ----------------------
+    other = None
+    if rank == 0 and not args.no_extra:
+        other = other_paths(torch, dwdf, device, x, target)
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         # dominant kernel = the adjoint (replay + reverse sweep); its algorithmic traffic is x + target
@@ -308,7 +364,7 @@ def main():
                          "algorithmic_bytes_per_sample": dom_bytes, "kernel_ms": dom_ms,
                          "step": {"forward_ms": fwd_ms, "adjoint_ms": adj_ms, "bytes_per_sample": BYTES_FWD + BYTES_ADJ, "achieved_GBs": step_bytes / ((fwd_ms + adj_ms) * 1e-3) / 1e9,
                                   "frac": step_bytes / ((fwd_ms + adj_ms) * 1e-3) / 1e9 / peak}},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "loss": loss,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "loss": loss, "other_paths": other,
         }
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1

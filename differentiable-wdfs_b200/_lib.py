@@ -28,7 +28,7 @@ STATUS = {0: "ok", 1: "invalid argument", 2: "unsupported", 3: "CUDA error", 4: 
 SYMBOLS = (
     "dwdf_program_create", "dwdf_program_destroy", "dwdf_program_is_clipper", "dwdf_program_n_states", "dwdf_ckpt_bytes", "dwdf_workspace_bytes",
     "dwdf_forward", "dwdf_backward", "dwdf_train_pass", "dwdf_adam_step", "dwdf_forward_host", "dwdf_grad_host", "dwdf_process_block",
-    "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_backward_neural", "dwdf_neural_ckpt_bytes", "dwdf_neural_workspace_bytes", "dwdf_adam_step_vec", "dwdf_last_error", "dwdf_build_info", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option", "dwdf_time_parallel_redone",
+    "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_backward_neural", "dwdf_neural_ckpt_bytes", "dwdf_neural_workspace_bytes", "dwdf_adam_step_vec", "dwdf_last_error", "dwdf_build_info", "dwdf_train_step", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option", "dwdf_time_parallel_redone",
 )
 
 
@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
     L.dwdf_train_pass_raw.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, sz, i64, i64, vp]
     L.dwdf_finalize.argtypes = [vp, vp, i32, i32, vp, vp]
     L.dwdf_adam_step.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, vp, C.c_float, C.c_float, C.c_float, C.c_double, vp, vp, vp]
+    L.dwdf_train_step.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, sz, vp, vp, vp, C.c_float, vp, C.c_float, C.c_float, C.c_float, vp, vp, i64, i64, vp]
     L.dwdf_forward_host.argtypes = [vp, vp, vp, vp, vp, i64, i64]
     L.dwdf_grad_host.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, i64, i64]
     L.dwdf_process_block.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, vp]

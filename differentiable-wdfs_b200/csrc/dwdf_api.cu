@@ -573,6 +573,18 @@ int dwdf_adam_step (float* params, const double* out, float* m, float* v, int32_
     return DWDF_OK;
 }
 
+int dwdf_train_step (const dwdf_program* prog, float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, float* z_ckpt, double* out, void* workspace,
+                     size_t workspace_bytes, float* m, float* v, int32_t* step, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, const float* lo, const float* hi, int64_t B, int64_t T, void* stream)
+{
+    if (prog == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if (int rc = dwdf_forward (prog, params, x, r, y, z_ckpt, B, T, stream))
+        return rc;
+    if (int rc = dwdf_backward (prog, params, x, r, y, z_ckpt, target, DWDF_GRAD_TARGET, loss_kind, skip, nullptr, out, workspace, workspace_bytes, B, T, stream))
+        return rc;
+    return dwdf_adam_step (params, out, m, v, step, prog->desc.n_params, lr, lr_per_slot, beta1, beta2, eps, 1.0, lo, hi, stream);
+}
+
 // ---- end-to-end calls with host buffers ----------------------------------------------------------
 // Library-owned device arena (grow-only, one per process) and a small set of streams: the batch is
 // cut into row chunks so that the host->device copy of chunk k+1, the kernels of chunk k and the

@@ -207,6 +207,12 @@ DWDF_API int dwdf_finalize (const dwdf_program* prog, const float* params, int32
  * trains R and C with different rates). lo/hi: per-slot clip bounds (device, n_params floats each) or NULL. */
 DWDF_API int dwdf_adam_step (float* params, const double* out, float* m, float* v, int32_t* step, int32_t n_params, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, double grad_scale, const float* lo, const float* hi, void* stream);
 
+/* One whole training step of clipper_pot.py:246-269 in ONE call: dwdf_forward + dwdf_backward (fused loss
+ * against `target`) + dwdf_adam_step. Everything is enqueued on `stream` and nothing synchronises, so a
+ * step — or a loop of steps — can be captured in a CUDA graph and replayed (small batches are launch-bound).
+ * y, z_ckpt, out, workspace as in dwdf_forward / dwdf_backward; m, v, step, lr_per_slot, lo, hi as in dwdf_adam_step. */
+DWDF_API int dwdf_train_step (const dwdf_program* prog, float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, float* z_ckpt, double* out, void* workspace, size_t workspace_bytes, float* m, float* v, int32_t* step, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, const float* lo, const float* hi, int64_t B, int64_t T, void* stream);
+
 /* End-to-end variants with HOST buffers (what a training script holding numpy batches calls):
  * host->device copies of x / r / target, the kernels, device->host copy of y / out, all on one
  * internal stream, synchronous on return. */

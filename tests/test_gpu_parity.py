@@ -440,3 +440,38 @@ def test_time_parallel_equals_serial(dwdf, oracle, mode, ordering, oord, amp):
         assert np.max(np.abs(g_tp / g_se - 1)) < 2e-5 and abs(l_tp / l_se - 1) < 1e-6
         if amp[1] <= 2.0 or mode == "exact":
             assert seq_rel_err(y_tp, oracle.clipper_forward(x, p, exact=(mode == "exact"), ordering=oord)) < FWD_TOL
+
+
+def test_training_step_in_a_cuda_graph(dwdf, oracle):
+    """dwdf_train_step (forward + adjoint + Adam, one call, no synchronisation) captured in a CUDA graph and
+    replayed gives the parameters of the same number of eager steps, bit for bit (config-3-like small batch:
+    the time-parallel kernels with their stream-ordered scratch are inside the graph)."""
+    p = ClipperParams()
+    x = dev(make_inputs(128, 1024, seed=41))
+    target = dev(oracle.clipper_forward(x.cpu().numpy(), perturbed(p), exact=True))
+
+    def fresh():
+        circ, _ = make_clipper(dwdf, p, "approx", "python")
+        opt = dwdf.Adam(circ, lr={s: 1e-3 * float(circ.params[s]) for s in range(circ.n_params)}, beta_1=0.5)
+        return circ, opt
+
+    circ_e, opt_e = fresh()
+    losses_e = []
+    for _ in range(6):
+        losses_e.append(float(circ_e.train_step(x, target, opt_e, loss="mse+esr", skip=50)["loss"]))
+    circ_g, opt_g = fresh()
+    y = torch.empty_like(x)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        circ_g.train_step(x, target, opt_g, loss="mse+esr", skip=50, out=y)  # step 1 eagerly (allocates scratch)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        circ_g.train_step(x, target, opt_g, loss="mse+esr", skip=50, out=y)  # step 2: captured, not run
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(circ_g.params, circ_e.params)
+    assert float(circ_g.out[dwdf._lib.OUT_LOSS]) == losses_e[-1]
+    assert losses_e[-1] < losses_e[0]
