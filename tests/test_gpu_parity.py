@@ -475,3 +475,29 @@ def test_training_step_in_a_cuda_graph(dwdf, oracle):
     assert torch.equal(circ_g.params, circ_e.params)
     assert float(circ_g.out[dwdf._lib.OUT_LOSS]) == losses_e[-1]
     assert losses_e[-1] < losses_e[0]
+
+
+def test_config4_full_training_step(dwdf, oracle):
+    """BASELINE config 4: asymmetric pair (N_up = 1, N_down = 2; OA1154 has no parameters in the reference, the
+    germanium-like placeholders of SURVEY.md §8d), exact root with a Newton tolerance of 1e-9, batch 4096 x 4096,
+    full training step = forward + MSE/ESR loss + backward + Adam on the device. The oracle checks sampled rows
+    and the first step's loss and gradients on a slice; training lowers the loss."""
+    p = ClipperParams(Is=1.0e-6, nabla=1.3, n_up=1, n_down=2)
+    B, T = 4096, 4096
+    x = make_inputs(B, T, seed=1236)
+    rows = np.random.default_rng(4).choice(B, 24, replace=False)
+    target_rows = oracle.clipper_forward(x[rows], perturbed(p), exact=True)
+    xd = dev(x)
+    teacher, _ = make_clipper(dwdf, perturbed(p), "exact", "python", newton_max_iter=4, newton_tol=1e-9)
+    target = teacher.forward(xd, keep_for_backward=False).clone()
+    assert seq_rel_err(target[rows].cpu().numpy(), target_rows) < FWD_TOL
+    circ, order = make_clipper(dwdf, p, "exact", "python", newton_max_iter=4, newton_tol=1e-9)
+    opt = dwdf.Adam(circ, lr={s: 2e-3 * float(circ.params[s]) for s in range(circ.n_params)}, beta_1=0.5)
+    # gradients of the first step on a slice against the fp64 oracle
+    sl = slice(0, 64)
+    circ.forward(xd[sl].contiguous())
+    res = circ.backward(target=target[sl].contiguous(), loss="mse+esr", skip=50)
+    ref = oracle.clipper_grad(x[sl], target[sl].cpu().numpy(), p, exact=True, mode="target", loss="mse+esr", skip=50, dtype=np.float64)
+    assert np.max(np.abs(res["grads"].cpu().numpy()[order] / ref["grads"] - 1)) < GRAD_TOL
+    losses = [float(circ.train_step(xd, target, opt, loss="mse+esr", skip=50)["loss"]) for _ in range(8)]
+    assert all(np.isfinite(losses)) and losses[-1] < 0.9 * losses[0]
