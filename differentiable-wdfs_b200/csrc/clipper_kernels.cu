@@ -834,8 +834,13 @@ __global__ void __launch_bounds__ (128) clipper_forward_stitch (const float* __r
     ClipConst c;
     load_consts (c, desc, params);
     const bool ls = (MODE == kModeApprox && ! GENERAL) ? fast_ok (c.pair.L) : rev_small_ok (c.pair);
-    float zend = ze[b * K];
-    for (int k = 1; k < K; ++k)
+    // the common case first, with independent loads: every chunk started from its predecessor's end state
+    int first_bad = K;
+    for (int k = K - 1; k >= 1; --k)
+        if (! (zs[b * K + k] == ze[b * K + k - 1]))
+            first_bad = k;
+    float zend = ze[b * K + (first_bad < K ? first_bad - 1 : K - 1)];
+    for (int k = first_bad; k < K; ++k)
     {
         const float assumed = zs[b * K + k];
         if (assumed == zend) // bit for bit: an accepted chunk is exactly what the serial recurrence computes
