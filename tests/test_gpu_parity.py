@@ -501,3 +501,40 @@ def test_config4_full_training_step(dwdf, oracle):
     assert np.max(np.abs(res["grads"].cpu().numpy()[order] / ref["grads"] - 1)) < GRAD_TOL
     losses = [float(circ.train_step(xd, target, opt, loss="mse+esr", skip=50)["loss"]) for _ in range(8)]
     assert all(np.isfinite(losses)) and losses[-1] < 0.9 * losses[0]
+
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+def test_tree_hpf_clipper(dwdf, oracle, mode):
+    """The plugin's second circuit (HPFDiodeClipper.h:25-37: Parallel(R, Series(ResistiveVs, C)) + diode pair,
+    probe on R between the sweeps, HPFDiodeClipper.cpp:43-55) on the tree interpreter: forward against the
+    oracle's tree executor, gradients w.r.t. every leaf against central finite differences of the oracle."""
+    fs, Rs, Cv, Rv = 48000.0, 1.0e4, 2.2e-9, 47000.0
+    p = ClipperParams()
+    x = make_inputs(40, 400, seed=51)
+
+    def build():
+        Vs = dwdf.ResistiveVoltageSource(Rs, True)
+        Cc = dwdf.Capacitor(Cv, fs, True)
+        Rr = dwdf.Resistor(Rv, True)
+        P1 = dwdf.Parallel(Rr, dwdf.Series(Vs, Cc))
+        dp = dwdf.DiodePair(P1, p.Is, p.Vt, p.nabla, trainable=True, mode=mode)
+        return dwdf.compile_circuit(dp, probe=Rr, ordering="plugin"), (Vs, Cc, Rr)
+
+    circ, (Vs, Cc, Rr) = build()
+    assert not circ.is_clipper
+    y = circ.forward(dev(x)).cpu().numpy()
+
+    def ref(Rs_=Rs, C_=Cv, R_=Rv, dtype=np.float32):
+        nodes = [(RESISTOR, -1, -1, R_), (RESVS, -1, -1, Rs_), (CAPACITOR, -1, -1, C_), (SERIES, 1, 2, 0.0), (PARALLEL, 0, 3, 0.0)]
+        return oracle.tree_run(nodes, fs, ROOT_DIODE_PAIR, x, probe=0, source=1, root_par=[float(mode == "exact"), 0, p.Is, p.Vt, p.nabla, 1, 1], ordering=ORDER_PLUGIN, dtype=dtype)
+
+    assert seq_rel_err(y, ref()) < FWD_TOL
+    gy = np.random.default_rng(5).standard_normal(x.shape).astype(np.float32)
+    res = circ.backward(gy=dev(gy))
+    g = res["grads"].cpu().numpy()
+    for elem, attr, val, kw in ((Vs, "R", Rs, "Rs_"), (Cc, "C", Cv, "C_"), (Rr, "R", Rv, "R_")):
+        h = 1e-4 * val
+        fd = float(np.sum(gy.astype(np.float64) * (ref(dtype=np.float64, **{kw: val + h}) - ref(dtype=np.float64, **{kw: val - h}))) / (2 * h))
+        # approx root: the gradient convention is omega' = omega / (1 + omega) applied to omega4's VALUE (what a custom
+        # gradient of the exact law gives), which is not the derivative of the omega4 approximation finite differences see
+        assert abs(g[circ.slot(elem, attr)] / fd - 1) < (2e-2 if mode == "approx" else 5e-4), (attr, g[circ.slot(elem, attr)], fd)
