@@ -490,8 +490,8 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
     {
         if (gx != nullptr)
             return fail (DWDF_ERR_UNSUPPORTED, "dL/dx is available for the diode-clipper program only");
-        if (r != nullptr)
-            return fail (DWDF_ERR_UNSUPPORTED, "gradients with a per-sample resistance channel are not implemented");
+        if ((prog->desc.r_node >= 0) != (r != nullptr))
+            return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
         float* tape = (float*) ((char*) workspace + (((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256) * 256);
         DWDF_CUDA (launch_tree_adjoint (prog->tree, params, x, r, gy_or_target, target, sk, partials, tape, B, T, stream));
         DWDF_CUDA (launch_tree_finalize (prog->tree, params, partials, n_groups (B), nullptr, raw_only, target, loss_kind, count, out, stream));

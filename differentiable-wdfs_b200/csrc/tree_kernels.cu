@@ -201,8 +201,50 @@ __global__ void __launch_bounds__ (32) tree_forward (const TreeProgram p, const 
     }
 }
 
+// Chain rule of ONE sample through calc_impedance: adjoints on the adaptor coefficients (gp[i] = dL/dp1R_i) and
+// on ell = ln(Rp Is) -> adjoints on the leaf values (R, C), added to gval[]. Needed per sample when a resistance
+// is an input channel (clipper_pot.py:116-117: the impedances differ from sample to sample); with constant
+// impedances the same chain runs once, in double, in tree_finalize.
+__device__ __forceinline__ void tree_impedance_adjoint (const TreeProgram& p, const float* __restrict__ val, const TreeImp& m, const float* __restrict__ gp, float gell, float* __restrict__ gval)
+{
+    const int top = p.n_nodes - 1;
+    float gR[kMaxN], gG[kMaxN];
+    for (int i = 0; i <= top; ++i)
+        gR[i] = gG[i] = 0.0f;
+    if (p.root_kind == DWDF_ROOT_DIODE_PAIR)
+        gR[top] += gell / m.R[top];
+    for (int i = top; i >= 0; --i)
+    {
+        const int c1 = p.c1[i], c2 = p.c2[i];
+        switch (p.kind[i])
+        {
+            case DWDF_SERIES: // R = R1 + R2, G = 1/R, p1R = R1 / R
+                gR[i] += gG[i] * (-1.0f / (m.R[i] * m.R[i])) + gp[i] * (-m.R[c1] / (m.R[i] * m.R[i]));
+                gR[c1] += gR[i] + gp[i] / m.R[i];
+                gR[c2] += gR[i];
+                break;
+            case DWDF_PARALLEL: // G = G1 + G2, R = 1/G, p1R = G1 / G
+                gG[i] += gR[i] * (-1.0f / (m.G[i] * m.G[i])) + gp[i] * (-m.G[c1] / (m.G[i] * m.G[i]));
+                gG[c1] += gG[i] + gp[i] / m.G[i];
+                gG[c2] += gG[i];
+                break;
+            case DWDF_INVERTER: // R = R1, G = 1/R
+                gR[c1] += gR[i] + gG[i] * (-1.0f / (m.R[i] * m.R[i]));
+                break;
+            case DWDF_CAPACITOR: // R = 1/(2 C fs), G = 1/R
+                gval[i] += (gR[i] + gG[i] * (-1.0f / (m.R[i] * m.R[i]))) * (-m.R[i] / val[i]);
+                break;
+            default: // Resistor / ResistiveVoltageSource: R = value, G = 1/R
+                gval[i] += gR[i] + gG[i] * (-1.0f / (m.R[i] * m.R[i]));
+                break;
+        }
+    }
+}
+
 // ---- reverse mode --------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const float* __restrict__ params, const float* __restrict__ x, const float* __restrict__ g, int target, int skip, double* __restrict__ partials, float* __restrict__ tape, int64_t B, int T)
+// r != nullptr: per-sample resistance channel on node p.r_node; partials[0..16) then hold dL/d(leaf value) per
+// node (already chained, see above) and partials[20] = 1 tells tree_finalize so.
+__global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const float* __restrict__ params, const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ g, int target, int skip, double* __restrict__ partials, float* __restrict__ tape, int64_t B, int T)
 {
     const int lane = threadIdx.x;
     const int64_t b = (int64_t) blockIdx.x * 32 + lane;
@@ -224,9 +266,16 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
         tree_pair_setup (p, params, m.R[top], pc);
         const float* xr = x + b * T;
         const float* gr = g + b * T;
+        const float* rr = r != nullptr ? r + b * T : nullptr;
         // pass 1: forward, recording the state each sample starts from
         for (int n = 0; n < T; ++n)
         {
+            if (rr != nullptr)
+            {
+                val[p.r_node] = __ldg (rr + n);
+                tree_impedance (p, val, m);
+                tree_pair_setup (p, params, m.R[top], pc);
+            }
             for (int i = 0; i <= top; ++i)
                 if (p.state_of[i] >= 0)
                     tape[((int64_t) n * ns1 + p.state_of[i]) * B + b] = z[i];
@@ -243,6 +292,15 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
             facc[i] = 0.0f;
         for (int n = T - 1; n >= 0; --n)
         {
+            float pf[kMaxN], pl = 0.0f; // this sample's adjoints on p1R per node and on ell
+            for (int i = 0; i < kMaxN; ++i)
+                pf[i] = 0.0f;
+            if (rr != nullptr)
+            {
+                val[p.r_node] = __ldg (rr + n);
+                tree_impedance (p, val, m);
+                tree_pair_setup (p, params, m.R[top], pc);
+            }
             for (int i = 0; i <= top; ++i)
                 if (p.state_of[i] >= 0)
                     z[i] = tape[((int64_t) n * ns1 + p.state_of[i]) * B + b];
@@ -286,7 +344,7 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
                         ab[c1] += gb1 * (1.0f - m.p1R[i]);
                         ab[c2] -= m.p1R[i] * gb1;
                         aa[i] -= m.p1R[i] * gb1 + g2;
-                        facc[i] -= gb1 * (w.a[i] + w.b[c1] + w.b[c2]);
+                        pf[i] -= gb1 * (w.a[i] + w.b[c1] + w.b[c2]);
                         break;
                     }
                     case DWDF_PARALLEL:
@@ -308,7 +366,8 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
             else
             {
                 ab[top] += gbroot * fma_ (-2.0f, d.S1, 1.0f);
-                fl = fma_ (gbroot, -pc.twoV * d.M1, fl);
+                pl = gbroot * (-pc.twoV * d.M1);
+                fl += pl;
                 fv = fma_ (gbroot, d.dV, fv);
             }
             // adjoint of the up-sweep, parents first
@@ -325,7 +384,7 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
                     {
                         const float gbt = abtemp[i] + ab[i];
                         const float gbd = abdiff[i] - m.p1R[i] * gbt;
-                        facc[i] -= w.bdiff[i] * gbt;
+                        pf[i] -= w.bdiff[i] * gbt;
                         ab[c2] += ab[i] + gbd;
                         ab[c1] -= gbd;
                         break;
@@ -335,6 +394,11 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
                     default: break;
                 }
             }
+            if (rr == nullptr)
+                for (int i = 0; i <= top; ++i)
+                    facc[i] += pf[i];
+            else
+                tree_impedance_adjoint (p, val, m, pf, pl, facc); // facc: dL/d(leaf value)
             if ((n & 15) == 0)
             { // fp32 inside a 16-sample block, double across blocks
                 for (int i = 0; i <= top; ++i)
@@ -359,6 +423,8 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
         if (lane == 0)
             partials[(int64_t) blockIdx.x * kTreeStride + k] = v;
     }
+    if (lane == 0)
+        partials[(int64_t) blockIdx.x * kTreeStride + 20] = r != nullptr ? 1.0 : 0.0;
 }
 
 // fixed-order reduction over groups, then the chain rule through calc_impedance to the leaf values
@@ -390,12 +456,14 @@ __global__ void __launch_bounds__ (256) tree_finalize (const TreeProgram p, cons
     double raw[20];
     for (int k = 0; k < 20; ++k)
         raw[k] = raw_in != nullptr ? raw_in[k] : sm[k][0];
+    const bool chained = raw_in != nullptr ? raw_in[20] != 0.0 : (n_groups > 0 && partials[20] != 0.0); // leaf gradients already (resistance channel)
     if (raw_in != nullptr)
         count = raw_in[23];
     if (raw_only)
     {
         for (int k = 0; k < DWDF_OUT_LEN; ++k)
             out[k] = k < 20 ? raw[k] : 0.0;
+        out[20] = chained ? 1.0 : 0.0;
         out[23] = count;
         return;
     }
@@ -436,6 +504,21 @@ __global__ void __launch_bounds__ (256) tree_finalize (const TreeProgram p, cons
     }
     for (int k = 0; k < DWDF_OUT_LEN; ++k)
         out[k] = 0.0;
+    if (chained)
+    { // per-sample impedances: the kernel has already chained to the leaf values; the resistance channel's node has no parameter gradient
+        for (int i = 0; i <= top; ++i)
+            if (p.param[i] >= 0 && i != p.r_node)
+                out[p.param[i]] += alpha * raw[i];
+        if (p.root_kind == DWDF_ROOT_DIODE_PAIR)
+        {
+            out[p.slot_Is] += alpha * raw[16] / (double) params[p.slot_Is];
+            out[p.slot_nabla] += alpha * raw[17] * (double) p.Vt;
+        }
+        out[DWDF_OUT_LOSS] = loss;
+        out[DWDF_OUT_MSE] = mse;
+        out[DWDF_OUT_ESR] = esr;
+        return;
+    }
     if (p.root_kind == DWDF_ROOT_DIODE_PAIR)
     {
         const double acc_l = raw[16], acc_v = raw[17];
@@ -487,8 +570,7 @@ cudaError_t launch_tree_forward (const TreeProgram& p, const float* params, cons
 
 cudaError_t launch_tree_adjoint (const TreeProgram& p, const float* params, const float* x, const float* r, const float* g, bool target, int64_t skip, double* partials, float* tape, int64_t B, int64_t T, cudaStream_t stream)
 {
-    (void) r;
-    tree_adjoint<<<(unsigned) ((B + 31) / 32), 32, 0, stream>>> (p, params, x, g, target ? 1 : 0, (int) skip, partials, tape, B, (int) T);
+    tree_adjoint<<<(unsigned) ((B + 31) / 32), 32, 0, stream>>> (p, params, x, r, g, target ? 1 : 0, (int) skip, partials, tape, B, (int) T);
     return cudaGetLastError ();
 }
 
