@@ -375,7 +375,7 @@ size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
     if (prog == nullptr || B <= 0 || T <= 0)
         return 0;
     size_t bytes = partials_bytes (B);
-    if (prog->is_clipper)
+    if (prog->is_clipper && B <= kChunkedAdjointMaxB)
         bytes += (size_t) B * (size_t) ((T + kTimeChunk - 1) / kTimeChunk) * kChunkOutFloats * sizeof (float); // time-parallel adjoint (small batches)
     if (! prog->is_clipper) // per-sample tape of the interpreter adjoint: (n_states + 1) floats per sample
         bytes += (size_t) B * (size_t) T * (size_t) (prog->n_states + 1) * sizeof (float);

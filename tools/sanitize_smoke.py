@@ -1,0 +1,28 @@
+"""Small end-to-end exercise of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import importlib, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+dwdf = importlib.import_module("differentiable-wdfs_b200")
+rng = np.random.default_rng(0)
+for mode in ("approx", "exact"):
+    for B, T in ((70, 96), (33, 2052), (5, 37)):
+        x = torch.from_numpy((rng.standard_normal((B, T)) * 0.5).astype(np.float32)).cuda()
+        Vs = dwdf.ResistiveVoltageSource(47000.0, True); Cc = dwdf.Capacitor(2.2e-9, 48000.0, True)
+        dp = dwdf.DiodePair(dwdf.Parallel(Vs, Cc), 4.352e-9, 25.85e-3, 1.906, trainable=True, mode=mode)
+        circ = dwdf.compile_circuit(dp, probe=Cc)
+        y = circ.forward(x)
+        res = circ.backward(target=(0.5 * y).contiguous(), loss="mse+esr", skip=8)
+        circ.train_pass(x, (0.5 * y).contiguous(), y=torch.empty_like(x))
+        circ.backward(gy=torch.ones_like(x), want_gx=True)
+nnv = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "nn_vectors.npz"))
+mj = dwdf.model_io.json_from_weights(nnv["2x8_weights"], [int(v) for v in nnv["2x8_sizes"]])
+Vs = dwdf.ResistiveVoltageSource(47000.0); Cc = dwdf.Capacitor(2.2e-9, 48000.0)
+cn = dwdf.compile_circuit(dwdf.DenseRootModel(mj), tree=dwdf.Parallel(Vs, Cc), probe=Cc)
+x = torch.from_numpy((rng.standard_normal((9, 130)) * 0.5).astype(np.float32)).cuda()
+y = cn.forward(x); cn.backward(target=(0.5 * y).contiguous())
+R1 = dwdf.Resistor(1000.0, True); C1 = dwdf.Capacitor(1.0e-6, 48000.0, True)
+ct = dwdf.compile_circuit(dwdf.IdealVoltageSource(), tree=dwdf.Inverter(dwdf.Series(R1, C1)), probe=C1)
+y = ct.forward(x); ct.backward(target=(0.5 * y).contiguous())
+torch.cuda.synchronize()
+print("sanitize smoke done")
