@@ -229,9 +229,10 @@ PolarityInverter = Inverter  # wdf_t.h:558
 
 
 def wright_omega(x: torch.Tensor, iters: int = 3) -> torch.Tensor:
-    """Wright omega on the real axis for the imperative API: start from the branches of
-    omega.h:159-169, then Halley iterations on w + ln w = x (converges to round-off in 3)."""
-    w = torch.where(x < -3.341459552768620, torch.exp(x), torch.where(x < 8.0, 0.6313183464296682 + x * (0.3631952663804445 + x * (0.04775931364975583 - x * 0.0013142931498778)),
+    """Wright omega on the real axis for the imperative API: start from e^x below -2 (the cubic of
+    omega.h:160-167 touches zero at -3.34 and is useless as a start near there), the cubic up to 8 and
+    x - ln x above, then Fritsch-Shafer-Crowley iterations on w + ln w = x (round-off in 3)."""
+    w = torch.where(x < -2.0, torch.exp(x), torch.where(x < 8.0, 0.6313183464296682 + x * (0.3631952663804445 + x * (0.04775931364975583 - x * 0.0013142931498778)),
                                                                      x - torch.log(torch.clamp(x, min=1.0))))
     w = torch.clamp(w, min=1e-30)
     for _ in range(iters):
