@@ -232,15 +232,16 @@ def wright_omega(x: torch.Tensor, iters: int = 3) -> torch.Tensor:
     """Wright omega on the real axis for the imperative API: start from e^x below -2 (the cubic of
     omega.h:160-167 touches zero at -3.34 and is useless as a start near there), the cubic up to 8 and
     x - ln x above, then Fritsch-Shafer-Crowley iterations on w + ln w = x (round-off in 3)."""
-    w = torch.where(x < -2.0, torch.exp(x), torch.where(x < 8.0, 0.6313183464296682 + x * (0.3631952663804445 + x * (0.04775931364975583 - x * 0.0013142931498778)),
-                                                                     x - torch.log(torch.clamp(x, min=1.0))))
-    w = torch.clamp(w, min=1e-30)
+    xs = torch.clamp(x, min=-20.0)  # below: omega(x) = e^x (1 - e^x + ...) to round-off; the iteration's residual would cancel
+    w = torch.where(xs < -2.0, torch.exp(xs), torch.where(xs < 8.0, 0.6313183464296682 + xs * (0.3631952663804445 + xs * (0.04775931364975583 - xs * 0.0013142931498778)),
+                                                                       xs - torch.log(torch.clamp(xs, min=1.0))))
     for _ in range(iters):
-        r = x - w - torch.log(w)
+        r = xs - w - torch.log(w)
         wp1 = w + 1.0
         q = 2.0 * wp1 * (wp1 + (2.0 / 3.0) * r)
         w = w * (1.0 + (r / wp1) * (q - r) / (q - 2.0 * r))
-    return w
+    e = torch.exp(torch.clamp(x, max=-20.0))
+    return torch.where(x < -20.0, e - e * e, w)
 
 
 class DiodePair(_Element):
