@@ -781,12 +781,32 @@ __device__ __forceinline__ float4 chunk4 (const ClipConst& c, float4 v, float& z
 template <int MODE, bool GENERAL, bool LSMALL, bool PY>
 __device__ __forceinline__ void run_span (const ClipConst& c, const float* __restrict__ xr, float* __restrict__ yr, float* __restrict__ ckpt, int64_t B, int64_t b, int n0, int n1, float& z)
 {
-    for (int n = n0; n < n1; n += 4)
+    // the loads run one 16-sample segment ahead of the recurrence (a lane's own latency is all there is to hide here)
+    const float4 zero4 = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+    float4 nx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        nx[q] = n0 + 4 * q < n1 ? __ldg (reinterpret_cast<const float4*> (xr + n0 + 4 * q)) : zero4;
+    for (int n = n0; n < n1; n += 16)
     {
-        if ((n & (kSeg - 1)) == 0 && ckpt != nullptr)
-            ckpt[(int64_t) (n / kSeg) * B + b] = z;
-        const float4 v = __ldg (reinterpret_cast<const float4*> (xr + n));
-        *reinterpret_cast<float4*> (yr + n) = chunk4<MODE, GENERAL, LSMALL, PY> (c, v, z);
+        float4 cur[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            cur[q] = nx[q];
+            nx[q] = n + 16 + 4 * q < n1 ? __ldg (reinterpret_cast<const float4*> (xr + n + 16 + 4 * q)) : zero4;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            const int m = n + 4 * q;
+            if (m < n1)
+            {
+                if ((m & (kSeg - 1)) == 0 && ckpt != nullptr)
+                    ckpt[(int64_t) (m / kSeg) * B + b] = z;
+                *reinterpret_cast<float4*> (yr + m) = chunk4<MODE, GENERAL, LSMALL, PY> (c, cur[q], z);
+            }
+        }
     }
 }
 
@@ -807,9 +827,12 @@ __global__ void __launch_bounds__ (128) clipper_forward_chunked (const float* __
     const float* xr = x + b * T;
     // warm-up from z = 0, or — when it reaches back to the first sample — from the true initial state (then nothing is assumed)
     float z = (n0 - W == 0 && state != nullptr) ? state[b] : 0.0f;
+    float4 vn = W > 0 ? __ldg (reinterpret_cast<const float4*> (xr + n0 - W)) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
     for (int n = n0 - W; n < n0; n += 4)
     {
-        const float4 v = __ldg (reinterpret_cast<const float4*> (xr + n));
+        const float4 v = vn;
+        if (n + 4 < n0)
+            vn = __ldg (reinterpret_cast<const float4*> (xr + n + 4));
         if (ls)
             (void) chunk4<MODE, GENERAL, true, PY> (c, v, z);
         else
@@ -884,27 +907,45 @@ __global__ void __launch_bounds__ (128) clipper_adjoint_chunked (const float* __
     for (int seg0 = ((n1 - 1) / kSeg) * kSeg; seg0 >= n0; seg0 -= kSeg)
     {
         const int nv = min (kSeg, n1 - seg0);
+        // every load of the segment up front (T % 4 == 0, 16-byte aligned rows): one memory latency per 16 samples
+        const float4 zero4 = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+        float4 y4[kSeg / 4], x4[kSeg / 4], g4[kSeg / 4];
+#pragma unroll
+        for (int q = 0; q < kSeg / 4; ++q)
+        {
+            const bool in = seg0 + 4 * q < n1;
+            y4[q] = in ? __ldg (reinterpret_cast<const float4*> (yr + seg0 + 4 * q)) : zero4;
+            x4[q] = in ? __ldg (reinterpret_cast<const float4*> (xr + seg0 + 4 * q)) : zero4;
+            g4[q] = in ? __ldg (reinterpret_cast<const float4*> (gr + seg0 + 4 * q)) : zero4;
+        }
         float zs[kSeg + 1];
         zs[0] = __ldg (ckpt + (int64_t) (seg0 / kSeg) * B + b);
-        float ys[kSeg];
+        const float znext = (! PY && seg0 + nv < T) ? __ldg (ckpt + (int64_t) ((seg0 + nv) / kSeg) * B + b) : 0.0f; // nv == kSeg whenever another segment follows
+        float ys[kSeg], xs[kSeg], gs[kSeg];
+#pragma unroll
+        for (int q = 0; q < kSeg / 4; ++q)
+        {
+            ys[4 * q] = y4[q].x, ys[4 * q + 1] = y4[q].y, ys[4 * q + 2] = y4[q].z, ys[4 * q + 3] = y4[q].w;
+            xs[4 * q] = x4[q].x, xs[4 * q + 1] = x4[q].y, xs[4 * q + 2] = x4[q].z, xs[4 * q + 3] = x4[q].w;
+            gs[4 * q] = g4[q].x, gs[4 * q + 1] = g4[q].y, gs[4 * q + 2] = g4[q].z, gs[4 * q + 3] = g4[q].w;
+        }
 #pragma unroll
         for (int q = 0; q < kSeg; ++q)
         {
-            ys[q] = q < nv ? __ldg (yr + seg0 + q) : 0.0f;
             if (PY)
                 zs[q + 1] = fma_ (2.0f, ys[q], -zs[q]);
             else
                 zs[q] = ys[q];
         }
         if (! PY)
-            zs[nv] = seg0 + nv < T ? __ldg (ckpt + (int64_t) ((seg0 + nv) / kSeg) * B + b) : 0.0f; // nv == kSeg whenever another segment follows
+            zs[nv] = znext;
 #pragma unroll
         for (int q = kSeg - 1; q >= 0; --q)
         {
             if (q < nv)
             {
                 const int n = seg0 + q;
-                float gy = __ldg (gr + n);
+                float gy = gs[q];
                 if (TARGET)
                 {
                     const bool on = n >= skip;
@@ -923,9 +964,9 @@ __global__ void __launch_bounds__ (128) clipper_adjoint_chunked (const float* __
                 {
                     StepTape tp;
                     if (ls)
-                        clip_step_recover<MODE, GENERAL, true> (c, __ldg (xr + n), zs[q], zs[q + 1], tp);
+                        clip_step_recover<MODE, GENERAL, true> (c, xs[q], zs[q], zs[q + 1], tp);
                     else
-                        clip_step_recover<MODE, GENERAL, false> (c, __ldg (xr + n), zs[q], zs[q + 1], tp);
+                        clip_step_recover<MODE, GENERAL, false> (c, xs[q], zs[q], zs[q + 1], tp);
                     if (PY)
                         Gp = fma_ (0.5f, gy, Gp);
                     s0[0] = fma_ (Gp, tp.cg, s0[0]), s0[1] = fma_ (Gp, tp.cl, s0[1]), s0[2] = fma_ (Gp, tp.cv, s0[2]);

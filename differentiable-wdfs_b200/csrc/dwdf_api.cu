@@ -104,9 +104,10 @@ bool is_leaf (int k) { return k == DWDF_RESISTOR || k == DWDF_CAPACITOR || k == 
 
 int64_t n_groups (int64_t B) { return (B + 31) / 32; }
 // time-parallel kernels: few sequences, long ones (fewer than ~1 warp per scheduler otherwise)
-// (measured crossovers at T = 4096: forward 0.15 vs 0.32 ms at B = 4096, 0.40 vs 0.32 at 8192; adjoint 0.13 vs 0.21 ms at 2048, 0.24 vs 0.21 at 4096)
-int time_chunks (int64_t B, int64_t T, int64_t max_B) { return (! (g_clip_opts & kOptNoChunks) && B <= max_B && T >= 2 * kTimeChunk) ? (int) ((T + kTimeChunk - 1) / kTimeChunk) : 0; }
-constexpr int64_t kChunkedForwardMaxB = 4096, kChunkedAdjointMaxB = 2048;
+// (measured at T = 4096, time-parallel vs one lane per sequence: forward 0.13 vs 0.32 ms at B = 4096, 0.19 vs 0.32 at 8192, 0.32 vs 0.32 at 16384;
+//  adjoint 0.085 vs 0.21 ms at 4096, 0.15 vs 0.21 at 8192, 0.23 vs 0.21 at 16384)
+int time_chunks (int64_t B, int64_t T, int64_t max_B) { return (! (g_clip_opts & kOptNoChunks) && (B <= max_B || (g_clip_opts & kOptForceChunks)) && T >= 2 * kTimeChunk) ? (int) ((T + kTimeChunk - 1) / kTimeChunk) : 0; }
+constexpr int64_t kChunkedForwardMaxB = 8192, kChunkedAdjointMaxB = 8192;
 size_t partials_bytes (int64_t B) { return ((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256 * 256 + 256; }
 int64_t n_segments (int64_t T) { return (T + kSeg - 1) / kSeg; }
 } // namespace
@@ -375,7 +376,7 @@ size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
     if (prog == nullptr || B <= 0 || T <= 0)
         return 0;
     size_t bytes = partials_bytes (B);
-    if (prog->is_clipper && B <= kChunkedAdjointMaxB)
+    if (prog->is_clipper && (B <= kChunkedAdjointMaxB || (g_clip_opts & kOptForceChunks)))
         bytes += (size_t) B * (size_t) ((T + kTimeChunk - 1) / kTimeChunk) * kChunkOutFloats * sizeof (float); // time-parallel adjoint (small batches)
     if (! prog->is_clipper) // per-sample tape of the interpreter adjoint: (n_states + 1) floats per sample
         bytes += (size_t) B * (size_t) T * (size_t) (prog->n_states + 1) * sizeof (float);
@@ -477,7 +478,8 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
             return fail (DWDF_ERR_INVALID, "the clipper adjoint reads the output y and the checkpoints z_ckpt that dwdf_forward wrote: %s is null", y == nullptr ? "y" : "z_ckpt");
         ClipTmaMaps maps;
         const bool tma = gx == nullptr && tma_usable (x, gy_or_target, y, B, T) && make_map (&maps.x, x, B, T, kSeg) && make_map (&maps.y, y, B, T, kSeg) && make_map (&maps.g, gy_or_target, B, T, kSeg);
-        if (gx == nullptr && time_chunks (B, T, kChunkedAdjointMaxB) > 1)
+        const bool al16 = T % 4 == 0 && (((uintptr_t) x | (uintptr_t) y | (uintptr_t) gy_or_target) & 15u) == 0;
+        if (gx == nullptr && al16 && time_chunks (B, T, kChunkedAdjointMaxB) > 1)
         {
             maps.chunks = time_chunks (B, T, kChunkedAdjointMaxB);
             maps.cout = (float*) ((char*) workspace + partials_bytes (B));

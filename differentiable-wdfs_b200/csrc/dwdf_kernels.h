@@ -32,6 +32,7 @@ enum : int
     kOptNoFastStep = 1, // forward, approx: per-sample warp vote (clip_step) instead of clip_step_fast chunks
     kOptNoPair = 2, // forward, approx: one sequence per lane instead of the packed-fp32x2 pair kernel
     kOptNoChunks = 8, // never use the time-parallel kernels
+    kOptForceChunks = 16, // use them whatever the batch size (crossover measurements)
     kOptL2Prefetch = 4 // cp.async.bulk.prefetch.tensor L2 run-ahead (measured: slower — forward 0.47 -> 0.58 ms, adjoint 0.63 -> 0.94 ms; off)
 };
 extern int g_clip_opts;
