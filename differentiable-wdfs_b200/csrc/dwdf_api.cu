@@ -108,6 +108,7 @@ int64_t n_groups (int64_t B) { return (B + 31) / 32; }
 //  adjoint 0.085 vs 0.21 ms at 4096, 0.15 vs 0.21 at 8192, 0.23 vs 0.21 at 16384)
 int time_chunks (int64_t B, int64_t T, int64_t max_B) { return (! (g_clip_opts & kOptNoChunks) && (B <= max_B || (g_clip_opts & kOptForceChunks)) && T >= 2 * kTimeChunk) ? (int) ((T + kTimeChunk - 1) / kTimeChunk) : 0; }
 constexpr int64_t kChunkedForwardMaxB = 8192, kChunkedAdjointMaxB = 8192;
+constexpr int64_t kNnChunkedMaxB = 16384; // neural root: the network makes every sample ~20x heavier, so lanes stay scarce longer
 size_t partials_bytes (int64_t B) { return ((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256 * 256 + 256; }
 int64_t n_segments (int64_t T) { return (T + kSeg - 1) / kSeg; }
 } // namespace
@@ -305,9 +306,21 @@ int dwdf_forward_neural (const dwdf_program* prog, const float* params, const fl
         return fail (DWDF_ERR_INVALID, "null argument");
     if ((prog->desc.r_node >= 0) != (r != nullptr))
         return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
+    // few sequences, long ones: time-parallel (one lane per pair and 256-sample chunk; clipper_kernels.cu explains the scheme)
+    int K = 1;
+    float* scratch = nullptr;
+    if (! (g_clip_opts & kOptNoChunks) && (B <= kNnChunkedMaxB || (g_clip_opts & kOptForceChunks)) && T >= 2 * kTimeChunk)
+    {
+        K = nn_time_chunks (T);
+        DWDF_CUDA (cudaMallocAsync ((void**) &scratch, (size_t) 4 * ((B + 1) / 2) * K * sizeof (float), (cudaStream_t) stream));
+        if (g_redone == nullptr && cudaMalloc ((void**) &g_redone, sizeof (int)) == cudaSuccess)
+            cudaMemset (g_redone, 0, sizeof (int));
+    }
     DWDF_CUDA (launch_nn_forward (prog->mlp.hidden, prog->mlp.n_hidden, prog->desc.ordering == DWDF_ORDER_PYTHON, x, r, y, params, prog->nodes[0].param, prog->nodes[1].param, prog->desc.fs, weights,
-                                  (int) dwdf_mlp_weight_count (&prog->mlp), state, z_ckpt, B, T, (cudaStream_t) stream));
-    g_launches.fetch_add (1);
+                                  (int) dwdf_mlp_weight_count (&prog->mlp), state, z_ckpt, B, T, K, scratch, g_redone, (cudaStream_t) stream));
+    if (scratch != nullptr)
+        DWDF_CUDA (cudaFreeAsync (scratch, (cudaStream_t) stream));
+    g_launches.fetch_add (K > 1 ? 2 : 1);
     return DWDF_OK;
 }
 

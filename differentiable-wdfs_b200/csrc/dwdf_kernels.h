@@ -79,7 +79,8 @@ cudaError_t launch_adam (float* params, const double* out, float* m, float* v, i
 
 // ---- neural diode-pair root (inference): clipper tree + b = -MLP(a, ln Rp), hidden width 4 / 8 / 16 ----------
 cudaError_t launch_nn_forward (int hidden, int n_hidden, bool pyorder, const float* x, const float* r, float* y, const float* params, int slot_R, int slot_C, float fs, const float* weights,
-                               int n_weights, float* state, float* ckpt, int64_t B, int64_t T, cudaStream_t stream);
+                               int n_weights, float* state, float* ckpt, int64_t B, int64_t T, int K, float* scratch, int* redone, cudaStream_t stream);
+int nn_time_chunks (int64_t T); // chunks of the time-parallel variant (K > 1 needs scratch of 4 * ceil(B/2) * K floats)
 // reverse sweep: dL/d(weights) partials per warp (64 sequences): [n_groups][n_weights + 8] doubles (then sse, st2)
 int64_t nn_ckpt_floats (int64_t B, int64_t T);
 int64_t nn_groups (int64_t B);
