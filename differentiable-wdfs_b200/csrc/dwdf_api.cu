@@ -289,9 +289,18 @@ size_t dwdf_neural_ckpt_bytes (const dwdf_program* prog, int64_t B, int64_t T)
 {
     return (prog == nullptr || ! prog->is_neural || B <= 0 || T <= 0) ? 0 : (size_t) nn_ckpt_floats (B, T) * sizeof (float);
 }
+static int nn_adjoint_chunks (int64_t B, int64_t T)
+{
+    return (! (g_clip_opts & kOptNoChunks) && (B <= kNnChunkedMaxB || (g_clip_opts & kOptForceChunks)) && T >= 2 * kTimeChunk) ? nn_time_chunks (T) : 1;
+}
 size_t dwdf_neural_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
 {
-    return (prog == nullptr || ! prog->is_neural || B <= 0 || T <= 0) ? 0 : (size_t) nn_groups (B) * (dwdf_mlp_weight_count (&prog->mlp) + 8) * sizeof (double);
+    if (prog == nullptr || ! prog->is_neural || B <= 0 || T <= 0)
+        return 0;
+    // worst case over the option switches: the time-parallel layout (more partial vectors, plus (P, Q) and G per chunk)
+    const int K = T >= 2 * kTimeChunk ? nn_time_chunks (T) : 1;
+    const size_t partials = ((size_t) nn_adjoint_ctas (B, K) * (dwdf_mlp_weight_count (&prog->mlp) + 8) * sizeof (double) + 255) / 256 * 256;
+    return partials + (size_t) ((B + 1) / 2) * K * 6 * sizeof (float) + 256;
 }
 
 int dwdf_forward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, float* y, float* state, float* z_ckpt, int64_t B, int64_t T, void* stream)
@@ -350,10 +359,13 @@ int dwdf_backward_neural (const dwdf_program* prog, const float* params, const f
     const bool target = grad_mode == DWDF_GRAD_TARGET;
     const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
     const int nw = (int) dwdf_mlp_weight_count (&prog->mlp);
+    const int K = nn_adjoint_chunks (B, T);
+    const size_t partials_bytes = ((size_t) nn_adjoint_ctas (B, K) * (nw + 8) * sizeof (double) + 255) / 256 * 256;
+    float* scratch = K > 1 ? (float*) ((char*) workspace + partials_bytes) : nullptr;
     DWDF_CUDA (launch_nn_adjoint (prog->mlp.hidden, prog->mlp.n_hidden, prog->desc.ordering == DWDF_ORDER_PYTHON, target, x, r, y, gy_or_target, z_ckpt, params, prog->nodes[0].param, prog->nodes[1].param,
-                                  prog->desc.fs, weights, nw, (double*) workspace, (int) sk, B, T, stream));
-    DWDF_CUDA (launch_nn_finalize ((const double*) workspace, nn_groups (B), nw, target, loss_kind, (double) B * (double) (T - sk), grad_w, out, stream));
-    g_launches.fetch_add (2);
+                                  prog->desc.fs, weights, nw, (double*) workspace, (int) sk, B, T, K, scratch, stream));
+    DWDF_CUDA (launch_nn_finalize ((const double*) workspace, nn_adjoint_ctas (B, K), nw, target, loss_kind, (double) B * (double) (T - sk), grad_w, out, stream));
+    g_launches.fetch_add (K > 1 ? 4 : 2);
     return DWDF_OK;
 }
 

@@ -85,7 +85,8 @@ int nn_time_chunks (int64_t T); // chunks of the time-parallel variant (K > 1 ne
 int64_t nn_ckpt_floats (int64_t B, int64_t T);
 int64_t nn_groups (int64_t B);
 cudaError_t launch_nn_adjoint (int hidden, int n_hidden, bool pyorder, bool target, const float* x, const float* r, const float* y, const float* g, const float* ckpt, const float* params, int slot_R, int slot_C,
-                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, cudaStream_t stream);
+                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, int K, float* scratch, cudaStream_t stream);
+int64_t nn_adjoint_ctas (int64_t B, int K);
 cudaError_t launch_nn_finalize (const double* partials, int64_t n_groups, int n_weights, bool target, int loss_kind, double count, double* grad_w, double* out, cudaStream_t stream);
 cudaError_t launch_adam_vec (float* w, const double* gw, float* m, float* v, int32_t* step, int64_t n, float lr, float beta1, float beta2, float eps, double grad_scale, cudaStream_t stream);
 

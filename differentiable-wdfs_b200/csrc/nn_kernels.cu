@@ -278,22 +278,32 @@ __global__ void __launch_bounds__ (128) nn_forward_stitch (const float* __restri
 // scaled by -G, every weight's gradient term. The terms are accumulated per lane in shared memory
 // (acc[weight][lane], conflict-free, no atomics), reduced over the warp at the end in a fixed order and
 // written as one fp64 partial vector per warp; nn_finalize sums the partials in order (bit-reproducible).
-template <int H, int NH, bool PY, bool TARGET>
+// Time-parallel variant (few long sequences; K chunks of kNnChunk samples per pair, one lane per (pair, chunk)):
+// the running adjoint is a linear recurrence given the trajectory, so
+//   PHASE 1  every chunk computes the affine map of its incoming G, (P, Q): network forwards + backwards, no accumulation;
+//   (nn_adjoint_stitch composes the maps of each pair's chunks last to first -> the G every chunk starts from)
+//   PHASE 2  every chunk runs again from its true incoming G and accumulates the weight-gradient terms.
+// 1.35x the work of PHASE 0 (the whole sequence in one lane), K x the parallelism.
+template <int H, int NH, bool PY, bool TARGET, int PHASE>
 __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ ckpt,
                                                           const float* __restrict__ params, int slot_R, int slot_C, float fs, const float* __restrict__ weights, int n_weights, double* __restrict__ partials,
-                                                          int skip, int64_t B, int T)
+                                                          int skip, int64_t B, int T, int K, float4* __restrict__ pq, const f2* __restrict__ gin)
 {
     extern __shared__ __align__ (16) float smem[];
     const int nw4 = (n_weights + 3) / 4 * 4;
     float* sw = smem; // weights
-    float* acc = smem + nw4; // [n_weights][32]
+    float* acc = smem + nw4; // [n_weights][32] (not in PHASE 1)
     const int lane = threadIdx.x;
     for (int i = lane; i < n_weights; i += 32)
         sw[i] = __ldg (weights + i);
-    for (int i = lane; i < n_weights * 32; i += 32)
-        acc[i] = 0.0f;
+    if (PHASE != 1)
+        for (int i = lane; i < n_weights * 32; i += 32)
+            acc[i] = 0.0f;
     __syncwarp ();
-    const int64_t pair = (int64_t) blockIdx.x * 32 + lane;
+    const int64_t item = (int64_t) blockIdx.x * 32 + lane;
+    const int64_t pair = item / K;
+    const int kc = (int) (item % K);
+    const int n_lo = PHASE == 0 ? 0 : kc * kNnChunk, n_hi = PHASE == 0 ? T : min (n_lo + kNnChunk, T);
     const int64_t rowA = 2 * pair, rowB = rowA + 1;
     const bool validA = rowA < B, validB = rowB < B;
     const int64_t ra_ = validA ? rowA : B - 1, rb_ = validB ? rowB : ra_;
@@ -305,12 +315,14 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
     const float Rp0 = 1.0f / (Gv0 + Gc);
     f2 gamma = bc (f2 {}, Gv0 * Rp0), lr = bc (f2 {}, logf (Rp0));
     const float* wout = sw + 3 * H + NH * (H * H + H);
-    const int nblk = (T + kNnSeg - 1) / kNnSeg;
-    f2 zn { __ldg (ckpt + (int64_t) nblk * B + ra_), __ldg (ckpt + (int64_t) nblk * B + rb_) }; // z[T]
-    f2 G { 0.0f, 0.0f };
+    const int nblk = (n_hi + kNnSeg - 1) / kNnSeg; // checkpoint holding z[n_hi] (n_hi is a multiple of kNnSeg, or T)
+    f2 zn { __ldg (ckpt + (int64_t) nblk * B + ra_), __ldg (ckpt + (int64_t) nblk * B + rb_) };
+    f2 G { 0.0f, 0.0f }, Gh { 1.0f, 1.0f }; // Gh: homogeneous solution (PHASE 1)
+    if (PHASE == 2 && validA)
+        G = gin[item];
     double sse = 0.0, st2 = 0.0;
     float sse_f = 0.0f, st2_f = 0.0f;
-    for (int n = T - 1; n >= 0; --n)
+    for (int n = n_hi - 1; n >= n_lo; --n)
     {
         const f2 yv { __ldg (ya + n), __ldg (yb + n) };
         f2 z = PY ? fmav (bc (f2 {}, 2.0f), yv, negv (zn)) : yv;
@@ -349,18 +361,20 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
         for (int l = 0; l < NH; ++l)
             dense<H, H, true> (sw + 3 * H + l * (H * H + H), sw + 3 * H + l * (H * H + H) + H * H, hs[l], hs[l + 1]);
         // ---- network backwards with seed 1; every weight's term scaled by s = -G (b = -N) -----------
-        const f2 s = last_plugin ? f2 { 0.0f, 0.0f } : negv (G);
+        const f2 s = (last_plugin || PHASE == 1) ? f2 { 0.0f, 0.0f } : negv (G);
         f2 d[H]; // dN/d(pre-activation) of the layer being visited
         int wofs = 3 * H + NH * (H * H + H);
         // output layer H -> 1
 #pragma unroll
         for (int i = 0; i < H; ++i)
         {
-            acc[(wofs + i) * 32 + lane] += s.x * hs[NH][i].x + s.y * hs[NH][i].y;
+            if (PHASE != 1)
+                acc[(wofs + i) * 32 + lane] += s.x * hs[NH][i].x + s.y * hs[NH][i].y;
             const f2 hh = hs[NH][i];
             d[i] = mulv (bc (f2 {}, wout[i]), fmav (negv (hh), hh, bc (f2 {}, 1.0f)));
         }
-        acc[(wofs + H) * 32 + lane] += s.x + s.y;
+        if (PHASE != 1)
+            acc[(wofs + H) * 32 + lane] += s.x + s.y;
         // hidden layers, last to first
 #pragma unroll
         for (int l = NH - 1; l >= 0; --l)
@@ -371,7 +385,8 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
             for (int j = 0; j < H; ++j)
             {
                 sd[j] = mulv (s, d[j]);
-                acc[(wofs + H * H + j) * 32 + lane] += sd[j].x + sd[j].y; // bias
+                if (PHASE != 1)
+                    acc[(wofs + H * H + j) * 32 + lane] += sd[j].x + sd[j].y; // bias
             }
 #pragma unroll
             for (int i = 0; i < H; ++i)
@@ -386,7 +401,8 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
                     for (int q = 0; q < 4; ++q)
                     {
                         sum = fmav (bc (f2 {}, ws[q]), d[j + q], sum);
-                        acc[(wofs + i * H + j + q) * 32 + lane] += hs[l][i].x * sd[j + q].x + hs[l][i].y * sd[j + q].y;
+                        if (PHASE != 1)
+                            acc[(wofs + i * H + j + q) * 32 + lane] += hs[l][i].x * sd[j + q].x + hs[l][i].y * sd[j + q].y;
                     }
                 }
                 const f2 hh = hs[l][i];
@@ -402,21 +418,32 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
         for (int j = 0; j < H; ++j)
         {
             const f2 sd = mulv (s, d[j]);
-            acc[j * 32 + lane] += a.x * sd.x + a.y * sd.y;
-            acc[(H + j) * 32 + lane] += lr.x * sd.x + lr.y * sd.y;
-            acc[(2 * H + j) * 32 + lane] += sd.x + sd.y;
+            if (PHASE != 1)
+            {
+                acc[j * 32 + lane] += a.x * sd.x + a.y * sd.y;
+                acc[(H + j) * 32 + lane] += lr.x * sd.x + lr.y * sd.y;
+                acc[(2 * H + j) * 32 + lane] += sd.x + sd.y;
+            }
             dNda = fmav (bc (f2 {}, sw[j]), d[j], dNda);
         }
         // ---- state recurrence: A = (1 - gamma) f'(a) - gamma, f' = -dN/da ---------------------------
         const f2 omg = addv (bc (f2 {}, 1.0f), negv (gamma));
         const f2 A = addv (mulv (omg, negv (dNda)), negv (gamma));
         G = last_plugin ? gy : fmav (G, A, PY ? mulv (bc (f2 {}, 0.5f), gy) : gy);
+        if (PHASE == 1)
+            Gh = last_plugin ? f2 { 0.0f, 0.0f } : mulv (Gh, A);
         zn = z;
         if ((n & 63) == 0)
         {
             sse += (double) sse_f, st2 += (double) st2_f;
             sse_f = st2_f = 0.0f;
         }
+    }
+    if (PHASE == 1)
+    {
+        if (validA)
+            pq[item] = make_float4 (Gh.x, Gh.y, G.x, G.y);
+        return;
     }
     __syncwarp ();
     // ---- per-warp reduction in a fixed order, one fp64 partial vector per warp ----------------------
@@ -438,6 +465,21 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
     {
         out[n_weights] = sse;
         out[n_weights + 1] = st2;
+    }
+}
+
+// one lane per pair: G entering chunk k (from chunk k + 1) by composing the affine maps last to first
+__global__ void __launch_bounds__ (128) nn_adjoint_stitch (const float4* __restrict__ pq, f2* __restrict__ gin, int64_t pairs, int K)
+{
+    const int64_t pair = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= pairs)
+        return;
+    f2 G { 0.0f, 0.0f };
+    for (int k = K - 1; k >= 0; --k)
+    {
+        gin[pair * K + k] = G;
+        const float4 m = pq[pair * K + k];
+        G = f2 { fma_ (m.x, G.x, m.z), fma_ (m.y, G.y, m.w) };
     }
 }
 
@@ -544,24 +586,42 @@ int nn_time_chunks (int64_t T) { return (int) ((T + kNnChunk - 1) / kNnChunk); }
 int64_t nn_ckpt_floats (int64_t B, int64_t T) { return ((T + kNnSeg - 1) / kNnSeg + 1) * B; }
 int64_t nn_groups (int64_t B) { return ((B + 1) / 2 + 31) / 32; }
 
+int64_t nn_adjoint_ctas (int64_t B, int K) { return (((B + 1) / 2) * K + 31) / 32; }
+
+// K == 1: one lane per pair (partials: nn_groups(B) vectors). K > 1: time-parallel, two phases; scratch holds
+// ceil(B/2) * K float4 (P, Q) followed by ceil(B/2) * K f2 (incoming G); partials: nn_adjoint_ctas(B, K) vectors.
 cudaError_t launch_nn_adjoint (int hidden, int n_hidden, bool pyorder, bool target, const float* x, const float* r, const float* y, const float* g, const float* ckpt, const float* params, int slot_R, int slot_C,
-                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, cudaStream_t stream)
+                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, int K, float* scratch, cudaStream_t stream)
 {
-    const unsigned grid = (unsigned) nn_groups (B);
-    const size_t smem = (size_t) ((n_weights + 3) / 4 * 4 + (size_t) n_weights * 32) * sizeof (float);
-    auto go = [&] (auto kern) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    const int64_t pairs = (B + 1) / 2;
+    const unsigned grid = (unsigned) nn_adjoint_ctas (B, K);
+    const size_t smem_w = (size_t) ((n_weights + 3) / 4 * 4) * sizeof (float), smem = smem_w + (size_t) n_weights * 32 * sizeof (float);
+    float4* pq = reinterpret_cast<float4*> (scratch);
+    f2* gin = scratch != nullptr ? reinterpret_cast<f2*> (pq + pairs * K) : nullptr;
+    auto go = [&] (auto full, auto phase1, auto phase2) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute (full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute (phase2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess)
             return e;
-        kern<<<grid, 32, smem, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T);
+        if (K == 1)
+            full<<<grid, 32, smem, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T, 1, nullptr, nullptr);
+        else
+        {
+            phase1<<<grid, 32, smem_w, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T, K, pq, nullptr);
+            nn_adjoint_stitch<<<(unsigned) ((pairs + 127) / 128), 128, 0, stream>>> (pq, gin, pairs, K);
+            phase2<<<grid, 32, smem, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T, K, nullptr, gin);
+        }
         return cudaGetLastError ();
     };
 #define DWDF_NNA(HH, NN) \
     if (hidden == HH && n_hidden == NN) \
     { \
         if (pyorder) \
-            return target ? go (nn_clipper_adjoint<HH, NN, true, true>) : go (nn_clipper_adjoint<HH, NN, true, false>); \
-        return target ? go (nn_clipper_adjoint<HH, NN, false, true>) : go (nn_clipper_adjoint<HH, NN, false, false>); \
+            return target ? go (nn_clipper_adjoint<HH, NN, true, true, 0>, nn_clipper_adjoint<HH, NN, true, true, 1>, nn_clipper_adjoint<HH, NN, true, true, 2>) \
+                          : go (nn_clipper_adjoint<HH, NN, true, false, 0>, nn_clipper_adjoint<HH, NN, true, false, 1>, nn_clipper_adjoint<HH, NN, true, false, 2>); \
+        return target ? go (nn_clipper_adjoint<HH, NN, false, true, 0>, nn_clipper_adjoint<HH, NN, false, true, 1>, nn_clipper_adjoint<HH, NN, false, true, 2>) \
+                      : go (nn_clipper_adjoint<HH, NN, false, false, 0>, nn_clipper_adjoint<HH, NN, false, false, 1>, nn_clipper_adjoint<HH, NN, false, false, 2>); \
     }
     DWDF_NNA (4, 2)
     DWDF_NNA (8, 2)

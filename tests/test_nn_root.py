@@ -211,3 +211,31 @@ def test_time_parallel_forward_equals_serial(dwdf, nnv, name, with_r):
         finally:
             dwdf.set_option(prev)
     assert seq_rel_err(outs[0].cpu().numpy(), outs[1].cpu().numpy()) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["2x8", "4x8", "2x16"])
+@pytest.mark.parametrize("ordering", ["plugin", "python"])
+def test_time_parallel_adjoint_equals_serial(dwdf, nnv, name, ordering):
+    """The two-phase time-parallel adjoint (affine maps per chunk, composed, then accumulation from the true incoming
+    adjoint) gives the one-lane-per-pair kernel's weight gradients and loss, and both agree with fp64 autograd."""
+    B, T = 7, 1100
+    xn = make_inputs(B, T, seed=81)
+    x = torch.from_numpy(xn).cuda()
+    w, sizes = nnv[f"{name}_weights"], [int(v) for v in nnv[f"{name}_sizes"]]
+    order = nn.ORDER_PLUGIN if ordering == "plugin" else nn.ORDER_PYTHON
+    target = (0.8 * nn.nn_clipper_forward(xn, w, sizes, 48000.0, 47000.0, 2.2e-9, order, dtype=np.float64) + 0.01).astype(np.float32)
+    outs = []
+    for opts in (0, 8):
+        prev = dwdf.set_option(opts)
+        try:
+            circ = make_circuit(dwdf, model_json(dwdf, nnv, name), ordering)
+            circ.forward(x)
+            res = circ.backward(target=torch.from_numpy(target).cuda(), loss="mse+esr", skip=50)
+            outs.append((res["grads"].cpu().numpy().copy(), float(res["loss"])))
+        finally:
+            dwdf.set_option(prev)
+    (g_tp, l_tp), (g_se, l_se) = outs
+    assert np.max(np.abs(g_tp - g_se)) < 2e-5 * np.max(np.abs(g_se)) and abs(l_tp / l_se - 1) < 1e-5
+    ref = nn.nn_clipper_grad_torch(xn, target, w, sizes, 48000.0, 47000.0, 2.2e-9, order, loss="mse+esr", skip=50)
+    assert np.max(np.abs(g_tp - ref["grad_w"])) < NN_GRAD_TOL * np.max(np.abs(ref["grad_w"]))

@@ -34,8 +34,9 @@ for name in a.models.split(","):
     for _ in range(3): circ.forward(x, r=r, out=y)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
+    redone = dwdf.time_parallel_redone()
     n_w = circ.weights.numel()
-    line = f"neural root {name} ({n_w} weights) B={a.B} T={a.T} r={a.r}: forward {ms:.3f} ms  {a.B*a.T/ms/1e6:.2f} Gsamples/s  ({2*n_w*a.B*a.T/ms/1e9:.1f} TFLOP/s in the network)"
+    line = f"neural root {name} ({n_w} weights) B={a.B} T={a.T} r={a.r}: forward {ms:.3f} ms [redone chunks so far {redone}]  {a.B*a.T/ms/1e6:.2f} Gsamples/s  ({2*n_w*a.B*a.T/ms/1e9:.1f} TFLOP/s in the network)"
     # CPU: oracle (numpy) is not a fair baseline; the reference's own RTNeural path lives in oracle/_ref (not on the GPU box unless built here)
     ref = os.path.join(ROOT, "oracle", "_ref", "libdwdf_ref_nn.so")
     print(line, flush=True)
