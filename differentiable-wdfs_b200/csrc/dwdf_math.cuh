@@ -404,7 +404,7 @@ DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
 struct ClipConst
 {
     float gamma; // p1R = Gv / G
-    float one_m_gamma;
+    float one_m_gamma, two_gamma;
     float Rp; // port resistance seen by the root
     PairConst pair;
 };
@@ -425,6 +425,7 @@ DWDF_HD void clip_setup (ClipConst& c, const ClipDesc& d, float R, float C, floa
     c.Rp = 1.0f / G;
     c.gamma = Gv / G;
     c.one_m_gamma = 1.0f - c.gamma;
+    c.two_gamma = 2.0f * c.gamma;
     pair_setup (c.pair, c.Rp, Is, d.Vt, nabla, d.n_up, d.n_down, d.n_iter, d.tol);
 }
 
@@ -452,8 +453,8 @@ DWDF_HD float clip_step (const ClipConst& c, float x, float& z)
 // arranged for this machine:
 //   * two circuit instances per lane in packed fp32x2 registers: every add / mul / fma is ONE FFMA2 /
 //     FADD2 / FMUL2 issue for both (sm_100a). Only the sign/exponent bit operations, the selects, the
-//     reciprocal (MUFU) and min/max stay per element. Inputs enter through a per-element multiply
-//     (gamma x) and outputs leave through a per-element add, so no register-pairing moves are needed;
+//     reciprocal (MUFU) and min/max stay per element. Inputs enter through a per-element subtraction
+//     (x - z) and outputs leave through a per-element add, so no register-pairing moves are needed;
 //   * fewer operations: the cubic of omega3 is evaluated in the log2(e)-scaled argument the exp needs
 //     anyway, z' = b + gamma (x - z) is taken as  -2V lambda (w0 - w1) + (2a - z),  and the Newton step
 //     y - (y - e)/(y + 1)  as  e r + y (1 - r),  r = 1/(y + 1);
@@ -509,8 +510,8 @@ DWDF_HD f2 xor_signv (f2 a, f2 s) { return f2 { xor_sign (a.x, s.x), xor_sign (a
 DWDF_HD f1 zero_below (f1 y, f1 u, float thr) { return f1 { u.x < thr ? 0.0f : y.x }; }
 DWDF_HD f2 zero_below (f2 y, f2 u, float thr) { return f2 { u.x < thr ? 0.0f : y.x, u.y < thr ? 0.0f : y.y }; }
 // element-wise, deliberately NOT packed: the way data enters and leaves the packed registers
-DWDF_HD f1 scale_in (float g, f1 x) { return f1 { g * x.x }; }
-DWDF_HD f2 scale_in (float g, f2 x) { return f2 { g * x.x, g * x.y }; }
+DWDF_HD f1 sub_in (f1 x, f1 z) { return f1 { add_ (x.x, -z.x) }; }
+DWDF_HD f2 sub_in (f2 x, f2 z) { return f2 { add_ (x.x, -z.x), add_ (x.y, -z.y) }; }
 DWDF_HD f1 add_out (f1 a, f1 b) { return f1 { a.x + b.x }; }
 DWDF_HD f2 add_out (f2 a, f2 b) { return f2 { a.x + b.x, a.y + b.y }; }
 
@@ -534,9 +535,12 @@ template <class V, bool PY>
 DWDF_HD V clip_step_fastv (const ClipConst& c, V x, V& z, V& hz, V& umax)
 {
     const PairConst& p = c.pair;
-    const V gx = scale_in (c.gamma, x);
-    const V a = fmav (bc (V {}, c.one_m_gamma), z, gx); // z + gamma (x - z)
-    const V a2z = fmav (bc (V {}, 2.0f), a, negv (z)); // a + gamma (x - z)
+    // a = z + gamma (x - z) exactly as the adaptor writes it (tf_wdf.py:185-192): the form (1 - gamma) z + gamma x
+    // rounds the pole 1 - 2 gamma by half an ulp of ONE, which a long RC memory amplifies by 1 / (2 gamma) into the
+    // DC gain (1e-5 relative at gamma = 1e-3; found by the randomised sweep, tests/test_gpu_fuzz.py)
+    const V xz = sub_in (x, z);
+    const V a = fmav (bc (V {}, c.gamma), xz, z);
+    const V a2z = fmav (bc (V {}, c.two_gamma), xz, z); // a + gamma (x - z)
     const V aa = absv (a);
     const V us = fmav (aa, bc (V {}, p.invVl2e), bc (V {}, p.Ll2e)); // u0 log2(e), u0 = L + |a| / V
     const V w1 = exp_approx_scaledv (fmav (aa, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e))); // omega4(L - |a|/V) = exp_approx

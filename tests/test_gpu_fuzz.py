@@ -1,0 +1,55 @@
+"""Randomised parity sweep (-m gpu): shapes, circuit constants, diode laws, root modes and probe orderings
+drawn from seeded distributions wide enough to leave every fast path's precondition (L < -3.34, L > -39,
+N_up = N_down, T % 4 = 0, B > 32, B <= 8192, ...) on both sides; forward against the C oracle
+(<= 1e-5 of the peak per sequence), gradients against its fp64 reverse sweep."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_inputs, seq_rel_err
+from oracle.cpu import ORDER_PLUGIN, ORDER_PYTHON, ClipperParams
+
+pytestmark = pytest.mark.gpu
+
+
+def draw(rng):
+    logu = lambda lo, hi: float(np.exp(rng.uniform(np.log(lo), np.log(hi))))
+    p = ClipperParams(fs=float(rng.choice([44100.0, 48000.0, 96000.0])), R=logu(1e3, 1e6), C=logu(1e-10, 1e-6), Is=logu(1e-13, 1e-5), nabla=float(rng.uniform(1.0, 2.5)),
+                      n_up=int(rng.choice([1, 1, 2, 3])), n_down=int(rng.choice([1, 1, 2, 3])))
+    B = int(rng.choice([1, 2, 31, 32, 33, 64, 65, 100, 257]))
+    T = int(rng.choice([1, 3, 4, 16, 17, 100, 512, 515, 1024, 1500, 2048]))
+    return p, B, T, str(rng.choice(["approx", "exact"])), str(rng.choice(["plugin", "python"])), float(rng.choice([0.3, 1.0, 3.0]))
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("DWDF_FUZZ_N", "48"))))
+def test_random_circuit(dwdf, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    p, B, T, mode, ordering, gain = draw(rng)
+    oord = ORDER_PLUGIN if ordering == "plugin" else ORDER_PYTHON
+    x = (make_inputs(B, T, fs=p.fs, seed=seed) * gain).astype(np.float32)
+    Vs = dwdf.ResistiveVoltageSource(p.R, True)
+    C = dwdf.Capacitor(p.C, p.fs, True)
+    dp = dwdf.DiodePair(dwdf.Parallel(Vs, C), p.Is, p.Vt, p.nabla, p.n_up, p.n_down, trainable=True, mode=mode)
+    circ = dwdf.compile_circuit(dp, probe=C, ordering=ordering)
+    xd = torch.from_numpy(x).cuda()
+    y = circ.forward(xd)
+    yn = y.cpu().numpy()
+    ref = oracle.clipper_forward(x, p, exact=(mode == "exact"), ordering=oord)
+    # How well is this circuit conditioned at all? The reference's own fp32 and fp64 runs part by `cond`: hard-conducting
+    # constants (L = ln(Rp Is / V) > 0: |dz'/dz| -> 1) and the seams of omega4 make some draws chaotic at the 1e-5 level.
+    cond = seq_rel_err(ref, oracle.clipper_forward(x, p, exact=(mode == "exact"), ordering=oord, dtype=np.float64))
+    assert np.all(np.isfinite(yn))
+    assert seq_rel_err(yn, ref) < max(1e-5, 3.0 * cond), (p, B, T, mode, ordering, gain, cond)
+    loud = cond > 3e-6
+    if T < 8:
+        return
+    target = (0.6 * ref + 0.01).astype(np.float32)
+    res = circ.backward(target=torch.from_numpy(target).cuda(), loss="mse+esr", skip=min(4, T // 2))
+    g = res["grads"].cpu().numpy()[[circ.slot(dp, "Is"), circ.slot(dp, "nabla"), circ.slot(Vs, "R"), circ.slot(C, "C")]]
+    assert np.all(np.isfinite(g))
+    if loud:
+        return
+    gref = oracle.clipper_grad(x, target, p, exact=(mode == "exact"), ordering=oord, mode="target", loss="mse+esr", skip=min(4, T // 2), dtype=np.float64)
+    scale = np.abs(gref["grads"]) + 1e-3 * np.max(np.abs(gref["grads"] * np.array([p.Is, p.nabla, p.R, p.C]))) / np.array([p.Is, p.nabla, p.R, p.C])
+    assert np.max(np.abs(g - gref["grads"]) / scale) < 2e-3, (p, B, T, mode, ordering, g, gref["grads"])
+    assert abs(float(res["loss"]) / gref["loss"] - 1) < 1e-4

@@ -180,3 +180,16 @@ def test_recover_pairs_equal_scalar(hm):
     assert rc == 0
     scale = np.max(np.abs(out[:, 4:]), axis=0)
     assert np.all(np.max(np.abs(out[:, :4] - out[:, 4:]), axis=0) <= 2e-6 * scale)
+
+
+def test_fast_step_long_time_constant(hm, oracle):
+    """gamma = 1e-3 (R 866 kOhm against 5.5 nF at 96 kHz: an RC memory of ~500 samples): the fast step must keep
+    a = z + gamma (x - z) in the adaptor's own form; (1 - gamma) z + gamma x rounds the pole by half an ulp of one
+    and the long memory amplifies that 1 / (2 gamma)-fold into the DC gain (1e-5; found by tests/test_gpu_fuzz.py)."""
+    p = ClipperParams(fs=96000.0, R=866000.0, C=5.5e-9, Is=1.3e-12, nabla=1.9)
+    x = (make_inputs(16, 3000, fs=p.fs, seed=7) * 0.3).astype(np.float32)
+    for py, oord in ((0, ORDER_PLUGIN), (1, ORDER_PYTHON)):
+        ref = oracle.clipper_forward(x, p, ordering=oord)
+        for pairs in (0, 1):
+            y, _ = fast(hm, pairs, py, p, x)
+            assert seq_rel_err(y, ref) < 2e-6
