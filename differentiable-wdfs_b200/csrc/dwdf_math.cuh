@@ -334,20 +334,30 @@ struct PairDeriv
     float S1, M1, dV;
 };
 
-// (S1, M1, dV) from the two omegas of one sample
+// (S1, M1, dV) from the two omegas of one sample.
+// dV is written without cancellation: with w - w' = w w' the textbook form (b - a)/V + 2 M1 + 2 (a/V) S1 equals
+//   -2 lambda (mu0 w0 w0' - mu1 w1 w1') + 2 (a/V) S1,
+// and while the diodes are off (w << 1) its first two terms cancel to second order in w — far below fp32's
+// resolution of b - a (dL/dnF of a quiet signal was off by tens of percent; found by tests/test_gpu_fuzz.py).
 template <bool GENERAL>
 DWDF_HD void pair_deriv (const PairConst& c, float a, float b, float w0, float w1, float mu0, float mu1, PairDeriv* d)
 {
+    (void) b;
     const float wp0 = w0 * rcp (1.0f + w0), wp1 = w1 * rcp (1.0f + w1);
     d->S1 = wp0 + wp1;
+    float ww;
     if (GENERAL)
     {
         const float lam = a == 0.0f ? 0.0f : copysignf (1.0f, a);
         d->M1 = lam * fma_ (mu0, wp0, -(mu1 * wp1));
+        ww = lam * fma_ (mu0 * w0, wp0, -(mu1 * w1 * wp1));
     }
     else
+    {
         d->M1 = xor_sign (wp0 - wp1, a); // wp0 == wp1 at a == 0
-    d->dV = fma_ (2.0f * a * c.invV, d->S1, fma_ (b - a, c.invV, 2.0f * d->M1));
+        ww = xor_sign (fma_ (w0, wp0, -(w1 * wp1)), a);
+    }
+    d->dV = fma_ (2.0f * a * c.invV, d->S1, -2.0f * ww);
 }
 
 // b = f(a).  Symmetric (eq. 39): wdf_t.h:917-924 == Toms917DiodePair.h:51-59.
@@ -618,7 +628,7 @@ DWDF_HD void clip_step_recover (const ClipConst& c, float x, float z, float zn, 
     const float b = fma_ (-c.gamma, xz, zn);
     const float aa = fabsf (a);
     const float dl = xor_sign (a - b, a); // lambda (a - b) >= 0
-    float w0, w1, mu0 = 1.0f, mu1 = 1.0f;
+    float w0, w1, mu0 = 1.0f, mu1 = 1.0f, u0;
     if (GENERAL)
     {
         const bool pos = a >= 0.0f;
@@ -626,6 +636,7 @@ DWDF_HD void clip_step_recover (const ClipConst& c, float x, float z, float zn, 
         mu1 = pos ? c.pair.n_up : c.pair.n_dn;
         w1 = root_omega_rev<MODE, LSMALL> (c.pair, (pos ? c.pair.L_up : c.pair.L_dn) - aa * (pos ? c.pair.inv_up : c.pair.inv_dn));
         w0 = fma_ (dl, c.pair.inv2V, mu1 * w1) * (pos ? c.pair.rn_dn : c.pair.rn_up);
+        u0 = (pos ? c.pair.L_dn : c.pair.L_up) + aa * (pos ? c.pair.inv_dn : c.pair.inv_up);
         if (a == 0.0f) // lambda = 0 hides w0 from b; rare, evaluate it
             w0 = root_omega<MODE> (c.pair, c.pair.L_dn);
     }
@@ -636,6 +647,16 @@ DWDF_HD void clip_step_recover (const ClipConst& c, float x, float z, float zn, 
         else
             w1 = root_omega_rev<MODE, LSMALL> (c.pair, c.pair.L - aa * c.pair.invV);
         w0 = fma_ (dl, c.pair.inv2V, w1);
+        u0 = fma_ (aa, c.pair.invV, c.pair.L);
+    }
+    // While the forward-biased diode is still off its omega is below fp32's resolution of a - b (2 V w0 against
+    // ulp(a)): read off the wave it would be noise — harmless for the state recurrence, but dL/dIs of a quiet signal is
+    // the sum of exactly these terms. There the omega is one cheap evaluation (omega4 = exp_approx below
+    // kOmega3Zero; the exact omega's x <= -2 region), so it is taken directly.
+    {
+        const float thr = MODE == kModeExact ? -2.0f : kOmega3Zero;
+        const float w0_lo = MODE == kModeExact ? omega_exact_low (u0) : exp_approx (u0);
+        w0 = u0 < thr ? w0_lo : w0;
     }
     PairDeriv d;
     pair_deriv<GENERAL> (c.pair, a, b, w0, w1, mu0, mu1, &d);
@@ -656,6 +677,8 @@ struct StepTapeV
 {
     V A, cg, cl, cv;
 };
+DWDF_HD f1 select_below (f1 lo, f1 hi, f1 u, float thr) { return f1 { u.x < thr ? lo.x : hi.x }; }
+DWDF_HD f2 select_below (f2 lo, f2 hi, f2 u, float thr) { return f2 { u.x < thr ? lo.x : hi.x, u.y < thr ? lo.y : hi.y }; }
 DWDF_HD f1 clamp_exp_arg (f1 a) { return f1 { fmaxf (a.x, -126.0f) }; }
 DWDF_HD f2 clamp_exp_arg (f2 a) { return f2 { fmaxf (a.x, -126.0f), fmaxf (a.y, -126.0f) }; }
 template <class V>
@@ -668,7 +691,10 @@ DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V
     const V aa = absv (a);
     const V w1 = exp_approx_scaledv (clamp_exp_arg (fmav (aa, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e))));
     const V d = addv (a, negv (b));
-    const V w0 = fmav (xor_signv (d, a), bc (V {}, p.inv2V), w1); // mu0 w0 = mu1 w1 + lambda (a - b) / (2 V)
+    V w0 = fmav (xor_signv (d, a), bc (V {}, p.inv2V), w1); // mu0 w0 = mu1 w1 + lambda (a - b) / (2 V)
+    // diode still off (u0 < kOmega3Zero): omega4 = exp_approx there, taken directly (see clip_step_recover)
+    const V us = fmav (aa, bc (V {}, p.invVl2e), bc (V {}, p.Ll2e));
+    w0 = select_below (exp_approx_scaledv (clamp_exp_arg (us)), w0, us, kOmega3Zero * kLog2e);
     const V wp0 = mulv (w0, rcpv (addv (w0, bc (V {}, 1.0f))));
     const V wp1 = mulv (w1, rcpv (addv (w1, bc (V {}, 1.0f))));
     const V S1 = addv (wp0, wp1);
@@ -677,7 +703,8 @@ DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V
     tp.A = fmav (fp1, bc (V {}, c.one_m_gamma), bc (V {}, -1.0f));
     tp.cg = mulv (xz, fp1);
     tp.cl = mulv (bc (V {}, -p.twoV), M1);
-    tp.cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, fmav (d, bc (V {}, -p.invV), addv (M1, M1)));
+    const V ww = xor_signv (fmav (w0, wp0, negv (mulv (w1, wp1))), a); // lambda (w0 w0' - w1 w1'): the cancellation-free form of pair_deriv
+    tp.cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, mulv (bc (V {}, -2.0f), ww));
 }
 
 template <bool PY>

@@ -39,7 +39,11 @@ def test_random_circuit(dwdf, oracle, seed):
     # constants (L = ln(Rp Is / V) > 0: |dz'/dz| -> 1) and the seams of omega4 make some draws chaotic at the 1e-5 level.
     cond = seq_rel_err(ref, oracle.clipper_forward(x, p, exact=(mode == "exact"), ordering=oord, dtype=np.float64))
     assert np.all(np.isfinite(yn))
-    assert seq_rel_err(yn, ref) < max(1e-5, 3.0 * cond), (p, B, T, mode, ordering, gain, cond)
+    # per sequence, relative to the output's peak — but not below -60 dB of the input's (a 4-sample sequence through a long RC
+    # has an output of a few microvolts, where 1e-11 V of rounding is "1e-5")
+    den = np.maximum(np.max(np.abs(ref), axis=1), 1e-3 * np.max(np.abs(x), axis=1) + 1e-30)
+    err = float(np.max(np.max(np.abs(yn - ref), axis=1) / den))
+    assert err < max(1e-5, 5.0 * cond), (p, B, T, mode, ordering, gain, cond)
     loud = cond > 3e-6
     if T < 8:
         return

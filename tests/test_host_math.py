@@ -193,3 +193,19 @@ def test_fast_step_long_time_constant(hm, oracle):
         for pairs in (0, 1):
             y, _ = fast(hm, pairs, py, p, x)
             assert seq_rel_err(y, ref) < 2e-6
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n_up,n_down", [(1, 1), (1, 2)])
+@pytest.mark.parametrize("recover", [False, True])
+def test_adjoint_sums_of_a_quiet_signal(hm, oracle, mode, n_up, n_down, recover):
+    """Diodes that never conduct (L = -17, |a| < 0.03 V): the parameter sensitivities are sums of terms far below
+    fp32's resolution of the waves themselves. Two formulations keep them exact (both found by tests/test_gpu_fuzz.py):
+    dV without the (b - a)/V + 2 M1 cancellation (pair_deriv), and the forward-biased omega evaluated directly while the
+    diode is off instead of read off a - b (clip_step_recover)."""
+    p = ClipperParams(fs=48000.0, R=9778.8, C=2.8895e-07, Is=3.6248e-11, nabla=1.0321, n_up=n_up, n_down=n_down)
+    x = make_inputs(3, 400, fs=p.fs, seed=475)
+    gy = np.random.default_rng(475).standard_normal(x.shape).astype(np.float32)
+    _, acc = clip(hm, mode, 1, p, x, gy, recover=recover)
+    ref = oracle.clipper_grad(x, gy, p, exact=bool(mode), ordering=ORDER_PYTHON, mode="upstream", dtype=np.float64)
+    assert np.max(np.abs(acc / ref["raw"][:3] - 1)) < 1e-4, acc / ref["raw"][:3] - 1
