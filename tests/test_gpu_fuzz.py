@@ -57,3 +57,49 @@ def test_random_circuit(dwdf, oracle, seed):
     scale = np.abs(gref["grads"]) + 1e-3 * np.max(np.abs(gref["grads"] * np.array([p.Is, p.nabla, p.R, p.C]))) / np.array([p.Is, p.nabla, p.R, p.C])
     assert np.max(np.abs(g - gref["grads"]) / scale) < 2e-3, (p, B, T, mode, ordering, g, gref["grads"])
     assert abs(float(res["loss"]) / gref["loss"] - 1) < 1e-4
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("DWDF_FUZZ_N2", "24"))))
+def test_random_circuit_other_entry_points(dwdf, oracle, seed):
+    """Same draws through the other entry points: upstream-gradient mode with dL/dx, the fused one-sweep training pass
+    against forward + adjoint, and streaming in ragged blocks against one long block."""
+    rng = np.random.default_rng(5000 + seed)
+    p, B, T, mode, ordering, gain = draw(rng)
+    T = max(T, 24)
+    oord = ORDER_PLUGIN if ordering == "plugin" else ORDER_PYTHON
+    x = (make_inputs(B, T, fs=p.fs, seed=seed) * gain).astype(np.float32)
+    ref = oracle.clipper_forward(x, p, exact=(mode == "exact"), ordering=oord)
+    cond = seq_rel_err(ref, oracle.clipper_forward(x, p, exact=(mode == "exact"), ordering=oord, dtype=np.float64))
+    Vs = dwdf.ResistiveVoltageSource(p.R, True)
+    C = dwdf.Capacitor(p.C, p.fs, True)
+    dp = dwdf.DiodePair(dwdf.Parallel(Vs, C), p.Is, p.Vt, p.nabla, p.n_up, p.n_down, trainable=True, mode=mode)
+    circ = dwdf.compile_circuit(dp, probe=C, ordering=ordering)
+    order = [circ.slot(dp, "Is"), circ.slot(dp, "nabla"), circ.slot(Vs, "R"), circ.slot(C, "C")]
+    xd = torch.from_numpy(x).cuda()
+    y = circ.forward(xd)
+    # streaming: three ragged blocks continue the same signal
+    cuts = sorted(set([0, T // 3 + 1, (2 * T) // 3 + 2, T]))
+    st = circ.new_state(B)
+    parts = [circ.process_block(xd[:, a:b].contiguous(), st) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert seq_rel_err(torch.cat(parts, 1).cpu().numpy(), y.cpu().numpy()) < max(2e-6, 5.0 * cond)
+    if cond > 3e-6:
+        return
+    # upstream gradient + dL/dx against the fp64 oracle
+    gy = np.random.default_rng(seed).standard_normal(x.shape).astype(np.float32)
+    res = circ.backward(gy=torch.from_numpy(gy).cuda(), want_gx=True)
+    gref = oracle.clipper_grad(x, gy, p, exact=(mode == "exact"), ordering=oord, mode="upstream", dtype=np.float64, want_gx=True)
+    g = res["grads"].cpu().numpy()[order]
+    pv = np.array([p.Is, p.nabla, p.R, p.C])
+    scale = np.abs(gref["grads"]) + 1e-3 * np.max(np.abs(gref["grads"] * pv)) / pv
+    assert np.max(np.abs(g - gref["grads"]) / scale) < 2e-3, (p, B, T, mode, ordering, g, gref["grads"])
+    gx = res["gx"].cpu().numpy()
+    assert np.max(np.abs(gx - gref["gx"])) < 2e-4 * np.max(np.abs(gref["gx"])), (p, B, T, mode, ordering)
+    # fused training pass == forward + adjoint
+    target = (0.6 * ref + 0.01).astype(np.float32)
+    td = torch.from_numpy(target).cuda()
+    circ.forward(xd)
+    a = circ.backward(target=td, loss="mse+esr", skip=4)
+    ga, la = a["grads"].cpu().numpy()[order].copy(), float(a["loss"])
+    b = circ.train_pass(xd, td, loss="mse+esr", skip=4)
+    gb, lb = b["grads"].cpu().numpy()[order], float(b["loss"])
+    assert abs(la / lb - 1) < 1e-4 and np.max(np.abs(ga - gb) / (np.abs(ga) + 1e-3 * np.max(np.abs(ga * pv)) / pv)) < 2e-3, (p, B, T, mode, ordering, ga, gb)
