@@ -103,3 +103,44 @@ def test_random_circuit_other_entry_points(dwdf, oracle, seed):
     b = circ.train_pass(xd, td, loss="mse+esr", skip=4)
     gb, lb = b["grads"].cpu().numpy()[order], float(b["loss"])
     assert abs(la / lb - 1) < 1e-4 and np.max(np.abs(ga - gb) / (np.abs(ga) + 1e-3 * np.max(np.abs(ga * pv)) / pv)) < 2e-3, (p, B, T, mode, ordering, ga, gb)
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("DWDF_FUZZ_N3", "16"))))
+def test_random_neural_root(dwdf, seed):
+    """Neural root with random (orthogonal-ish) weights of every supported shape, random circuit constants, with and
+    without the per-sample resistance channel: forward against the numpy oracle, weight gradients against fp64 autograd."""
+    from oracle import nn
+
+    rng = np.random.default_rng(9000 + seed)
+    n_hidden, H = [(2, 4), (2, 8), (2, 16), (4, 4), (4, 8)][int(rng.integers(5))]
+    sizes = [2] + [H] * (n_hidden + 1) + [1]
+    w = []
+    for i, o in zip(sizes[:-1], sizes[1:]):
+        w += [(rng.standard_normal((i, o)) * (0.9 / np.sqrt(i))).astype(np.float32).ravel(), (0.1 * rng.standard_normal(o)).astype(np.float32)]
+    w = np.concatenate(w)
+    fs = float(rng.choice([44100.0, 48000.0, 50000.0]))
+    R, Cv = float(np.exp(rng.uniform(np.log(5e3), np.log(2e5)))), float(np.exp(rng.uniform(np.log(1e-9), np.log(5e-8))))
+    B, T = int(rng.choice([1, 2, 3, 65, 130])), int(rng.choice([8, 100, 700, 1100]))
+    ordering = str(rng.choice(["plugin", "python"]))
+    order = nn.ORDER_PLUGIN if ordering == "plugin" else nn.ORDER_PYTHON
+    with_r = bool(rng.integers(2))
+    x = make_inputs(B, T, fs=fs, seed=seed)
+    r = (np.exp(rng.uniform(np.log(1e4), np.log(1e5), (B, 1))) * np.ones((1, T))).astype(np.float32) if with_r else None
+    Vs, Cc = dwdf.ResistiveVoltageSource(R), dwdf.Capacitor(Cv, fs)
+    circ = dwdf.compile_circuit(dwdf.DenseRootModel(dwdf.model_io.json_from_weights(w, sizes)), tree=dwdf.Parallel(Vs, Cc), probe=Cc, ordering=ordering, r_element=Vs if with_r else None)
+    xd = torch.from_numpy(x).cuda()
+    rd = torch.from_numpy(r).cuda() if with_r else None
+    y = circ.forward(xd, r=rd).cpu().numpy()
+    ref = nn.nn_clipper_forward(x, w, sizes, fs, R, Cv, order, r=r, dtype=np.float64)
+    assert np.all(np.isfinite(y))
+    # (a random network need not be contractive like a diode: compare where the fp32 and fp64 oracles agree themselves)
+    cond = seq_rel_err(nn.nn_clipper_forward(x, w, sizes, fs, R, Cv, order, r=r, dtype=np.float32), ref)
+    assert seq_rel_err(y, ref) < max(5e-5, 5.0 * cond), (sizes, B, T, ordering, with_r, cond)
+    if cond > 1e-5 or B * T > 20000:
+        return
+    target = (0.7 * ref + 0.02).astype(np.float32)
+    res = circ.backward(target=torch.from_numpy(target).cuda(), loss="mse+esr", skip=min(4, T // 2))
+    gref = nn.nn_clipper_grad_torch(x, target, w, sizes, fs, R, Cv, order, r=r, loss="mse+esr", skip=min(4, T // 2))
+    g = res["grads"].cpu().numpy()
+    assert np.max(np.abs(g - gref["grad_w"])) < 5e-4 * np.max(np.abs(gref["grad_w"])), (sizes, B, T, ordering, with_r)
+    assert abs(float(res["loss"]) / gref["loss"] - 1) < 1e-4
