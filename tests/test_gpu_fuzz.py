@@ -144,3 +144,111 @@ def test_random_neural_root(dwdf, seed):
     g = res["grads"].cpu().numpy()
     assert np.max(np.abs(g - gref["grad_w"])) < 5e-4 * np.max(np.abs(gref["grad_w"])), (sizes, B, T, ordering, with_r)
     assert abs(float(res["loss"]) / gref["loss"] - 1) < 1e-4
+
+
+def _random_tree(rng, dwdf, fs, need_source):
+    """A random binary tree of the reference's elements; returns (top element, oracle node list, leaves, source, index map)."""
+    from oracle.cpu import CAPACITOR, INVERTER, PARALLEL, RESISTOR, RESVS, SERIES
+
+    nodes, elems = [], []
+
+    def leaf(kind):
+        if kind == "R":
+            v = float(np.exp(rng.uniform(np.log(500.0), np.log(2e5))))
+            e = dwdf.Resistor(v, True)
+            nodes.append((RESISTOR, -1, -1, v))
+        elif kind == "C":
+            v = float(np.exp(rng.uniform(np.log(1e-9), np.log(1e-6))))
+            e = dwdf.Capacitor(v, fs, True)
+            nodes.append((CAPACITOR, -1, -1, v))
+        else:
+            v = float(np.exp(rng.uniform(np.log(500.0), np.log(2e5))))
+            e = dwdf.ResistiveVoltageSource(v, True)
+            nodes.append((RESVS, -1, -1, v))
+        elems.append(e)
+        return len(nodes) - 1
+
+    def build(kinds):
+        if len(kinds) == 1:
+            return leaf(kinds[0])
+        k = int(rng.integers(1, len(kinds)))
+        a, b = build(kinds[:k]), build(kinds[k:])
+        if rng.random() < 0.5:
+            e = dwdf.Series(elems[a], elems[b])
+            nodes.append((SERIES, a, b, 0.0))
+        else:
+            e = dwdf.Parallel(elems[a], elems[b])
+            nodes.append((PARALLEL, a, b, 0.0))
+        elems.append(e)
+        i = len(nodes) - 1
+        if rng.random() < 0.25:
+            elems.append(dwdf.Inverter(elems[i]))
+            nodes.append((INVERTER, i, -1, 0.0))
+            i = len(nodes) - 1
+        return i
+
+    n_leaves = int(rng.integers(2, 6))
+    kinds = ["C"] + [str(rng.choice(["R", "C"])) for _ in range(n_leaves - 1)]
+    if need_source:
+        kinds[int(rng.integers(1, n_leaves))] = "V"
+    order = rng.permutation(n_leaves)
+    kinds = [kinds[i] for i in order]
+    top = build(kinds)
+    return elems[top], nodes, elems
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("DWDF_FUZZ_N4", "24"))))
+def test_random_tree(dwdf, oracle, seed):
+    """The generic interpreter on random trees (2-5 leaves of R / C / one resistive source, Series / Parallel /
+    Inverter adaptors) closed by an ideal voltage source or a diode pair, probe on a random leaf: forward against
+    the oracle's tree executor; gradients are finite and reproducible."""
+    from oracle.cpu import ROOT_DIODE_PAIR, ROOT_IDEAL_VS
+
+    rng = np.random.default_rng(13000 + seed)
+    fs = float(rng.choice([44100.0, 48000.0, 96000.0]))
+    diode = bool(rng.integers(2))
+    mode = str(rng.choice(["approx", "exact"]))
+    ordering = str(rng.choice(["plugin", "python"]))
+    oord = ORDER_PLUGIN if ordering == "plugin" else ORDER_PYTHON
+    top, nodes, elems = _random_tree(rng, dwdf, fs, need_source=diode)
+    leaves = [i for i, n in enumerate(nodes) if n[1] < 0]
+    probe = int(rng.choice(leaves))
+    B, T = int(rng.choice([1, 5, 40])), int(rng.choice([3, 50, 300]))
+    x = (make_inputs(B, T, fs=fs, seed=seed) * float(rng.choice([0.3, 1.0]))).astype(np.float32)
+    p = ClipperParams()
+    if diode:
+        root = dwdf.DiodePair(top, p.Is, p.Vt, p.nabla, trainable=True, mode=mode)
+        source = [i for i, e in enumerate(elems) if isinstance(e, dwdf.ResistiveVoltageSource)][0]
+        ref_args = dict(root_kind=ROOT_DIODE_PAIR, source=source, root_par=[float(mode == "exact"), 0, p.Is, p.Vt, p.nabla, 1, 1])
+    else:
+        root = dwdf.IdealVoltageSource()
+        ref_args = dict(root_kind=ROOT_IDEAL_VS, source=-1, root_par=None)
+    circ = dwdf.compile_circuit(root, tree=top, probe=elems[probe], ordering=ordering)
+    xd = torch.from_numpy(x).cuda()
+    y = circ.forward(xd).cpu().numpy()
+    ref = oracle.tree_run(nodes, fs, ref_args["root_kind"], x, probe=probe, source=ref_args["source"], root_par=ref_args["root_par"], ordering=oord)
+    ref64 = oracle.tree_run(nodes, fs, ref_args["root_kind"], x, probe=probe, source=ref_args["source"], root_par=ref_args["root_par"], ordering=oord, dtype=np.float64)
+    den = np.maximum(np.max(np.abs(ref), axis=1), 1e-3 * np.max(np.abs(x), axis=1) + 1e-30)
+    cond = float(np.max(np.max(np.abs(ref - ref64), axis=1) / den))
+    err = float(np.max(np.max(np.abs(y - ref), axis=1) / den))
+    assert np.all(np.isfinite(y)) and err < max(1e-5, 5.0 * cond), (nodes, probe, diode, mode, ordering, err, cond)
+    if T >= 8 and not circ.is_clipper:
+        g1 = circ.backward(target=torch.from_numpy((0.5 * ref).astype(np.float32)).cuda(), loss="mse")["grads"].clone()
+        circ.forward(xd)
+        g2 = circ.backward(target=torch.from_numpy((0.5 * ref).astype(np.float32)).cuda(), loss="mse")["grads"]
+        assert torch.all(torch.isfinite(g1)) and torch.equal(g1, g2)
+    if T >= 50 and not circ.is_clipper and (not diode or mode == "exact") and cond < 1e-6:
+        # leaf gradients against central differences of the fp64 oracle (exact root or linear circuit: smooth in the values)
+        gy = np.random.default_rng(seed).standard_normal(x.shape).astype(np.float32)
+        circ.forward(xd)
+        g = circ.backward(gy=torch.from_numpy(gy).cuda())["grads"].cpu().numpy()
+        fds, gs = [], []
+        for i in leaves:
+            h = 1e-5 * nodes[i][3]
+            yp, ym = [oracle.tree_run([n if j != i else (n[0], n[1], n[2], n[3] + sgn * h) for j, n in enumerate(nodes)], fs, ref_args["root_kind"], x, probe=probe, source=ref_args["source"],
+                                      root_par=ref_args["root_par"], ordering=oord, dtype=np.float64) for sgn in (1, -1)]
+            fds.append(float(np.sum(gy.astype(np.float64) * (yp - ym)) / (2 * h)) * nodes[i][3])
+            gs.append(float(g[circ.slot(elems[i], "C" if isinstance(elems[i], dwdf.Capacitor) else "R")]) * nodes[i][3])
+        fds, gs = np.array(fds), np.array(gs)  # d/d ln(value): comparable across R (ohms) and C (farads)
+        floor = 1e-6 * float(np.linalg.norm(gy) * np.linalg.norm(ref64))  # sensitivities that are zero by topology: finite-difference noise
+        assert np.max(np.abs(gs - fds)) < 2e-3 * np.max(np.abs(fds)) + floor, (nodes, probe, diode, mode, ordering, gs, fds)
