@@ -241,6 +241,39 @@ def test_full_size_properties(dwdf, oracle, B, T):
     assert torch.equal(torch.cat(parts, 1), whole)
 
 
+def test_more_than_2_31_samples(dwdf, oracle):
+    """Maximum sizes: 2.2e9 samples in one call (> 2^31 elements and > 8 GiB per array) — every index on the path is
+    64-bit. Forward: first and last rows against the oracle. Adjoint: the target equals the output except on the last
+    four rows, so the gradients must be those of these four rows alone (run as a batch of four), scaled by 4/B."""
+    B, T, tail = 540_000, 4096, 4
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs 60 GiB of free HBM")
+    assert B * T > 2 ** 31
+    p = ClipperParams()
+    small = make_inputs(4096, T, seed=77)
+    xd = dev(small).repeat(B // 4096 + 1, 1)[:B].contiguous()
+    xd[-tail:] *= 0.5  # the last rows are not copies of early ones
+    circ, order = make_clipper(dwdf, p, "approx", "python")
+    y = circ.forward(xd)
+    rows = [0, 1, 2, 3, B - 4, B - 3, B - 2, B - 1]
+    assert seq_rel_err(y[rows].cpu().numpy(), oracle.clipper_forward(xd[rows].cpu().numpy(), p)) < FWD_TOL
+    assert torch.equal(y[4096 * 100:4096 * 101], y[:4096])  # the repeated block, far above 2^31 / T rows in
+    target = y.clone()
+    target[-tail:] += 0.05
+    big = circ.backward(target=target, loss="mse", skip=0)
+    g_big = big["grads"].cpu().numpy()[order] * (B / tail)
+    mse_big = float(big["mse"]) * (B / tail)
+    del target, y
+    circ4, order4 = make_clipper(dwdf, p, "approx", "python")
+    x4 = xd[-tail:].contiguous()
+    y4 = circ4.forward(x4)
+    res4 = circ4.backward(target=(y4 + 0.05).contiguous(), loss="mse", skip=0)
+    g4 = res4["grads"].cpu().numpy()[order4]
+    assert np.max(np.abs(g_big / g4 - 1.0)) < 1e-5, (g_big, g4)
+    assert abs(mse_big / float(res4["mse"]) - 1.0) < 1e-5
+
+
 # ---- generic tree interpreter ------------------------------------------------------------------------------
 
 def test_tree_rc_lowpass(dwdf, golden):
