@@ -275,30 +275,98 @@ __global__ void __launch_bounds__ (128) nn_forward_stitch (const float* __restri
 // re-anchored at a checkpoint every kNnSeg samples; plugin ordering z[n] = y[n]). Per sample the network is
 // evaluated once forwards (keeping the H activations of every layer in registers) and once backwards with
 // seed 1: that gives f'(a) = -dN/da for the state recurrence  G <- G ((1 - gamma) f' - gamma) + dL/dy  and,
-// scaled by -G, every weight's gradient term. The terms are accumulated per lane in shared memory
-// (acc[weight][lane], conflict-free, no atomics), reduced over the warp at the end in a fixed order and
-// written as one fp64 partial vector per warp; nn_finalize sums the partials in order (bit-reproducible).
+// scaled by s = -G, the deltas whose outer products with the activations are the weight gradients.
+//
+// Weight gradients: dW_l = sum over samples of h_l (x) s delta_l is a small GEMM whose reduction dimension is
+// the samples, which live in DIFFERENT lanes. Every step the warp stages its 64 samples' activations and scaled
+// deltas of one layer in shared memory ([sample pair][unit], packed pairs, 16-byte padded rows), and each lane
+// then owns a 2 x 4 tile of the H x H gradient in REGISTERS and runs over the staged samples: one 16-byte load
+// of activations and two of deltas feed eight FFMA2. (H < 16: 32 / tiles lanes share a tile and split the
+// samples.) Biases, the 2 -> H input layer and the H -> 1 output layer are column sums of the same staged
+// matrices, lane = (column, sample group). Every kNnSeg steps the fp32 register accumulators (<= 2048 terms
+// each) are folded in a fixed order into an fp64 vector in shared memory; one fp64 partial vector per warp
+// leaves the kernel and nn_finalize sums the partials in order (bit-reproducible, no atomics).
+//
 // Time-parallel variant (few long sequences; K chunks of kNnChunk samples per pair, one lane per (pair, chunk)):
 // the running adjoint is a linear recurrence given the trajectory, so
 //   PHASE 1  every chunk computes the affine map of its incoming G, (P, Q): network forwards + backwards, no accumulation;
 //   (nn_adjoint_stitch composes the maps of each pair's chunks last to first -> the G every chunk starts from)
 //   PHASE 2  every chunk runs again from its true incoming G and accumulates the weight-gradient terms.
 // 1.35x the work of PHASE 0 (the whole sequence in one lane), K x the parallelism.
+template <int H>
+struct NnStage
+{
+    static constexpr int kRow = 2 * H + 4; // floats per staged row: H packed pairs + 16 bytes (16-byte stores of 32 lanes conflict-free at H = 4, 8, 16)
+    static constexpr int kMat = 32 * kRow; // one staged matrix [sample pair = lane][unit]
+    static constexpr int kSet = 2 * kMat + 32 * 4; // activations, scaled deltas, per-sample scalars (s | a, ln Rp)
+    static constexpr int kTilesJ = H / 4, kTiles = (H / 2) * kTilesJ, kRep = 32 / kTiles; // 2 x 4 tiles of an H x H matrix; kRep lanes per tile
+    static constexpr int kRepV = 32 / H; // column passes: lane = (column, sample group)
+};
+
+template <int H>
+__device__ __forceinline__ void nn_stage_rows (float* __restrict__ mat, int lane, const f2 (&v)[H])
+{
+    float4* row = reinterpret_cast<float4*> (mat + lane * NnStage<H>::kRow);
+#pragma unroll
+    for (int i = 0; i < H; i += 2)
+        row[i / 2] = make_float4 (v[i].x, v[i].y, v[i + 1].x, v[i + 1].y);
+}
+
+// acc[r * 4 + c] += sum over this lane's samples of h[2 ti + r] * sd[4 tj + c]
+template <int H>
+__device__ __forceinline__ void nn_tile_pass (const float* __restrict__ stH, const float* __restrict__ stD, int lane, f2 (&acc)[8])
+{
+    using St = NnStage<H>;
+    const int tile = lane % St::kTiles, grp = lane / St::kTiles, ti = tile / St::kTilesJ, tj = tile % St::kTilesJ;
+    const float* ph = stH + grp * St::kRow + ti * 4;
+    const float* pd = stD + grp * St::kRow + tj * 8;
+#pragma unroll 8
+    for (int q = 0; q < St::kTiles; ++q)
+    {
+        const float4 h4 = *reinterpret_cast<const float4*> (ph + q * St::kRep * St::kRow);
+        const float4 d0 = *reinterpret_cast<const float4*> (pd + q * St::kRep * St::kRow);
+        const float4 d1 = *reinterpret_cast<const float4*> (pd + q * St::kRep * St::kRow + 4);
+        const f2 h0 { h4.x, h4.y }, h1 { h4.z, h4.w };
+        const f2 da { d0.x, d0.y }, db { d0.z, d0.w }, dc { d1.x, d1.y }, dd { d1.z, d1.w };
+        acc[0] = fmav (h0, da, acc[0]), acc[1] = fmav (h0, db, acc[1]), acc[2] = fmav (h0, dc, acc[2]), acc[3] = fmav (h0, dd, acc[3]);
+        acc[4] = fmav (h1, da, acc[4]), acc[5] = fmav (h1, db, acc[5]), acc[6] = fmav (h1, dc, acc[6]), acc[7] = fmav (h1, dd, acc[7]);
+    }
+}
+
+// column j = lane % H of a staged matrix, samples p = q kRepV + lane / H
+template <int H, class F>
+__device__ __forceinline__ void nn_column_pass (const float* __restrict__ mat, const float* __restrict__ stS, int lane, F&& f)
+{
+    using St = NnStage<H>;
+    const int j = lane % H, grp = lane / H;
+    const float* pm = mat + grp * St::kRow + 2 * j;
+    const float* ps = stS + grp * 4;
+#pragma unroll 8
+    for (int q = 0; q < H; ++q)
+    {
+        const float2 v = *reinterpret_cast<const float2*> (pm + q * St::kRepV * St::kRow);
+        const float4 sc = *reinterpret_cast<const float4*> (ps + q * St::kRepV * 4);
+        f (f2 { v.x, v.y }, sc);
+    }
+}
+
 template <int H, int NH, bool PY, bool TARGET, int PHASE>
 __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ ckpt,
                                                           const float* __restrict__ params, int slot_R, int slot_C, float fs, const float* __restrict__ weights, int n_weights, double* __restrict__ partials,
                                                           int skip, int64_t B, int T, int K, float4* __restrict__ pq, const f2* __restrict__ gin)
 {
+    using St = NnStage<H>;
     extern __shared__ __align__ (16) float smem[];
     const int nw4 = (n_weights + 3) / 4 * 4;
     float* sw = smem; // weights
-    float* acc = smem + nw4; // [n_weights][32] (not in PHASE 1)
+    float* sets = smem + nw4; // two staging sets, used alternately (not in PHASE 1)
+    double* red = reinterpret_cast<double*> (sets + 2 * St::kSet); // [n_weights] fp64 sums of this warp (not in PHASE 1)
     const int lane = threadIdx.x;
     for (int i = lane; i < n_weights; i += 32)
         sw[i] = __ldg (weights + i);
     if (PHASE != 1)
-        for (int i = lane; i < n_weights * 32; i += 32)
-            acc[i] = 0.0f;
+        for (int i = lane; i < n_weights; i += 32)
+            red[i] = 0.0;
     __syncwarp ();
     const int64_t item = (int64_t) blockIdx.x * 32 + lane;
     const int64_t pair = item / K;
@@ -314,7 +382,7 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
     const float Gv0 = 1.0f / __ldg (params + slot_R);
     const float Rp0 = 1.0f / (Gv0 + Gc);
     f2 gamma = bc (f2 {}, Gv0 * Rp0), lr = bc (f2 {}, logf (Rp0));
-    const float* wout = sw + 3 * H + NH * (H * H + H);
+    constexpr int kHid = H * H + H, kOut = 3 * H + NH * kHid; // weight offsets: hidden layer stride, output layer
     const int nblk = (n_hi + kNnSeg - 1) / kNnSeg; // checkpoint holding z[n_hi] (n_hi is a multiple of kNnSeg, or T)
     f2 zn { __ldg (ckpt + (int64_t) nblk * B + ra_), __ldg (ckpt + (int64_t) nblk * B + rb_) };
     f2 G { 0.0f, 0.0f }, Gh { 1.0f, 1.0f }; // Gh: homogeneous solution (PHASE 1)
@@ -322,26 +390,65 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
         G = gin[item];
     double sse = 0.0, st2 = 0.0;
     float sse_f = 0.0f, st2_f = 0.0f;
-    for (int n = n_hi - 1; n >= n_lo; --n)
+    // register accumulators (PHASE != 1): tiles of the hidden matrices, columns of everything else
+    f2 accT[NH][8], accB[NH], accIn[3], accOut, accS;
+#pragma unroll
+    for (int l = 0; l < NH; ++l)
     {
-        const f2 yv { __ldg (ya + n), __ldg (yb + n) };
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            accT[l][k] = f2 { 0.0f, 0.0f };
+        accB[l] = f2 { 0.0f, 0.0f };
+    }
+    accIn[0] = accIn[1] = accIn[2] = accOut = accS = f2 { 0.0f, 0.0f };
+    const int tile = lane % St::kTiles, grpT = lane / St::kTiles, ti = tile / St::kTilesJ, tj = tile % St::kTilesJ;
+    const int jv = lane % H, grpV = lane / H;
+    // every lane of the warp runs the same number of steps (the staged passes are warp-wide); a lane whose chunk is
+    // shorter (the last chunk of a sequence) idles with s = 0
+    const int len = PHASE == 0 ? T : kNnChunk;
+    // the step's inputs are loaded one step ahead (a lane walks its own rows: nothing else hides the L2 latency)
+    struct StepIn
+    {
+        f2 y, x, g, rr;
+    };
+    auto load_step = [&] (int m) {
+        const int nn = n_hi - 1 - m, n = nn >= n_lo ? nn : n_lo;
+        StepIn v;
+        v.y = f2 { __ldg (ya + n), __ldg (yb + n) };
+        v.x = f2 { __ldg (xa + n), __ldg (xb + n) };
+        v.g = f2 { __ldg (ga + n), __ldg (gb + n) };
+        v.rr = rpa != nullptr ? f2 { __ldg (rpa + n), __ldg (rpb + n) } : f2 { 1.0f, 1.0f };
+        return v;
+    };
+    StepIn cur = load_step (0);
+    for (int m = 0; m < len; ++m)
+    {
+        const StepIn nxt = load_step (m + 1 < len ? m + 1 : m);
+        // PHASE 1 never writes shared memory, so the compiler would hoist all the (loop-invariant) weight loads out of the
+        // sample loop and spill them; an opaque copy of the pointer per iteration keeps the loads where they are used
+        const float* swl = sw;
+        if (PHASE == 1)
+            asm volatile ("" : "+l"(swl));
+        const bool act = n_hi - 1 - m >= n_lo;
+        const int n = act ? n_hi - 1 - m : n_lo;
+        const f2 yv = cur.y;
         f2 z = PY ? fmav (bc (f2 {}, 2.0f), yv, negv (zn)) : yv;
         if ((n & (kNnSeg - 1)) == 0)
             z = f2 { __ldg (ckpt + (int64_t) (n / kNnSeg) * B + ra_), __ldg (ckpt + (int64_t) (n / kNnSeg) * B + rb_) };
         if (rpa != nullptr)
         {
-            const float GvA = 1.0f / __ldg (rpa + n), GvB = 1.0f / __ldg (rpb + n);
+            const float GvA = 1.0f / cur.rr.x, GvB = 1.0f / cur.rr.y;
             const float RpA = 1.0f / (GvA + Gc), RpB = 1.0f / (GvB + Gc);
             gamma = f2 { GvA * RpA, GvB * RpB };
             lr = f2 { logf (RpA), logf (RpB) };
         }
-        const f2 xv { __ldg (xa + n), __ldg (xb + n) };
+        const f2 xv = cur.x;
         const f2 a = fmav (gamma, addv (xv, negv (z)), z);
         // dL/dy[n]
-        f2 gy { __ldg (ga + n), __ldg (gb + n) };
+        f2 gy = cur.g;
         if (TARGET)
         {
-            const bool on = n >= skip;
+            const bool on = n >= skip && act;
             const f2 yk = PY ? mulv (bc (f2 {}, 0.5f), addv (zn, z)) : z;
             const f2 tv = gy;
             gy = f2 { (on && validA) ? yk.x - tv.x : 0.0f, (on && validB) ? yk.y - tv.y : 0.0f };
@@ -349,45 +456,59 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
             st2_f += ((on && validA) ? tv.x * tv.x : 0.0f) + ((on && validB) ? tv.y * tv.y : 0.0f);
         }
         else
-            gy = f2 { validA ? gy.x : 0.0f, validB ? gy.y : 0.0f };
+            gy = f2 { (validA && act) ? gy.x : 0.0f, (validB && act) ? gy.y : 0.0f };
         const bool last_plugin = ! PY && n == T - 1; // plugin ordering never observes z[T]
-        if (PY)
+        if (PY && act)
             G = fmav (bc (f2 {}, 0.5f), gy, G);
         // ---- network forwards, activations kept ---------------------------------------------------
         f2 in[2] = { a, lr };
         f2 hs[NH + 1][H];
-        dense<2, H, true> (sw, sw + 2 * H, in, hs[0]);
+        dense<2, H, true> (swl, swl + 2 * H, in, hs[0]);
 #pragma unroll
         for (int l = 0; l < NH; ++l)
-            dense<H, H, true> (sw + 3 * H + l * (H * H + H), sw + 3 * H + l * (H * H + H) + H * H, hs[l], hs[l + 1]);
-        // ---- network backwards with seed 1; every weight's term scaled by s = -G (b = -N) -----------
-        const f2 s = (last_plugin || PHASE == 1) ? f2 { 0.0f, 0.0f } : negv (G);
+            dense<H, H, true> (swl + 3 * H + l * kHid, swl + 3 * H + l * kHid + H * H, hs[l], hs[l + 1]);
+        if (PHASE == 1)
+            __syncwarp ();
+        // ---- network backwards with seed 1; the weight-gradient terms carry s = -G (b = -N) -----------
+        const f2 s = (last_plugin || PHASE == 1 || ! act) ? f2 { 0.0f, 0.0f } : negv (G);
+        int round = 0;
         f2 d[H]; // dN/d(pre-activation) of the layer being visited
-        int wofs = 3 * H + NH * (H * H + H);
-        // output layer H -> 1
+        if (PHASE != 1)
+        { // output layer H -> 1: dW = s h, db = s
+            float* set = sets + (round++ & 1) * St::kSet;
+            nn_stage_rows<H> (set, lane, hs[NH]);
+            *reinterpret_cast<float4*> (set + 2 * St::kMat + lane * 4) = make_float4 (s.x, s.y, 0.0f, 0.0f);
+            accS = addv (accS, s);
+            __syncwarp ();
+            nn_column_pass<H> (set, set + 2 * St::kMat, lane, [&] (f2 h, float4 sc) { accOut = fmav (h, f2 { sc.x, sc.y }, accOut); });
+        }
 #pragma unroll
         for (int i = 0; i < H; ++i)
         {
-            if (PHASE != 1)
-                acc[(wofs + i) * 32 + lane] += s.x * hs[NH][i].x + s.y * hs[NH][i].y;
             const f2 hh = hs[NH][i];
-            d[i] = mulv (bc (f2 {}, wout[i]), fmav (negv (hh), hh, bc (f2 {}, 1.0f)));
+            d[i] = mulv (bc (f2 {}, swl[kOut + i]), fmav (negv (hh), hh, bc (f2 {}, 1.0f)));
         }
-        if (PHASE != 1)
-            acc[(wofs + H) * 32 + lane] += s.x + s.y;
         // hidden layers, last to first
 #pragma unroll
         for (int l = NH - 1; l >= 0; --l)
         {
-            wofs = 3 * H + l * (H * H + H);
-            f2 sd[H], dp[H];
-#pragma unroll
-            for (int j = 0; j < H; ++j)
+            const int wofs = 3 * H + l * kHid;
+            if (PHASE == 1)
+                __syncwarp (); // scheduling fence: keeps this layer's weight loads from being issued layers ahead (register pressure)
+            if (PHASE != 1)
             {
-                sd[j] = mulv (s, d[j]);
-                if (PHASE != 1)
-                    acc[(wofs + H * H + j) * 32 + lane] += sd[j].x + sd[j].y; // bias
+                float* set = sets + (round++ & 1) * St::kSet;
+                f2 sd[H];
+#pragma unroll
+                for (int j = 0; j < H; ++j)
+                    sd[j] = mulv (s, d[j]);
+                nn_stage_rows<H> (set, lane, hs[l]);
+                nn_stage_rows<H> (set + St::kMat, lane, sd);
+                __syncwarp ();
+                nn_tile_pass<H> (set, set + St::kMat, lane, accT[l]);
+                nn_column_pass<H> (set + St::kMat, set + 2 * St::kMat, lane, [&] (f2 v, float4) { accB[l] = addv (accB[l], v); });
             }
+            f2 dp[H];
 #pragma unroll
             for (int i = 0; i < H; ++i)
             {
@@ -395,15 +516,11 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
 #pragma unroll
                 for (int j = 0; j < H; j += 4)
                 {
-                    const float4 w4 = *reinterpret_cast<const float4*> (sw + wofs + i * H + j);
-                    const float ws[4] = { w4.x, w4.y, w4.z, w4.w };
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                    {
-                        sum = fmav (bc (f2 {}, ws[q]), d[j + q], sum);
-                        if (PHASE != 1)
-                            acc[(wofs + i * H + j + q) * 32 + lane] += hs[l][i].x * sd[j + q].x + hs[l][i].y * sd[j + q].y;
-                    }
+                    const float4 w4 = *reinterpret_cast<const float4*> (swl + wofs + i * H + j);
+                    sum = fmav (bc (f2 {}, w4.x), d[j], sum);
+                    sum = fmav (bc (f2 {}, w4.y), d[j + 1], sum);
+                    sum = fmav (bc (f2 {}, w4.z), d[j + 2], sum);
+                    sum = fmav (bc (f2 {}, w4.w), d[j + 3], sum);
                 }
                 const f2 hh = hs[l][i];
                 dp[i] = mulv (sum, fmav (negv (hh), hh, bc (f2 {}, 1.0f)));
@@ -412,31 +529,85 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
             for (int i = 0; i < H; ++i)
                 d[i] = dp[i];
         }
-        // input layer 2 -> H
+        // input layer 2 -> H: dW = (a, ln Rp) (x) s d, db = s d
+        if (PHASE != 1)
+        {
+            float* set = sets + (round++ & 1) * St::kSet;
+            f2 sd[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j)
+                sd[j] = mulv (s, d[j]);
+            nn_stage_rows<H> (set + St::kMat, lane, sd);
+            *reinterpret_cast<float4*> (set + 2 * St::kMat + lane * 4) = make_float4 (a.x, a.y, lr.x, lr.y);
+            __syncwarp ();
+            nn_column_pass<H> (set + St::kMat, set + 2 * St::kMat, lane, [&] (f2 v, float4 sc) {
+                accIn[0] = fmav (v, f2 { sc.x, sc.y }, accIn[0]);
+                accIn[1] = fmav (v, f2 { sc.z, sc.w }, accIn[1]);
+                accIn[2] = addv (accIn[2], v);
+            });
+        }
         f2 dNda = bc (f2 {}, 0.0f);
 #pragma unroll
         for (int j = 0; j < H; ++j)
-        {
-            const f2 sd = mulv (s, d[j]);
-            if (PHASE != 1)
-            {
-                acc[j * 32 + lane] += a.x * sd.x + a.y * sd.y;
-                acc[(H + j) * 32 + lane] += lr.x * sd.x + lr.y * sd.y;
-                acc[(2 * H + j) * 32 + lane] += sd.x + sd.y;
-            }
-            dNda = fmav (bc (f2 {}, sw[j]), d[j], dNda);
-        }
+            dNda = fmav (bc (f2 {}, swl[j]), d[j], dNda);
         // ---- state recurrence: A = (1 - gamma) f'(a) - gamma, f' = -dN/da ---------------------------
         const f2 omg = addv (bc (f2 {}, 1.0f), negv (gamma));
         const f2 A = addv (mulv (omg, negv (dNda)), negv (gamma));
-        G = last_plugin ? gy : fmav (G, A, PY ? mulv (bc (f2 {}, 0.5f), gy) : gy);
-        if (PHASE == 1)
-            Gh = last_plugin ? f2 { 0.0f, 0.0f } : mulv (Gh, A);
-        zn = z;
-        if ((n & 63) == 0)
+        if (act)
+        {
+            G = last_plugin ? gy : fmav (G, A, PY ? mulv (bc (f2 {}, 0.5f), gy) : gy);
+            if (PHASE == 1)
+                Gh = last_plugin ? f2 { 0.0f, 0.0f } : mulv (Gh, A);
+            zn = z;
+        }
+        cur = nxt;
+        if ((m & (kNnSeg - 1)) == kNnSeg - 1 || m == len - 1)
         {
             sse += (double) sse_f, st2 += (double) st2_f;
             sse_f = st2_f = 0.0f;
+            if (PHASE != 1)
+            { // fold the fp32 register accumulators into the warp's fp64 vector: lanes sharing an entry take turns in a fixed order
+                __syncwarp ();
+                for (int gsel = 0; gsel < St::kRep; ++gsel)
+                {
+                    if (grpT == gsel)
+#pragma unroll
+                        for (int l = 0; l < NH; ++l)
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                red[3 * H + l * kHid + (2 * ti + (k >> 2)) * H + 4 * tj + (k & 3)] += (double) (accT[l][k].x + accT[l][k].y);
+                    __syncwarp ();
+                }
+                for (int gsel = 0; gsel < St::kRepV; ++gsel)
+                {
+                    if (grpV == gsel)
+                    {
+#pragma unroll
+                        for (int l = 0; l < NH; ++l)
+                            red[3 * H + l * kHid + H * H + jv] += (double) (accB[l].x + accB[l].y);
+                        red[jv] += (double) (accIn[0].x + accIn[0].y);
+                        red[H + jv] += (double) (accIn[1].x + accIn[1].y);
+                        red[2 * H + jv] += (double) (accIn[2].x + accIn[2].y);
+                        red[kOut + jv] += (double) (accOut.x + accOut.y);
+                    }
+                    __syncwarp ();
+                }
+                float so = accS.x + accS.y;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    so += __shfl_xor_sync (0xffffffffu, so, o);
+                if (lane == 0)
+                    red[kOut + H] += (double) so;
+#pragma unroll
+                for (int l = 0; l < NH; ++l)
+                {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        accT[l][k] = f2 { 0.0f, 0.0f };
+                    accB[l] = f2 { 0.0f, 0.0f };
+                }
+                accIn[0] = accIn[1] = accIn[2] = accOut = accS = f2 { 0.0f, 0.0f };
+            }
         }
     }
     if (PHASE == 1)
@@ -446,15 +617,10 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
         return;
     }
     __syncwarp ();
-    // ---- per-warp reduction in a fixed order, one fp64 partial vector per warp ----------------------
+    // ---- one fp64 partial vector per warp ----------------------------------------------------------
     double* out = partials + (int64_t) blockIdx.x * (n_weights + 8);
     for (int w = lane; w < n_weights; w += 32)
-    {
-        double sum = 0.0;
-        for (int k = 0; k < 32; ++k)
-            sum += (double) acc[w * 32 + ((k + lane) & 31)]; // skewed: conflict-free; the order is fixed per (w, lane)
-        out[w] = sum;
-    }
+        out[w] = red[w];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
     {
@@ -595,7 +761,9 @@ cudaError_t launch_nn_adjoint (int hidden, int n_hidden, bool pyorder, bool targ
 {
     const int64_t pairs = (B + 1) / 2;
     const unsigned grid = (unsigned) nn_adjoint_ctas (B, K);
-    const size_t smem_w = (size_t) ((n_weights + 3) / 4 * 4) * sizeof (float), smem = smem_w + (size_t) n_weights * 32 * sizeof (float);
+    const size_t smem_w = (size_t) ((n_weights + 3) / 4 * 4) * sizeof (float);
+    // + two staging sets (activations, scaled deltas, per-sample scalars) + the warp's fp64 sums
+    const size_t smem = smem_w + (size_t) 2 * (2 * 32 * (2 * hidden + 4) + 32 * 4) * sizeof (float) + (size_t) n_weights * sizeof (double);
     float4* pq = reinterpret_cast<float4*> (scratch);
     f2* gin = scratch != nullptr ? reinterpret_cast<f2*> (pq + pairs * K) : nullptr;
     auto go = [&] (auto full, auto phase1, auto phase2) -> cudaError_t {

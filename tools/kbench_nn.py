@@ -15,10 +15,13 @@ ap.add_argument("--T", type=int, default=4096)
 ap.add_argument("--models", default="2x4,2x8,2x16,4x4,4x8")
 ap.add_argument("--r", action="store_true")
 ap.add_argument("--cpu-rows", type=int, default=64)
+ap.add_argument("--opt", type=int, default=0, help="dwdf_set_option bits (8: no time-parallel kernels, 16: force them)")
 a = ap.parse_args()
 dwdf = importlib.import_module("differentiable-wdfs_b200")
 nnv = np.load(os.path.join(ROOT, "tests", "golden", "nn_vectors.npz"))
 dev = torch.device("cuda", 0)
+if a.opt:
+    dwdf.set_option(a.opt)
 bench.T = a.T
 x = synth_inputs(torch, a.B, 1, dev)
 r = torch.full_like(x, 47000.0) if a.r else None
