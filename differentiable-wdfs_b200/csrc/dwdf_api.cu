@@ -34,7 +34,37 @@ namespace
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches { 0 };
 std::atomic<int> g_use_tma { 1 };
-int* g_redone = nullptr; // device counter: chunks the time-parallel forward had to recompute (diagnostics)
+std::atomic<int*> g_redone { nullptr }; // device counter: chunks the time-parallel forward had to recompute (diagnostics)
+
+// allocated on first use, once per process (one process drives one GPU); nullptr if the allocation failed — the kernels skip the count then
+int* redone_counter ()
+{
+    static int* const counter = [] {
+        int* p = nullptr;
+        if (cudaMalloc ((void**) &p, sizeof (int)) != cudaSuccess || cudaMemset (p, 0, sizeof (int)) != cudaSuccess)
+            p = nullptr;
+        g_redone.store (p);
+        return p;
+    }();
+    return counter;
+}
+
+// stream-ordered scratch that is released on every way out of the calling function
+struct AsyncScratch
+{
+    float* p = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaError_t alloc (size_t bytes, cudaStream_t s)
+    {
+        stream = s;
+        return cudaMallocAsync ((void**) &p, bytes, s);
+    }
+    ~AsyncScratch ()
+    {
+        if (p != nullptr)
+            cudaFreeAsync (p, stream);
+    }
+};
 
 int fail (int code, const char* fmt, ...)
 {
@@ -123,7 +153,7 @@ int dwdf_set_tma (int enable) { return g_use_tma.exchange (enable ? 1 : 0); }
 int64_t dwdf_time_parallel_redone (void)
 {
     int v = 0;
-    if (g_redone != nullptr && cudaMemcpy (&v, g_redone, sizeof (int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (g_redone.load () != nullptr && cudaMemcpy (&v, g_redone.load (), sizeof (int), cudaMemcpyDeviceToHost) != cudaSuccess)
         return -1;
     return v;
 }
@@ -317,18 +347,14 @@ int dwdf_forward_neural (const dwdf_program* prog, const float* params, const fl
         return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
     // few sequences, long ones: time-parallel (one lane per pair and 256-sample chunk; clipper_kernels.cu explains the scheme)
     int K = 1;
-    float* scratch = nullptr;
+    AsyncScratch scratch;
     if (! (g_clip_opts & kOptNoChunks) && (B <= kNnChunkedMaxB || (g_clip_opts & kOptForceChunks)) && T >= 2 * kTimeChunk)
     {
         K = nn_time_chunks (T);
-        DWDF_CUDA (cudaMallocAsync ((void**) &scratch, (size_t) 4 * ((B + 1) / 2) * K * sizeof (float), (cudaStream_t) stream));
-        if (g_redone == nullptr && cudaMalloc ((void**) &g_redone, sizeof (int)) == cudaSuccess)
-            cudaMemset (g_redone, 0, sizeof (int));
+        DWDF_CUDA (scratch.alloc ((size_t) 4 * ((B + 1) / 2) * K * sizeof (float), (cudaStream_t) stream));
     }
     DWDF_CUDA (launch_nn_forward (prog->mlp.hidden, prog->mlp.n_hidden, prog->desc.ordering == DWDF_ORDER_PYTHON, x, r, y, params, prog->nodes[0].param, prog->nodes[1].param, prog->desc.fs, weights,
-                                  (int) dwdf_mlp_weight_count (&prog->mlp), state, z_ckpt, B, T, K, scratch, g_redone, (cudaStream_t) stream));
-    if (scratch != nullptr)
-        DWDF_CUDA (cudaFreeAsync (scratch, (cudaStream_t) stream));
+                                  (int) dwdf_mlp_weight_count (&prog->mlp), state, z_ckpt, B, T, K, scratch.p, K > 1 ? redone_counter () : nullptr, (cudaStream_t) stream));
     g_launches.fetch_add (K > 1 ? 2 : 1);
     return DWDF_OK;
 }
@@ -434,25 +460,20 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
         ClipTmaMaps maps;
         const bool tma = tma_usable (x, y, nullptr, B, T) && make_map (&maps.x, x, B, T, 32) && make_map (&maps.y, y, B, T, 32);
         // approx root, symmetric pair, more than one warp's worth of sequences: two sequences per lane (packed fp32x2)
-        float* scratch = nullptr;
+        AsyncScratch scratch;
         const int K = (T % 4 == 0 && ((uintptr_t) x & 15u) == 0 && ((uintptr_t) y & 15u) == 0) ? time_chunks (B, T, kChunkedForwardMaxB) : 0;
         if (K > 1)
         {
-            DWDF_CUDA (cudaMallocAsync ((void**) &scratch, (size_t) 2 * B * K * sizeof (float), stream));
-            if (g_redone == nullptr && cudaMalloc ((void**) &g_redone, sizeof (int)) == cudaSuccess)
-                cudaMemset (g_redone, 0, sizeof (int));
-            maps.redone = g_redone;
+            DWDF_CUDA (scratch.alloc ((size_t) 2 * B * K * sizeof (float), stream));
+            maps.redone = redone_counter ();
             maps.chunks = K;
-            maps.zs = scratch;
-            maps.ze = scratch + (size_t) B * K;
+            maps.zs = scratch.p;
+            maps.ze = scratch.p + (size_t) B * K;
         }
         maps.pair = tma && prog->variant.mode == kModeApprox && ! prog->variant.general && B > 32 && ! (g_clip_opts & kOptNoPair) && make_map (&maps.x2, x, B, T, 32, 64) && make_map (&maps.y2, y, B, T, 32, 64);
         DWDF_CUDA (launch_clipper_forward (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, state, B, T, stream));
-        if (scratch != nullptr)
-        {
-            DWDF_CUDA (cudaFreeAsync (scratch, stream));
+        if (K > 1)
             g_launches.fetch_add (1);
-        }
     }
     else
     {
