@@ -217,6 +217,14 @@ def other_paths(torch, dwdf, device, x, target):
                 xs, ts = x[:b].contiguous(), target[:b].contiguous()
                 out[f"neural_root_{name}_forward"] = {"value": xs.numel() / timed(lambda: cn.forward(xs, keep_for_backward=False)), "unit": UNIT, "B": b, "T": T}
                 out[f"neural_root_{name}_fwd_bwd"] = {"value": xs.numel() / timed(lambda: fwd_bwd(cn, xs, ts), reps=2), "unit": UNIT, "B": b, "T": T}
+                if name == "2x16":  # the reference's largest network at the headline batch (one lane per pair of sequences)
+                    out["neural_root_2x16_fwd_bwd_B65536"] = {"value": x.numel() / timed(lambda: fwd_bwd(cn, x, target), reps=2), "unit": UNIT, "B": x.shape[0], "T": T}
+        # the generic tree interpreter on lpf.py's circuit (IdealVoltageSource root, Inverter(Series(R, C)), probe C)
+        R1, C1 = dwdf.Resistor(1000.0, True), dwdf.Capacitor(1.0e-6, FS, True)
+        ct = dwdf.compile_circuit(dwdf.IdealVoltageSource(), tree=dwdf.Inverter(dwdf.Series(R1, C1)), probe=C1, device=device)
+        b = min(8192, x.shape[0])
+        xs, ts = x[:b].contiguous(), target[:b].contiguous()
+        out["tree_interpreter_rc_lowpass_fwd_bwd"] = {"value": xs.numel() / timed(lambda: fwd_bwd(ct, xs, ts), reps=2), "unit": UNIT, "B": b, "T": T}
     except Exception as e:  # the headline line must not depend on these
         out["error"] = repr(e)
     return out
