@@ -214,7 +214,7 @@ constexpr int kPairTileBytes = kPairRows * kFwdTileT * 4; // 8 KB
 constexpr int kPairStages = 3;
 constexpr int kFwdL2Ahead = 3; // tiles the L2 prefetch runs ahead of the shared-memory ring
 
-template <bool PY>
+template <int MODE, bool PY>
 __global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T, int opts)
 {
     __shared__ __align__ (1024) uint8_t smem[kPairStages * kPairTileBytes];
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __gri
     const int64_t rowA = (int64_t) b0 + lane, rowB = rowA + kLanes;
     const bool validA = rowA < B, validB = rowB < B;
     f2 z { (state != nullptr && validA) ? state[rowA] : 0.0f, (state != nullptr && validB) ? state[rowB] : 0.0f };
-    const bool fast = fast_ok (c.pair.L); // warp-uniform (same parameters for every lane)
+    const bool fast = MODE == kModeExact ? exact_fast_ok (c.pair) : fast_ok (c.pair.L); // warp-uniform (same parameters for every lane)
     const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
     if (lane == 0)
     {
@@ -269,14 +269,25 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __gri
                 const float4 va = lds128 (addrA), vb = lds128 (addrB);
                 float4 oa, ob;
                 if (fast)
-                    forward_chunk2<PY> (c, va, vb, z, oa, ob);
+                {
+                    if (MODE == kModeExact)
+                    {
+                        const f2 xs[4] = { { va.x, vb.x }, { va.y, vb.y }, { va.z, vb.z }, { va.w, vb.w } };
+                        f2 o[4];
+                        clip_chunk_exact2<PY> (c, xs, z, o);
+                        oa = make_float4 (o[0].x, o[1].x, o[2].x, o[3].x);
+                        ob = make_float4 (o[0].y, o[1].y, o[2].y, o[3].y);
+                    }
+                    else
+                        forward_chunk2<PY> (c, va, vb, z, oa, ob);
+                }
                 else
-                { // parameters outside the fast path's range: the general step, one instance after the other
+                { // parameters outside the packed path's range: the general step, one instance after the other
                     const float xa[4] = { va.x, va.y, va.z, va.w }, xb[4] = { vb.x, vb.y, vb.z, vb.w };
                     float os[4];
-                    clip_chunk_general<PY> (c, xa, z.x, os);
+                    clip_chunk_any<MODE, PY> (c, xa, z.x, os);
                     oa = make_float4 (os[0], os[1], os[2], os[3]);
-                    clip_chunk_general<PY> (c, xb, z.y, os);
+                    clip_chunk_any<MODE, PY> (c, xb, z.y, os);
                     ob = make_float4 (os[0], os[1], os[2], os[3]);
                 }
                 sts128 (addrA, oa);
@@ -459,7 +470,7 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
 // (approx root, symmetric pair, fast-path parameters) on pairs of consecutive samples in packed fp32x2:
 // 8 pair-steps of clip_step_recoverv<f2> instead of 16 scalar ones; only the state reconstruction
 // (one FMA per sample) and the adjoint recurrence (two FMAs per sample) run per element.
-template <bool PY, bool TARGET, class IO>
+template <int MODE, bool PY, bool TARGET, class IO>
 __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& io, float z0, float zend, float& G, AdjAcc& acc)
 {
     constexpr int NP = kSeg / 2;
@@ -508,7 +519,7 @@ __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& i
             const f2 x2 = h ? f2 { xv.z, xv.w } : f2 { xv.x, xv.y };
             const f2 g2 = h ? f2 { gv.z, gv.w } : f2 { gv.x, gv.y };
             StepTapeV<f2> tp;
-            clip_step_recoverv<f2> (c, x2, z2[p], zn2[p], tp);
+            clip_step_recoverv<f2, MODE> (c, x2, z2[p], zn2[p], tp);
             f2 gy = g2;
             if (TARGET)
             {
@@ -553,8 +564,8 @@ __device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, flo
 {
     if (nvalid == kSeg && n0 >= skip && (PY || last >= kSeg))
     {
-        if (MODE == kModeApprox && ! GENERAL && LSMALL && ! WANT_GX)
-            adjoint_segment_pairs<PY, TARGET> (c, io, z0, zend, G, acc);
+        if ((MODE == kModeApprox || MODE == kModeExact) && ! GENERAL && LSMALL && ! WANT_GX)
+            adjoint_segment_pairs<MODE, PY, TARGET> (c, io, z0, zend, G, acc);
         else
             adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, true> (c, io, z0, zend, G, acc, n0, nvalid, skip, last);
     }
@@ -1198,11 +1209,11 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
             clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, K, maps->redone);
             return;
         }
-        if constexpr (kM == kModeApprox && ! kG)
+        if constexpr ((kM == kModeApprox || kM == kModeExact) && ! kG)
         {
             if (use_tma && maps->pair)
             {
-                clipper_forward_pair_tma<p><<<(unsigned) ((B + kPairRows - 1) / kPairRows), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, B, (int) T, g_clip_opts);
+                clipper_forward_pair_tma<kM, p><<<(unsigned) ((B + kPairRows - 1) / kPairRows), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, B, (int) T, g_clip_opts);
                 return;
             }
         }

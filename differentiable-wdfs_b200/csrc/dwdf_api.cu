@@ -470,7 +470,7 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
             maps.zs = scratch.p;
             maps.ze = scratch.p + (size_t) B * K;
         }
-        maps.pair = tma && prog->variant.mode == kModeApprox && ! prog->variant.general && B > 32 && ! (g_clip_opts & kOptNoPair) && make_map (&maps.x2, x, B, T, 32, 64) && make_map (&maps.y2, y, B, T, 32, 64);
+        maps.pair = tma && (prog->variant.mode == kModeApprox || prog->variant.mode == kModeExact) && ! prog->variant.general && B > 32 && ! (g_clip_opts & kOptNoPair) && make_map (&maps.x2, x, B, T, 32, 64) && make_map (&maps.y2, y, B, T, 32, 64);
         DWDF_CUDA (launch_clipper_forward (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, state, B, T, stream));
         if (K > 1)
             g_launches.fetch_add (1);

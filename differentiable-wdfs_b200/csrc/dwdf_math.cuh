@@ -445,7 +445,9 @@ DWDF_HD void clip_setup (ClipConst& c, const ClipDesc& d, float R, float C, floa
 //   down-sweep z' = b + b_temp  (Capacitor.incident, tf_wdf.py:120-122,179-183)
 //   probe      voltage(C): python ordering (z' + z)/2, plugin ordering z
 template <int MODE, bool GENERAL, bool LSMALL, bool PYORDER>
-DWDF_HD float clip_step (const ClipConst& c, float x, float& z)
+DWDF_HD float clip_step (const ClipConst& c, float x, float& z); // defined at the end: dispatches the exact root's common case to clip_step_exactv<f1>
+template <int MODE, bool GENERAL, bool LSMALL, bool PYORDER>
+DWDF_HD float clip_step_scalar (const ClipConst& c, float x, float& z)
 {
     const float t = -c.gamma * (z - x);
     const float a = z + t;
@@ -488,8 +490,8 @@ struct f2
 DWDF_HD f1 bc (f1, float a) { return f1 { a }; }
 DWDF_HD f2 bc (f2, float a) { return f2 { a, a }; }
 DWDF_HD f1 fmav (f1 a, f1 b, f1 c) { return f1 { fma_ (a.x, b.x, c.x) }; }
-DWDF_HD f1 addv (f1 a, f1 b) { return f1 { a.x + b.x }; }
-DWDF_HD f1 mulv (f1 a, f1 b) { return f1 { a.x * b.x }; }
+DWDF_HD f1 addv (f1 a, f1 b) { return f1 { add_ (a.x, b.x) }; } // (never contracted into an fma: the packed forms are not either)
+DWDF_HD f1 mulv (f1 a, f1 b) { return f1 { mul_ (a.x, b.x) }; }
 DWDF_HD f1 addv_rd (f1 a, f1 b) { return f1 { add_rd (a.x, b.x) }; }
 #if defined(__CUDA_ARCH__)
 DWDF_HD float2 as_float2 (f2 a) { return make_float2 (a.x, a.y); }
@@ -681,7 +683,107 @@ DWDF_HD f1 select_below (f1 lo, f1 hi, f1 u, float thr) { return f1 { u.x < thr 
 DWDF_HD f2 select_below (f2 lo, f2 hi, f2 u, float thr) { return f2 { u.x < thr ? lo.x : hi.x, u.y < thr ? lo.y : hi.y }; }
 DWDF_HD f1 clamp_exp_arg (f1 a) { return f1 { fmaxf (a.x, -126.0f) }; }
 DWDF_HD f2 clamp_exp_arg (f2 a) { return f2 { fmaxf (a.x, -126.0f), fmaxf (a.y, -126.0f) }; }
+// The packed intrinsics (__fmul2_rn, __fadd2_rn) ARE contracted into FFMA2 by the compiler where a product feeds a sum
+// (the scalar __fmul_rn / __fadd_rn never are), so V-form code that must agree bit for bit between V = f1 and V = f2
+// spells every fused multiply-add out as fmav and never adds a bare product; where a product must be subtracted
+// unfused (omega(x0) - omega(x1), which has to cancel exactly at a == 0), opaque() hides it from the optimiser.
+DWDF_HD f1 opaque (f1 a)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile ("" : "+f"(a.x));
+#endif
+    return a;
+}
+DWDF_HD f2 opaque (f2 a)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile ("" : "+f"(a.x), "+f"(a.y));
+#endif
+    return a;
+}
+DWDF_HD f1 minv (f1 a, float b) { return f1 { fminf (a.x, b) }; }
+DWDF_HD f2 minv (f2 a, float b) { return f2 { fminf (a.x, b), fminf (a.y, b) }; }
+DWDF_HD f1 ex2v (f1 a) { return f1 { ex2_ (a.x) }; }
+DWDF_HD f2 ex2v (f2 a) { return f2 { ex2_ (a.x), ex2_ (a.y) }; }
+// exp_nonpos / omega_exact_low over V: the same operations in the same order
 template <class V>
+DWDF_HD V exp_nonposv (V x)
+{
+    const V kHi = bc (V {}, 1.44269502162933349609375f);
+    const V t = mulv (x, kHi);
+    const V lo = fmav (x, bc (V {}, 1.925963033500011e-8f), fmav (x, kHi, negv (t)));
+    const V e0 = ex2v (t);
+    return fmav (e0, mulv (bc (V {}, 0.693147180559945f), lo), e0);
+}
+template <class V>
+DWDF_HD V omega_exact_lowv (V x)
+{
+    const V E = exp_nonposv (minv (x, 0.0f));
+    const V Ec = minv (E, 0.1353352832f);
+    const V s = fmav (Ec, fmav (Ec, fmav (Ec, fmav (Ec, bc (V {}, 5.2083333333333333f), bc (V {}, -2.6666666666666667f)), bc (V {}, 1.5f)), bc (V {}, -1.0f)), bc (V {}, 1.0f));
+    const V ex = ex2v (mulv (bc (V {}, -1.442695040888963f), mulv (Ec, s)));
+    return mulv (E, fmav (negv (addv (s, negv (ex))), rcpv (fmav (Ec, ex, bc (V {}, 1.0f))), s));
+}
+
+DWDF_HD f1 lg2v (f1 a) { return f1 { lg2_ (a.x) }; }
+DWDF_HD f2 lg2v (f2 a) { return f2 { lg2_ (a.x), lg2_ (a.y) }; }
+DWDF_HD f1 select_le (f1 u, float thr, f1 lo, f1 hi) { return f1 { u.x <= thr ? lo.x : hi.x }; }
+DWDF_HD f2 select_le (f2 u, float thr, f2 lo, f2 hi) { return f2 { u.x <= thr ? lo.x : hi.x, u.y <= thr ? lo.y : hi.y }; }
+constexpr float kLn2f = 0.693147180559945f;
+template <class V>
+DWDF_HD V fsc_stepv (V w, V r)
+{
+    const V wp1 = addv (w, bc (V {}, 1.0f));
+    const V w2 = mulv (bc (V {}, 2.0f), wp1), f = fmav (bc (V {}, 0.66666666666666667f), r, wp1);
+    const V q = mulv (w2, f), qmr = fmav (w2, f, negv (r)); // q and q - r
+    const V e = mulv (mulv (r, qmr), rcpv (mulv (wp1, fmav (bc (V {}, -2.0f), r, q))));
+    return fmav (w, e, w);
+}
+// omega_exact with one FSC iteration (n_iter == 1, the default) over V: every kernel's exact-root forward step goes
+// through this one function (V = f1: one sequence per lane, V = f2: two), so they agree bit for bit per sequence.
+template <class V>
+DWDF_HD V omega_exact1v (V x)
+{
+    const V one = bc (V {}, 1.0f);
+    const V w_lo = omega_exact_lowv (x);
+    // -2 < x <= 1 + pi
+    const V p = addv (x, bc (V {}, -1.0f));
+    const V ser = fmav (p, fmav (p, fmav (p, bc (V {}, 2.1158854166666667e-4f), bc (V {}, -3.2552083333333333e-4f)), bc (V {}, -5.2083333333333333e-3f)), bc (V {}, 0.0625f));
+    const V w_mid = fmav (mulv (p, p), ser, fmav (bc (V {}, 0.5f), x, bc (V {}, 0.5f)));
+    // x > 1 + pi
+    const V xc = maxv (x, one);
+    const V l2 = lg2v (xc);
+    const V l = mulv (bc (V {}, kLn2f), l2);
+    const V it = rcpv (xc);
+    const V li = mulv (l, it);
+    const V inner = fmav (it, fmav (l, fmav (l, bc (V {}, 0.33333333333333333f), bc (V {}, -1.5f)), one), fmav (bc (V {}, 0.5f), l, bc (V {}, -1.0f)));
+    const V w_hi = fmav (li, fmav (it, inner, one), fmav (bc (V {}, -kLn2f), l2, xc));
+    V w = maxv (select_le (x, 4.141592653589793f, w_mid, w_hi), bc (V {}, 0.05f)); // (the floor only ever acts on elements that end up taking w_lo)
+    w = fsc_stepv (w, fmav (bc (V {}, -kLn2f), lg2v (w), addv (x, negv (w)))); // residual (x - w) - ln w
+    return select_le (x, -2.0f, w_lo, w);
+}
+DWDF_HD bool exact_fast_ok (const PairConst& c) { return rev_small_ok (c) && c.n_iter == 1; }
+// One sample of the clipper with the exact root and the symmetric pair (clip_step's equations), exact_fast_ok parameters.
+template <class V, bool PYORDER>
+DWDF_HD V clip_step_exactv (const ClipConst& c, V x, V& z)
+{
+    const PairConst& p = c.pair;
+    const V xz = addv (x, negv (z));
+    const V a = fmav (bc (V {}, c.gamma), xz, z); // the adaptor's own form (see clip_step_fastv)
+    const V aa = absv (a);
+    const V w0 = opaque (omega_exact1v (fmav (aa, bc (V {}, p.invV), bc (V {}, p.L))));
+    const V w1 = opaque (omega_exact_lowv (fmav (aa, bc (V {}, -p.invV), bc (V {}, p.L))));
+    // a == 0 makes both branches the same computation (L <= -2: both take omega_exact_low(L)), w0 - w1 == 0 and b == a
+    const V b = fmav (bc (V {}, -p.twoV), xor_signv (addv (w0, negv (w1)), a), a);
+    const V zn = fmav (bc (V {}, c.gamma), xz, b);
+    const V y = PYORDER ? mulv (bc (V {}, 0.5f), addv (zn, z)) : z;
+    z = zn;
+    return y;
+}
+
+// MODE kModeApprox: fast-path parameters (lsmall_ok(L)); kModeExact: rev_small_ok (the reverse-biased argument stays
+// in TOMS-917's x <= -2 region, and so does the forward-biased one wherever it is evaluated directly)
+template <class V, int MODE = kModeApprox>
 DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V>& tp)
 {
     const PairConst& p = c.pair;
@@ -689,12 +791,23 @@ DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V
     const V a = fmav (bc (V {}, c.gamma), xz, z);
     const V b = fmav (bc (V {}, -c.gamma), xz, zn);
     const V aa = absv (a);
-    const V w1 = exp_approx_scaledv (clamp_exp_arg (fmav (aa, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e))));
     const V d = addv (a, negv (b));
-    V w0 = fmav (xor_signv (d, a), bc (V {}, p.inv2V), w1); // mu0 w0 = mu1 w1 + lambda (a - b) / (2 V)
-    // diode still off (u0 < kOmega3Zero): omega4 = exp_approx there, taken directly (see clip_step_recover)
-    const V us = fmav (aa, bc (V {}, p.invVl2e), bc (V {}, p.Ll2e));
-    w0 = select_below (exp_approx_scaledv (clamp_exp_arg (us)), w0, us, kOmega3Zero * kLog2e);
+    V w0, w1;
+    if (MODE == kModeExact)
+    {
+        w1 = omega_exact_lowv (fmav (aa, bc (V {}, -p.invV), bc (V {}, p.L)));
+        w0 = fmav (xor_signv (d, a), bc (V {}, p.inv2V), w1); // mu0 w0 = mu1 w1 + lambda (a - b) / (2 V)
+        const V u0 = fmav (aa, bc (V {}, p.invV), bc (V {}, p.L));
+        w0 = select_below (omega_exact_lowv (u0), w0, u0, -2.0f); // diode still off: evaluated directly (see clip_step_recover)
+    }
+    else
+    {
+        w1 = exp_approx_scaledv (clamp_exp_arg (fmav (aa, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e))));
+        w0 = fmav (xor_signv (d, a), bc (V {}, p.inv2V), w1);
+        // diode still off (u0 < kOmega3Zero): omega4 = exp_approx there, taken directly (see clip_step_recover)
+        const V us = fmav (aa, bc (V {}, p.invVl2e), bc (V {}, p.Ll2e));
+        w0 = select_below (exp_approx_scaledv (clamp_exp_arg (us)), w0, us, kOmega3Zero * kLog2e);
+    }
     const V wp0 = mulv (w0, rcpv (addv (w0, bc (V {}, 1.0f))));
     const V wp1 = mulv (w1, rcpv (addv (w1, bc (V {}, 1.0f))));
     const V S1 = addv (wp0, wp1);
@@ -707,6 +820,21 @@ DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V
     tp.cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, mulv (bc (V {}, -2.0f), ww));
 }
 
+// The forward step every kernel calls. Exact root, symmetric pair, rev_small_ok parameters, one FSC iteration: the
+// V-form step (so that the packed two-sequences-per-lane kernel and the one-per-lane kernels agree bit for bit).
+template <int MODE, bool GENERAL, bool LSMALL, bool PYORDER>
+DWDF_HD float clip_step (const ClipConst& c, float x, float& z)
+{
+    if (MODE == kModeExact && ! GENERAL && LSMALL && c.pair.n_iter == 1)
+    {
+        f1 zz { z };
+        const f1 y = clip_step_exactv<f1, PYORDER> (c, f1 { x }, zz);
+        z = zz.x;
+        return y.x;
+    }
+    return clip_step_scalar<MODE, GENERAL, LSMALL, PYORDER> (c, x, z);
+}
+
 template <bool PY>
 DWDF_HD void clip_chunk_general (const ClipConst& c, const float (&x)[4], float& z, float (&o)[4])
 {
@@ -714,6 +842,25 @@ DWDF_HD void clip_chunk_general (const ClipConst& c, const float (&x)[4], float&
     o[1] = clip_step<kModeApprox, false, false, PY> (c, x[1], z);
     o[2] = clip_step<kModeApprox, false, false, PY> (c, x[2], z);
     o[3] = clip_step<kModeApprox, false, false, PY> (c, x[3], z);
+}
+
+// four samples of two sequences, exact root (exact_fast_ok parameters)
+template <bool PY>
+DWDF_HD void clip_chunk_exact2 (const ClipConst& c, const f2 (&x)[4], f2& z, f2 (&o)[4])
+{
+    o[0] = clip_step_exactv<f2, PY> (c, x[0], z);
+    o[1] = clip_step_exactv<f2, PY> (c, x[1], z);
+    o[2] = clip_step_exactv<f2, PY> (c, x[2], z);
+    o[3] = clip_step_exactv<f2, PY> (c, x[3], z);
+}
+// four samples of one sequence the general way, any root mode (parameters outside the packed paths' range)
+template <int MODE, bool PY>
+DWDF_HD void clip_chunk_any (const ClipConst& c, const float (&x)[4], float& z, float (&o)[4])
+{
+    o[0] = clip_step<MODE, false, false, PY> (c, x[0], z);
+    o[1] = clip_step<MODE, false, false, PY> (c, x[1], z);
+    o[2] = clip_step<MODE, false, false, PY> (c, x[2], z);
+    o[3] = clip_step<MODE, false, false, PY> (c, x[3], z);
 }
 
 } // namespace dwdf

@@ -259,6 +259,39 @@ extern "C" int hm_clipper_fast (int pairs, int pyorder, float fs, float R, float
 
 // clip_step_recoverv<f2> (the adjoint kernel's packed pair step) against the scalar clip_step_recover on
 // the same (x, z, z') triples: out[8 i ...] = { A, cg, cl, cv } packed, then scalar.
+template <int MODE>
+static void recover_pairs_run (const ClipConst& c, const float* x, const float* z, const float* zn, float* out, int64_t n)
+{
+    for (int64_t i = 0; i + 1 < n; i += 2)
+    {
+        StepTapeV<f2> tp;
+        clip_step_recoverv<f2, MODE> (c, f2 { x[i], x[i + 1] }, f2 { z[i], z[i + 1] }, f2 { zn[i], zn[i + 1] }, tp);
+        const float pk[2][4] = { { tp.A.x, tp.cg.x, tp.cl.x, tp.cv.x }, { tp.A.y, tp.cg.y, tp.cl.y, tp.cv.y } };
+        for (int k = 0; k < 2; ++k)
+        {
+            StepTape ts;
+            clip_step_recover<MODE, false, true> (c, x[i + k], z[i + k], zn[i + k], ts);
+            const float sc[4] = { ts.A, ts.cg, ts.cl, ts.cv };
+            for (int j = 0; j < 4; ++j)
+            {
+                out[8 * (i + k) + j] = pk[k][j];
+                out[8 * (i + k) + 4 + j] = sc[j];
+            }
+        }
+    }
+}
+
+extern "C" int hm_recover_pairs_mode (int exact, float fs, float R, float C, float Is, float Vt, float nabla, const float* x, const float* z, const float* zn, float* out, int64_t n)
+{
+    ClipDesc d { fs, Vt, 1.0f, 1.0f, 0.0f, 2, 0, 1, 2, 3 };
+    ClipConst c;
+    clip_setup (c, d, R, C, Is, nabla);
+    if (! rev_small_ok (c.pair))
+        return 1;
+    exact ? recover_pairs_run<kModeExact> (c, x, z, zn, out, n) : recover_pairs_run<kModeApprox> (c, x, z, zn, out, n);
+    return 0;
+}
+
 extern "C" int hm_recover_pairs (float fs, float R, float C, float Is, float Vt, float nabla, const float* x, const float* z, const float* zn, float* out, int64_t n)
 {
     ClipDesc d { fs, Vt, 1.0f, 1.0f, 0.0f, 2, 0, 1, 2, 3 };

@@ -241,6 +241,38 @@ def test_full_size_properties(dwdf, oracle, B, T):
     assert torch.equal(torch.cat(parts, 1), whole)
 
 
+@pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
+def test_exact_root_packed_kernel(dwdf, oracle, ordering, oord):
+    """Exact (TOMS-917) root on the two-sequences-per-lane kernel (packed fp32x2): bit-identical per sequence to the
+    one-sequence-per-lane kernels (the packed intrinsics are contracted by the compiler where the scalar ones are
+    not — the V-form step spells every fma out), silence in gives silence out exactly (the two omegas cancel at
+    a == 0), and parameters outside the packed path's range (more Newton iterations) fall back to the scalar step."""
+    p = ClipperParams()
+    B, T = 96 + 5, 1024
+    x = make_inputs(B, T, seed=41, amp=(0.05, 8.0))
+    xd = dev(x)
+    circ, _ = make_clipper(dwdf, p, "exact", ordering)
+    y = circ.forward(xd, keep_for_backward=False)
+    assert seq_rel_err(y.cpu().numpy(), oracle.clipper_forward(x, p, exact=True, ordering=oord)) < FWD_TOL
+    prev = dwdf.set_tma(False)
+    try:
+        y_direct = circ.forward(xd, keep_for_backward=False)
+    finally:
+        dwdf.set_tma(prev)
+    assert torch.equal(y, y_direct)
+    assert torch.equal(circ.forward(xd[:32].contiguous(), keep_for_backward=False), y[:32])  # one warp's worth: the one-per-lane TMA kernel
+    assert not circ.forward(torch.zeros_like(xd), keep_for_backward=False).any()
+    assert torch.equal(circ.forward((-xd).contiguous(), keep_for_backward=False), -y)
+    circ3, _ = make_clipper(dwdf, p, "exact", ordering, newton_max_iter=3, newton_tol=1e-9)
+    y3 = circ3.forward(xd, keep_for_backward=False)
+    assert seq_rel_err(y3.cpu().numpy(), oracle.clipper_forward(x, p, exact=True, ordering=oord)) < FWD_TOL
+    prev = dwdf.set_tma(False)
+    try:
+        assert torch.equal(circ3.forward(xd, keep_for_backward=False), y3)
+    finally:
+        dwdf.set_tma(prev)
+
+
 def test_more_than_2_31_samples(dwdf, oracle):
     """Maximum sizes: 2.2e9 samples in one call (> 2^31 elements and > 8 GiB per array) — every index on the path is
     64-bit. Forward: first and last rows against the oracle. Adjoint: the target equals the output except on the last

@@ -182,6 +182,21 @@ def test_recover_pairs_equal_scalar(hm):
     assert np.all(np.max(np.abs(out[:, :4] - out[:, 4:]), axis=0) <= 2e-6 * scale)
 
 
+def test_recover_step_on_pairs_exact_root(hm, oracle):
+    """The same for the exact (TOMS-917) root: omega_exact_low over packed pairs against the scalar step."""
+    p = ClipperParams()
+    x = make_inputs(8, 600, seed=12)
+    y = oracle.clipper_forward(x, p, exact=True, ordering=ORDER_PLUGIN)  # plugin ordering: y[n] = z[n]
+    xs, z, zn = x[:, :-1].ravel(), y[:, :-1].ravel(), y[:, 1:].ravel()
+    n = xs.size - xs.size % 2
+    out = np.zeros((n, 8), np.float32)
+    rc = hm.hm_recover_pairs_mode(C.c_int(1), C.c_float(p.fs), C.c_float(p.R), C.c_float(p.C), C.c_float(p.Is), C.c_float(p.Vt), C.c_float(p.nabla), P(np.ascontiguousarray(xs[:n])),
+                                  P(np.ascontiguousarray(z[:n])), P(np.ascontiguousarray(zn[:n])), P(out), C.c_int64(n))
+    assert rc == 0
+    scale = np.max(np.abs(out[:, 4:]), axis=0)
+    assert np.all(np.max(np.abs(out[:, :4] - out[:, 4:]), axis=0) <= 2e-6 * scale)
+
+
 def test_fast_step_long_time_constant(hm, oracle):
     """gamma = 1e-3 (R 866 kOhm against 5.5 nF at 96 kHz: an RC memory of ~500 samples): the fast step must keep
     a = z + gamma (x - z) in the adaptor's own form; (1 - gamma) z + gamma x rounds the pole by half an ulp of one
