@@ -10,7 +10,10 @@ KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.sum', 'sm__inst_executed_pipe_alu.sum', 'sm__inst_executed_pipe_xu.sum',
         'sm__inst_executed_pipe_lsu.sum', 'sm__inst_executed_pipe_fp64.sum', 'smsp__thread_inst_executed.sum', 'sm__sass_thread_inst_executed_op_ffma_pred_on.sum',
         'sm__sass_thread_inst_executed_op_fadd_pred_on.sum', 'sm__sass_thread_inst_executed_op_fmul_pred_on.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-        'lts__t_sector_hit_rate.pct']
+        'lts__t_sector_hit_rate.pct', 'inst_executed', 'thread_inst_executed_true', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed', 'smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed',
+        'smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed', 'sm__sass_thread_inst_executed_op_ffma_pred_on.sum.peak_sustained']
 
 
 def main(path):
