@@ -21,6 +21,18 @@ Vs = dwdf.ResistiveVoltageSource(47000.0); Cc = dwdf.Capacitor(2.2e-9, 48000.0)
 cn = dwdf.compile_circuit(dwdf.DenseRootModel(mj), tree=dwdf.Parallel(Vs, Cc), probe=Cc)
 x = torch.from_numpy((rng.standard_normal((9, 130)) * 0.5).astype(np.float32)).cuda()
 y = cn.forward(x); cn.backward(target=(0.5 * y).contiguous())
+# the staged outer-product adjoint at every tile shape (H = 4, 8, 16; 2 and 4 hidden layers), ragged pairs, several warps,
+# and its time-parallel phases (option 16 forces them)
+for name, B, T in (("2x16", 70, 140), ("4x8", 67, 96), ("2x4", 3, 70), ("4x4", 40, 65)):
+    mjn = dwdf.model_io.json_from_weights(nnv[f"{name}_weights"], [int(v) for v in nnv[f"{name}_sizes"]])
+    Vn = dwdf.ResistiveVoltageSource(47000.0); Cn = dwdf.Capacitor(2.2e-9, 48000.0)
+    cnn = dwdf.compile_circuit(dwdf.DenseRootModel(mjn), tree=dwdf.Parallel(Vn, Cn), probe=Cn)
+    xn = torch.from_numpy((rng.standard_normal((B, T)) * 0.5).astype(np.float32)).cuda()
+    yn = cnn.forward(xn); cnn.backward(target=(0.5 * yn).contiguous(), loss="mse+esr", skip=5)
+prev = dwdf.set_option(16)
+xn = torch.from_numpy((rng.standard_normal((5, 600)) * 0.5).astype(np.float32)).cuda()
+yn = cn.forward(xn); cn.backward(target=(0.5 * yn).contiguous())
+dwdf.set_option(prev)
 R1 = dwdf.Resistor(1000.0, True); C1 = dwdf.Capacitor(1.0e-6, 48000.0, True)
 ct = dwdf.compile_circuit(dwdf.IdealVoltageSource(), tree=dwdf.Inverter(dwdf.Series(R1, C1)), probe=C1)
 y = ct.forward(x); ct.backward(target=(0.5 * y).contiguous())
