@@ -257,6 +257,42 @@ extern "C" int hm_clipper_fast (int pairs, int pyorder, float fs, float R, float
     return 0;
 }
 
+// clip_step_exactv — the exact root's forward sample (V = f2: packed pairs, V = f1: one sequence) — over whole sequences
+template <class V, bool PY>
+static void exactv_run (const ClipConst& c, const float* x, float* y, int64_t B, int64_t T)
+{
+    constexpr int W = sizeof (V) / sizeof (float);
+    for (int64_t s = 0; s < B; s += W)
+    {
+        const int64_t row[2] = { s, s + 1 < B ? s + 1 : s };
+        V z;
+        for (int w = 0; w < W; ++w)
+            ((float*) &z)[w] = 0.0f;
+        for (int64_t n = 0; n < T; ++n)
+        {
+            V xv;
+            for (int w = 0; w < W; ++w)
+                ((float*) &xv)[w] = x[row[w] * T + n];
+            const V o = clip_step_exactv<V, PY> (c, xv, z);
+            for (int w = 0; w < W; ++w)
+                y[row[w] * T + n] = ((const float*) &o)[w];
+        }
+    }
+}
+extern "C" int hm_clipper_exactv (int pairs, int pyorder, float fs, float R, float C, float Is, float Vt, float nabla, const float* x, float* y, int64_t B, int64_t T)
+{
+    ClipDesc d { fs, Vt, 1.0f, 1.0f, 0.0f, 1, 0, 1, 2, 3 };
+    ClipConst c;
+    clip_setup (c, d, R, C, Is, nabla);
+    if (! exact_fast_ok (c.pair))
+        return 1;
+    if (pairs)
+        pyorder ? exactv_run<f2, true> (c, x, y, B, T) : exactv_run<f2, false> (c, x, y, B, T);
+    else
+        pyorder ? exactv_run<f1, true> (c, x, y, B, T) : exactv_run<f1, false> (c, x, y, B, T);
+    return 0;
+}
+
 // clip_step_recoverv<f2> (the adjoint kernel's packed pair step) against the scalar clip_step_recover on
 // the same (x, z, z') triples: out[8 i ...] = { A, cg, cl, cv } packed, then scalar.
 template <int MODE>

@@ -182,6 +182,29 @@ def test_recover_pairs_equal_scalar(hm):
     assert np.all(np.max(np.abs(out[:, :4] - out[:, 4:]), axis=0) <= 2e-6 * scale)
 
 
+@pytest.mark.parametrize("circuit", ["plugin", "training"])
+@pytest.mark.parametrize("py,oname", [(0, "plugin"), (1, "python")])
+def test_exact_forward_step_against_reference_vectors(hm, golden, circuit, py, oname):
+    """clip_step_exactv — the exact (TOMS-917) root's forward sample as the kernels run it, packed pairs (f2) and its
+    one-sequence twin (f1) — against the reference's own C++ outputs, quiet and loud; f1 and f2 agree bit for bit;
+    silence in, silence out."""
+    p = ClipperParams() if circuit == "plugin" else ClipperParams(R=45000.0, C=4.7e-9)
+    outs = []
+    for pairs in (0, 1):
+        x = np.ascontiguousarray(golden["clip_x"], np.float32)
+        y = np.empty_like(x)
+        rc = hm.hm_clipper_exactv(C.c_int(pairs), C.c_int(py), C.c_float(p.fs), C.c_float(p.R), C.c_float(p.C), C.c_float(p.Is), C.c_float(p.Vt), C.c_float(p.nabla), P(x), P(y),
+                                  C.c_int64(x.shape[0]), C.c_int64(x.shape[1]))
+        assert rc == 0
+        assert seq_rel_err(y, golden[f"clip_{circuit}_exact_{oname}_f64"]) < 3e-6
+        outs.append(y)
+    assert np.array_equal(outs[0], outs[1])
+    z = np.zeros((3, 40), np.float32)
+    yz = np.ones_like(z)
+    assert hm.hm_clipper_exactv(C.c_int(1), C.c_int(py), C.c_float(p.fs), C.c_float(p.R), C.c_float(p.C), C.c_float(p.Is), C.c_float(p.Vt), C.c_float(p.nabla), P(z), P(yz), C.c_int64(3), C.c_int64(40)) == 0
+    assert not yz.any()
+
+
 def test_recover_step_on_pairs_exact_root(hm, oracle):
     """The same for the exact (TOMS-917) root: omega_exact_low over packed pairs against the scalar step."""
     p = ClipperParams()
