@@ -5,7 +5,7 @@
 
 namespace dwdf
 {
-int g_clip_opts = 0;
+std::atomic<int> g_clip_opts { 0 };
 
 namespace
 {

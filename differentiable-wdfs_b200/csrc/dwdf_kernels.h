@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <type_traits>
 
@@ -35,7 +36,7 @@ enum : int
     kOptForceChunks = 16, // use them whatever the batch size (crossover measurements)
     kOptL2Prefetch = 4 // cp.async.bulk.prefetch.tensor L2 run-ahead (measured: slower — forward 0.47 -> 0.58 ms, adjoint 0.63 -> 0.94 ms; off)
 };
-extern int g_clip_opts;
+extern std::atomic<int> g_clip_opts; // diagnostic switches (dwdf_set_option); read once per launch
 
 struct ClipVariant
 {
