@@ -1151,6 +1151,195 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_train_tma (const __grid_c
     write_partials (acc, partials, blockIdx.x, lane);
 }
 
+// ---- the fused pass on two sequences per lane (approx root, symmetric pair, fast-path parameters) --------------
+// The forward wave is bound by its per-step dependency chain with about half of the issue slots idle; the tangent
+// recurrences hang off that chain (they need each step's linearisation, nothing feeds back into z), so in the packed
+// form forward + loss + gradients cost little more than the forward alone. [64 x 16] tiles of x (y written in place)
+// and target, 64-byte swizzle, 3-stage ring (24 KB: 9 one-warp CTAs per SM).
+constexpr int kTrainPairTileBytes = kPairRows * kSeg * 4; // 4 KB
+constexpr int kTrainPairStageBytes = 2 * kTrainPairTileBytes;
+constexpr int kTrainPairStages = 3;
+
+template <bool PY>
+struct TrainStateV
+{
+    f2 z { 0.0f, 0.0f }, hz { 0.0f, 0.0f }, sg { 0.0f, 0.0f }, sl { 0.0f, 0.0f }, sv { 0.0f, 0.0f };
+    f2 ag { 0.0f, 0.0f }, al { 0.0f, 0.0f }, av { 0.0f, 0.0f }, sse { 0.0f, 0.0f }, st2 { 0.0f, 0.0f };
+    __device__ __forceinline__ f2 step (const ClipConst& c, f2 x, f2 t, bool onA, bool onB, f2& umax)
+    {
+        StepTapeV<f2> tp;
+        const f2 y = clip_step_fastv_impl<f2, PY, true> (c, x, z, hz, umax, &tp);
+        const f2 e { onA ? y.x - t.x : 0.0f, onB ? y.y - t.y : 0.0f };
+        const f2 tm { onA ? t.x : 0.0f, onB ? t.y : 0.0f };
+        const f2 ng = fmav (tp.A, sg, tp.cg), nl = fmav (tp.A, sl, tp.cl), nv = fmav (tp.A, sv, tp.cv);
+        if (PY)
+        {
+            const f2 h = mulv (bc (f2 {}, 0.5f), e);
+            ag = fmav (h, addv (ng, sg), ag);
+            al = fmav (h, addv (nl, sl), al);
+            av = fmav (h, addv (nv, sv), av);
+        }
+        else
+        {
+            ag = fmav (e, sg, ag);
+            al = fmav (e, sl, al);
+            av = fmav (e, sv, av);
+        }
+        sse = fmav (e, e, sse);
+        st2 = fmav (tm, tm, st2);
+        sg = ng, sl = nl, sv = nv;
+        return y;
+    }
+    // one element (0: .x, 1: .y) as the scalar state of the general step, and back
+    __device__ __forceinline__ TrainState<kModeApprox, false, false, PY> get (int k) const
+    {
+        TrainState<kModeApprox, false, false, PY> s;
+        s.z = k ? z.y : z.x, s.sg = k ? sg.y : sg.x, s.sl = k ? sl.y : sl.x, s.sv = k ? sv.y : sv.x;
+        s.ag = k ? ag.y : ag.x, s.al = k ? al.y : al.x, s.av = k ? av.y : av.x, s.sse = k ? sse.y : sse.x, s.st2 = k ? st2.y : st2.x;
+        return s;
+    }
+    __device__ __forceinline__ void put (int k, const TrainState<kModeApprox, false, false, PY>& s)
+    {
+        if (k)
+            z.y = s.z, hz.y = 0.5f * s.z, sg.y = s.sg, sl.y = s.sl, sv.y = s.sv, ag.y = s.ag, al.y = s.al, av.y = s.av, sse.y = s.sse, st2.y = s.st2;
+        else
+            z.x = s.z, hz.x = 0.5f * s.z, sg.x = s.sg, sl.x = s.sl, sv.x = s.sv, ag.x = s.ag, al.x = s.al, av.x = s.av, sse.x = s.sse, st2.x = s.st2;
+    }
+    __device__ __forceinline__ void flush (AdjAcc& acc)
+    {
+        acc.g += (double) (ag.x + ag.y);
+        acc.l += (double) (al.x + al.y);
+        acc.v += (double) (av.x + av.y);
+        acc.sse += (double) (sse.x + sse.y);
+        acc.st2 += (double) (st2.x + st2.y);
+        ag = al = av = sse = st2 = f2 { 0.0f, 0.0f };
+    }
+};
+
+template <bool PY>
+__global__ void __launch_bounds__ (kLanes) clipper_train_pair_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmt, const __grid_constant__ CUtensorMap tmy, const int want_y, const float* __restrict__ params, const ClipDesc desc, double* __restrict__ partials, int64_t B, int T, int skip, int n_groups)
+{
+    __shared__ __align__ (1024) uint8_t smem[kTrainPairStages * kTrainPairStageBytes];
+    __shared__ __align__ (8) uint64_t bar_mem[kTrainPairStages];
+    const int lane = threadIdx.x;
+    const int b0 = blockIdx.x * kPairRows;
+    const uint32_t tiles = smem_u32 (smem), bars = smem_u32 (bar_mem);
+    if (lane == 0)
+    {
+        tma_prefetch_desc (&tmx);
+        tma_prefetch_desc (&tmt);
+        for (int s = 0; s < kTrainPairStages; ++s)
+            mbar_init (bars + 8 * s, 1);
+        fence_mbar_init ();
+    }
+    __syncwarp ();
+    ClipConst c;
+    load_consts (c, desc, params);
+    const bool validA = (int64_t) b0 + lane < B, validB = (int64_t) b0 + kLanes + lane < B;
+    const bool fast = fast_ok (c.pair.L); // warp-uniform
+    const int ntiles = (T + kSeg - 1) / kSeg;
+    auto load_stage = [&] (int j) {
+        const int sj = j % kTrainPairStages;
+        mbar_expect_tx (bars + 8 * sj, kTrainPairStageBytes);
+        tma_load_2d (tiles + sj * kTrainPairStageBytes, &tmx, j * kSeg, b0, bars + 8 * sj);
+        tma_load_2d (tiles + sj * kTrainPairStageBytes + kTrainPairTileBytes, &tmt, j * kSeg, b0, bars + 8 * sj);
+    };
+    if (lane == 0)
+        for (int s = 0; s < kTrainPairStages - 1 && s < ntiles; ++s)
+            load_stage (s);
+    TrainStateV<PY> st;
+    AdjAcc acc;
+    for (int i = 0; i < ntiles; ++i)
+    {
+        const int s = i % kTrainPairStages;
+        const uint32_t xt = tiles + s * kTrainPairStageBytes, tt = xt + kTrainPairTileBytes;
+        mbar_wait (bars + 8 * s, (i / kTrainPairStages) & 1);
+        const int nch = min (kSeg / 4, (T - i * kSeg) >> 2);
+#pragma unroll 2
+        for (int cc = 0; cc < kSeg / 4; ++cc)
+        {
+            if (cc < nch)
+            {
+                const uint32_t addrA = chunk64 (xt, lane, cc), addrB = addrA + kLanes * 64; // row + 32: same swizzle phase
+                const uint32_t tadrA = chunk64 (tt, lane, cc), tadrB = tadrA + kLanes * 64;
+                const float4 va = lds128 (addrA), vb = lds128 (addrB), ta = lds128 (tadrA), tb = lds128 (tadrB);
+                const float xa[4] = { va.x, va.y, va.z, va.w }, xb[4] = { vb.x, vb.y, vb.z, vb.w };
+                const float tga[4] = { ta.x, ta.y, ta.z, ta.w }, tgb[4] = { tb.x, tb.y, tb.z, tb.w };
+                const int n = i * kSeg + cc * 4;
+                float oa[4], ob[4];
+                const TrainStateV<PY> saved = st;
+                f2 um { -1.0e30f, -1.0e30f };
+                if (fast)
+                {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const bool on = n + k >= skip;
+                        const f2 y = st.step (c, f2 { xa[k], xb[k] }, f2 { tga[k], tgb[k] }, on && validA, on && validB, um);
+                        oa[k] = y.x, ob[k] = y.y;
+                    }
+                }
+                // an instance that crossed omega3's log branch in this chunk (or parameters outside the fast path's range):
+                // that instance's four samples again, the general way, from the state it had before the chunk
+                const bool redoA = ! fast || um.x >= kFastLoud, redoB = ! fast || um.y >= kFastLoud;
+                if (redoA || redoB)
+                {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                    {
+                        if (e == 0 ? redoA : redoB)
+                        {
+                            auto ss = saved.get (e);
+                            const bool valid = e == 0 ? validA : validB;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                            {
+                                const float yv = ss.step (c, e == 0 ? xa[k] : xb[k], e == 0 ? tga[k] : tgb[k], n + k >= skip && valid);
+                                if (e == 0)
+                                    oa[k] = yv;
+                                else
+                                    ob[k] = yv;
+                            }
+                            st.put (e, ss);
+                        }
+                    }
+                }
+                if (want_y)
+                {
+                    sts128 (addrA, make_float4 (oa[0], oa[1], oa[2], oa[3]));
+                    sts128 (addrB, make_float4 (ob[0], ob[1], ob[2], ob[3]));
+                }
+            }
+        }
+        st.flush (acc);
+        fence_proxy_async ();
+        __syncwarp ();
+        if (lane == 0)
+        {
+            if (want_y)
+            {
+                tma_store_2d (&tmy, i * kSeg, b0, xt);
+                tma_commit ();
+            }
+            const int j = i + kTrainPairStages - 1;
+            if (j < ntiles)
+            {
+                tma_wait_read<1> ();
+                load_stage (j);
+            }
+        }
+    }
+    if (lane == 0 && want_y)
+        tma_wait_all<0> ();
+    // this CTA covers two 32-row groups of the partials array: its sums go to the first, zeros to the second
+    write_partials (acc, partials, 2 * blockIdx.x, lane);
+    if (2 * (int) blockIdx.x + 1 < n_groups)
+    {
+        AdjAcc zero;
+        write_partials (zero, partials, 2 * blockIdx.x + 1, lane);
+    }
+}
+
 template <int MODE, bool GENERAL, bool PY>
 __global__ void __launch_bounds__ (kLanes) clipper_train_direct (const float* __restrict__ x, const float* __restrict__ target, float* __restrict__ y, const float* __restrict__ params, const ClipDesc desc, double* __restrict__ partials, int64_t B, int T, int skip)
 {
@@ -1259,6 +1448,14 @@ cudaError_t clipper_train_part<kM, kG> (bool py, bool use_tma, const ClipTmaMaps
     const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
     auto go = [&] (auto P) {
         constexpr bool p = decltype (P)::value;
+        if constexpr (kM == kModeApprox && ! kG)
+        {
+            if (use_tma && maps[0].pair)
+            {
+                clipper_train_pair_tma<p><<<(unsigned) ((B + kPairRows - 1) / kPairRows), kLanes, 0, stream>>> (maps[0].x2, maps[0].y2, maps[1].y2, y != nullptr ? 1 : 0, params, desc, partials, B, (int) T, skip, (int) ((B + kLanes - 1) / kLanes));
+                return;
+            }
+        }
         if (use_tma)
             clipper_train_tma<kM, kG, p><<<grid, kLanes, 0, stream>>> (maps[0].x, maps[0].y, maps[1].y, y != nullptr ? 1 : 0, params, desc, partials, (int) T, skip);
         else

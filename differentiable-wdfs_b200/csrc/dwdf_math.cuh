@@ -543,8 +543,13 @@ DWDF_HD V exp_approx_scaledv (V xp)
 
 // One sample. State: z = z[n] and hz = z[n]/2 (python ordering's output is hz[n+1] + hz[n]).
 // umax = max(umax, u0 log2(e)). Returns y[n].
-template <class V, bool PY>
-DWDF_HD V clip_step_fastv (const ClipConst& c, V x, V& z, V& hz, V& umax)
+template <class V>
+struct StepTapeV;
+template <class V>
+DWDF_HD void fast_step_tape (const ClipConst& c, V xz, V a, V w0, V w1, StepTapeV<V>* tp);
+// TAPE: also the step's linearisation (A, cg, cl, cv as in clip_step_tape), for the fused forward-mode training pass
+template <class V, bool PY, bool TAPE>
+DWDF_HD V clip_step_fastv_impl (const ClipConst& c, V x, V& z, V& hz, V& umax, StepTapeV<V>* tp)
 {
     const PairConst& p = c.pair;
     // a = z + gamma (x - z) exactly as the adaptor writes it (tf_wdf.py:185-192): the form (1 - gamma) z + gamma x
@@ -569,9 +574,16 @@ DWDF_HD V clip_step_fastv (const ClipConst& c, V x, V& z, V& hz, V& umax)
     const V zn = fmav (bc (V {}, -p.twoV), ds, a2z); // b + gamma (x - z),  b = a - 2 V lambda (w0 - w1)
     const V hzn = mulv (bc (V {}, 0.5f), zn);
     const V yo = PY ? add_out (hzn, hz) : z;
+    if (TAPE)
+        fast_step_tape (c, xz, a, w0, w1, tp);
     z = zn;
     hz = hzn;
     return yo;
+}
+template <class V, bool PY>
+DWDF_HD V clip_step_fastv (const ClipConst& c, V x, V& z, V& hz, V& umax)
+{
+    return clip_step_fastv_impl<V, PY, false> (c, x, z, hz, umax, nullptr);
 }
 
 // Four consecutive samples (one 16-byte chunk of a row) through the fast step.
@@ -679,6 +691,22 @@ struct StepTapeV
 {
     V A, cg, cl, cv;
 };
+// (A, cg, cl, cv) from the two omegas of a fast step: pair_deriv's formulas (cancellation-free dV) over V
+template <class V>
+DWDF_HD void fast_step_tape (const ClipConst& c, V xz, V a, V w0, V w1, StepTapeV<V>* tp)
+{
+    const PairConst& p = c.pair;
+    const V wp0 = mulv (w0, rcpv (addv (w0, bc (V {}, 1.0f))));
+    const V wp1 = mulv (w1, rcpv (addv (w1, bc (V {}, 1.0f))));
+    const V S1 = addv (wp0, wp1);
+    const V M1 = xor_signv (addv (wp0, negv (wp1)), a);
+    const V fp1 = fmav (bc (V {}, -2.0f), S1, bc (V {}, 2.0f)); // f'(a) + 1
+    tp->A = fmav (fp1, bc (V {}, c.one_m_gamma), bc (V {}, -1.0f));
+    tp->cg = mulv (xz, fp1);
+    tp->cl = mulv (bc (V {}, -p.twoV), M1);
+    const V ww = xor_signv (fmav (w0, wp0, negv (mulv (w1, wp1))), a);
+    tp->cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, mulv (bc (V {}, -2.0f), ww));
+}
 DWDF_HD f1 select_below (f1 lo, f1 hi, f1 u, float thr) { return f1 { u.x < thr ? lo.x : hi.x }; }
 DWDF_HD f2 select_below (f2 lo, f2 hi, f2 u, float thr) { return f2 { u.x < thr ? lo.x : hi.x, u.y < thr ? lo.y : hi.y }; }
 DWDF_HD f1 clamp_exp_arg (f1 a) { return f1 { fmaxf (a.x, -126.0f) }; }
