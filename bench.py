@@ -204,6 +204,16 @@ def other_paths(torch, dwdf, device, x, target):
         ce = clipper("exact")
         out["exact_root_fwd_bwd"] = {"value": x.numel() / timed(lambda: fwd_bwd(ce, x, target)), "unit": UNIT, "B": x.shape[0], "T": T}
         ca = clipper("approx")
+        # the whole training step in ONE sweep (forward + loss + gradients by forward-mode tangents, two sequences per lane) + Adam;
+        # not the headline path (north_star asks for the reverse-mode adjoint kernel), reported beside it
+        oa = dwdf.Adam(ca, lr={s: 1e-4 * float(ca.params[s]) for s in range(ca.n_params)}, beta_1=0.5)
+        yb = torch.empty_like(x)
+
+        def fused_step():
+            ca.train_pass(x, target, loss="mse", y=yb)
+            oa.apply()
+        out["fused_tangent_training_step"] = {"value": x.numel() / timed(fused_step, reps=5), "unit": UNIT, "B": x.shape[0], "T": T, "kernels": "clipper_train_pair_tma + finalize + adam"}
+        del yb
         for name, b in (("config2_B256_fwd_bwd", 256), ("config3_B1024_fwd_bwd", 1024)):
             xs, ts = x[:b].contiguous(), target[:b].contiguous()
             out[name] = {"value": xs.numel() / timed(lambda: fwd_bwd(ca, xs, ts), reps=20), "unit": UNIT, "B": b, "T": T, "kernels": "time-parallel (256-sample chunks)"}

@@ -56,6 +56,15 @@ struct AsyncScratch
     cudaStream_t stream = nullptr;
     cudaError_t alloc (size_t bytes, cudaStream_t s)
     {
+        // keep freed scratch in the device's pool across synchronisations (the default threshold of 0 hands it back to the
+        // driver at every sync — a training loop that reads its loss each step would re-allocate from the OS each step)
+        static const bool pool_kept = [] {
+            int dev = 0;
+            cudaMemPool_t pool = nullptr;
+            uint64_t keep = UINT64_MAX;
+            return cudaGetDevice (&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool (&pool, dev) == cudaSuccess && cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+        }();
+        (void) pool_kept;
         stream = s;
         return cudaMallocAsync ((void**) &p, bytes, s);
     }
