@@ -34,19 +34,52 @@ namespace
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches { 0 };
 std::atomic<int> g_use_tma { 1 };
-std::atomic<int*> g_redone { nullptr }; // device counter: chunks the time-parallel forward had to recompute (diagnostics)
+// ---- per-device state -------------------------------------------------------------------------------
+// Created eagerly by dwdf_program_create for the device current at that moment (never lazily in a launch path: a
+// cudaMalloc there would break a stream capture) and keyed by device, so that circuits on different GPUs of one
+// process do not share device pointers:
+//   * a diagnostics counter (chunks the time-parallel forward had to recompute);
+//   * a LIBRARY-OWNED memory pool for the stream-ordered scratch, with the release threshold raised so that freed
+//     scratch stays in the pool across synchronisations (with the default of 0 a training loop that reads its loss
+//     each step would re-allocate from the driver each step). The host application's default pool is left alone.
+constexpr int kMaxDevices = 64;
+struct DeviceState
+{
+    std::once_flag once;
+    int* redone = nullptr;
+    cudaMemPool_t pool = nullptr;
+};
+DeviceState g_dev[kMaxDevices];
 
-// allocated on first use, once per process (one process drives one GPU); nullptr if the allocation failed — the kernels skip the count then
+DeviceState* device_state ()
+{
+    int dev = -1;
+    if (cudaGetDevice (&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+    {
+        (void) cudaGetLastError (); // no device: the compute entry points report it; creating a program needs none
+        return nullptr;
+    }
+    DeviceState& st = g_dev[dev];
+    std::call_once (st.once, [&st, dev] {
+        if (cudaMalloc ((void**) &st.redone, sizeof (int)) != cudaSuccess || cudaMemset (st.redone, 0, sizeof (int)) != cudaSuccess)
+            st.redone = nullptr;
+        cudaMemPoolProps props {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        uint64_t keep = UINT64_MAX;
+        if (cudaMemPoolCreate (&st.pool, &props) != cudaSuccess || cudaMemPoolSetAttribute (st.pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess)
+            st.pool = nullptr;
+        (void) cudaGetLastError ();
+    });
+    return &st;
+}
+
 int* redone_counter ()
 {
-    static int* const counter = [] {
-        int* p = nullptr;
-        if (cudaMalloc ((void**) &p, sizeof (int)) != cudaSuccess || cudaMemset (p, 0, sizeof (int)) != cudaSuccess)
-            p = nullptr;
-        g_redone.store (p);
-        return p;
-    }();
-    return counter;
+    DeviceState* st = device_state ();
+    return st != nullptr ? st->redone : nullptr;
 }
 
 // stream-ordered scratch that is released on every way out of the calling function
@@ -56,16 +89,10 @@ struct AsyncScratch
     cudaStream_t stream = nullptr;
     cudaError_t alloc (size_t bytes, cudaStream_t s)
     {
-        // keep freed scratch in the device's pool across synchronisations (the default threshold of 0 hands it back to the
-        // driver at every sync — a training loop that reads its loss each step would re-allocate from the OS each step)
-        static const bool pool_kept = [] {
-            int dev = 0;
-            cudaMemPool_t pool = nullptr;
-            uint64_t keep = UINT64_MAX;
-            return cudaGetDevice (&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool (&pool, dev) == cudaSuccess && cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
-        }();
-        (void) pool_kept;
         stream = s;
+        DeviceState* st = device_state ();
+        if (st != nullptr && st->pool != nullptr)
+            return cudaMallocFromPoolAsync ((void**) &p, bytes, st->pool, s);
         return cudaMallocAsync ((void**) &p, bytes, s);
     }
     ~AsyncScratch ()
@@ -162,7 +189,8 @@ int dwdf_set_tma (int enable) { return g_use_tma.exchange (enable ? 1 : 0); }
 int64_t dwdf_time_parallel_redone (void)
 {
     int v = 0;
-    if (g_redone.load () != nullptr && cudaMemcpy (&v, g_redone.load (), sizeof (int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    int* counter = redone_counter (); // of the current device
+    if (counter != nullptr && cudaMemcpy (&v, counter, sizeof (int), cudaMemcpyDeviceToHost) != cudaSuccess)
         return -1;
     return v;
 }
@@ -245,6 +273,7 @@ int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_cir
     dwdf_program* p = new (std::nothrow) dwdf_program;
     if (p == nullptr)
         return fail (DWDF_ERR_INVALID, "out of memory");
+    (void) device_state (); // per-device counter and scratch pool, created here rather than in a launch path
     p->nodes.assign (nodes, nodes + n_nodes);
     p->desc = *d;
     p->n_states = n_states;

@@ -20,12 +20,26 @@ def _squeeze_to(a, ndim):
     return a
 
 
+def _last_dim(shape) -> int:
+    """The feature width of a Keras shape as the reference's files spell it: [None, 2], [[None, 2]] or a bare 2."""
+    while isinstance(shape, (list, tuple)):
+        if len(shape) == 0:
+            raise ValueError("empty shape")
+        shape = shape[-1]
+    return int(shape)
+
+
 def layers_from_json(model_json: dict) -> Tuple[List[Tuple[np.ndarray, np.ndarray, str]], List[int]]:
     """-> ([(kernel (in, out), bias (out,), activation)], sizes [in, h1, ..., out])."""
-    sizes = [int(model_json["in_shape"][-1])]
+    sizes = [_last_dim(model_json["in_shape"])]
     layers = []
     for layer in model_json["layers"]:
         if layer["type"] != "dense":
+            # layers.py:57 builds the model from the dense entries only; the Keras-written pretrained files
+            # (models/pretrained/*.json) open with the InputLayer as {"type": "unknown", "weights": []}.
+            # A non-dense entry that carries weights (gru, lstm, conv1d ...) would change the function: refuse it.
+            if len(layer.get("weights", [])) == 0:
+                continue
             raise ValueError(f"layer type {layer['type']!r}: only dense layers make a WDF root model (layers.py:57-70)")
         W = _squeeze_to(layer["weights"][0], 2)
         b = _squeeze_to(layer["weights"][1], 1)

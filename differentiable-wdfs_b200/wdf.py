@@ -21,6 +21,7 @@ Two ways to run a circuit built from these objects:
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Optional
 
 import torch
@@ -356,6 +357,21 @@ def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _on_device(method):
+    """Runs a CompiledCircuit / optimizer method with the circuit's device current: the library launches on the
+    caller's stream, allocates stream-ordered scratch and builds TMA descriptors for the CURRENT device."""
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        dev = self.device if hasattr(self, "device") else self.c.device
+        if torch.cuda.current_device() == dev.index:
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return method(self, *args, **kwargs)
+
+    return wrapper
+
+
 class CompiledCircuit:
     """A circuit lowered to the flat program of include/dwdf.h, bound to one CUDA device.
 
@@ -369,6 +385,10 @@ class CompiledCircuit:
             raise RuntimeError("differentiable-wdfs_b200: the compiled path is CUDA-only and no CUDA device is visible (there is no CPU fallback)")
         self.lib = L.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("the compiled path is CUDA-only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.root = root
         self.tree = tree if tree is not None else getattr(root, "next", None)
         if self.tree is None:
@@ -458,13 +478,14 @@ class CompiledCircuit:
         arr = (L.Node * len(nodes))(*nodes)
         handle = C.c_void_p()
         self.is_neural = isinstance(root, DenseRootModel)
-        if self.is_neural:
-            L.check(self.lib.dwdf_program_create_neural(arr, len(nodes), C.byref(d), C.byref(self.mlp), C.byref(handle)))
-            w = root.weight_vector()
-            assert w.size == self.lib.dwdf_mlp_weight_count(C.byref(self.mlp))
-            self.weights = torch.from_numpy(w).to(self.device if device is not None else torch.device("cuda", torch.cuda.current_device()))
-        else:
-            L.check(self.lib.dwdf_program_create(arr, len(nodes), C.byref(d), C.byref(handle)))
+        with torch.cuda.device(self.device):  # the library prepares its per-device state for the device current at creation
+            if self.is_neural:
+                L.check(self.lib.dwdf_program_create_neural(arr, len(nodes), C.byref(d), C.byref(self.mlp), C.byref(handle)))
+                w = root.weight_vector()
+                assert w.size == self.lib.dwdf_mlp_weight_count(C.byref(self.mlp))
+                self.weights = torch.from_numpy(w).to(self.device)
+            else:
+                L.check(self.lib.dwdf_program_create(arr, len(nodes), C.byref(d), C.byref(handle)))
         self.handle = handle
         self.is_clipper = bool(self.lib.dwdf_program_is_clipper(handle))
         self.n_states = int(self.lib.dwdf_program_n_states(handle))
@@ -474,7 +495,9 @@ class CompiledCircuit:
         hi = [float("inf")] * self.n_params
         for (eid, attr), s in self.slots.items():
             e = self._owner(eid)
-            if attr in ("R", "C") and hasattr(e, "clip"):
+            # Keras applies a variable's constraint inside apply_gradients, i.e. to the TRAINABLE variables only
+            # (tf_wdf.py:74,104): a frozen element outside the range keeps its value
+            if attr in ("R", "C") and hasattr(e, "clip") and getattr(e, "trainable", False):
                 lo[s], hi[s] = e.clip
         self.clip_lo = torch.tensor(lo, dtype=torch.float32, device=self.device)
         self.clip_hi = torch.tensor(hi, dtype=torch.float32, device=self.device)
@@ -503,12 +526,23 @@ class CompiledCircuit:
         return self.slots[(id(element), attr)]
 
     # ---- buffers -------------------------------------------------------------------------------
-    def _check_xy(self, x, name="x"):
+    def _check_xy(self, x, name="x", shape=None):
+        """Every companion buffer of a launch is checked against x's (B, T): the kernels index all of them with it."""
         if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()):
             raise ValueError(f"{name} must be a contiguous float32 CUDA tensor of shape (B, T)")
         if x.device != self.device:
             raise ValueError(f"{name} lives on {x.device}, the circuit on {self.device}")
+        if shape is not None and tuple(x.shape) != tuple(shape):
+            raise ValueError(f"{name} has shape {tuple(x.shape)}, expected {tuple(shape)} (the shape of x)")
         return x.shape
+
+    @staticmethod
+    def _check_host(t, name, shape=None):
+        if not (torch.is_tensor(t) and not t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()):
+            raise ValueError(f"{name} must be a contiguous float32 CPU tensor of shape (B, T)")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)} (the shape of x)")
+        return t.shape
 
     def _scratch(self, attr, nbytes):
         buf = getattr(self, attr)
@@ -518,13 +552,14 @@ class CompiledCircuit:
         return buf
 
     # ---- forward / backward ----------------------------------------------------------------------
+    @_on_device
     def forward(self, x, r=None, out=None, keep_for_backward=True):
         """y = circuit(x): (B, T) float32 CUDA tensors, every sequence from reset state."""
         B, T = self._check_xy(x)
         if r is not None:
-            self._check_xy(r, "r")
+            self._check_xy(r, "r", (B, T))
         y = torch.empty_like(x) if out is None else out
-        self._check_xy(y, "out")
+        self._check_xy(y, "out", (B, T))
         if B * T == 0:
             self._last = None
             return y
@@ -544,6 +579,7 @@ class CompiledCircuit:
         """The reference's output convention: (T, B, 1) as stacked by TensorArray (lpf.py:48, clipper_pot.py:126)."""
         return self.forward(x, r).t().unsqueeze(-1)
 
+    @_on_device
     def backward(self, gy=None, target=None, loss="mse", skip=0, want_gx=False, raw=False):
         """Gradients of the last ``forward``: upstream ``gy = dL/dy`` or a fused loss against ``target``.
         The adjoint kernel reads the output tensor that ``forward`` returned; do not modify it in between.
@@ -557,9 +593,7 @@ class CompiledCircuit:
             raise ValueError("give exactly one of gy (upstream gradient) or target (fused loss)")
         x, r, y, B, T = self._last
         g = gy if gy is not None else target
-        self._check_xy(g, "gy/target")
-        if tuple(g.shape) != (B, T):
-            raise ValueError("gy/target must have the shape of x")
+        self._check_xy(g, "gy/target", (B, T))
         if self.is_neural:
             if want_gx or raw:
                 raise NotImplementedError("neural root: dL/dx and raw (pre-all-reduce) sums are not implemented")
@@ -584,18 +618,20 @@ class CompiledCircuit:
                                            _ptr(self.out), _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
         return self._result(gx)
 
+    @_on_device
     def finalize(self, target=True, loss="mse"):
         """Turns the (all-reduced) raw sums in ``self.out`` into gradients and loss, in place."""
         L.check(self.lib.dwdf_finalize(self.handle, _ptr(self.params), L.GRAD_TARGET if target else L.GRAD_UPSTREAM, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, _ptr(self.out),
                                        _stream_ptr(self.device)))
         return self._result(None)
 
+    @_on_device
     def train_pass(self, x, target, loss="mse", skip=0, y=None, raw=False):
         """Fused forward + loss + parameter gradients in one sweep (diode clipper only)."""
         B, T = self._check_xy(x)
-        self._check_xy(target, "target")
+        self._check_xy(target, "target", (B, T))
         if y is not None:
-            self._check_xy(y, "y")
+            self._check_xy(y, "y", (B, T))
         work = self._scratch("_work", self.lib.dwdf_workspace_bytes(self.handle, B, T))
         if raw:
             L.check(self.lib.dwdf_train_pass_raw(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), int(skip), _ptr(y), _ptr(self.out), _ptr(work), work.numel(), B, T,
@@ -605,13 +641,15 @@ class CompiledCircuit:
                                              _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
         return self._result(None)
 
+    @_on_device
     def train_step(self, x, target, optimizer: "Adam", loss="mse", skip=0, out=None):
         """forward + adjoint (fused loss) + Adam in one library call, nothing synchronises: capturable in a
         ``torch.cuda.CUDAGraph`` and replayable (small batches are launch-bound). Returns the result dict of
         ``backward`` (device tensors, overwritten by the next step)."""
         B, T = self._check_xy(x)
-        self._check_xy(target, "target")
+        self._check_xy(target, "target", (B, T))
         y = torch.empty_like(x) if out is None else out
+        self._check_xy(y, "out", (B, T))
         ck = self._scratch("_ckpt", self.lib.dwdf_ckpt_bytes(self.handle, B, T))
         work = self._scratch("_work", self.lib.dwdf_workspace_bytes(self.handle, B, T))
         o = optimizer
@@ -625,12 +663,16 @@ class CompiledCircuit:
         o = self.out
         return {"grads": o[: self.n_params], "loss": o[L.OUT_LOSS], "mse": o[L.OUT_MSE], "esr": o[L.OUT_ESR], "gx": gx, "out": o}
 
+    @_on_device
     def process_block(self, x, state, r=None, out=None):
         """Streaming twin of DiodeClipperWDF::process: continues from ``state`` ((n_states, B) float32) and updates it."""
         B, T = self._check_xy(x)
         if not (torch.is_tensor(state) and state.is_cuda and state.dtype == torch.float32 and state.numel() == self.n_states * B and state.is_contiguous()):
             raise ValueError(f"state must be a contiguous float32 CUDA tensor with {self.n_states} x B elements")
+        if r is not None:
+            self._check_xy(r, "r", (B, T))
         y = torch.empty_like(x) if out is None else out
+        self._check_xy(y, "out", (B, T))
         if self.is_neural:
             L.check(self.lib.dwdf_forward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), _ptr(state), None, B, T, _stream_ptr(self.device)))
             return y
@@ -641,18 +683,33 @@ class CompiledCircuit:
         return torch.zeros(self.n_states, B, dtype=torch.float32, device=self.device)
 
     # ---- end-to-end with host (numpy / pinned torch) buffers ------------------------------------------
+    @_on_device
     def forward_host(self, x_host: torch.Tensor, y_host: torch.Tensor, params_host: Optional[torch.Tensor] = None):
-        B, T = x_host.shape
-        p = self.params.cpu() if params_host is None else params_host
+        B, T = self._check_host(x_host, "x_host")
+        self._check_host(y_host, "y_host", (B, T))
+        p = self._host_params(params_host)
         L.check(self.lib.dwdf_forward_host(self.handle, _ptr(p), _ptr(x_host), None, _ptr(y_host), B, T))
         return y_host
 
+    @_on_device
     def grad_host(self, x_host, g_host, out_host, y_host=None, params_host=None, target=True, loss="mse", skip=0):
-        B, T = x_host.shape
-        p = self.params.cpu() if params_host is None else params_host
+        B, T = self._check_host(x_host, "x_host")
+        self._check_host(g_host, "g_host", (B, T))
+        if y_host is not None:
+            self._check_host(y_host, "y_host", (B, T))
+        if not (torch.is_tensor(out_host) and not out_host.is_cuda and out_host.dtype == torch.float64 and out_host.is_contiguous() and out_host.numel() >= L.OUT_LEN):
+            raise ValueError(f"out_host must be a contiguous float64 CPU tensor of at least {L.OUT_LEN} elements")
+        p = self._host_params(params_host)
         L.check(self.lib.dwdf_grad_host(self.handle, _ptr(p), _ptr(x_host), None, _ptr(g_host), L.GRAD_TARGET if target else L.GRAD_UPSTREAM, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE,
                                         int(skip), _ptr(y_host), _ptr(out_host), B, T))
         return out_host
+
+    def _host_params(self, params_host):
+        if params_host is None:
+            return self.params.cpu()
+        if not (torch.is_tensor(params_host) and not params_host.is_cuda and params_host.dtype == torch.float32 and params_host.is_contiguous() and params_host.numel() == self.n_params):
+            raise ValueError(f"params_host must be a contiguous float32 CPU tensor of {self.n_params} elements")
+        return params_host
 
     # ---- parameters ------------------------------------------------------------------------------------
     def sync_from_elements(self):
@@ -685,6 +742,7 @@ class AdamWeights:
         self.step_count = torch.zeros(1, dtype=torch.int32, device=circuit.device)
         self.lr, self.beta_1, self.beta_2, self.epsilon = float(lr), float(beta_1), float(beta_2), float(epsilon)
 
+    @_on_device
     def apply(self, grad_scale=1.0):
         c = self.c
         L.check(c.lib.dwdf_adam_step_vec(_ptr(c.weights), _ptr(c.grad_w), _ptr(self.m), _ptr(self.v), _ptr(self.step_count), c.weights.numel(), self.lr, self.beta_1, self.beta_2, self.epsilon,
@@ -713,6 +771,7 @@ class Adam:
                 rates[int(s)] = float(lr)
         self.lr = torch.tensor(rates, dtype=torch.float32, device=dev)
 
+    @_on_device
     def apply(self, grad_scale=1.0):
         c = self.c
         L.check(c.lib.dwdf_adam_step(_ptr(c.params), _ptr(c.out), _ptr(self.m), _ptr(self.v), _ptr(self.step_count), c.n_params, 0.0, _ptr(self.lr), float(self.beta_1), float(self.beta_2),
