@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdwdf.so")
+LIB_PATH = os.environ.get("DWDF_LIBRARY") or os.path.join(_HERE, "libdwdf.so")  # (DWDF_LIBRARY: a side-by-side build variant, see csrc/Makefile)
 
 # enums of include/dwdf.h
 RESISTOR, CAPACITOR, RESISTIVE_VS, SERIES, PARALLEL, INVERTER = range(6)

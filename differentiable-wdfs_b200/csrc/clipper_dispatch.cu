@@ -6,6 +6,7 @@
 namespace dwdf
 {
 std::atomic<int> g_clip_opts { 0 };
+std::atomic<int64_t> g_extra_launches { 0 };
 
 namespace
 {

@@ -29,9 +29,13 @@ namespace dwdf
 namespace
 {
 constexpr int kLanes = 32;
-constexpr int kFwdTileT = 32; // samples per forward tile: 32 x 4 B = one 128-byte swizzle row
-constexpr int kFwdTileBytes = kLanes * kFwdTileT * 4; // 4 KB
-constexpr int kFwdStages = 3;
+constexpr int kFwdTileT = kFwdTileSamples; // dwdf_kernels.h
+static_assert (kFwdTileT == 32 || kFwdTileT == 16, "forward tiles are 32 or 16 samples wide");
+constexpr int kFwdChunks = kFwdTileT / 4; // 16-byte chunks per tile row
+constexpr int kFwdTileBytes = kLanes * kFwdTileT * 4; // one-sequence-per-lane kernel: 4 KB / 2 KB
+constexpr int kFwdStages = DWDF_FWD_STAGES;
+constexpr int kTrainTileT = 32; // fused one-sequence-per-lane training pass
+constexpr int kTrainTileBytes = kLanes * kTrainTileT * 4;
 constexpr int kAdjTileT = kSeg; // samples per adjoint tile = one checkpoint segment (64-byte rows)
 constexpr int kAdjTileBytes = kLanes * kAdjTileT * 4; // 2 KB
 constexpr int kAdjStages = 2;
@@ -40,6 +44,7 @@ constexpr int kAdjL2Ahead = 4; // segments the L2 prefetch runs ahead of the sha
 // 16-byte chunk `c` (4 samples) of row `lane` inside a swizzled tile
 __device__ __forceinline__ uint32_t chunk128 (uint32_t tile, int lane, int c) { return tile + lane * 128 + ((c ^ (lane & 7)) << 4); } // CU_TENSOR_MAP_SWIZZLE_128B
 __device__ __forceinline__ uint32_t chunk64 (uint32_t tile, int lane, int c) { return tile + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4); } // CU_TENSOR_MAP_SWIZZLE_64B
+__device__ __forceinline__ uint32_t chunk_fwd (uint32_t tile, int lane, int c) { return kFwdTileT == 32 ? chunk128 (tile, lane, c) : chunk64 (tile, lane, c); }
 
 __device__ __forceinline__ void load_consts (ClipConst& c, const ClipDesc& d, const float* __restrict__ params)
 {
@@ -108,33 +113,135 @@ __device__ __forceinline__ void forward_chunk2 (const ClipConst& c, float4 va, f
     z = zz;
 }
 
-template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool FAST = true>
-__device__ __forceinline__ void forward_tma_body (const ClipConst& c, const CUtensorMap* tmx, const CUtensorMap* tmy, uint32_t tiles, uint32_t bars, float* __restrict__ ckpt, float& z, int64_t B, int T, int lane, int b0)
+// ---- time chunks ------------------------------------------------------------------------------------
+// With one lane per sequence (or per two) a batch of B sequences gives B / 32 (B / 64) warps however long the
+// sequences are: 128 warps for config 5's per-GPU shard under strong scaling (8192 x 4096), 8 for config 2 — a B200
+// has 592 schedulers and each warp is one serial dependency chain. The recurrence is strictly serial in time, but it
+// is CONTRACTIVE (|dz'/dz| = |f'(a)(1 - gamma) - gamma| < 1: with the diodes off it forgets its state like the RC time
+// constant, faster when they conduct), so the TMA kernels take a second grid dimension: CTA (g, k) runs the rows of
+// group g over the tiles of time chunk k.
+//   forward  chunk k > 0 starts Wt tiles early from z = 0 and discards that warm-up (no stores); W is chosen in the
+//            kernel from gamma so that the off-state decay (1 - 2 gamma)^W is below 1e-13. It records the state it
+//            assumed at its first sample (zs) and the state it ended with (ze). clipper_forward_stitch then walks each
+//            sequence's chunks in order and ACCEPTS chunk k only if its assumed start equals the true end of chunk
+//            k-1 BIT FOR BIT (a contractive map in fp32 merges two trajectories exactly once they are within an ulp or
+//            so); otherwise it recomputes from the true state until the recomputed state meets the speculated
+//            trajectory at a checkpoint, bit for bit (usually within a segment or two), or to the end of the chunk.
+//            The output is therefore identical to the serial recurrence whatever the chunking: the result never rests
+//            on the speculation being right, and the same batch gives the same bits on 1 GPU or sharded over 8.
+//   adjoint  needs no speculation: given the trajectory (recovered from y), the running adjoint is a LINEAR
+//            recurrence G <- A[n] G + q[n], so a chunk returns the affine map of its incoming G (P, Q) and of its
+//            parameter sums (S0 + G_in S1); clipper_adjoint_stitch composes the chunks of each sequence in reverse
+//            order. Exact up to fp32 summation order.
+// The host only proposes a chunk count (grid.y = kmax: as many CTAs as the SMs hold at once); the plan itself is made
+// on the device from gamma, the same way in every kernel of a pass: chunks never get shorter than their warm-up, and a
+// circuit whose memory is longer than the sequence (tiny gamma) simply runs as one chunk.
+struct ChunkPlan
 {
-    const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
-    const bool valid = (int64_t) b0 + lane < B;
-    if (lane == 0)
+    int chunk; // tiles per chunk
+    int K; // chunks in use (<= kmax); CTAs with blockIdx.y >= K exit
+    int Wt; // warm-up tiles
+};
+
+__device__ __forceinline__ int warmup_samples_raw (const ClipConst& c)
+{
+    // off-state contraction per sample: dz'/dz = 1 - 2 gamma (f' = 1). (1 - 2 gamma)^W <= 1e-13: far enough below
+    // one ulp of a quiet signal that the speculated and the true trajectory have merged bit for bit
+    const float rho = fmaxf (fabsf (1.0f - 2.0f * c.gamma), 0.5f);
+    const float w = -29.9f / logf (fminf (rho, 0.999999f));
+    return (int) fminf (w, 1.0e6f);
+}
+
+__device__ __forceinline__ ChunkPlan plan_chunks (const ClipConst& c, int ntiles, int kmax)
+{
+    ChunkPlan p { ntiles, 1, 0 };
+    if (kmax > 1)
     {
-        for (int s = 0; s < kFwdStages - 1 && s < ntiles; ++s)
+        p.Wt = (warmup_samples_raw (c) + kFwdTileT - 1) / kFwdTileT;
+        p.chunk = min (max ((ntiles + kmax - 1) / kmax, max (p.Wt, 1)), ntiles); // the warm-up at most doubles a chunk's work
+        p.K = (ntiles + p.chunk - 1) / p.chunk;
+    }
+    return p;
+}
+
+// One warp's ring of [ROWS x kFwdTileT] tiles over the tiles [f0, t1) of the rows starting at b0: TMA loads run
+// kFwdStages - 1 tiles ahead, results are written in place and stored from the same slot.
+template <int ROWS>
+struct FwdRing
+{
+    static constexpr int kBytes = ROWS * kFwdTileT * 4;
+    uint32_t tiles, bars;
+    const CUtensorMap *tmx, *tmy;
+    int b0, f0, t1;
+    __device__ __forceinline__ void load (int j) const
+    {
+        const int s = j % kFwdStages;
+        mbar_expect_tx (bars + 8 * s, kBytes);
+        tma_load_2d (tiles + s * kBytes, tmx, (f0 + j) * kFwdTileT, b0, bars + 8 * s);
+    }
+    __device__ __forceinline__ void prologue (int lane) const
+    {
+        if (lane == 0)
+            for (int j = 0; j < kFwdStages - 1 && f0 + j < t1; ++j)
+                load (j);
+    }
+    __device__ __forceinline__ uint32_t acquire (int j) const
+    {
+        mbar_wait (bars + 8 * (j % kFwdStages), (j / kFwdStages) & 1);
+        return tiles + (j % kFwdStages) * kBytes;
+    }
+    // two-slot ring: the next tile goes into the slot tile j-1 was stored from, a quarter tile into tile j (the store has had time to drain)
+    __device__ __forceinline__ void early (int j, int lane) const
+    {
+        if (kFwdStages == 2 && lane == 0 && f0 + j + 1 < t1)
         {
-            mbar_expect_tx (bars + 8 * s, kFwdTileBytes);
-            tma_load_2d (tiles + s * kFwdTileBytes, tmx, s * kFwdTileT, b0, bars + 8 * s);
+            tma_wait_read<0> ();
+            load (j + 1);
         }
     }
-    for (int i = 0; i < ntiles; ++i)
+    __device__ __forceinline__ void release (int j, bool store, int lane) const
     {
-        const int s = i % kFwdStages;
-        const uint32_t tile = tiles + s * kFwdTileBytes;
-        mbar_wait (bars + 8 * s, (i / kFwdStages) & 1);
-        const int nch = min (8, (T - i * kFwdTileT) >> 2);
-#pragma unroll 2 // the hot loop stays well inside the 32 KB instruction cache
-        for (int cc = 0; cc < 8; ++cc)
+        fence_proxy_async (); // my st.shared results -> visible to the TMA unit
+        __syncwarp ();
+        if (lane == 0)
         {
+            if (store)
+            {
+                tma_store_2d (tmy, (f0 + j) * kFwdTileT, b0, tiles + (j % kFwdStages) * kBytes);
+                tma_commit ();
+            }
+            const int jn = j + kFwdStages - 1; // next tile to fetch goes into the slot tile j-1 was stored from
+            if (kFwdStages > 2 && f0 + jn < t1)
+            {
+                tma_wait_read<1> ();
+                load (jn);
+            }
+        }
+    }
+};
+
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool FAST = true>
+__device__ __forceinline__ void forward_tma_body (const ClipConst& c, const FwdRing<kLanes>& ring, int t0, float* __restrict__ ckpt, float* __restrict__ zs_k, float& z, int64_t B, int T, int lane, bool valid)
+{
+    ring.prologue (lane);
+    for (int i = ring.f0; i < ring.t1; ++i)
+    {
+        const int j = i - ring.f0;
+        const uint32_t tile = ring.acquire (j);
+        const bool live = i >= t0; // warm-up tiles are computed and dropped
+        if (i == t0 && zs_k != nullptr && valid)
+            zs_k[ring.b0 + lane] = z; // the state this chunk assumes at its first sample
+        const int nch = min (kFwdChunks, (T - i * kFwdTileT) >> 2);
+#pragma unroll 2 // the hot loop stays well inside the 32 KB instruction cache
+        for (int cc = 0; cc < kFwdChunks; ++cc)
+        {
+            if (cc == kFwdChunks / 4)
+                ring.early (j, lane);
             if (cc < nch)
             {
-                if ((cc & 3) == 0 && ckpt != nullptr && valid)
-                    ckpt[(int64_t) (i * 2 + (cc >> 2)) * B + b0 + lane] = z;
-                const uint32_t addr = chunk128 (tile, lane, cc);
+                if ((cc & 3) == 0 && ckpt != nullptr && valid && live)
+                    ckpt[(int64_t) (i * (kFwdTileT / kSeg) + (cc >> 2)) * B + ring.b0 + lane] = z;
+                const uint32_t addr = chunk_fwd (tile, lane, cc);
                 const float4 v = lds128 (addr);
                 float4 o;
                 if (MODE == kModeApprox && ! GENERAL && LSMALL && FAST)
@@ -146,36 +253,31 @@ __device__ __forceinline__ void forward_tma_body (const ClipConst& c, const CUte
                     o.z = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.z, z);
                     o.w = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.w, z);
                 }
-                sts128 (addr, o);
+                if (live)
+                    sts128 (addr, o);
             }
         }
-        fence_proxy_async (); // my st.shared results -> visible to the TMA unit
-        __syncwarp ();
-        if (lane == 0)
-        {
-            tma_store_2d (tmy, i * kFwdTileT, b0, tile);
-            tma_commit ();
-            const int j = i + kFwdStages - 1; // next tile to fetch goes into the slot tile i-1 was stored from
-            if (j < ntiles)
-            {
-                tma_wait_read<1> ();
-                const int sj = j % kFwdStages;
-                mbar_expect_tx (bars + 8 * sj, kFwdTileBytes);
-                tma_load_2d (tiles + sj * kFwdTileBytes, tmx, j * kFwdTileT, b0, bars + 8 * sj);
-            }
-        }
+        ring.release (j, live, lane);
     }
     if (lane == 0)
         tma_wait_all<0> ();
 }
 
+// grid = (ceil(B / 32), kmax). zs / ze: [kmax][B] floats (only touched when the plan has more than one chunk).
 template <int MODE, bool GENERAL, bool PY>
-__global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T, int opts)
+__global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, float* __restrict__ zs, float* __restrict__ ze, int64_t B, int T, int opts)
 {
     __shared__ __align__ (1024) uint8_t smem[kFwdStages * kFwdTileBytes];
     __shared__ __align__ (8) uint64_t bar_mem[kFwdStages];
     const int lane = threadIdx.x;
     const int b0 = blockIdx.x * kLanes;
+    ClipConst c;
+    load_consts (c, desc, params);
+    const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
+    const ChunkPlan pl = plan_chunks (c, ntiles, gridDim.y);
+    const int k = blockIdx.y;
+    if (k >= pl.K)
+        return;
     const uint32_t tiles = smem_u32 (smem), bars = smem_u32 (bar_mem);
     if (lane == 0)
     {
@@ -186,86 +288,103 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_con
         fence_mbar_init ();
     }
     __syncwarp ();
-    ClipConst c;
-    load_consts (c, desc, params);
+    const int t0 = k * pl.chunk;
+    const FwdRing<kLanes> ring { tiles, bars, &tmx, &tmy, b0, max (t0 - pl.Wt, 0), min (t0 + pl.chunk, ntiles) };
     const bool valid = (int64_t) b0 + lane < B;
-    float z = (state != nullptr && valid) ? state[b0 + lane] : 0.0f;
+    // a chunk whose warm-up reaches back to the first sample starts from the true initial state (then nothing is assumed)
+    float z = (ring.f0 == 0 && state != nullptr && valid) ? state[b0 + lane] : 0.0f;
+    auto run = [&] (auto LS, auto FS) {
+        constexpr bool ls = decltype (LS)::value, fs = decltype (FS)::value;
+        forward_tma_body<MODE, GENERAL, ls, PY, fs> (c, ring, t0, ckpt, pl.K > 1 ? zs + (int64_t) k * B : nullptr, z, B, T, lane, valid);
+    };
     if (MODE == kModeApprox && ! GENERAL && fast_ok (c.pair.L))
     {
         if (opts & kOptNoFastStep) // A/B switch (dwdf_set_option): per-sample vote instead of the latency-arranged chunk
-            forward_tma_body<MODE, GENERAL, true, PY, false> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
+            run (std::true_type {}, std::false_type {});
         else
-            forward_tma_body<MODE, GENERAL, true, PY, true> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
+            run (std::true_type {}, std::true_type {});
     }
     else if ((MODE != kModeApprox || GENERAL) && rev_small_ok (c.pair)) // exact root / N_up != N_down law: cheap reverse-biased branch
-        forward_tma_body<MODE, GENERAL, true, PY, false> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
+        run (std::true_type {}, std::false_type {});
     else
-        forward_tma_body<MODE, GENERAL, false, PY> (c, &tmx, &tmy, tiles, bars, ckpt, z, B, T, lane, b0);
-    if (state != nullptr && valid)
+        run (std::false_type {}, std::true_type {});
+    if (pl.K > 1)
+    {
+        if (valid)
+            ze[(int64_t) k * B + b0 + lane] = z;
+    }
+    else if (state != nullptr && valid)
         state[b0 + lane] = z;
 }
-
-// ---- two sequences per lane: the packed-fp32x2 forward (approx root, symmetric pair) -----------------
-// One warp owns 64 sequences (lane l: rows b0 + l and b0 + 32 + l) and moves [64 x 32] tiles. Half the
-// issue slots per sample (clip_step_fastv<f2>); with one or two such warps per scheduler the kernel runs at
-// the latency of one sample chain and the HBM stream, not the issue port, sets the pace.
+// ---- two sequences per lane: the packed-fp32x2 forward (symmetric pair, approx and exact root) ------------
+// One warp owns 64 sequences (lane l: rows b0 + l and b0 + 32 + l) and moves [64 x kFwdTileT] tiles. Half the
+// issue slots per sample (clip_step_fastv<f2>); the kernel runs at the latency of one sample chain, so what sets the
+// pace is how many such chains an SM holds at once (shared memory per CTA) — and, with time chunks, how short they are.
 constexpr int kPairRows = 2 * kLanes;
-constexpr int kPairTileBytes = kPairRows * kFwdTileT * 4; // 8 KB
-constexpr int kPairStages = 3;
-constexpr int kFwdL2Ahead = 3; // tiles the L2 prefetch runs ahead of the shared-memory ring
+constexpr int kPairTileBytes = kPairRows * kFwdTileT * 4; // 8 KB / 4 KB
 
 template <int MODE, bool PY>
-__global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T, int opts)
+__global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, float* __restrict__ zs, float* __restrict__ ze, int64_t B, int T, int opts)
 {
-    __shared__ __align__ (1024) uint8_t smem[kPairStages * kPairTileBytes];
-    __shared__ __align__ (8) uint64_t bar_mem[kPairStages];
+    __shared__ __align__ (1024) uint8_t smem[kFwdStages * kPairTileBytes];
+    __shared__ __align__ (8) uint64_t bar_mem[kFwdStages];
     const int lane = threadIdx.x;
     const int b0 = blockIdx.x * kPairRows;
+    ClipConst c;
+    load_consts (c, desc, params);
+    const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
+    const ChunkPlan pl = plan_chunks (c, ntiles, gridDim.y);
+    const int k = blockIdx.y;
+    if (k >= pl.K)
+        return;
     const uint32_t tiles = smem_u32 (smem), bars = smem_u32 (bar_mem);
     if (lane == 0)
     {
         tma_prefetch_desc (&tmx);
         tma_prefetch_desc (&tmy);
-        for (int s = 0; s < kPairStages; ++s)
+        for (int s = 0; s < kFwdStages; ++s)
             mbar_init (bars + 8 * s, 1);
         fence_mbar_init ();
     }
     __syncwarp ();
-    ClipConst c;
-    load_consts (c, desc, params);
+    const int t0 = k * pl.chunk;
+    const FwdRing<kPairRows> ring { tiles, bars, &tmx, &tmy, b0, max (t0 - pl.Wt, 0), min (t0 + pl.chunk, ntiles) };
     const int64_t rowA = (int64_t) b0 + lane, rowB = rowA + kLanes;
     const bool validA = rowA < B, validB = rowB < B;
-    f2 z { (state != nullptr && validA) ? state[rowA] : 0.0f, (state != nullptr && validB) ? state[rowB] : 0.0f };
+    const bool from_state = ring.f0 == 0 && state != nullptr; // a warm-up that reaches the first sample starts from the true initial state
+    f2 z { (from_state && validA) ? state[rowA] : 0.0f, (from_state && validB) ? state[rowB] : 0.0f };
     const bool fast = MODE == kModeExact ? exact_fast_ok (c.pair) : fast_ok (c.pair.L); // warp-uniform (same parameters for every lane)
-    const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
-    if (lane == 0)
+    (void) opts;
+    ring.prologue (lane);
+    for (int i = ring.f0; i < ring.t1; ++i)
     {
-        for (int s = 0; s < kPairStages - 1 && s < ntiles; ++s)
-        {
-            mbar_expect_tx (bars + 8 * s, kPairTileBytes);
-            tma_load_2d (tiles + s * kPairTileBytes, &tmx, s * kFwdTileT, b0, bars + 8 * s);
+        const int j = i - ring.f0;
+        const uint32_t tile = ring.acquire (j);
+        const bool live = i >= t0; // warm-up tiles are computed and dropped
+        if (i == t0 && pl.K > 1)
+        { // the state this chunk assumes at its first sample
+            if (validA)
+                zs[(int64_t) k * B + rowA] = z.x;
+            if (validB)
+                zs[(int64_t) k * B + rowB] = z.y;
         }
-    }
-    for (int i = 0; i < ntiles; ++i)
-    {
-        const int s = i % kPairStages;
-        const uint32_t tile = tiles + s * kPairTileBytes;
-        mbar_wait (bars + 8 * s, (i / kPairStages) & 1);
-        const int nch = min (8, (T - i * kFwdTileT) >> 2);
+        const int nch = min (kFwdChunks, (T - i * kFwdTileT) >> 2);
 #pragma unroll 2
-        for (int cc = 0; cc < 8; ++cc)
+        for (int cc = 0; cc < kFwdChunks; ++cc)
         {
+            if (cc == kFwdChunks / 4)
+                ring.early (j, lane);
             if (cc < nch)
             {
-                if ((cc & 3) == 0 && ckpt != nullptr)
+                if ((cc & 3) == 0 && ckpt != nullptr && live)
                 {
-                    float* ck = ckpt + (int64_t) (i * 2 + (cc >> 2)) * B;
+                    float* ck = ckpt + (int64_t) (i * (kFwdTileT / kSeg) + (cc >> 2)) * B;
                     if (validA)
                         ck[rowA] = z.x;
                     if (validB)
                         ck[rowB] = z.y;
                 }
-                const uint32_t addrA = chunk128 (tile, lane, cc), addrB = addrA + kLanes * 128; // row + 32: same swizzle phase
+                const uint32_t addrA = chunk_fwd (tile, lane, cc), addrB = addrA + kLanes * kFwdTileT * 4; // row + 32: same swizzle phase
                 const float4 va = lds128 (addrA), vb = lds128 (addrB);
                 float4 oa, ob;
                 if (fast)
@@ -290,31 +409,25 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __gri
                     clip_chunk_any<MODE, PY> (c, xb, z.y, os);
                     ob = make_float4 (os[0], os[1], os[2], os[3]);
                 }
-                sts128 (addrA, oa);
-                sts128 (addrB, ob);
+                if (live)
+                {
+                    sts128 (addrA, oa);
+                    sts128 (addrB, ob);
+                }
             }
         }
-        fence_proxy_async ();
-        __syncwarp ();
-        if (lane == 0)
-        {
-            tma_store_2d (&tmy, i * kFwdTileT, b0, tile);
-            tma_commit ();
-            const int j = i + kPairStages - 1;
-            if (j + kFwdL2Ahead < ntiles && (opts & kOptL2Prefetch) != 0)
-                tma_prefetch_l2_2d (&tmx, (j + kFwdL2Ahead) * kFwdTileT, b0);
-            if (j < ntiles)
-            {
-                tma_wait_read<1> ();
-                const int sj = j % kPairStages;
-                mbar_expect_tx (bars + 8 * sj, kPairTileBytes);
-                tma_load_2d (tiles + sj * kPairTileBytes, &tmx, j * kFwdTileT, b0, bars + 8 * sj);
-            }
-        }
+        ring.release (j, live, lane);
     }
     if (lane == 0)
         tma_wait_all<0> ();
-    if (state != nullptr)
+    if (pl.K > 1)
+    {
+        if (validA)
+            ze[(int64_t) k * B + rowA] = z.x;
+        if (validB)
+            ze[(int64_t) k * B + rowB] = z.y;
+    }
+    else if (state != nullptr)
     {
         if (validA)
             state[rowA] = z.x;
@@ -377,6 +490,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_direct (const float* 
 struct AdjAcc
 {
     double g = 0.0, l = 0.0, v = 0.0, sse = 0.0, st2 = 0.0;
+    double hg = 0.0, hl = 0.0, hv = 0.0; // time chunks: the same sums for the homogeneous solution (no sources, G_in = 1)
 };
 
 // One checkpoint segment of the reverse sweep. Nothing of the forward pass is replayed: the states
@@ -388,8 +502,10 @@ struct AdjAcc
 //   IO::x4 / y4 / g4 (cc): 4 samples of x / forward output / (dL/dy or target); IO::put_gx: dL/dx.
 //   FULL: all kSeg samples are valid, none is skipped by the loss and (plugin ordering) none is the
 //   sequence's last — the common case, free of per-sample predicates.
-template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, bool FULL, class IO>
-__device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io, float z0, float zend, float& G, AdjAcc& acc, int n0, int nvalid, int skip, int last)
+//   HOMOG (time chunks): the chunk does not know its incoming adjoint, so next to the particular solution G (sources,
+//   G_in = 0) it carries the homogeneous one H (no sources, G_in = 1) and the parameter sums weighted with it.
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, bool FULL, bool HOMOG, class IO>
+__device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc, int n0, int nvalid, int skip, int last)
 {
     float zs[kSeg + 1];
     zs[0] = z0;
@@ -409,7 +525,7 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
     }
     if (! PY)
         zs[kSeg] = zend;
-    float ag = 0.0f, al = 0.0f, av = 0.0f, sse = 0.0f, st2 = 0.0f;
+    float ag = 0.0f, al = 0.0f, av = 0.0f, sse = 0.0f, st2 = 0.0f, hg = 0.0f, hl = 0.0f, hv = 0.0f;
     const float gxk = c.gamma / c.one_m_gamma; // dz'/dx = gamma (f'+1) = (A + 1) gamma / (1 - gamma)
 #pragma unroll
     for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
@@ -436,7 +552,11 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
                         st2 = on ? fma_ (gs[k], gs[k], st2) : st2;
                     }
                     if (! FULL && ! PY && idx == last)
+                    {
                         G = gy; // plugin ordering never observes z[T]: the final step has nothing to recover and feeds nothing back
+                        if (HOMOG)
+                            H = 0.0f;
+                    }
                     else
                     {
                         StepTape tp;
@@ -449,6 +569,13 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
                         if (WANT_GX)
                             gxs[k] = G * (tp.A + 1.0f) * gxk;
                         G = fma_ (G, tp.A, PY ? 0.5f * gy : gy);
+                        if (HOMOG)
+                        {
+                            hg = fma_ (H, tp.cg, hg);
+                            hl = fma_ (H, tp.cl, hl);
+                            hv = fma_ (H, tp.cv, hv);
+                            H *= tp.A;
+                        }
                     }
                 }
             }
@@ -459,6 +586,12 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
     acc.g += (double) ag;
     acc.l += (double) al;
     acc.v += (double) av;
+    if (HOMOG)
+    {
+        acc.hg += (double) hg;
+        acc.hl += (double) hl;
+        acc.hv += (double) hv;
+    }
     if (TARGET)
     {
         acc.sse += (double) sse;
@@ -470,8 +603,8 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
 // (approx root, symmetric pair, fast-path parameters) on pairs of consecutive samples in packed fp32x2:
 // 8 pair-steps of clip_step_recoverv<f2> instead of 16 scalar ones; only the state reconstruction
 // (one FMA per sample) and the adjoint recurrence (two FMAs per sample) run per element.
-template <int MODE, bool PY, bool TARGET, class IO>
-__device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& io, float z0, float zend, float& G, AdjAcc& acc)
+template <int MODE, bool PY, bool TARGET, bool HOMOG, class IO>
+__device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc)
 {
     constexpr int NP = kSeg / 2;
     f2 z2[NP], zn2[NP]; // (z[2p], z[2p+1]) and (z[2p+1], z[2p+2])
@@ -505,6 +638,7 @@ __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& i
     if (! PY)
         zn2[NP - 1].y = zend;
     f2 ag { 0.0f, 0.0f }, al { 0.0f, 0.0f }, av { 0.0f, 0.0f }, sse { 0.0f, 0.0f }, st2 { 0.0f, 0.0f };
+    f2 hg { 0.0f, 0.0f }, hl { 0.0f, 0.0f }, hv { 0.0f, 0.0f };
 #pragma unroll
     for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
     {
@@ -547,11 +681,28 @@ __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& i
             ag = fmav (Gm, tp.cg, ag);
             al = fmav (Gm, tp.cl, al);
             av = fmav (Gm, tp.cv, av);
+            if (HOMOG)
+            { // the homogeneous solution has no sources: each sample's terms are weighted with H before its own step
+                f2 Hm;
+                Hm.y = H;
+                H *= tp.A.y;
+                Hm.x = H;
+                H *= tp.A.x;
+                hg = fmav (Hm, tp.cg, hg);
+                hl = fmav (Hm, tp.cl, hl);
+                hv = fmav (Hm, tp.cv, hv);
+            }
         }
     }
     acc.g += (double) (ag.x + ag.y);
     acc.l += (double) (al.x + al.y);
     acc.v += (double) (av.x + av.y);
+    if (HOMOG)
+    {
+        acc.hg += (double) (hg.x + hg.y);
+        acc.hl += (double) (hl.x + hl.y);
+        acc.hv += (double) (hv.x + hv.y);
+    }
     if (TARGET)
     {
         acc.sse += (double) (sse.x + sse.y);
@@ -559,18 +710,18 @@ __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& i
     }
 }
 
-template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, class IO>
-__device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, float z0, float zend, float& G, AdjAcc& acc, int n0, int nvalid, int skip, int last)
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, bool HOMOG, class IO>
+__device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc, int n0, int nvalid, int skip, int last)
 {
     if (nvalid == kSeg && n0 >= skip && (PY || last >= kSeg))
     {
         if ((MODE == kModeApprox || MODE == kModeExact) && ! GENERAL && LSMALL && ! WANT_GX)
-            adjoint_segment_pairs<MODE, PY, TARGET> (c, io, z0, zend, G, acc);
+            adjoint_segment_pairs<MODE, PY, TARGET, HOMOG> (c, io, z0, zend, G, H, acc);
         else
-            adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, true> (c, io, z0, zend, G, acc, n0, nvalid, skip, last);
+            adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, true, HOMOG> (c, io, z0, zend, G, H, acc, n0, nvalid, skip, last);
     }
     else
-        adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, false> (c, io, z0, zend, G, acc, n0, nvalid, skip, last);
+        adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, false, HOMOG> (c, io, z0, zend, G, H, acc, n0, nvalid, skip, last);
 }
 
 __device__ __forceinline__ void write_partials (AdjAcc& acc, double* __restrict__ partials, int group, int lane)
@@ -598,22 +749,23 @@ struct TileIO
     __device__ __forceinline__ void put_gx (int, float4) const {}
 };
 
-template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET>
-__device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUtensorMap* tmx, const CUtensorMap* tmy, const CUtensorMap* tmg, uint32_t tiles, uint32_t bars, const float* __restrict__ ckpt, AdjAcc& acc, int64_t B, int T, int skip, int lane, int b0, bool l2_ahead)
+// Segments [s0, s1) of the rows starting at b0, last to first.
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool HOMOG>
+__device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUtensorMap* tmx, const CUtensorMap* tmy, const CUtensorMap* tmg, uint32_t tiles, uint32_t bars, const float* __restrict__ ckpt, AdjAcc& acc, float& G, float& H, int64_t B, int T, int skip, int lane, int b0, int s0, int s1, bool l2_ahead)
 {
-    const int nseg = (T + kSeg - 1) / kSeg;
+    const int nseg = s1 - s0; // of this chunk
     const bool valid = (int64_t) b0 + lane < B;
     constexpr int kStageBytes = 3 * kAdjTileBytes;
     auto prefetch = [&] (int k) { // HBM -> L2, kAdjL2Ahead segments ahead of the ring
-        const int i = nseg - 1 - k;
+        const int i = s1 - 1 - k;
         tma_prefetch_l2_2d (tmx, i * kSeg, b0);
         tma_prefetch_l2_2d (tmy, i * kSeg, b0);
         tma_prefetch_l2_2d (tmg, i * kSeg, b0);
     };
-    auto fetch = [&] (int k) { // the k-th processed segment is i = nseg - 1 - k
+    auto fetch = [&] (int k) { // the k-th processed segment is i = s1 - 1 - k
         if (k + kAdjL2Ahead < nseg && l2_ahead)
             prefetch (k + kAdjL2Ahead);
-        const int i = nseg - 1 - k, s = k % kAdjStages;
+        const int i = s1 - 1 - k, s = k % kAdjStages;
         const uint32_t dst = tiles + s * kStageBytes, bar = bars + 8 * s;
         mbar_expect_tx (bar, kStageBytes);
         tma_load_2d (dst, tmx, i * kSeg, b0, bar);
@@ -628,15 +780,15 @@ __device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUte
         for (int k = 0; k < kAdjStages - 1 && k < nseg; ++k)
             fetch (k);
     }
-    float G = 0.0f;
-    float zend = 0.0f; // plugin ordering: state after the segment = checkpoint of the next one (nothing depends on it past the end)
-    float znext = valid ? __ldg (ckpt + (int64_t) (nseg - 1) * B + b0 + lane) : 0.0f;
+    // plugin ordering: the state after a segment = the checkpoint of the next one (nothing depends on it past the sequence's end)
+    float zend = (! PY && valid && (int64_t) s1 * kSeg < T) ? __ldg (ckpt + (int64_t) s1 * B + b0 + lane) : 0.0f;
+    float znext = valid ? __ldg (ckpt + (int64_t) (s1 - 1) * B + b0 + lane) : 0.0f;
     for (int k = 0; k < nseg; ++k)
     {
-        const int i = nseg - 1 - k;
+        const int i = s1 - 1 - k;
         const int s = k % kAdjStages;
         const float z0 = znext;
-        if (i > 0 && valid)
+        if (i > s0 && valid)
             znext = __ldg (ckpt + (int64_t) (i - 1) * B + b0 + lane); // in flight while this segment is processed
         if (k + kAdjStages - 1 < nseg)
         { // refill the slot the previous segment was read from
@@ -647,13 +799,17 @@ __device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUte
         }
         mbar_wait (bars + 8 * s, (k / kAdjStages) & 1);
         TileIO io { tiles + s * kStageBytes, tiles + s * kStageBytes + kAdjTileBytes, tiles + s * kStageBytes + 2 * kAdjTileBytes, lane };
-        adjoint_segment<MODE, GENERAL, LSMALL, PY, TARGET, false> (c, io, z0, zend, G, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
+        adjoint_segment<MODE, GENERAL, LSMALL, PY, TARGET, false, HOMOG> (c, io, z0, zend, G, H, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
         zend = z0;
     }
 }
 
+constexpr int kMapFloats = kMapFloatsPerChunk; // per (chunk, sequence): P, Q, S0[3], S1[3], sse, st2 — stored [chunk][field][B]
+
+// grid = (ceil(B / 32), K): CTA (g, k) sweeps the segments of time chunk k (chunk_segs each). K == 1: the sums go
+// straight to partials[g]; K > 1: every lane writes the affine map of its (sequence, chunk) to cmaps.
 template <int MODE, bool GENERAL, bool PY, bool TARGET>
-__global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg, const float* __restrict__ params, const ClipDesc desc, const float* __restrict__ ckpt, double* __restrict__ partials, int64_t B, int T, int skip, int opts)
+__global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg, const float* __restrict__ params, const ClipDesc desc, const float* __restrict__ ckpt, double* __restrict__ partials, float* __restrict__ cmaps, int chunk_segs, int64_t B, int T, int skip, int opts)
 {
     __shared__ __align__ (1024) uint8_t smem[kAdjStages * 3 * kAdjTileBytes];
     __shared__ __align__ (8) uint64_t bar_mem[kAdjStages];
@@ -673,10 +829,54 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid
     ClipConst c;
     load_consts (c, desc, params);
     AdjAcc acc;
+    float G = 0.0f, H = 1.0f;
+    const int nseg = (T + kSeg - 1) / kSeg;
+    const bool l2 = (opts & kOptL2Prefetch) != 0;
+    if (gridDim.y == 1)
+    {
+        if (rev_small_ok (c.pair))
+            adjoint_tma_body<MODE, GENERAL, true, PY, TARGET, false> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, 0, nseg, l2);
+        else
+            adjoint_tma_body<MODE, GENERAL, false, PY, TARGET, false> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, 0, nseg, l2);
+        write_partials (acc, partials, blockIdx.x, lane);
+        return;
+    }
+    const int s0 = blockIdx.y * chunk_segs, s1 = min (s0 + chunk_segs, nseg);
     if (rev_small_ok (c.pair))
-        adjoint_tma_body<MODE, GENERAL, true, PY, TARGET> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, B, T, skip, lane, b0, (opts & kOptL2Prefetch) != 0);
+        adjoint_tma_body<MODE, GENERAL, true, PY, TARGET, true> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, s0, s1, l2);
     else
-        adjoint_tma_body<MODE, GENERAL, false, PY, TARGET> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, B, T, skip, lane, b0, (opts & kOptL2Prefetch) != 0);
+        adjoint_tma_body<MODE, GENERAL, false, PY, TARGET, true> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, s0, s1, l2);
+    if ((int64_t) b0 + lane < B)
+    {
+        float* o = cmaps + (int64_t) blockIdx.y * kMapFloats * B + b0 + lane;
+        o[0] = H, o[B] = G;
+        o[2 * B] = (float) acc.g, o[3 * B] = (float) acc.l, o[4 * B] = (float) acc.v;
+        o[5 * B] = (float) acc.hg, o[6 * B] = (float) acc.hl, o[7 * B] = (float) acc.hv;
+        o[8 * B] = (float) acc.sse, o[9 * B] = (float) acc.st2;
+    }
+}
+
+// one lane per sequence: compose the chunks' affine maps last to first; one partial per group of 32 sequences
+template <int PART> // (one instance per translation unit of this file)
+__global__ void __launch_bounds__ (kLanes) clipper_adjoint_stitch (const float* __restrict__ cmaps, double* __restrict__ partials, int64_t B, int K)
+{
+    const int lane = threadIdx.x;
+    const int64_t b = (int64_t) blockIdx.x * kLanes + lane;
+    AdjAcc acc;
+    if (b < B)
+    {
+        double G = 0.0;
+        for (int k = K - 1; k >= 0; --k)
+        {
+            const float* o = cmaps + (int64_t) k * kMapFloats * B + b;
+            acc.g += (double) o[2 * B] + G * (double) o[5 * B];
+            acc.l += (double) o[3 * B] + G * (double) o[6 * B];
+            acc.v += (double) o[4 * B] + G * (double) o[7 * B];
+            acc.sse += (double) o[8 * B];
+            acc.st2 += (double) o[9 * B];
+            G = (double) o[0] * G + (double) o[B];
+        }
+    }
     write_partials (acc, partials, blockIdx.x, lane);
 }
 
@@ -712,13 +912,13 @@ template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_G
 __device__ __forceinline__ void adjoint_direct_body (const ClipConst& c, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g, float* __restrict__ gx, const float* __restrict__ ckpt, AdjAcc& acc, int64_t B, int64_t b, int T, int skip)
 {
     const int nseg = (T + kSeg - 1) / kSeg;
-    float G = 0.0f, zend = 0.0f;
+    float G = 0.0f, H = 1.0f, zend = 0.0f;
     GlobalIO io { x + b * T, y + b * T, g + b * T, WANT_GX ? gx + b * T : nullptr, 0, T };
     for (int i = nseg - 1; i >= 0; --i)
     {
         io.n0 = i * kSeg;
         const float z0 = __ldg (ckpt + (int64_t) i * B + b);
-        adjoint_segment<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX> (c, io, z0, zend, G, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
+        adjoint_segment<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, false> (c, io, z0, zend, G, H, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
         zend = z0;
     }
 }
@@ -742,39 +942,9 @@ __global__ void __launch_bounds__ (kLanes, 12) clipper_adjoint_direct (const flo
 }
 
 // =================================================================================================
-// time-parallel kernels for small batches
+// time chunks: verification of the forward pass (the scheme is described above plan_chunks)
 // =================================================================================================
-// With one lane per sequence a batch of B sequences gives B / 32 warps however long the sequences are:
-// 8 warps for config 2 (256 x 4096), 32 for config 3 — a B200 has 592 schedulers. The recurrence is
-// strictly serial in time, but it is CONTRACTIVE (|dz'/dz| = |f'(a)(1 - gamma) - gamma| < 1; with the
-// diodes off it forgets its state like the RC time constant, faster when they conduct), so a sequence is
-// cut into chunks of kChunk samples that run concurrently, one lane per (sequence, chunk):
-//   forward  chunk k > 0 starts W samples early from z = 0 and discards that warm-up; W is chosen in the
-//            kernel from gamma so that the off-state decay (1 - 2 gamma)^W is below 1e-13. It records the
-//            state it assumed at its first sample and the state it ended with. A second, tiny kernel walks
-//            each sequence's chunks in order and ACCEPTS chunk k only if its assumed start equals the
-//            true end of chunk k-1 BIT FOR BIT (a contractive map in fp32 merges two trajectories exactly
-//            once they are within an ulp or so); otherwise that chunk is recomputed from the true state
-//            (hard-driven inputs, where the contraction is slow). The output is therefore identical to the
-//            serial kernels' whatever the chunking: the result never rests on the speculation being right.
-//   adjoint  needs no speculation: given the trajectory (recovered from y), the running adjoint is a
-//            LINEAR recurrence G <- A[n] G + q[n], so a chunk returns the affine map of its incoming G
-//            (P, Q) and of its parameter sums (S0 + G_in S1); a second kernel composes the chunks of each
-//            sequence in reverse order. Exact up to fp32 summation order.
-constexpr int kChunk = kTimeChunk; // samples per chunk (a multiple of kSeg)
-
-__device__ __forceinline__ int warmup_samples (const ClipConst& c, int n0)
-{
-    // off-state contraction per sample: dz'/dz = 1 - 2 gamma (f' = 1). (1 - 2 gamma)^W <= 1e-13: far enough below
-    // one ulp of a quiet signal that the speculated and the true trajectory have merged bit for bit
-    const float rho = fmaxf (fabsf (1.0f - 2.0f * c.gamma), 0.5f);
-    const float w = -29.9f / logf (fminf (rho, 0.99f));
-    int W = (int) fminf (w, 1.0e6f);
-    W = (W + 3) & ~3;
-    return W < n0 ? W : n0;
-}
-
-// 4 samples of one sequence, any variant
+// 4 samples of one sequence, any variant — the same arithmetic as the TMA kernels, bit for bit per sequence
 template <int MODE, bool GENERAL, bool LSMALL, bool PY>
 __device__ __forceinline__ float4 chunk4 (const ClipConst& c, float4 v, float& z)
 {
@@ -788,234 +958,68 @@ __device__ __forceinline__ float4 chunk4 (const ClipConst& c, float4 v, float& z
     return o;
 }
 
-// samples [n0, n1) of row b from state z: outputs, checkpoints; returns the end state in z. T % 4 == 0, 16-byte aligned rows.
+// Chunk [n0, n1) of row b again, from the true state z, until the recomputed state meets the speculated trajectory
+// at a checkpoint bit for bit (everything after that point is what the serial recurrence computes) or the chunk
+// ends. Returns true if it merged. T % 4 == 0, 16-byte aligned rows; rewrites y and the checkpoints it passes.
 template <int MODE, bool GENERAL, bool LSMALL, bool PY>
-__device__ __forceinline__ void run_span (const ClipConst& c, const float* __restrict__ xr, float* __restrict__ yr, float* __restrict__ ckpt, int64_t B, int64_t b, int n0, int n1, float& z)
+__device__ __forceinline__ bool redo_until_merged (const ClipConst& c, const float* __restrict__ xr, float* __restrict__ yr, float* __restrict__ ckpt, int64_t B, int64_t b, int n0, int n1, float& z)
 {
-    // the loads run one 16-sample segment ahead of the recurrence (a lane's own latency is all there is to hide here)
-    const float4 zero4 = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-    float4 nx[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        nx[q] = n0 + 4 * q < n1 ? __ldg (reinterpret_cast<const float4*> (xr + n0 + 4 * q)) : zero4;
-    for (int n = n0; n < n1; n += 16)
+    for (int n = n0; n < n1; n += kSeg)
     {
-        float4 cur[4];
+        float* ck = ckpt + (int64_t) (n / kSeg) * B + b;
+        if (n > n0 && __float_as_int (*ck) == __float_as_int (z))
+            return true;
+        *ck = z;
+        float4 v[kSeg / 4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-        {
-            cur[q] = nx[q];
-            nx[q] = n + 16 + 4 * q < n1 ? __ldg (reinterpret_cast<const float4*> (xr + n + 16 + 4 * q)) : zero4;
-        }
+        for (int q = 0; q < kSeg / 4; ++q)
+            v[q] = n + 4 * q < n1 ? __ldg (reinterpret_cast<const float4*> (xr + n + 4 * q)) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-        {
-            const int m = n + 4 * q;
-            if (m < n1)
-            {
-                if ((m & (kSeg - 1)) == 0 && ckpt != nullptr)
-                    ckpt[(int64_t) (m / kSeg) * B + b] = z;
-                *reinterpret_cast<float4*> (yr + m) = chunk4<MODE, GENERAL, LSMALL, PY> (c, cur[q], z);
-            }
-        }
+        for (int q = 0; q < kSeg / 4; ++q)
+            if (n + 4 * q < n1)
+                *reinterpret_cast<float4*> (yr + n + 4 * q) = chunk4<MODE, GENERAL, LSMALL, PY> (c, v[q], z);
     }
+    return false;
 }
 
-template <int MODE, bool GENERAL, bool PY>
-__global__ void __launch_bounds__ (128) clipper_forward_chunked (const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, const float* __restrict__ state,
-                                                                float* __restrict__ zs, float* __restrict__ ze, int64_t B, int T, int K)
-{
-    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * K)
-        return;
-    const int64_t b = i / K;
-    const int k = (int) (i % K);
-    ClipConst c;
-    load_consts (c, desc, params);
-    const bool ls = (MODE == kModeApprox && ! GENERAL) ? fast_ok (c.pair.L) : rev_small_ok (c.pair);
-    const int n0 = k * kChunk, n1 = min (n0 + kChunk, T);
-    const int W = warmup_samples (c, n0);
-    const float* xr = x + b * T;
-    // warm-up from z = 0, or — when it reaches back to the first sample — from the true initial state (then nothing is assumed)
-    float z = (n0 - W == 0 && state != nullptr) ? state[b] : 0.0f;
-    float4 vn = W > 0 ? __ldg (reinterpret_cast<const float4*> (xr + n0 - W)) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-    for (int n = n0 - W; n < n0; n += 4)
-    {
-        const float4 v = vn;
-        if (n + 4 < n0)
-            vn = __ldg (reinterpret_cast<const float4*> (xr + n + 4));
-        if (ls)
-            (void) chunk4<MODE, GENERAL, true, PY> (c, v, z);
-        else
-            (void) chunk4<MODE, GENERAL, false, PY> (c, v, z);
-    }
-    zs[i] = z; // the state this chunk assumes at its first sample
-    if (ls)
-        run_span<MODE, GENERAL, true, PY> (c, xr, y + b * T, ckpt, B, b, n0, n1, z);
-    else
-        run_span<MODE, GENERAL, false, PY> (c, xr, y + b * T, ckpt, B, b, n0, n1, z);
-    ze[i] = z;
-}
-
-// one lane per sequence: accept or redo each chunk in order; writes the final state
+// one lane per sequence: accept or redo each chunk in order; writes the final state. `pair`: the forward ran on the
+// two-sequences-per-lane kernel (whose choice of step for out-of-range parameters this kernel has to repeat).
 template <int MODE, bool GENERAL, bool PY>
 __global__ void __launch_bounds__ (128) clipper_forward_stitch (const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state,
-                                                               const float* __restrict__ zs, const float* __restrict__ ze, int64_t B, int T, int K, int* __restrict__ redone)
+                                                               const float* __restrict__ zs, const float* __restrict__ ze, int64_t B, int T, int kmax, int pair, int* __restrict__ redone)
 {
     const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B)
         return;
     ClipConst c;
     load_consts (c, desc, params);
-    const bool ls = (MODE == kModeApprox && ! GENERAL) ? fast_ok (c.pair.L) : rev_small_ok (c.pair);
+    const ChunkPlan pl = plan_chunks (c, (T + kFwdTileT - 1) / kFwdTileT, kmax);
+    const int K = pl.K;
+    if (K <= 1)
+        return; // one chunk after all (long circuit memory): the forward kernel has written the state itself
+    const bool ls = (MODE == kModeApprox && ! GENERAL) ? fast_ok (c.pair.L) : ((pair && MODE == kModeExact) ? exact_fast_ok (c.pair) : rev_small_ok (c.pair));
     // the common case first, with independent loads: every chunk started from its predecessor's end state
     int first_bad = K;
     for (int k = K - 1; k >= 1; --k)
-        if (! (zs[b * K + k] == ze[b * K + k - 1]))
+        if (__float_as_int (zs[(int64_t) k * B + b]) != __float_as_int (ze[(int64_t) (k - 1) * B + b]))
             first_bad = k;
-    float zend = ze[b * K + (first_bad < K ? first_bad - 1 : K - 1)];
+    float zend = ze[(int64_t) (first_bad < K ? first_bad - 1 : K - 1) * B + b];
     for (int k = first_bad; k < K; ++k)
     {
-        const float assumed = zs[b * K + k];
-        if (assumed == zend) // bit for bit: an accepted chunk is exactly what the serial recurrence computes
+        if (__float_as_int (zs[(int64_t) k * B + b]) == __float_as_int (zend)) // bit for bit: an accepted chunk is exactly what the serial recurrence computes
         {
-            zend = ze[b * K + k];
+            zend = ze[(int64_t) k * B + b];
             continue;
         }
         float z = zend; // the speculation missed: this chunk again, from the true state
-        const int n0 = k * kChunk, n1 = min (n0 + kChunk, T);
-        if (ls)
-            run_span<MODE, GENERAL, true, PY> (c, x + b * T, y + b * T, ckpt, B, b, n0, n1, z);
-        else
-            run_span<MODE, GENERAL, false, PY> (c, x + b * T, y + b * T, ckpt, B, b, n0, n1, z);
-        zend = z;
+        const int n0 = k * pl.chunk * kFwdTileT, n1 = min (n0 + pl.chunk * kFwdTileT, T);
+        const bool merged = ls ? redo_until_merged<MODE, GENERAL, true, PY> (c, x + b * T, y + b * T, ckpt, B, b, n0, n1, z) : redo_until_merged<MODE, GENERAL, false, PY> (c, x + b * T, y + b * T, ckpt, B, b, n0, n1, z);
+        zend = merged ? ze[(int64_t) k * B + b] : z;
         if (redone != nullptr)
             atomicAdd (redone, 1);
     }
     if (state != nullptr)
         state[b] = zend;
-}
-
-// ---- adjoint ---------------------------------------------------------------------------------------
-constexpr int kChunkOut = 12; // floats per (sequence, chunk): P, Q, S0[3], S1[3], sse, st2, pad
-
-template <int MODE, bool GENERAL, bool PY, bool TARGET>
-__global__ void __launch_bounds__ (128) clipper_adjoint_chunked (const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ params, const ClipDesc desc,
-                                                                const float* __restrict__ ckpt, float* __restrict__ cout, int64_t B, int T, int K, int skip)
-{
-    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * K)
-        return;
-    const int64_t b = i / K;
-    const int k = (int) (i % K);
-    ClipConst c;
-    load_consts (c, desc, params);
-    const bool ls = rev_small_ok (c.pair);
-    const int n0 = k * kChunk, n1 = min (n0 + kChunk, T);
-    const float *xr = x + b * T, *yr = y + b * T, *gr = g + b * T;
-    float Gp = 0.0f, Gh = 1.0f; // particular (sources, G_in = 0) and homogeneous (no sources, G_in = 1) solutions
-    float s0[3] = { 0.0f, 0.0f, 0.0f }, s1[3] = { 0.0f, 0.0f, 0.0f }, sse = 0.0f, st2 = 0.0f;
-    for (int seg0 = ((n1 - 1) / kSeg) * kSeg; seg0 >= n0; seg0 -= kSeg)
-    {
-        const int nv = min (kSeg, n1 - seg0);
-        // every load of the segment up front (T % 4 == 0, 16-byte aligned rows): one memory latency per 16 samples
-        const float4 zero4 = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-        float4 y4[kSeg / 4], x4[kSeg / 4], g4[kSeg / 4];
-#pragma unroll
-        for (int q = 0; q < kSeg / 4; ++q)
-        {
-            const bool in = seg0 + 4 * q < n1;
-            y4[q] = in ? __ldg (reinterpret_cast<const float4*> (yr + seg0 + 4 * q)) : zero4;
-            x4[q] = in ? __ldg (reinterpret_cast<const float4*> (xr + seg0 + 4 * q)) : zero4;
-            g4[q] = in ? __ldg (reinterpret_cast<const float4*> (gr + seg0 + 4 * q)) : zero4;
-        }
-        float zs[kSeg + 1];
-        zs[0] = __ldg (ckpt + (int64_t) (seg0 / kSeg) * B + b);
-        const float znext = (! PY && seg0 + nv < T) ? __ldg (ckpt + (int64_t) ((seg0 + nv) / kSeg) * B + b) : 0.0f; // nv == kSeg whenever another segment follows
-        float ys[kSeg], xs[kSeg], gs[kSeg];
-#pragma unroll
-        for (int q = 0; q < kSeg / 4; ++q)
-        {
-            ys[4 * q] = y4[q].x, ys[4 * q + 1] = y4[q].y, ys[4 * q + 2] = y4[q].z, ys[4 * q + 3] = y4[q].w;
-            xs[4 * q] = x4[q].x, xs[4 * q + 1] = x4[q].y, xs[4 * q + 2] = x4[q].z, xs[4 * q + 3] = x4[q].w;
-            gs[4 * q] = g4[q].x, gs[4 * q + 1] = g4[q].y, gs[4 * q + 2] = g4[q].z, gs[4 * q + 3] = g4[q].w;
-        }
-#pragma unroll
-        for (int q = 0; q < kSeg; ++q)
-        {
-            if (PY)
-                zs[q + 1] = fma_ (2.0f, ys[q], -zs[q]);
-            else
-                zs[q] = ys[q];
-        }
-        if (! PY)
-            zs[nv] = znext;
-#pragma unroll
-        for (int q = kSeg - 1; q >= 0; --q)
-        {
-            if (q < nv)
-            {
-                const int n = seg0 + q;
-                float gy = gs[q];
-                if (TARGET)
-                {
-                    const bool on = n >= skip;
-                    const float yk = PY ? 0.5f * (zs[q + 1] + zs[q]) : zs[q];
-                    const float tv = gy;
-                    gy = on ? yk - tv : 0.0f;
-                    sse = fma_ (gy, gy, sse);
-                    st2 = on ? fma_ (tv, tv, st2) : st2;
-                }
-                if (! PY && n == T - 1)
-                { // plugin ordering never observes z[T]
-                    Gp = gy;
-                    Gh = 0.0f;
-                }
-                else
-                {
-                    StepTape tp;
-                    if (ls)
-                        clip_step_recover<MODE, GENERAL, true> (c, xs[q], zs[q], zs[q + 1], tp);
-                    else
-                        clip_step_recover<MODE, GENERAL, false> (c, xs[q], zs[q], zs[q + 1], tp);
-                    if (PY)
-                        Gp = fma_ (0.5f, gy, Gp);
-                    s0[0] = fma_ (Gp, tp.cg, s0[0]), s0[1] = fma_ (Gp, tp.cl, s0[1]), s0[2] = fma_ (Gp, tp.cv, s0[2]);
-                    s1[0] = fma_ (Gh, tp.cg, s1[0]), s1[1] = fma_ (Gh, tp.cl, s1[1]), s1[2] = fma_ (Gh, tp.cv, s1[2]);
-                    Gp = fma_ (Gp, tp.A, PY ? 0.5f * gy : gy);
-                    Gh *= tp.A;
-                }
-            }
-        }
-    }
-    float* o = cout + i * kChunkOut;
-    o[0] = Gh, o[1] = Gp;
-    o[2] = s0[0], o[3] = s0[1], o[4] = s0[2];
-    o[5] = s1[0], o[6] = s1[1], o[7] = s1[2];
-    o[8] = sse, o[9] = st2;
-}
-
-// one lane per sequence: compose the chunks' affine maps last to first; one partial per group of 32 sequences
-__global__ void __launch_bounds__ (kLanes) clipper_adjoint_stitch (const float* __restrict__ cout, double* __restrict__ partials, int64_t B, int K)
-{
-    const int lane = threadIdx.x;
-    const int64_t b = (int64_t) blockIdx.x * kLanes + lane;
-    AdjAcc acc;
-    if (b < B)
-    {
-        double G = 0.0;
-        for (int k = K - 1; k >= 0; --k)
-        {
-            const float* o = cout + (b * K + k) * kChunkOut;
-            acc.g += (double) o[2] + G * (double) o[5];
-            acc.l += (double) o[3] + G * (double) o[6];
-            acc.v += (double) o[4] + G * (double) o[7];
-            acc.sse += (double) o[8];
-            acc.st2 += (double) o[9];
-            G = (double) o[0] * G + (double) o[1];
-        }
-    }
-    write_partials (acc, partials, blockIdx.x, lane);
 }
 
 // =================================================================================================
@@ -1069,22 +1073,22 @@ struct TrainState
 template <int MODE, bool GENERAL, bool LSMALL, bool PY>
 __device__ __forceinline__ void train_tma_body (const ClipConst& c, const CUtensorMap* tmx, const CUtensorMap* tmt, const CUtensorMap* tmy, bool want_y, uint32_t tiles, uint32_t bars, AdjAcc& acc, int T, int skip, int lane, int b0)
 {
-    constexpr int kStageBytes = 2 * kFwdTileBytes; // x tile (outputs written in place) + target tile
+    constexpr int kStageBytes = 2 * kTrainTileBytes; // x tile (outputs written in place) + target tile
     constexpr int kStages = 2;
-    const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
+    const int ntiles = (T + kTrainTileT - 1) / kTrainTileT;
     if (lane == 0)
     {
         mbar_expect_tx (bars, kStageBytes);
         tma_load_2d (tiles, tmx, 0, b0, bars);
-        tma_load_2d (tiles + kFwdTileBytes, tmt, 0, b0, bars);
+        tma_load_2d (tiles + kTrainTileBytes, tmt, 0, b0, bars);
     }
     TrainState<MODE, GENERAL, LSMALL, PY> st;
     for (int i = 0; i < ntiles; ++i)
     {
         const int s = i % kStages;
-        const uint32_t xt = tiles + s * kStageBytes, tt = xt + kFwdTileBytes;
+        const uint32_t xt = tiles + s * kStageBytes, tt = xt + kTrainTileBytes;
         mbar_wait (bars + 8 * s, (i / kStages) & 1);
-        const int nch = min (8, (T - i * kFwdTileT) >> 2);
+        const int nch = min (8, (T - i * kTrainTileT) >> 2);
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc)
         {
@@ -1094,14 +1098,14 @@ __device__ __forceinline__ void train_tma_body (const ClipConst& c, const CUtens
                 if (want_y)
                     tma_wait_read<0> ();
                 mbar_expect_tx (bars + 8 * sn, kStageBytes);
-                tma_load_2d (tiles + sn * kStageBytes, tmx, (i + 1) * kFwdTileT, b0, bars + 8 * sn);
-                tma_load_2d (tiles + sn * kStageBytes + kFwdTileBytes, tmt, (i + 1) * kFwdTileT, b0, bars + 8 * sn);
+                tma_load_2d (tiles + sn * kStageBytes, tmx, (i + 1) * kTrainTileT, b0, bars + 8 * sn);
+                tma_load_2d (tiles + sn * kStageBytes + kTrainTileBytes, tmt, (i + 1) * kTrainTileT, b0, bars + 8 * sn);
             }
             if (cc < nch)
             {
                 const uint32_t addr = chunk128 (xt, lane, cc);
                 const float4 v = lds128 (addr), t = lds128 (chunk128 (tt, lane, cc));
-                const int n = i * kFwdTileT + cc * 4;
+                const int n = i * kTrainTileT + cc * 4;
                 float4 o;
                 o.x = st.step (c, v.x, t.x, n >= skip);
                 o.y = st.step (c, v.y, t.y, n + 1 >= skip);
@@ -1118,7 +1122,7 @@ __device__ __forceinline__ void train_tma_body (const ClipConst& c, const CUtens
         __syncwarp ();
         if (lane == 0 && want_y)
         {
-            tma_store_2d (tmy, i * kFwdTileT, b0, xt);
+            tma_store_2d (tmy, i * kTrainTileT, b0, xt);
             tma_commit ();
         }
     }
@@ -1129,7 +1133,7 @@ __device__ __forceinline__ void train_tma_body (const ClipConst& c, const CUtens
 template <int MODE, bool GENERAL, bool PY>
 __global__ void __launch_bounds__ (kLanes, 16) clipper_train_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmt, const __grid_constant__ CUtensorMap tmy, const int want_y, const float* __restrict__ params, const ClipDesc desc, double* __restrict__ partials, int T, int skip)
 {
-    __shared__ __align__ (1024) uint8_t smem[2 * 2 * kFwdTileBytes];
+    __shared__ __align__ (1024) uint8_t smem[2 * 2 * kTrainTileBytes];
     __shared__ __align__ (8) uint64_t bar_mem[2];
     const int lane = threadIdx.x;
     const int b0 = blockIdx.x * kLanes;
@@ -1385,31 +1389,74 @@ __global__ void __launch_bounds__ (kLanes) clipper_train_direct (const float* __
 constexpr int kM = DWDF_PART_MODE;
 constexpr bool kG = DWDF_PART_GENERAL != 0;
 
+// one-warp CTAs of `kern` the current device holds at once (registers and shared memory permitting): the time chunks
+// are sized so that one wave covers the whole launch
+template <class Kern>
+static int resident_ctas (Kern kern)
+{
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice (&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return 1;
+    int v = cache[dev].load ();
+    if (v > 0)
+        return v;
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, kern, kLanes, 0) != cudaSuccess || cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return 1;
+    v = per_sm * sms > 0 ? per_sm * sms : 1;
+    cache[dev].store (v);
+    return v;
+}
+
+// chunk count proposed to the kernels: as many CTAs as fit in one wave, never more than the scratch was sized for
+static int propose_chunks (int resident, int64_t groups, int64_t units, int cap)
+{
+    if (cap <= 1 || (g_clip_opts & kOptNoChunks))
+        return 1;
+    int64_t k = resident / (groups > 0 ? groups : 1);
+    if (g_clip_opts & kOptForceChunks)
+        k = k > 4 ? k : 4;
+    k = k < cap ? k : cap;
+    k = k < units ? k : units;
+    return (int) (k > 1 ? k : 1);
+}
+
 template <>
 cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, float* y, float* ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream)
 {
     const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
+    const int ntiles = (int) ((T + kFwdTileT - 1) / kFwdTileT);
     auto go = [&] (auto P) {
         constexpr bool p = decltype (P)::value;
-        if (maps != nullptr && maps->chunks > 1)
-        { // small batch, long sequences: time-parallel
-            const int K = maps->chunks;
-            clipper_forward_chunked<kM, kG, p><<<(unsigned) ((B * K + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, K);
-            clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, K, maps->redone);
+        if (! use_tma)
+        {
+            clipper_forward_direct<kM, kG, p><<<grid, kLanes, 0, stream>>> (x, y, params, desc, ckpt, state, B, (int) T);
             return;
         }
+        const int cap = (ckpt != nullptr && maps->zs != nullptr) ? maps->kcap_fwd : 1; // the verification pass compares checkpoints
         if constexpr ((kM == kModeApprox || kM == kModeExact) && ! kG)
         {
-            if (use_tma && maps->pair)
+            if (maps->pair)
             {
-                clipper_forward_pair_tma<kM, p><<<(unsigned) ((B + kPairRows - 1) / kPairRows), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, B, (int) T, g_clip_opts);
+                const unsigned groups = (unsigned) ((B + kPairRows - 1) / kPairRows);
+                const int kmax = propose_chunks (resident_ctas (clipper_forward_pair_tma<kM, p>), groups, ntiles, cap);
+                clipper_forward_pair_tma<kM, p><<<dim3 (groups, (unsigned) kmax), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, g_clip_opts);
+                if (kmax > 1)
+                {
+                    clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 1, maps->redone);
+                    g_extra_launches.fetch_add (1);
+                }
                 return;
             }
         }
-        if (use_tma)
-            clipper_forward_tma<kM, kG, p><<<grid, kLanes, 0, stream>>> (maps->x, maps->y, params, desc, ckpt, state, B, (int) T, g_clip_opts);
-        else
-            clipper_forward_direct<kM, kG, p><<<grid, kLanes, 0, stream>>> (x, y, params, desc, ckpt, state, B, (int) T);
+        const int kmax = propose_chunks (resident_ctas (clipper_forward_tma<kM, kG, p>), grid, ntiles, cap);
+        clipper_forward_tma<kM, kG, p><<<dim3 (grid, (unsigned) kmax), kLanes, 0, stream>>> (maps->x, maps->y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, g_clip_opts);
+        if (kmax > 1)
+        {
+            clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 0, maps->redone);
+            g_extra_launches.fetch_add (1);
+        }
     };
     py ? go (std::true_type {}) : go (std::false_type {});
     return cudaGetLastError ();
@@ -1421,15 +1468,19 @@ cudaError_t clipper_adjoint_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
     const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
     auto go = [&] (auto P, auto TG) {
         constexpr bool p = decltype (P)::value, tg = decltype (TG)::value;
-        if (maps != nullptr && maps->chunks > 1 && gx == nullptr)
-        {
-            const int K = maps->chunks;
-            clipper_adjoint_chunked<kM, kG, p, tg><<<(unsigned) ((B * K + 127) / 128), 128, 0, stream>>> (x, y, g, params, desc, ckpt, maps->cout, B, (int) T, K, skip);
-            clipper_adjoint_stitch<<<grid, kLanes, 0, stream>>> (maps->cout, partials, B, K);
-            return;
-        }
         if (use_tma && gx == nullptr)
-            clipper_adjoint_tma<kM, kG, p, tg><<<grid, kLanes, 0, stream>>> (maps->x, maps->y, maps->g, params, desc, ckpt, partials, B, (int) T, skip, g_clip_opts);
+        {
+            const int nseg = (int) ((T + kSeg - 1) / kSeg);
+            int K = propose_chunks (resident_ctas (clipper_adjoint_tma<kM, kG, p, tg>), grid, nseg / 4 > 0 ? nseg / 4 : 1, maps->cmaps != nullptr ? maps->kcap_adj : 1); // chunks of at least 4 segments
+            const int chunk_segs = (nseg + K - 1) / K;
+            K = (nseg + chunk_segs - 1) / chunk_segs;
+            clipper_adjoint_tma<kM, kG, p, tg><<<dim3 (grid, (unsigned) K), kLanes, 0, stream>>> (maps->x, maps->y, maps->g, params, desc, ckpt, partials, maps->cmaps, chunk_segs, B, (int) T, skip, g_clip_opts);
+            if (K > 1)
+            {
+                clipper_adjoint_stitch<kM * 2 + (kG ? 1 : 0)><<<grid, kLanes, 0, stream>>> (maps->cmaps, partials, B, K);
+                g_extra_launches.fetch_add (1);
+            }
+        }
         else if (gx != nullptr)
             clipper_adjoint_direct<kM, kG, p, tg, true><<<grid, kLanes, 0, stream>>> (x, y, g, gx, params, desc, ckpt, partials, B, (int) T, skip);
         else

@@ -169,14 +169,26 @@ bool tma_usable (const void* a, const void* b, const void* c, int64_t B, int64_t
 bool is_leaf (int k) { return k == DWDF_RESISTOR || k == DWDF_CAPACITOR || k == DWDF_RESISTIVE_VS; }
 
 int64_t n_groups (int64_t B) { return (B + 31) / 32; }
-// time-parallel kernels: few sequences, long ones (fewer than ~1 warp per scheduler otherwise)
-// (measured at T = 4096, time-parallel vs one lane per sequence: forward 0.13 vs 0.32 ms at B = 4096, 0.19 vs 0.32 at 8192, 0.32 vs 0.32 at 16384;
-//  adjoint 0.085 vs 0.21 ms at 4096, 0.15 vs 0.21 at 8192, 0.23 vs 0.21 at 16384)
-int time_chunks (int64_t B, int64_t T, int64_t max_B) { return (! (g_clip_opts & kOptNoChunks) && (B <= max_B || (g_clip_opts & kOptForceChunks)) && T >= 2 * kTimeChunk) ? (int) ((T + kTimeChunk - 1) / kTimeChunk) : 0; }
-constexpr int64_t kChunkedForwardMaxB = 8192, kChunkedAdjointMaxB = 8192;
+// Time chunks (fewer sequences than the SMs hold warps; clipper_kernels.cu explains the scheme): upper bounds of the
+// chunk counts the launchers may propose, for sizing the scratch. The launchers pick the actual count from the kernel's
+// measured residency, the kernels make the final plan from gamma.
+int chunk_cap (int64_t groups, int64_t units)
+{
+    if (g_clip_opts & kOptNoChunks)
+        return 1;
+    int64_t k = kMaxResidentCtas / (groups > 0 ? groups : 1);
+    if (g_clip_opts & kOptForceChunks)
+        k = k > 4 ? k : 4;
+    k = k < units ? k : units;
+    return (int) (k > 1 ? k : 1);
+}
+int64_t n_fwd_tiles16 (int64_t T) { return (T + 15) / 16; }
+int fwd_chunk_cap (int64_t B, int64_t T) { return T >= 128 ? chunk_cap ((B + 63) / 64, n_fwd_tiles16 (T)) : 1; } // (the one-sequence-per-lane kernel launches twice the groups: its proposal is clamped to this)
+int adj_chunk_cap (int64_t B, int64_t T) { return T >= 128 ? chunk_cap ((B + 31) / 32, (T + 63) / 64) : 1; }
 constexpr int64_t kNnChunkedMaxB = 16384; // neural root: the network makes every sample ~20x heavier, so lanes stay scarce longer
 size_t partials_bytes (int64_t B) { return ((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256 * 256 + 256; }
 int64_t n_segments (int64_t T) { return (T + kSeg - 1) / kSeg; }
+size_t adj_maps_bytes (int64_t B, int64_t T) { const int k = adj_chunk_cap (B, T); return k > 1 ? (size_t) k * kMapFloatsPerChunk * (size_t) B * sizeof (float) : 0; }
 } // namespace
 
 extern "C" {
@@ -184,7 +196,7 @@ static int check_batch (const dwdf_program* prog, const void* params, const void
 
 const char* dwdf_last_error (void) { return g_err; }
 const char* dwdf_build_info (void) { return "libdwdf v3 sm_100a cuda-12.9 tma+mbarrier fp32x2 no-cpu-fallback"; }
-int64_t dwdf_launch_count (void) { return g_launches.load (); }
+int64_t dwdf_launch_count (void) { return g_launches.load () + g_extra_launches.load (); }
 int dwdf_set_tma (int enable) { return g_use_tma.exchange (enable ? 1 : 0); }
 int64_t dwdf_time_parallel_redone (void)
 {
@@ -465,8 +477,8 @@ size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
     if (prog == nullptr || B <= 0 || T <= 0)
         return 0;
     size_t bytes = partials_bytes (B);
-    if (prog->is_clipper && (B <= kChunkedAdjointMaxB || (g_clip_opts & kOptForceChunks)))
-        bytes += (size_t) B * (size_t) ((T + kTimeChunk - 1) / kTimeChunk) * kChunkOutFloats * sizeof (float); // time-parallel adjoint (small batches)
+    if (prog->is_clipper)
+        bytes += adj_maps_bytes (B, T); // affine maps of the adjoint's time chunks (small batches)
     if (! prog->is_clipper) // per-sample tape of the interpreter adjoint: (n_states + 1) floats per sample
         bytes += (size_t) B * (size_t) T * (size_t) (prog->n_states + 1) * sizeof (float);
     return bytes;
@@ -496,22 +508,25 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
     if (prog->is_clipper)
     {
         ClipTmaMaps maps;
-        const bool tma = tma_usable (x, y, nullptr, B, T) && make_map (&maps.x, x, B, T, 32) && make_map (&maps.y, y, B, T, 32);
-        // approx root, symmetric pair, more than one warp's worth of sequences: two sequences per lane (packed fp32x2)
+        const bool tma = tma_usable (x, y, nullptr, B, T) && make_map (&maps.x, x, B, T, kFwdTileSamples) && make_map (&maps.y, y, B, T, kFwdTileSamples);
+        // symmetric pair, more than one warp's worth of sequences: two sequences per lane (packed fp32x2)
+        maps.pair = tma && (prog->variant.mode == kModeApprox || prog->variant.mode == kModeExact) && ! prog->variant.general && B > 32 && ! (g_clip_opts & kOptNoPair) && make_map (&maps.x2, x, B, T, kFwdTileSamples, 64) && make_map (&maps.y2, y, B, T, kFwdTileSamples, 64);
+        // fewer sequences than the SMs hold warps: time chunks. Scratch: assumed / end state per (chunk, sequence) and, when
+        // the caller keeps no checkpoints, a checkpoint buffer for the verification pass
         AsyncScratch scratch;
-        const int K = (T % 4 == 0 && ((uintptr_t) x & 15u) == 0 && ((uintptr_t) y & 15u) == 0) ? time_chunks (B, T, kChunkedForwardMaxB) : 0;
-        if (K > 1)
+        const int cap = tma ? fwd_chunk_cap (B, T) : 1;
+        if (cap > 1)
         {
-            DWDF_CUDA (scratch.alloc ((size_t) 2 * B * K * sizeof (float), stream));
-            maps.redone = redone_counter ();
-            maps.chunks = K;
+            const size_t zfloats = (size_t) cap * (size_t) B, ckfloats = z_ckpt == nullptr ? (size_t) n_segments (T) * (size_t) B : 0;
+            DWDF_CUDA (scratch.alloc ((2 * zfloats + ckfloats) * sizeof (float), stream));
+            maps.kcap_fwd = cap;
             maps.zs = scratch.p;
-            maps.ze = scratch.p + (size_t) B * K;
+            maps.ze = scratch.p + zfloats;
+            maps.redone = redone_counter ();
+            if (z_ckpt == nullptr)
+                z_ckpt = scratch.p + 2 * zfloats;
         }
-        maps.pair = tma && (prog->variant.mode == kModeApprox || prog->variant.mode == kModeExact) && ! prog->variant.general && B > 32 && ! (g_clip_opts & kOptNoPair) && make_map (&maps.x2, x, B, T, 32, 64) && make_map (&maps.y2, y, B, T, 32, 64);
         DWDF_CUDA (launch_clipper_forward (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, state, B, T, stream));
-        if (K > 1)
-            g_launches.fetch_add (1);
     }
     else
     {
@@ -562,12 +577,10 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
             return fail (DWDF_ERR_INVALID, "the clipper adjoint reads the output y and the checkpoints z_ckpt that dwdf_forward wrote: %s is null", y == nullptr ? "y" : "z_ckpt");
         ClipTmaMaps maps;
         const bool tma = gx == nullptr && tma_usable (x, gy_or_target, y, B, T) && make_map (&maps.x, x, B, T, kSeg) && make_map (&maps.y, y, B, T, kSeg) && make_map (&maps.g, gy_or_target, B, T, kSeg);
-        const bool al16 = T % 4 == 0 && (((uintptr_t) x | (uintptr_t) y | (uintptr_t) gy_or_target) & 15u) == 0;
-        if (gx == nullptr && al16 && time_chunks (B, T, kChunkedAdjointMaxB) > 1)
+        if (tma && adj_chunk_cap (B, T) > 1)
         {
-            maps.chunks = time_chunks (B, T, kChunkedAdjointMaxB);
-            maps.cout = (float*) ((char*) workspace + partials_bytes (B));
-            g_launches.fetch_add (1);
+            maps.kcap_adj = adj_chunk_cap (B, T);
+            maps.cmaps = (float*) ((char*) workspace + partials_bytes (B));
         }
         DWDF_CUDA (launch_clipper_adjoint (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, gy_or_target, target, sk, gx, partials, B, T, stream));
         DWDF_CUDA (launch_clipper_finalize (prog->clip, params, partials, n_groups (B), nullptr, raw_only, target, loss_kind, count, out, stream));

@@ -12,9 +12,20 @@
 namespace dwdf
 {
 
+// Forward tiles: [rows x kFwdTileSamples samples]. 32 samples = 128-byte rows (128-byte swizzle), 16 samples = 64-byte
+// rows (64-byte swizzle, half the shared memory per stage: more resident one-warp CTAs per SM). Build-time choice
+// (-DDWDF_FWD_TILE_T / -DDWDF_FWD_STAGES; measured on the B200).
+#ifndef DWDF_FWD_TILE_T
+#define DWDF_FWD_TILE_T 32
+#endif
+#ifndef DWDF_FWD_STAGES
+#define DWDF_FWD_STAGES 3
+#endif
+constexpr int kFwdTileSamples = DWDF_FWD_TILE_T;
 constexpr int kSeg = 16; // capacitor-state checkpoint spacing [samples]; also the adjoint's segment
-constexpr int kTimeChunk = 256; // samples per chunk of the time-parallel (small-batch) kernels
-constexpr int kChunkOutFloats = 12; // adjoint: floats per (sequence, chunk)
+constexpr int kTimeChunk = 256; // samples per chunk of the neural root's time-parallel kernels
+constexpr int kMapFloatsPerChunk = 10; // clipper adjoint with time chunks: floats per (sequence, chunk)
+constexpr int kMaxResidentCtas = 148 * 32; // upper bound of one-warp CTAs a B200 holds at once: sizes the time-chunk scratch
 constexpr int kPartialStride = 8; // doubles per sequence-group in the clipper partials buffer
 constexpr int kTreePartialStride = 24; // ... in the tree interpreter partials buffer
 // partial sums one warp (32 sequences) hands to the finalize kernel
@@ -37,6 +48,7 @@ enum : int
     kOptL2Prefetch = 4 // cp.async.bulk.prefetch.tensor L2 run-ahead (measured: slower — forward 0.47 -> 0.58 ms, adjoint 0.63 -> 0.94 ms; off)
 };
 extern std::atomic<int> g_clip_opts; // diagnostic switches (dwdf_set_option); read once per launch
+extern std::atomic<int64_t> g_extra_launches; // kernels the launchers add on their own (the time-chunk stitch passes)
 
 struct ClipVariant
 {
@@ -51,10 +63,11 @@ struct ClipTmaMaps
     CUtensorMap x, y, g; // forward (x, y): 32 x 32 tiles, 128-byte swizzle; adjoint (x, y, g): 16 x 32 tiles, 64-byte swizzle
     CUtensorMap x2, y2; // paired forward: [64 sequences x 32 samples] tiles
     bool pair = false; // x2 / y2 are valid and the paired kernel is wanted
-    // time-parallel path (small batches): chunks > 1 selects it; scratch of B * chunks floats each (forward) / B * chunks * 12 (adjoint)
-    int chunks = 0;
-    float *zs = nullptr, *ze = nullptr, *cout = nullptr;
-    int* redone = nullptr; // optional counter of chunks the forward had to recompute
+    // time chunks (fewer sequences than the SMs hold warps): the launcher proposes up to kcap chunks. Forward scratch zs / ze:
+    // kcap_fwd * B floats each; adjoint scratch cmaps: kcap_adj * kMapFloatsPerChunk * B floats. nullptr / 1: no chunks.
+    int kcap_fwd = 1, kcap_adj = 1;
+    float *zs = nullptr, *ze = nullptr, *cmaps = nullptr;
+    int* redone = nullptr; // optional counter of chunks the forward verification had to recompute
 };
 
 // per-(root mode, law) launchers, each specialised in its own translation unit (clipper_kernels.cu, 4 parts)

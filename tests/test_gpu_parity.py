@@ -259,8 +259,16 @@ def test_full_size_properties(dwdf, oracle, B, T):
         g3 = circ.backward(target=target, loss="mse+esr", skip=50)["out"].clone()
     finally:
         dwdf.set_tma(prev)
-    assert torch.equal(y, y_direct)
-    assert torch.allclose(g1, g3, rtol=1e-12, atol=0)
+    assert torch.equal(y, y_direct)  # time chunks or not, the outputs are the serial recurrence's, bit for bit
+    n = circ.n_params
+    assert torch.allclose(g1[:n], g3[:n], rtol=2e-5, atol=0) and torch.allclose(g1[16:19], g3[16:19], rtol=1e-6, atol=0)  # the chunked adjoint composes fp32 affine maps: equal up to summation order
+    prev_o = dwdf.set_option(8)  # kOptNoChunks: same kernels as one chunk -> the fixed-order reduction gives the direct path's bits
+    try:
+        circ.forward(xd)
+        g4 = circ.backward(target=target, loss="mse+esr", skip=50)["out"].clone()
+    finally:
+        dwdf.set_option(prev_o)
+    assert torch.allclose(g4, g3, rtol=1e-12, atol=0)
     perm = torch.randperm(B, device="cuda")
     assert torch.equal(circ.forward(xd[perm].contiguous(), keep_for_backward=False), y[perm])
     assert torch.equal(circ.forward((-xd).contiguous(), keep_for_backward=False), -y)
@@ -493,7 +501,14 @@ def test_host_entry_points(dwdf, oracle, B):
     yh2 = torch.empty_like(xh).pin_memory()
     circ.grad_host(xh, th, outh, y_host=yh2, loss="mse+esr", skip=10)
     assert torch.equal(yh2, yd.cpu())
-    assert torch.allclose(outh, gd.cpu(), rtol=1e-10, atol=0)
+    assert torch.allclose(outh, gd.cpu(), rtol=2e-5, atol=0)  # (the device path may run the adjoint in time chunks: equal up to fp32 summation order)
+    prev = dwdf.set_option(8)  # one chunk on the device path too: same reduction order, same bits to fp64 round-off
+    try:
+        circ.forward(dev(x))
+        g1 = circ.backward(target=target, loss="mse+esr", skip=10)["out"].clone()
+    finally:
+        dwdf.set_option(prev)
+    assert torch.allclose(outh, g1.cpu(), rtol=1e-10, atol=0)
 
 
 def test_errors_are_loud(dwdf):
@@ -507,16 +522,16 @@ def test_errors_are_loud(dwdf):
         circ.backward()
 
 
-# ---- time-parallel kernels (small batches) ---------------------------------------------------------------
+# ---- time chunks (fewer sequences than the SMs hold warps) ------------------------------------------------
 
 @pytest.mark.parametrize("mode", ["approx", "exact"])
 @pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
 @pytest.mark.parametrize("amp", [(0.1, 2.0), (2.0, 10.0)])
 def test_time_parallel_equals_serial(dwdf, oracle, mode, ordering, oord, amp):
-    """Configs 2-3 (few long sequences) run one lane per (sequence, 256-sample chunk): speculative warm-up +
-    verification in the forward pass, affine composition in the adjoint. Same outputs and gradients as the
-    one-lane-per-sequence kernels (and the oracle), also for loud inputs whose slow contraction defeats the
-    speculation (those chunks are recomputed), for the training constants (longer RC memory) and ragged T."""
+    """Configs 2-3 (few long sequences) run CTA (row group, time chunk): speculative warm-up + verification in the
+    forward pass, affine composition in the adjoint. Same outputs (bit for bit) and gradients as one chunk per
+    sequence (and the oracle), also for loud inputs whose slow contraction defeats the speculation (those chunks
+    are recomputed until they meet the speculated trajectory), for the training constants (longer RC memory) and ragged T."""
     for p, B, T in ((ClipperParams(), 256, 4096), (ClipperParams(R=45000.0, C=4.7e-9), 70, 1000 if mode == "approx" else 2052)):
         x = make_inputs(B, T, seed=31, amp=amp)
         target = oracle.clipper_forward(x, perturbed(p), exact=True, ordering=oord)
@@ -535,6 +550,61 @@ def test_time_parallel_equals_serial(dwdf, oracle, mode, ordering, oord, amp):
         assert np.max(np.abs(g_tp / g_se - 1)) < 2e-5 and abs(l_tp / l_se - 1) < 1e-6
         if amp[1] <= 2.0 or mode == "exact":
             assert seq_rel_err(y_tp, oracle.clipper_forward(x, p, exact=(mode == "exact"), ordering=oord)) < FWD_TOL
+
+
+@pytest.mark.parametrize("B,T", [(33, 512), (64, 4096), (100, 2052), (5000, 1024), (8192, 4096), (20000, 256)])
+@pytest.mark.parametrize("n_up,n_down", [(1, 1), (1, 2)])
+def test_time_chunks_shapes_state_and_misses(dwdf, oracle, B, T, n_up, n_down):
+    """The chunk grid over odd shapes (rows past the last full group, partial last tile, last chunk shorter, chunk
+    counts the device plan clamps), both kernels (two sequences per lane; one per lane for N_up != N_down), forced
+    at batch sizes that would not chunk on their own, streaming from a non-zero state, and a circuit whose memory is
+    longer than the sequence (the plan falls back to one chunk). Always: outputs, final states and checkpoint-driven
+    gradients equal the unchunked run's — outputs and states bit for bit."""
+    for p in (ClipperParams(n_up=n_up, n_down=n_down), ClipperParams(R=220000.0, C=47e-9, n_up=n_up, n_down=n_down)):  # gamma 0.09 (W = 148 samples) and 1e-3 (W > T: one chunk)
+        x = make_inputs(B, T, seed=B + T, amp=(0.05, 6.0))
+        xd = dev(x)
+        target = dev(np.roll(x, 1, 0) * 0.2)
+        res = []
+        for opts in (16, 8):  # kOptForceChunks, kOptNoChunks
+            prev = dwdf.set_option(opts)
+            try:
+                circ, order = make_clipper(dwdf, p, "approx", "python")
+                y = circ.forward(xd).clone()
+                g = circ.backward(target=target, loss="mse", skip=7)["out"].clone()
+                st = circ.new_state(B)
+                st.uniform_(-0.2, 0.2, generator=torch.Generator(device="cuda").manual_seed(3))
+                st0 = st.clone()
+                ys = circ.process_block(xd, st).clone()
+                res.append((y, g, ys, st.clone(), st0))
+            finally:
+                dwdf.set_option(prev)
+        (y1, g1, ys1, st1, _), (y0, g0, ys0, st0, _) = res
+        assert torch.equal(y1, y0) and torch.equal(ys1, ys0) and torch.equal(st1, st0)
+        n = 4
+        assert torch.allclose(g1[:n], g0[:n], rtol=3e-5, atol=1e-30) and torch.allclose(g1[16:19], g0[16:19], rtol=1e-6, atol=0)
+        if B <= 100 and p.R < 1e5:
+            assert seq_rel_err(y1.cpu().numpy(), oracle.clipper_forward(x, p)) < FWD_TOL
+
+
+def test_time_chunk_misses_are_recomputed(dwdf):
+    """Hard-driven inputs keep the diodes conducting through a chunk's warm-up in a way the speculation (which starts
+    from z = 0) cannot always reproduce to the bit; the verification pass must catch every such chunk. The recompute
+    counter shows the path ran; equality with the unchunked run shows it repaired what it found."""
+    p = ClipperParams(R=100000.0, C=10e-9)  # gamma 0.0103: W = 1437 samples, chunks of at least that
+    B, T = 96, 16384
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xd = (torch.rand(B, T, device="cuda", generator=g) - 0.5) * 30.0
+    outs = []
+    before = dwdf.time_parallel_redone()
+    for opts in (16, 8):
+        prev = dwdf.set_option(opts)
+        try:
+            circ, _ = make_clipper(dwdf, p, "approx", "python")
+            outs.append(circ.forward(xd).clone())
+        finally:
+            dwdf.set_option(prev)
+    assert torch.equal(outs[0], outs[1])
+    print("chunks recomputed:", dwdf.time_parallel_redone() - before)
 
 
 def test_training_step_in_a_cuda_graph(dwdf, oracle):
