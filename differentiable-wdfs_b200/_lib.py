@@ -29,6 +29,7 @@ SYMBOLS = (
     "dwdf_program_create", "dwdf_program_destroy", "dwdf_program_is_clipper", "dwdf_program_n_states", "dwdf_ckpt_bytes", "dwdf_workspace_bytes",
     "dwdf_forward", "dwdf_backward", "dwdf_train_pass", "dwdf_adam_step", "dwdf_forward_host", "dwdf_grad_host", "dwdf_process_block",
     "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_backward_neural", "dwdf_neural_ckpt_bytes", "dwdf_neural_workspace_bytes", "dwdf_adam_step_vec", "dwdf_last_error", "dwdf_build_info", "dwdf_train_step", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option", "dwdf_time_parallel_redone",
+    "dwdf_comm_create", "dwdf_comm_handle_bytes", "dwdf_comm_get_handle", "dwdf_comm_connect", "dwdf_comm_set_timeout", "dwdf_comm_destroy", "dwdf_allreduce_sum", "dwdf_train_step_dp", "dwdf_profile_begin", "dwdf_profile_end",
 )
 
 
@@ -83,6 +84,16 @@ def lib() -> C.CDLL:
     L.dwdf_finalize.argtypes = [vp, vp, i32, i32, vp, vp]
     L.dwdf_adam_step.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, vp, C.c_float, C.c_float, C.c_float, C.c_double, vp, vp, vp]
     L.dwdf_train_step.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, sz, vp, vp, vp, C.c_float, vp, C.c_float, C.c_float, C.c_float, vp, vp, i64, i64, vp]
+    L.dwdf_comm_create.argtypes = [i32, i32, C.POINTER(vp)]
+    L.dwdf_comm_handle_bytes.restype = sz
+    L.dwdf_comm_get_handle.argtypes = [vp, vp]
+    L.dwdf_comm_connect.argtypes = [vp, vp]
+    L.dwdf_comm_set_timeout.argtypes = [vp, C.c_double]
+    L.dwdf_comm_destroy.argtypes = [vp]
+    L.dwdf_allreduce_sum.argtypes = [vp, vp, i64, vp]
+    L.dwdf_train_step_dp.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, sz, vp, vp, vp, C.c_float, vp, C.c_float, C.c_float, C.c_float, vp, vp, i64, i64, vp]
+    L.dwdf_profile_begin.argtypes = [i32]
+    L.dwdf_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32)]
     L.dwdf_forward_host.argtypes = [vp, vp, vp, vp, vp, i64, i64]
     L.dwdf_grad_host.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, i64, i64]
     L.dwdf_process_block.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, vp]
@@ -129,3 +140,14 @@ def set_option(bits: int) -> int:
 
 def time_parallel_redone() -> int:
     return int(lib().dwdf_time_parallel_redone())
+
+
+def profile_begin(max_steps: int) -> None:
+    check(lib().dwdf_profile_begin(int(max_steps)))
+
+
+def profile_end():
+    """-> (ms_forward, ms_adjoint, ms_tail, steps): mean device time per phase of the training steps since profile_begin."""
+    f, a, t, n = C.c_double(), C.c_double(), C.c_double(), C.c_int32()
+    check(lib().dwdf_profile_end(C.byref(f), C.byref(a), C.byref(t), C.byref(n)))
+    return f.value, a.value, t.value, n.value

@@ -16,48 +16,34 @@ namespace
 // Loss: tf.keras.losses.MeanSquaredError (clipper_pot.py:176) [+ esr_loss, clipper_pot.py:148-156
 // with eps = float64 eps (:145)]; loss = mse + esr (:177). In upstream mode the sums already carry
 // the caller's dL/dy scale.
-__global__ void __launch_bounds__ (256) clipper_finalize (const ClipDesc desc, const float* __restrict__ params, const double* __restrict__ partials, int64_t n_groups, const double* raw_in, int raw_only, int target, int loss_kind, double count, double* out)
+
+// block-wide fixed-order sum of the per-group partials; the totals land in sm[k][0]
+__device__ __forceinline__ void reduce_partials (double (&sm)[5][256], const double* __restrict__ partials, int64_t n_groups)
 {
-    __shared__ double sm[5][256];
     const int tid = threadIdx.x;
-    if (raw_in == nullptr)
-    {
-        double a[5] = { 0, 0, 0, 0, 0 };
-        for (int64_t g = tid; g < n_groups; g += 256)
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-                a[k] += partials[g * kPartialStride + k];
+    double a[5] = { 0, 0, 0, 0, 0 };
+    for (int64_t g = tid; g < n_groups; g += 256)
 #pragma unroll
         for (int k = 0; k < 5; ++k)
-            sm[k][tid] = a[k];
-        __syncthreads ();
-        for (int o = 128; o > 0; o >>= 1)
-        {
-            if (tid < o)
+            a[k] += partials[g * kPartialStride + k];
 #pragma unroll
-                for (int k = 0; k < 5; ++k)
-                    sm[k][tid] += sm[k][tid + o];
-            __syncthreads ();
-        }
-    }
-    if (tid != 0)
-        return;
-    double acc_g, acc_l, acc_v, sse, st2;
-    if (raw_in != nullptr)
-    { // sums that were reduced (and possibly all-reduced over ranks) earlier
-        acc_g = raw_in[kAccGamma], acc_l = raw_in[kAccEll], acc_v = raw_in[kAccV], sse = raw_in[kAccSse], st2 = raw_in[kAccSt2];
-        count = raw_in[23];
-    }
-    else
-        acc_g = sm[kAccGamma][0], acc_l = sm[kAccEll][0], acc_v = sm[kAccV][0], sse = sm[kAccSse][0], st2 = sm[kAccSt2][0];
-    if (raw_only)
+    for (int k = 0; k < 5; ++k)
+        sm[k][tid] = a[k];
+    __syncthreads ();
+    for (int o = 128; o > 0; o >>= 1)
     {
-        for (int k = 0; k < 24; ++k)
-            out[k] = 0.0;
-        out[kAccGamma] = acc_g, out[kAccEll] = acc_l, out[kAccV] = acc_v, out[kAccSse] = sse, out[kAccSt2] = st2;
-        out[23] = count;
-        return;
+        if (tid < o)
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                sm[k][tid] += sm[k][tid + o];
+        __syncthreads ();
     }
+}
+
+// raw sums (kAcc* slots, raw[23] = number of samples in the loss) -> out[DWDF_OUT_LEN]: gradients per slot, loss, mse, esr
+__device__ __forceinline__ void finalize_math (const ClipDesc& desc, const float* __restrict__ params, const double* raw, int target, int loss_kind, double* out)
+{
+    const double acc_g = raw[kAccGamma], acc_l = raw[kAccEll], acc_v = raw[kAccV], sse = raw[kAccSse], st2 = raw[kAccSt2], count = raw[23];
     double alpha = 1.0, loss = 0.0, mse = 0.0, esr = 0.0;
     if (target)
     {
@@ -90,30 +76,201 @@ __global__ void __launch_bounds__ (256) clipper_finalize (const ClipDesc desc, c
     out[18] = esr;
 }
 
-// Adam (clipper_pot.py:180: Adam(1e-4, beta_1=0.5)) + the Keras clip constraints of tf_wdf.py:74,104
+__global__ void __launch_bounds__ (256) clipper_finalize (const ClipDesc desc, const float* __restrict__ params, const double* __restrict__ partials, int64_t n_groups, const double* raw_in, int raw_only, int target, int loss_kind, double count, double* out)
+{
+    __shared__ double sm[5][256];
+    const int tid = threadIdx.x;
+    if (raw_in == nullptr)
+        reduce_partials (sm, partials, n_groups);
+    if (tid != 0)
+        return;
+    double raw[24];
+    for (int k = 0; k < 24; ++k)
+        raw[k] = 0.0;
+    if (raw_in != nullptr)
+    { // sums that were reduced (and possibly all-reduced over ranks) earlier
+        raw[kAccGamma] = raw_in[kAccGamma], raw[kAccEll] = raw_in[kAccEll], raw[kAccV] = raw_in[kAccV], raw[kAccSse] = raw_in[kAccSse], raw[kAccSt2] = raw_in[kAccSt2];
+        raw[23] = raw_in[23];
+    }
+    else
+    {
+        raw[kAccGamma] = sm[kAccGamma][0], raw[kAccEll] = sm[kAccEll][0], raw[kAccV] = sm[kAccV][0], raw[kAccSse] = sm[kAccSse][0], raw[kAccSt2] = sm[kAccSt2][0];
+        raw[23] = count;
+    }
+    if (raw_only)
+    {
+        for (int k = 0; k < 24; ++k)
+            out[k] = raw[k];
+        return;
+    }
+    finalize_math (desc, params, raw, target, loss_kind, out);
+}
+
+// Adam (clipper_pot.py:180: Adam(1e-4, beta_1=0.5)) + the Keras clip constraints of tf_wdf.py:74,104; slot k, step number t
+__device__ __forceinline__ void adam_update (int k, int t, float* __restrict__ params, double grad, float* __restrict__ m, float* __restrict__ v, float lr, float beta1, float beta2, float eps, const float* __restrict__ lo, const float* __restrict__ hi)
+{
+    const float g = (float) grad;
+    const float mk = beta1 * m[k] + (1.0f - beta1) * g;
+    const float vk = beta2 * v[k] + (1.0f - beta2) * g * g;
+    m[k] = mk;
+    v[k] = vk;
+    // Keras: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  p -= lr_t * m / (sqrt(v) + eps)
+    const float lr_t = lr * sqrtf (1.0f - powf (beta2, (float) t)) / (1.0f - powf (beta1, (float) t));
+    float p = params[k] - lr_t * mk / (sqrtf (vk) + eps);
+    if (lo != nullptr)
+        p = fmaxf (p, lo[k]);
+    if (hi != nullptr)
+        p = fminf (p, hi[k]);
+    params[k] = p;
+}
+
 __global__ void adam_kernel (float* __restrict__ params, const double* __restrict__ out, float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ step, int n_params, float lr, const float* __restrict__ lr_vec, float beta1, float beta2, float eps, double grad_scale, const float* __restrict__ lo, const float* __restrict__ hi)
 {
     const int k = threadIdx.x;
     const int t = *step + 1;
     if (k < n_params)
-    {
-        const float g = (float) (out[k] * grad_scale);
-        const float mk = beta1 * m[k] + (1.0f - beta1) * g;
-        const float vk = beta2 * v[k] + (1.0f - beta2) * g * g;
-        m[k] = mk;
-        v[k] = vk;
-        // Keras: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  p -= lr_t * m / (sqrt(v) + eps)
-        const float lr_t = (lr_vec != nullptr ? lr_vec[k] : lr) * sqrtf (1.0f - powf (beta2, (float) t)) / (1.0f - powf (beta1, (float) t));
-        float p = params[k] - lr_t * mk / (sqrtf (vk) + eps);
-        if (lo != nullptr)
-            p = fmaxf (p, lo[k]);
-        if (hi != nullptr)
-            p = fminf (p, hi[k]);
-        params[k] = p;
-    }
+        adam_update (k, t, params, out[k] * grad_scale, m, v, lr_vec != nullptr ? lr_vec[k] : lr, beta1, beta2, eps, lo, hi);
     __syncthreads ();
     if (k == 0)
         *step = t;
+}
+
+// =================================================================================================
+// multi-GPU: the step's one exchange, over peer memory
+// =================================================================================================
+// Sequences shard over GPUs with no data-path collective; what a training step exchanges is the sum
+// over ranks of a handful of doubles (24 for the analytic root, the weight-gradient vector for the neural root). That
+// message is pure latency, so instead of a library all-reduce between two tiny kernels, the reduction kernel does the
+// exchange itself through NVLink peer memory: every rank owns a MAILBOX (device memory its peers map with CUDA IPC),
+// with one slot per sender and epoch parity. A step's kernel
+//     1. writes its vector into slot[my rank] of EVERY rank's mailbox (remote stores, then a system-scope release of
+//        the slot's epoch flag),
+//     2. waits until all slots of its OWN mailbox carry this epoch (system-scope acquire loads, local memory),
+//     3. sums the slots in rank order — every rank adds the same numbers in the same order, so the results (and
+//        after Adam the parameters) are bit-identical on all ranks without a broadcast.
+// Slots alternate with the epoch's parity: a rank can only be one epoch ahead of a peer (it needs that peer's flag of
+// the current epoch to finish), so the slot it writes next is never one a peer is still reading. A peer that never
+// arrives is reported after a timeout (the result block is filled with NaN) instead of hanging the GPU.
+__device__ __forceinline__ void st_release_sys (unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys (const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns ()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// vals[0..n) (shared or global memory of this block) <- sum over ranks. All 256 threads of the single block call it.
+// Returns false on timeout (some thread saw a peer missing); the caller decides what to report.
+__device__ __forceinline__ bool peer_allreduce (double* vals, int n, const DpPeers& dp, unsigned long long epoch, int* timed_out_sm)
+{
+    const int tid = threadIdx.x;
+    const size_t slot_bytes = (size_t) kDpSlotDoubles * sizeof (double);
+    const size_t parity_off = (size_t) (epoch & 1ull) * dp.world * slot_bytes;
+    for (int p = 0; p < dp.world; ++p)
+    {
+        double* dst = reinterpret_cast<double*> (dp.mailbox[p] + parity_off + (size_t) dp.rank * slot_bytes);
+        for (int i = tid; i < n; i += blockDim.x)
+            dst[i] = vals[i];
+    }
+    __threadfence_system ();
+    __syncthreads ();
+    if (tid < dp.world)
+    {
+        st_release_sys (reinterpret_cast<unsigned long long*> (dp.mailbox[tid] + parity_off + (size_t) dp.rank * slot_bytes) + (kDpSlotDoubles - 1), epoch);
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*> (dp.mailbox[dp.rank] + parity_off + (size_t) tid * slot_bytes) + (kDpSlotDoubles - 1);
+        const unsigned long long t0 = global_timer_ns ();
+        while (ld_acquire_sys (flag) != epoch)
+        {
+            if (global_timer_ns () - t0 > dp.timeout_ns)
+            {
+                *timed_out_sm = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads ();
+    const bool ok = *timed_out_sm == 0;
+    for (int i = tid; i < n; i += blockDim.x)
+    {
+        double s = 0.0;
+        for (int p = 0; p < dp.world; ++p)
+            s += reinterpret_cast<const volatile double*> (dp.mailbox[dp.rank] + parity_off + (size_t) p * slot_bytes)[i];
+        vals[i] = ok ? s : __longlong_as_double (0x7ff8000000000000ll);
+    }
+    __syncthreads ();
+    return ok;
+}
+
+__device__ __forceinline__ unsigned long long next_epoch (const DpPeers& dp, unsigned long long* epoch_sm)
+{
+    if (threadIdx.x == 0)
+    {
+        unsigned long long* ctr = reinterpret_cast<unsigned long long*> (dp.mailbox[dp.rank] + (size_t) 2 * dp.world * kDpSlotDoubles * sizeof (double));
+        *epoch_sm = *ctr + 1;
+        *ctr = *epoch_sm;
+    }
+    __syncthreads ();
+    return *epoch_sm;
+}
+
+// generic: inout[0..n) <- sum over ranks (n <= kDpSlotDoubles - 1)
+__global__ void __launch_bounds__ (256) peer_allreduce_kernel (double* __restrict__ inout, int n, const DpPeers dp)
+{
+    __shared__ unsigned long long epoch_sm;
+    __shared__ int timed_out;
+    if (threadIdx.x == 0)
+        timed_out = 0;
+    const unsigned long long epoch = next_epoch (dp, &epoch_sm);
+    peer_allreduce (inout, n, dp, epoch, &timed_out);
+}
+
+// The data-parallel training step's tail in ONE kernel: fixed-order reduction of this rank's partials -> exchange of
+// the raw sums over peer memory -> chain rule and loss -> Adam. count = this rank's samples in the loss.
+__global__ void __launch_bounds__ (256) clipper_finalize_dp (const ClipDesc desc, float* __restrict__ params, const double* __restrict__ partials, int64_t n_groups, int target, int loss_kind, double count, double* __restrict__ out, const DpPeers dp,
+                                                            float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ step, int n_params, float lr, const float* __restrict__ lr_vec, float beta1, float beta2, float eps, const float* __restrict__ lo, const float* __restrict__ hi)
+{
+    __shared__ double sm[5][256];
+    __shared__ double raw[24], res[24];
+    __shared__ unsigned long long epoch_sm;
+    __shared__ int timed_out;
+    const int tid = threadIdx.x;
+    reduce_partials (sm, partials, n_groups);
+    if (tid == 0)
+    {
+        timed_out = 0;
+        for (int k = 0; k < 24; ++k)
+            raw[k] = 0.0;
+        raw[kAccGamma] = sm[kAccGamma][0], raw[kAccEll] = sm[kAccEll][0], raw[kAccV] = sm[kAccV][0], raw[kAccSse] = sm[kAccSse][0], raw[kAccSt2] = sm[kAccSt2][0];
+        raw[23] = count;
+    }
+    __syncthreads ();
+    if (dp.world > 1)
+    {
+        const unsigned long long epoch = next_epoch (dp, &epoch_sm);
+        peer_allreduce (raw, 24, dp, epoch, &timed_out);
+    }
+    if (tid == 0)
+    {
+        finalize_math (desc, params, raw, target, loss_kind, res);
+        for (int k = 0; k < 24; ++k)
+            out[k] = res[k];
+    }
+    __syncthreads ();
+    if (m != nullptr)
+    {
+        const int t = *step + 1;
+        __syncthreads ();
+        if (tid < n_params)
+            adam_update (tid, t, params, res[tid], m, v, lr_vec != nullptr ? lr_vec[tid] : lr, beta1, beta2, eps, lo, hi);
+        if (tid == 0)
+            *step = t;
+    }
 }
 
 } // namespace
@@ -150,6 +307,19 @@ cudaError_t launch_clipper_train (const ClipVariant& v, bool use_tma, const Clip
 cudaError_t launch_clipper_finalize (const ClipDesc& desc, const float* params, const double* partials, int64_t n_groups, const double* raw_in, bool raw_only, bool target, int loss_kind, double count, double* out, cudaStream_t stream)
 {
     clipper_finalize<<<1, 256, 0, stream>>> (desc, params, partials, n_groups, raw_in, raw_only ? 1 : 0, target ? 1 : 0, loss_kind, count, out);
+    return cudaGetLastError ();
+}
+
+cudaError_t launch_clipper_finalize_dp (const ClipDesc& desc, float* params, const double* partials, int64_t n_groups, bool target, int loss_kind, double count, double* out, const DpPeers& dp, float* m, float* v, int32_t* step, int n_params,
+                                        float lr, const float* lr_vec, float beta1, float beta2, float eps, const float* lo, const float* hi, cudaStream_t stream)
+{
+    clipper_finalize_dp<<<1, 256, 0, stream>>> (desc, params, partials, n_groups, target ? 1 : 0, loss_kind, count, out, dp, m, v, step, n_params, lr, lr_vec, beta1, beta2, eps, lo, hi);
+    return cudaGetLastError ();
+}
+
+cudaError_t launch_peer_allreduce (double* inout, int n, const DpPeers& dp, cudaStream_t stream)
+{
+    peer_allreduce_kernel<<<1, 256, 0, stream>>> (inout, n, dp);
     return cudaGetLastError ();
 }
 

@@ -102,6 +102,29 @@ struct AsyncScratch
     }
 };
 
+// ---- per-phase timing of the training step (dwdf_profile_begin / _end) ------------------------------------------------
+// CUDA events recorded on the caller's stream at the kernel boundaries of dwdf_train_step / dwdf_train_step_dp: start,
+// after the forward pass (with its verification kernel), after the adjoint (with its composition kernel), after the tail
+// (reduction + exchange + chain rule + Adam). bench.py reads the dominant kernel's duration inside its timed region this way.
+struct Profiler
+{
+    std::mutex mu;
+    bool on = false;
+    int cap = 0, n = 0;
+    std::vector<cudaEvent_t> ev;
+    void mark (int k, cudaStream_t s)
+    {
+        if (! on)
+            return;
+        std::lock_guard<std::mutex> lock (mu);
+        if (on && n < cap)
+            cudaEventRecord (ev[(size_t) 4 * n + k], s);
+        if (on && k == 3 && n < cap)
+            ++n;
+    }
+};
+Profiler g_prof;
+
 int fail (int code, const char* fmt, ...)
 {
     va_list ap;
@@ -548,7 +571,7 @@ int dwdf_process_block (const dwdf_program* prog, const float* params, const flo
     return forward_impl (prog, params, x, r, y, nullptr, state, B, T, (cudaStream_t) stream);
 }
 
-static int backward_impl (bool raw_only, const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream_)
+static int backward_impl (int raw_only, const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t) stream_;
     if (int rc = check_batch (prog, params, x, B, T))
@@ -583,7 +606,12 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
             maps.cmaps = (float*) ((char*) workspace + partials_bytes (B));
         }
         DWDF_CUDA (launch_clipper_adjoint (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, gy_or_target, target, sk, gx, partials, B, T, stream));
-        DWDF_CUDA (launch_clipper_finalize (prog->clip, params, partials, n_groups (B), nullptr, raw_only, target, loss_kind, count, out, stream));
+        if (raw_only == 2)
+        { // the caller reduces the partials itself (dwdf_train_step_dp: reduction + exchange + chain rule + Adam in one kernel)
+            g_launches.fetch_add (1);
+            return DWDF_OK;
+        }
+        DWDF_CUDA (launch_clipper_finalize (prog->clip, params, partials, n_groups (B), nullptr, raw_only != 0, target, loss_kind, count, out, stream));
     }
     else
     {
@@ -593,7 +621,7 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
             return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
         float* tape = (float*) ((char*) workspace + (((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256) * 256);
         DWDF_CUDA (launch_tree_adjoint (prog->tree, params, x, r, gy_or_target, target, sk, partials, tape, B, T, stream));
-        DWDF_CUDA (launch_tree_finalize (prog->tree, params, partials, n_groups (B), nullptr, raw_only, target, loss_kind, count, out, stream));
+        DWDF_CUDA (launch_tree_finalize (prog->tree, params, partials, n_groups (B), nullptr, raw_only != 0, target, loss_kind, count, out, stream));
     }
     g_launches.fetch_add (2);
     return DWDF_OK;
@@ -601,12 +629,12 @@ static int backward_impl (bool raw_only, const dwdf_program* prog, const float* 
 
 int dwdf_backward (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
 {
-    return backward_impl (false, prog, params, x, r, y, z_ckpt, gy_or_target, grad_mode, loss_kind, skip, gx, out, workspace, workspace_bytes, B, T, stream);
+    return backward_impl (0, prog, params, x, r, y, z_ckpt, gy_or_target, grad_mode, loss_kind, skip, gx, out, workspace, workspace_bytes, B, T, stream);
 }
 
 int dwdf_backward_raw (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int64_t skip, float* gx, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
 {
-    return backward_impl (true, prog, params, x, r, y, z_ckpt, gy_or_target, grad_mode, DWDF_LOSS_MSE, skip, gx, raw, workspace, workspace_bytes, B, T, stream);
+    return backward_impl (1, prog, params, x, r, y, z_ckpt, gy_or_target, grad_mode, DWDF_LOSS_MSE, skip, gx, raw, workspace, workspace_bytes, B, T, stream);
 }
 
 int dwdf_finalize (const dwdf_program* prog, const float* params, int32_t grad_mode, int32_t loss_kind, double* raw_inout, void* stream)
@@ -679,16 +707,228 @@ int dwdf_adam_step (float* params, const double* out, float* m, float* v, int32_
     return DWDF_OK;
 }
 
+// ---- multi-GPU: one process per GPU, the step's single exchange over peer memory --------------------------------
+struct dwdf_comm
+{
+    int rank = 0, world = 1, device = 0;
+    char* mailbox = nullptr; // this rank's mailbox (cudaMalloc: exportable with CUDA IPC)
+    char* peers[kDpMaxWorld] = {};
+    bool opened[kDpMaxWorld] = {};
+    bool connected = false;
+    double timeout_s = 20.0;
+};
+
+static bool comm_peers (const dwdf_comm* c, DpPeers& dp)
+{
+    if (c == nullptr || ! c->connected)
+        return false;
+    dp.rank = c->rank;
+    dp.world = c->world;
+    dp.timeout_ns = (unsigned long long) (c->timeout_s * 1e9);
+    for (int p = 0; p < kDpMaxWorld; ++p)
+        dp.mailbox[p] = p < c->world ? c->peers[p] : nullptr;
+    return true;
+}
+
+int dwdf_comm_create (int32_t rank, int32_t world, dwdf_comm** out)
+{
+    if (out == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (world < 1 || world > kDpMaxWorld || rank < 0 || rank >= world)
+        return fail (DWDF_ERR_INVALID, "rank %d / world %d (at most %d ranks of one node)", rank, world, kDpMaxWorld);
+    dwdf_comm* c = new (std::nothrow) dwdf_comm;
+    if (c == nullptr)
+        return fail (DWDF_ERR_INVALID, "out of memory");
+    c->rank = rank;
+    c->world = world;
+    cudaError_t e = cudaGetDevice (&c->device);
+    if (e == cudaSuccess)
+        e = cudaMalloc ((void**) &c->mailbox, dp_mailbox_bytes (world));
+    if (e == cudaSuccess)
+        e = cudaMemset (c->mailbox, 0, dp_mailbox_bytes (world));
+    if (e == cudaSuccess)
+        e = cudaDeviceSynchronize ();
+    if (e != cudaSuccess)
+    {
+        delete c;
+        return cuda_fail (e, "dwdf_comm_create");
+    }
+    c->peers[rank] = c->mailbox;
+    c->connected = world == 1;
+    *out = c;
+    return DWDF_OK;
+}
+
+size_t dwdf_comm_handle_bytes (void) { return sizeof (cudaIpcMemHandle_t); }
+
+int dwdf_comm_get_handle (const dwdf_comm* comm, void* handle_out)
+{
+    if (comm == nullptr || handle_out == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    DWDF_CUDA (cudaIpcGetMemHandle (&h, comm->mailbox));
+    std::memcpy (handle_out, &h, sizeof (h));
+    return DWDF_OK;
+}
+
+int dwdf_comm_connect (dwdf_comm* comm, const void* handles)
+{
+    if (comm == nullptr || handles == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    for (int p = 0; p < comm->world; ++p)
+    {
+        if (p == comm->rank || comm->opened[p])
+            continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy (&h, (const char*) handles + (size_t) p * sizeof (h), sizeof (h));
+        void* ptr = nullptr;
+        DWDF_CUDA (cudaIpcOpenMemHandle (&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        comm->peers[p] = (char*) ptr;
+        comm->opened[p] = true;
+    }
+    comm->connected = true;
+    return DWDF_OK;
+}
+
+int dwdf_comm_set_timeout (dwdf_comm* comm, double seconds)
+{
+    if (comm == nullptr || ! (seconds > 0.0))
+        return fail (DWDF_ERR_INVALID, "bad argument");
+    comm->timeout_s = seconds;
+    return DWDF_OK;
+}
+
+int dwdf_comm_destroy (dwdf_comm* comm)
+{
+    if (comm == nullptr)
+        return DWDF_OK;
+    for (int p = 0; p < comm->world; ++p)
+        if (comm->opened[p])
+            cudaIpcCloseMemHandle (comm->peers[p]);
+    if (comm->mailbox != nullptr)
+        cudaFree (comm->mailbox);
+    delete comm;
+    return DWDF_OK;
+}
+
+int dwdf_allreduce_sum (const dwdf_comm* comm, double* inout, int64_t n, void* stream)
+{
+    DpPeers dp;
+    if (inout == nullptr || ! comm_peers (comm, dp))
+        return fail (DWDF_ERR_INVALID, "dwdf_allreduce_sum needs a connected communicator (dwdf_comm_create / _connect)");
+    if (n < 1 || n > kDpSlotDoubles - 1)
+        return fail (DWDF_ERR_INVALID, "%lld doubles: one exchange carries at most %d", (long long) n, kDpSlotDoubles - 1);
+    if (dp.world == 1)
+        return DWDF_OK;
+    DWDF_CUDA (launch_peer_allreduce (inout, (int) n, dp, (cudaStream_t) stream));
+    g_launches.fetch_add (1);
+    return DWDF_OK;
+}
+
+static int train_step_impl (const dwdf_program* prog, const DpPeers& dp, float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, float* z_ckpt, double* out, void* workspace,
+                            size_t workspace_bytes, float* m, float* v, int32_t* step, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, const float* lo, const float* hi, int64_t B, int64_t T, cudaStream_t stream)
+{
+    if (B < 1 || T < 1)
+        return fail (DWDF_ERR_INVALID, "a training step needs at least one sequence (B = %lld, T = %lld)", (long long) B, (long long) T);
+    if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
+        return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
+    g_prof.mark (0, stream);
+    if (int rc = dwdf_forward (prog, params, x, r, y, z_ckpt, B, T, stream))
+        return rc;
+    g_prof.mark (1, stream);
+    const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
+    if (prog->is_clipper)
+    { // adjoint -> ONE kernel: reduction of the partials + exchange over peer memory + chain rule + loss + Adam
+        if (int rc = backward_impl (2, prog, params, x, r, y, z_ckpt, target, DWDF_GRAD_TARGET, loss_kind, skip, nullptr, out, workspace, workspace_bytes, B, T, stream))
+            return rc;
+        g_prof.mark (2, stream);
+        DWDF_CUDA (launch_clipper_finalize_dp (prog->clip, params, (const double*) workspace, n_groups (B), true, loss_kind, (double) B * (double) (T - sk), out, dp, m, v, step, prog->desc.n_params, lr, lr_per_slot, beta1, beta2, eps, lo, hi,
+                                               stream));
+        g_launches.fetch_add (1);
+        g_prof.mark (3, stream);
+        return DWDF_OK;
+    }
+    // other trees: raw sums -> exchange -> finalize -> Adam
+    if (int rc = backward_impl (dp.world > 1 ? 1 : 0, prog, params, x, r, y, z_ckpt, target, DWDF_GRAD_TARGET, dp.world > 1 ? DWDF_LOSS_MSE : loss_kind, skip, nullptr, out, workspace, workspace_bytes, B, T, stream))
+        return rc;
+    g_prof.mark (2, stream);
+    if (dp.world > 1)
+    {
+        DWDF_CUDA (launch_peer_allreduce (out, DWDF_OUT_LEN, dp, stream));
+        g_launches.fetch_add (1);
+        if (int rc = dwdf_finalize (prog, params, DWDF_GRAD_TARGET, loss_kind, out, stream))
+            return rc;
+    }
+    int rc = m == nullptr ? DWDF_OK : dwdf_adam_step (params, out, m, v, step, prog->desc.n_params, lr, lr_per_slot, beta1, beta2, eps, 1.0, lo, hi, stream);
+    g_prof.mark (3, stream);
+    return rc;
+}
+
 int dwdf_train_step (const dwdf_program* prog, float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, float* z_ckpt, double* out, void* workspace,
                      size_t workspace_bytes, float* m, float* v, int32_t* step, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, const float* lo, const float* hi, int64_t B, int64_t T, void* stream)
 {
     if (prog == nullptr)
         return fail (DWDF_ERR_INVALID, "null argument");
-    if (int rc = dwdf_forward (prog, params, x, r, y, z_ckpt, B, T, stream))
-        return rc;
-    if (int rc = dwdf_backward (prog, params, x, r, y, z_ckpt, target, DWDF_GRAD_TARGET, loss_kind, skip, nullptr, out, workspace, workspace_bytes, B, T, stream))
-        return rc;
-    return dwdf_adam_step (params, out, m, v, step, prog->desc.n_params, lr, lr_per_slot, beta1, beta2, eps, 1.0, lo, hi, stream);
+    DpPeers solo {};
+    solo.world = 1;
+    return train_step_impl (prog, solo, params, x, r, target, loss_kind, skip, y, z_ckpt, out, workspace, workspace_bytes, m, v, step, lr, lr_per_slot, beta1, beta2, eps, lo, hi, B, T, (cudaStream_t) stream);
+}
+
+int dwdf_train_step_dp (const dwdf_program* prog, const dwdf_comm* comm, float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, float* z_ckpt, double* out, void* workspace,
+                        size_t workspace_bytes, float* m, float* v, int32_t* step, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, const float* lo, const float* hi, int64_t B, int64_t T, void* stream)
+{
+    DpPeers dp;
+    if (prog == nullptr || ! comm_peers (comm, dp))
+        return fail (DWDF_ERR_INVALID, "dwdf_train_step_dp needs a program and a connected communicator");
+    return train_step_impl (prog, dp, params, x, r, target, loss_kind, skip, y, z_ckpt, out, workspace, workspace_bytes, m, v, step, lr, lr_per_slot, beta1, beta2, eps, lo, hi, B, T, (cudaStream_t) stream);
+}
+
+int dwdf_profile_begin (int32_t max_steps)
+{
+    if (max_steps < 1 || max_steps > 65536)
+        return fail (DWDF_ERR_INVALID, "max_steps outside [1, 65536]");
+    std::lock_guard<std::mutex> lock (g_prof.mu);
+    for (cudaEvent_t e : g_prof.ev)
+        cudaEventDestroy (e);
+    g_prof.ev.assign ((size_t) 4 * max_steps, nullptr);
+    for (cudaEvent_t& e : g_prof.ev)
+        DWDF_CUDA (cudaEventCreate (&e));
+    g_prof.cap = max_steps;
+    g_prof.n = 0;
+    g_prof.on = true;
+    return DWDF_OK;
+}
+
+int dwdf_profile_end (double* ms_forward, double* ms_adjoint, double* ms_tail, int32_t* steps)
+{
+    std::lock_guard<std::mutex> lock (g_prof.mu);
+    g_prof.on = false;
+    double sum[3] = { 0.0, 0.0, 0.0 };
+    const int n = g_prof.n;
+    for (int i = 0; i < n; ++i)
+    {
+        DWDF_CUDA (cudaEventSynchronize (g_prof.ev[(size_t) 4 * i + 3]));
+        for (int k = 0; k < 3; ++k)
+        {
+            float ms = 0.0f;
+            DWDF_CUDA (cudaEventElapsedTime (&ms, g_prof.ev[(size_t) 4 * i + k], g_prof.ev[(size_t) 4 * i + k + 1]));
+            sum[k] += ms;
+        }
+    }
+    if (ms_forward != nullptr)
+        *ms_forward = n > 0 ? sum[0] / n : 0.0;
+    if (ms_adjoint != nullptr)
+        *ms_adjoint = n > 0 ? sum[1] / n : 0.0;
+    if (ms_tail != nullptr)
+        *ms_tail = n > 0 ? sum[2] / n : 0.0;
+    if (steps != nullptr)
+        *steps = n;
+    for (cudaEvent_t e : g_prof.ev)
+        cudaEventDestroy (e);
+    g_prof.ev.clear ();
+    g_prof.cap = g_prof.n = 0;
+    return DWDF_OK;
 }
 
 // ---- end-to-end calls with host buffers ----------------------------------------------------------

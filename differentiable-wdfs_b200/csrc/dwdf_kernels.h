@@ -89,6 +89,20 @@ cudaError_t launch_clipper_train (const ClipVariant& v, bool use_tma, const Clip
 // fixed-order reduction of the partials + chain rule to (Is, nabla, R, C) + loss -> out[DWDF_OUT_LEN]
 cudaError_t launch_clipper_finalize (const ClipDesc& desc, const float* params, const double* partials, int64_t n_groups, const double* raw_in, bool raw_only, bool target, int loss_kind, double count, double* out, cudaStream_t stream);
 
+// ---- multi-GPU exchange over peer memory (clipper_dispatch.cu explains the protocol) ----------------------------
+constexpr int kDpMaxWorld = 16; // ranks of one node
+constexpr int kDpSlotDoubles = 2048; // doubles per mailbox slot; the last one is the slot's epoch flag
+struct DpPeers // by-value kernel argument
+{
+    int rank, world;
+    unsigned long long timeout_ns;
+    char* mailbox[kDpMaxWorld]; // every rank's mailbox as mapped into this process; mailbox[rank] is this rank's own
+};
+inline size_t dp_mailbox_bytes (int world) { return (size_t) 2 * world * kDpSlotDoubles * sizeof (double) + 256; } // two parities x world slots, then the epoch counter
+cudaError_t launch_clipper_finalize_dp (const ClipDesc& desc, float* params, const double* partials, int64_t n_groups, bool target, int loss_kind, double count, double* out, const DpPeers& dp, float* m, float* v, int32_t* step, int n_params,
+                                        float lr, const float* lr_vec, float beta1, float beta2, float eps, const float* lo, const float* hi, cudaStream_t stream);
+cudaError_t launch_peer_allreduce (double* inout, int n, const DpPeers& dp, cudaStream_t stream);
+
 cudaError_t launch_adam (float* params, const double* out, float* m, float* v, int32_t* step, int n_params, float lr, const float* lr_vec, float beta1, float beta2, float eps, double grad_scale, const float* lo, const float* hi, cudaStream_t stream);
 
 // ---- neural diode-pair root (inference): clipper tree + b = -MLP(a, ln Rp), hidden width 4 / 8 / 16 ----------

@@ -6,15 +6,24 @@ clipper_pot.py:110-124), so the batch axis shards trivially: rank r owns rows
 all-reduce (sum) per step of the DWDF_OUT_LEN raw gradient/loss sums — 192 bytes, pure latency —
 issued on the compute stream right after the adjoint's fixed-order reduction; every rank then runs
 the identical finalize (chain rule, loss) and optimizer update, so parameters stay bit-identical
-across ranks without a broadcast. One process per GPU (torchrun); NCCL over NVLink for the real
-thing, gloo in the CPU tests of the host logic.
+across ranks without a broadcast. One process per GPU (torchrun).
+
+Two ways to run the exchange:
+* ``PeerComm`` — the engine's own: the step's reduction kernel exchanges the sums itself over NVLink peer memory
+  (``dwdf_train_step_dp`` / ``dwdf_allreduce_sum``, include/dwdf.h: mailboxes mapped with CUDA IPC). torch.distributed
+  only carries the 64-byte IPC handles once, at start-up (any backend: nccl, or gloo in the tests).
+* ``DataParallelTrainer`` with ``torch.distributed.all_reduce`` between ``backward(raw=True)`` and ``finalize`` — the
+  library-collective version, kept as the reference to compare against (and what the gloo CPU tests of the host logic run).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Callable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import _lib as L
 
 
 def shard_rows(B: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -66,3 +75,50 @@ def clipper_trainer(circuit, optimizer=None, loss="mse", skip=0, fused=False, gr
         return circuit.finalize(target=True, loss=loss)
 
     return DataParallelTrainer(local_raw, finalize, (lambda: optimizer.apply()) if optimizer is not None else None, group)
+
+
+class PeerComm:
+    """This rank's end of the peer-memory exchange (``dwdf_comm``): allocates the mailbox on ``device``, gathers the
+    CUDA IPC handles of all ranks through ``torch.distributed`` (``group``; any backend) and maps the peers' mailboxes.
+    ``world_size == 1`` (or no process group) gives a trivial communicator. Raises ``DwdfError`` if CUDA IPC / peer
+    access is unavailable — callers may then fall back to ``torch.distributed.all_reduce``."""
+
+    def __init__(self, device, group=None, timeout_s: float = 20.0):
+        self.lib = L.lib()
+        self.device = torch.device(device)
+        active = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if active else 0
+        self.world_size = dist.get_world_size(group) if active else 1
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.dwdf_comm_create(self.rank, self.world_size, C.byref(self.handle)))
+            L.check(self.lib.dwdf_comm_set_timeout(self.handle, float(timeout_s)))
+            if self.world_size > 1:
+                n = int(self.lib.dwdf_comm_handle_bytes())
+                mine = C.create_string_buffer(n)
+                L.check(self.lib.dwdf_comm_get_handle(self.handle, mine))
+                gathered = [None] * self.world_size
+                dist.all_gather_object(gathered, bytes(mine.raw), group=group)
+                blob = C.create_string_buffer(b"".join(gathered), n * self.world_size)
+                L.check(self.lib.dwdf_comm_connect(self.handle, blob))
+                dist.barrier(group=group)  # every mailbox is zeroed and mapped before anyone's first exchange
+
+    def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum over ranks of a float64 device vector (at most 2047 elements), on the current stream."""
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device == self.device):
+            raise ValueError("all_reduce_ takes a contiguous float64 tensor on the communicator's device")
+        with torch.cuda.device(self.device):
+            L.check(self.lib.dwdf_allreduce_sum(self.handle, C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return t
+
+    def close(self):
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.dwdf_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -642,10 +642,12 @@ class CompiledCircuit:
         return self._result(None)
 
     @_on_device
-    def train_step(self, x, target, optimizer: "Adam", loss="mse", skip=0, out=None):
+    def train_step(self, x, target, optimizer: "Adam", loss="mse", skip=0, out=None, comm=None):
         """forward + adjoint (fused loss) + Adam in one library call, nothing synchronises: capturable in a
         ``torch.cuda.CUDAGraph`` and replayable (small batches are launch-bound). Returns the result dict of
-        ``backward`` (device tensors, overwritten by the next step)."""
+        ``backward`` (device tensors, overwritten by the next step). ``comm`` (a ``data_parallel.PeerComm``): x and
+        target are THIS RANK'S shard; the step's reduction kernel exchanges the raw sums with the other ranks over peer
+        memory, loss and gradients are those of the global batch and every rank applies the same update."""
         B, T = self._check_xy(x)
         self._check_xy(target, "target", (B, T))
         y = torch.empty_like(x) if out is None else out
@@ -653,9 +655,16 @@ class CompiledCircuit:
         ck = self._scratch("_ckpt", self.lib.dwdf_ckpt_bytes(self.handle, B, T))
         work = self._scratch("_work", self.lib.dwdf_workspace_bytes(self.handle, B, T))
         o = optimizer
-        L.check(self.lib.dwdf_train_step(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(y), _ptr(ck), _ptr(self.out),
-                                         _ptr(work), work.numel(), _ptr(o.m), _ptr(o.v), _ptr(o.step_count), 0.0, _ptr(o.lr), float(o.beta_1), float(o.beta_2), float(o.epsilon), _ptr(self.clip_lo),
-                                         _ptr(self.clip_hi), B, T, _stream_ptr(self.device)))
+        if comm is not None:
+            if comm.device != self.device:
+                raise ValueError(f"the communicator lives on {comm.device}, the circuit on {self.device}")
+            L.check(self.lib.dwdf_train_step_dp(self.handle, comm.handle, _ptr(self.params), _ptr(x), None, _ptr(target), L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(y), _ptr(ck), _ptr(self.out),
+                                                _ptr(work), work.numel(), _ptr(o.m), _ptr(o.v), _ptr(o.step_count), 0.0, _ptr(o.lr), float(o.beta_1), float(o.beta_2), float(o.epsilon), _ptr(self.clip_lo),
+                                                _ptr(self.clip_hi), B, T, _stream_ptr(self.device)))
+        else:
+            L.check(self.lib.dwdf_train_step(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(y), _ptr(ck), _ptr(self.out),
+                                             _ptr(work), work.numel(), _ptr(o.m), _ptr(o.v), _ptr(o.step_count), 0.0, _ptr(o.lr), float(o.beta_1), float(o.beta_2), float(o.epsilon), _ptr(self.clip_lo),
+                                             _ptr(self.clip_hi), B, T, _stream_ptr(self.device)))
         self._last = (x, None, y, B, T)
         return self._result(None)
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DWDF_VERSION 3
+#define DWDF_VERSION 4
 #if defined(__GNUC__)
 #define DWDF_API __attribute__ ((visibility ("default")))
 #else
@@ -212,6 +212,40 @@ DWDF_API int dwdf_adam_step (float* params, const double* out, float* m, float* 
  * step — or a loop of steps — can be captured in a CUDA graph and replayed (small batches are launch-bound).
  * y, z_ckpt, out, workspace as in dwdf_forward / dwdf_backward; m, v, step, lr_per_slot, lo, hi as in dwdf_adam_step. */
 DWDF_API int dwdf_train_step (const dwdf_program* prog, float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, float* z_ckpt, double* out, void* workspace, size_t workspace_bytes, float* m, float* v, int32_t* step, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, const float* lo, const float* hi, int64_t B, int64_t T, void* stream);
+
+/* ---- multi-GPU: one process per GPU --------------------------------------------------------------------
+ * Replaces: nothing in the reference (it trains on one CPU); realises BASELINE config 5 / SURVEY.md §8e: sequences shard
+ * over GPUs with no data-path collective, and a training step exchanges ONE small vector (the DWDF_OUT_LEN raw sums; the
+ * weight-gradient vector for the neural root). That message is pure latency, so the exchange runs INSIDE the step's
+ * reduction kernel over NVLink peer memory instead of as a library collective between two tiny kernels: every rank owns a
+ * mailbox (device memory, mapped by its peers with CUDA IPC); a step writes its vector into its slot of every mailbox,
+ * waits for all slots of its own, and sums them in rank order (bit-identical results on every rank, no broadcast).
+ *   dwdf_comm_create      allocates this rank's mailbox on the CURRENT device
+ *   dwdf_comm_get_handle  the mailbox's CUDA IPC handle (dwdf_comm_handle_bytes() bytes), to be gathered by the launcher
+ *                         (torch.distributed / MPI / a file — any out-of-band channel)
+ *   dwdf_comm_connect     maps the peers' mailboxes: `handles` = world handles in rank order; every rank must have
+ *                         connected (barrier on the launcher's side) before the first exchange
+ *   dwdf_allreduce_sum    inout[0 .. n) <- sum over ranks, n <= 2047 doubles, one single-block kernel on `stream`
+ *   dwdf_train_step_dp    dwdf_train_step on this rank's shard of B sequences: forward + adjoint + ONE kernel doing the
+ *                         fixed-order reduction, the exchange, the chain rule / loss over the GLOBAL batch and Adam.
+ *                         Nothing synchronises with the host: capturable in a CUDA graph. m == NULL skips Adam.
+ * A peer that does not arrive within the timeout (default 20 s) makes the result block NaN instead of hanging the GPU. */
+typedef struct dwdf_comm dwdf_comm;
+DWDF_API int dwdf_comm_create (int32_t rank, int32_t world, dwdf_comm** out);
+DWDF_API size_t dwdf_comm_handle_bytes (void);
+DWDF_API int dwdf_comm_get_handle (const dwdf_comm* comm, void* handle_out);
+DWDF_API int dwdf_comm_connect (dwdf_comm* comm, const void* handles);
+DWDF_API int dwdf_comm_set_timeout (dwdf_comm* comm, double seconds);
+DWDF_API int dwdf_comm_destroy (dwdf_comm* comm);
+DWDF_API int dwdf_allreduce_sum (const dwdf_comm* comm, double* inout, int64_t n, void* stream);
+DWDF_API int dwdf_train_step_dp (const dwdf_program* prog, const dwdf_comm* comm, float* params, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, float* z_ckpt, double* out, void* workspace, size_t workspace_bytes, float* m, float* v, int32_t* step, float lr, const float* lr_per_slot, float beta1, float beta2, float eps, const float* lo, const float* hi, int64_t B, int64_t T, void* stream);
+
+/* Per-phase device timing of dwdf_train_step / dwdf_train_step_dp: between dwdf_profile_begin and dwdf_profile_end the
+ * library records CUDA events on the caller's stream at the step's kernel boundaries (at most max_steps steps) and
+ * dwdf_profile_end returns the mean milliseconds of the forward pass, the adjoint pass and the tail (reduction, exchange,
+ * chain rule, Adam) over the `steps` recorded — the roofline figures of bench.py, taken inside its timed region. */
+DWDF_API int dwdf_profile_begin (int32_t max_steps);
+DWDF_API int dwdf_profile_end (double* ms_forward, double* ms_adjoint, double* ms_tail, int32_t* steps);
 
 /* End-to-end variants with HOST buffers (what a training script holding numpy batches calls):
  * host->device copies of x / r / target, the kernels, device->host copy of y / out, all on one
