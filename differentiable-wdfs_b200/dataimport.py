@@ -63,8 +63,29 @@ def data_path_for_diode(n_up: int, n_down: int, base_dir: str, family: str = "1N
     return os.path.join(root, f"{n_up}up{n_down}down")
 
 
-def load_diode_data(data_path: str, start_offset: int = 0, csv_samples: int = -1):
-    """dataimport.py:82-137: -> (train (3, N_train), N_train, val (3, N_val), N_val, FS), rows = (x, R, y_ref)."""
+def get_data_path_for_diode(diode, BASE_DIR, HPF2: bool = False) -> str:
+    """dataimport.py:60-78 with the reference's own signature: the configuration tuple (diode_config.DiodeConfig) picks the folder."""
+    family = "1N4148" if "1N4148" in diode.name else "OA1154" if "OA1154" in diode.name else None
+    if family is None:
+        raise ValueError("No data available for this diode!")
+    return data_path_for_diode(int(diode.N_up), int(diode.N_down), str(BASE_DIR), family, hpf=bool(HPF2))
+
+
+createDataset = create_dataset  # the reference's spelling (dataimport.py:25)
+
+
+def load_diode_data(data_path, BASE_DIR=None, start_offset: int = 0, csv_samples: int = -1, plot: bool = False, HPF: bool = False):
+    """dataimport.py:82-137: -> (train (3, N_train), N_train, val (3, N_val), N_val, FS), rows = (x, R, y_ref).
+
+    Called like the reference, ``load_diode_data(diode, BASE_DIR, start_offset, csv_samples)``, or with the folder of
+    one configuration, ``load_diode_data(path, start_offset=..., csv_samples=...)``. (``plot`` is accepted and ignored.)"""
+    if hasattr(data_path, "name") and hasattr(data_path, "N_up"):
+        if BASE_DIR is None:
+            raise ValueError("load_diode_data(diode, BASE_DIR): the dataset's base directory is missing")
+        data_path = get_data_path_for_diode(data_path, BASE_DIR, HPF2=HPF)
+    elif BASE_DIR is not None and not isinstance(BASE_DIR, (str, os.PathLike)):
+        start_offset, BASE_DIR = int(BASE_DIR), None  # load_diode_data(path, start_offset, ...) of this package's first version
+    data_path = str(data_path)
     train, val, fs = [], [], 0.0
     for name in sorted(os.listdir(data_path)):
         if not name.endswith(".csv"):
