@@ -18,29 +18,73 @@ namespace
 // the caller's dL/dy scale.
 
 // block-wide fixed-order sum of the per-group partials; the totals land in sm[k][0]
-__device__ __forceinline__ void reduce_partials (double (&sm)[5][256], const double* __restrict__ partials, int64_t n_groups)
+template <int N>
+__device__ __forceinline__ void reduce_partials (double (&sm)[N][256], const double* __restrict__ partials, int64_t n_groups)
 {
     const int tid = threadIdx.x;
-    double a[5] = { 0, 0, 0, 0, 0 };
+    double a[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        a[k] = 0.0;
     for (int64_t g = tid; g < n_groups; g += 256)
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
+        for (int k = 0; k < N; ++k)
             a[k] += partials[g * kPartialStride + k];
 #pragma unroll
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < N; ++k)
         sm[k][tid] = a[k];
     __syncthreads ();
     for (int o = 128; o > 0; o >>= 1)
     {
         if (tid < o)
 #pragma unroll
-            for (int k = 0; k < 5; ++k)
+            for (int k = 0; k < N; ++k)
                 sm[k][tid] += sm[k][tid + o];
         __syncthreads ();
     }
 }
 
 // raw sums (kAcc* slots, raw[23] = number of samples in the loss) -> out[DWDF_OUT_LEN]: gradients per slot, loss, mse, esr
+// the same with the source resistance as an input channel: gamma and Rp vary per sample, so the adjoint kernel has already
+// folded them in (kAccGamma = sum G cg gamma (1 - gamma), kAccEllRp = sum G cl Rp); what is left is constant
+__device__ __forceinline__ void finalize_math_r (const ClipDesc& desc, const float* __restrict__ params, const double* raw, int target, int loss_kind, double* out);
+
+__device__ __forceinline__ void loss_scale (const double* raw, int target, int loss_kind, double& alpha, double& loss, double& mse, double& esr)
+{
+    const double sse = raw[kAccSse], st2 = raw[kAccSt2], count = raw[23];
+    alpha = 1.0, loss = 0.0, mse = 0.0, esr = 0.0;
+    if (target)
+    {
+        const double N = count > 0.0 ? count : 1.0;
+        mse = sse / N;
+        alpha = 2.0 / N;
+        loss = mse;
+        if (loss_kind == 1)
+        {
+            const double energy = st2 + 2.220446049250313e-16;
+            esr = sqrt (sse / energy / N);
+            loss += esr;
+            if (esr > 0.0)
+                alpha += 1.0 / (esr * energy * N);
+        }
+    }
+}
+
+__device__ __forceinline__ void finalize_math_r (const ClipDesc& desc, const float* __restrict__ params, const double* raw, int target, int loss_kind, double* out)
+{
+    double alpha, loss, mse, esr;
+    loss_scale (raw, target, loss_kind, alpha, loss, mse, esr);
+    const double C = params[desc.slot_C], Is = params[desc.slot_Is];
+    for (int k = 0; k < 24; ++k)
+        out[k] = 0.0;
+    out[desc.slot_Is] = alpha * raw[kAccEll] / Is; // ell = ln Rp + ln Is
+    out[desc.slot_nabla] = alpha * raw[kAccV] * (double) desc.Vt;
+    out[desc.slot_C] = alpha * (-raw[kAccGamma] / C - 2.0 * (double) desc.fs * raw[kAccEllRp]); // dgamma/dC = -gamma (1 - gamma) / C, d ell/dC = -2 fs Rp
+    out[16] = loss; // (slot_R stays 0: the resistance is an input here, tf_wdf.py:51-52)
+    out[17] = mse;
+    out[18] = esr;
+}
+
 __device__ __forceinline__ void finalize_math (const ClipDesc& desc, const float* __restrict__ params, const double* raw, int target, int loss_kind, double* out)
 {
     const double acc_g = raw[kAccGamma], acc_l = raw[kAccEll], acc_v = raw[kAccV], sse = raw[kAccSse], st2 = raw[kAccSt2], count = raw[23];
@@ -104,6 +148,29 @@ __global__ void __launch_bounds__ (256) clipper_finalize (const ClipDesc desc, c
         return;
     }
     finalize_math (desc, params, raw, target, loss_kind, out);
+}
+
+__global__ void __launch_bounds__ (256) clipper_finalize_r (const ClipDesc desc, const float* __restrict__ params, const double* __restrict__ partials, int64_t n_groups, const double* raw_in, int raw_only, int target, int loss_kind, double count, double* out)
+{
+    __shared__ double sm[6][256];
+    const int tid = threadIdx.x;
+    if (raw_in == nullptr)
+        reduce_partials (sm, partials, n_groups);
+    if (tid != 0)
+        return;
+    double raw[24];
+    for (int k = 0; k < 24; ++k)
+        raw[k] = 0.0;
+    for (int k = 0; k < 6; ++k)
+        raw[k] = raw_in != nullptr ? raw_in[k] : sm[k][0];
+    raw[23] = raw_in != nullptr ? raw_in[23] : count;
+    if (raw_only)
+    {
+        for (int k = 0; k < 24; ++k)
+            out[k] = raw[k];
+        return;
+    }
+    finalize_math_r (desc, params, raw, target, loss_kind, out);
 }
 
 // Adam (clipper_pot.py:180: Adam(1e-4, beta_1=0.5)) + the Keras clip constraints of tf_wdf.py:74,104; slot k, step number t
@@ -302,6 +369,22 @@ cudaError_t launch_clipper_adjoint (const ClipVariant& v, bool use_tma, const Cl
 cudaError_t launch_clipper_train (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* target, int64_t skip, float* y, double* partials, int64_t B, int64_t T, cudaStream_t stream)
 {
     return by_part (v, [&] (auto M, auto G) { return clipper_train_part<decltype (M)::value, decltype (G)::value> (v.pyorder, use_tma, maps, desc, params, x, target, clamp_skip (skip, T), y, partials, B, T, stream); });
+}
+
+cudaError_t launch_clipper_forward_r (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* r, float* y, float* ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream)
+{
+    return by_part (v, [&] (auto M, auto G) { return clipper_forward_r_part<decltype (M)::value, decltype (G)::value> (v.pyorder, use_tma, maps, desc, params, x, r, y, ckpt, state, B, T, stream); });
+}
+
+cudaError_t launch_clipper_adjoint_r (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* r, const float* y, const float* ckpt, const float* g, bool target, int64_t skip, double* partials, int64_t B, int64_t T, cudaStream_t stream)
+{
+    return by_part (v, [&] (auto M, auto G) { return clipper_adjoint_r_part<decltype (M)::value, decltype (G)::value> (v.pyorder, use_tma, maps, desc, params, x, r, y, ckpt, g, target, clamp_skip (skip, T), partials, B, T, stream); });
+}
+
+cudaError_t launch_clipper_finalize_r (const ClipDesc& desc, const float* params, const double* partials, int64_t n_groups, const double* raw_in, bool raw_only, bool target, int loss_kind, double count, double* out, cudaStream_t stream)
+{
+    clipper_finalize_r<<<1, 256, 0, stream>>> (desc, params, partials, n_groups, raw_in, raw_only ? 1 : 0, target ? 1 : 0, loss_kind, count, out);
+    return cudaGetLastError ();
 }
 
 cudaError_t launch_clipper_finalize (const ClipDesc& desc, const float* params, const double* partials, int64_t n_groups, const double* raw_in, bool raw_only, bool target, int loss_kind, double count, double* out, cudaStream_t stream)

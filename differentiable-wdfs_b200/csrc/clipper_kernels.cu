@@ -491,6 +491,8 @@ struct AdjAcc
 {
     double g = 0.0, l = 0.0, v = 0.0, sse = 0.0, st2 = 0.0;
     double hg = 0.0, hl = 0.0, hv = 0.0; // time chunks: the same sums for the homogeneous solution (no sources, G_in = 1)
+    double hlr = 0.0; // (homogeneous counterpart of lr)
+    double lr = 0.0; // resistance channel: sum G dz'/d ell Rp[n] (the capacitor's share of d ell varies with the sample's port resistance)
 };
 
 // One checkpoint segment of the reverse sweep. Nothing of the forward pass is replayed: the states
@@ -737,12 +739,21 @@ __device__ __forceinline__ void write_partials (AdjAcc& acc, double* __restrict_
         p[kAccSt2] = st2;
     }
 }
+__device__ __forceinline__ void write_partials_r (AdjAcc& acc, double* __restrict__ partials, int group, int lane)
+{
+    const double lr = warp_sum (acc.lr);
+    write_partials (acc, partials, group, lane);
+    if (lane == 0)
+        partials[(int64_t) group * kPartialStride + kAccEllRp] = lr;
+}
 
 // shared-memory tile IO of the TMA adjoint: x, y and g tiles of one 16-sample segment, 64-byte swizzle
 struct TileIO
 {
     uint32_t xt, yt, gt;
     int lane;
+    uint32_t rt = 0; // resistance channel tile (the *_r kernels)
+    __device__ __forceinline__ float4 r4 (int cc) const { return lds128 (chunk64 (rt, lane, cc)); }
     __device__ __forceinline__ float4 x4 (int cc) const { return lds128 (chunk64 (xt, lane, cc)); }
     __device__ __forceinline__ float4 y4 (int cc) const { return lds128 (chunk64 (yt, lane, cc)); }
     __device__ __forceinline__ float4 g4 (int cc) const { return lds128 (chunk64 (gt, lane, cc)); }
@@ -804,7 +815,15 @@ __device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUte
     }
 }
 
-constexpr int kMapFloats = kMapFloatsPerChunk; // per (chunk, sequence): P, Q, S0[3], S1[3], sse, st2 — stored [chunk][field][B]
+constexpr int kMapFloats = kMapFloatsPerChunk; // per (chunk, sequence): P, Q, S0[4], S1[4], sse, st2 — stored [chunk][field][B]
+static_assert (kMapFloats == 12, "write_map / clipper_adjoint_stitch lay out 12 fields");
+__device__ __forceinline__ void write_map (float* __restrict__ o, int64_t B, float G, float H, const AdjAcc& acc)
+{
+    o[0] = H, o[B] = G;
+    o[2 * B] = (float) acc.g, o[3 * B] = (float) acc.l, o[4 * B] = (float) acc.v, o[5 * B] = (float) acc.lr;
+    o[6 * B] = (float) acc.hg, o[7 * B] = (float) acc.hl, o[8 * B] = (float) acc.hv, o[9 * B] = (float) acc.hlr;
+    o[10 * B] = (float) acc.sse, o[11 * B] = (float) acc.st2;
+}
 
 // grid = (ceil(B / 32), K): CTA (g, k) sweeps the segments of time chunk k (chunk_segs each). K == 1: the sums go
 // straight to partials[g]; K > 1: every lane writes the affine map of its (sequence, chunk) to cmaps.
@@ -847,13 +866,7 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid
     else
         adjoint_tma_body<MODE, GENERAL, false, PY, TARGET, true> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, s0, s1, l2);
     if ((int64_t) b0 + lane < B)
-    {
-        float* o = cmaps + (int64_t) blockIdx.y * kMapFloats * B + b0 + lane;
-        o[0] = H, o[B] = G;
-        o[2 * B] = (float) acc.g, o[3 * B] = (float) acc.l, o[4 * B] = (float) acc.v;
-        o[5 * B] = (float) acc.hg, o[6 * B] = (float) acc.hl, o[7 * B] = (float) acc.hv;
-        o[8 * B] = (float) acc.sse, o[9 * B] = (float) acc.st2;
-    }
+        write_map (cmaps + (int64_t) blockIdx.y * kMapFloats * B + b0 + lane, B, G, H, acc);
 }
 
 // one lane per sequence: compose the chunks' affine maps last to first; one partial per group of 32 sequences
@@ -869,15 +882,16 @@ __global__ void __launch_bounds__ (kLanes) clipper_adjoint_stitch (const float* 
         for (int k = K - 1; k >= 0; --k)
         {
             const float* o = cmaps + (int64_t) k * kMapFloats * B + b;
-            acc.g += (double) o[2 * B] + G * (double) o[5 * B];
-            acc.l += (double) o[3 * B] + G * (double) o[6 * B];
-            acc.v += (double) o[4 * B] + G * (double) o[7 * B];
-            acc.sse += (double) o[8 * B];
-            acc.st2 += (double) o[9 * B];
+            acc.g += (double) o[2 * B] + G * (double) o[6 * B];
+            acc.l += (double) o[3 * B] + G * (double) o[7 * B];
+            acc.v += (double) o[4 * B] + G * (double) o[8 * B];
+            acc.lr += (double) o[5 * B] + G * (double) o[9 * B];
+            acc.sse += (double) o[10 * B];
+            acc.st2 += (double) o[11 * B];
             G = (double) o[0] * G + (double) o[B];
         }
     }
-    write_partials (acc, partials, blockIdx.x, lane);
+    write_partials_r (acc, partials, blockIdx.x, lane);
 }
 
 // direct-access IO (any T / alignment, optional dL/dx)
@@ -888,6 +902,8 @@ struct GlobalIO
     const float* __restrict__ gr;
     float* __restrict__ gxr;
     int n0, T;
+    const float* __restrict__ rr = nullptr; // resistance channel row (the *_r kernels)
+    __device__ __forceinline__ float4 r4 (int cc) const { return row4 (rr, cc); }
     __device__ __forceinline__ float at (const float* __restrict__ p, int n) const { return n < T ? __ldg (p + n) : 0.0f; }
     __device__ __forceinline__ float4 row4 (const float* __restrict__ p, int cc) const
     {
@@ -1379,6 +1395,378 @@ __global__ void __launch_bounds__ (kLanes) clipper_train_direct (const float* __
     write_partials (acc, partials, blockIdx.x, lane);
 }
 
+// =================================================================================================
+// the source resistance as a per-sample input channel
+// =================================================================================================
+// The layout the reference trains on (clipper_pot.py:67-69: input (B, T, 2) = (x, R); :114-117: set_resistance and
+// calc_impedance every sample). Same decomposition as the kernels above — one lane per sequence, TMA tiles through a
+// shared-memory ring, states recovered from the forward output in the adjoint — with a third (fourth) tile stream for
+// r and the port constants (gamma, Rp, ln(Rp Is / V)) derived per sample (clip_set_r). The chain rule through
+// calc_impedance is per sample too: the adjoint accumulates sum G cg gamma (1 - gamma) and sum G cl Rp for the capacitor
+// (gamma = Gv / (Gv + Gc), ell = ln Rp + ln Is), sum G cl for Is and sum G cv for the ideality factor; the resistance
+// itself is an input, not a parameter (tf_wdf.py:51-52). Both omegas are evaluated in full (no fast paths that rest on
+// a constant port resistance).
+// The rarely taken general forms, kept out of line so that the unrolled hot loops stay small. They work on a COPY of
+// the constants made in the cold branch: the hot path's own set never has its address taken and stays in registers.
+template <int MODE, bool GENERAL, bool PY>
+__device__ __noinline__ float clip_step_r_cold (const ClipConst* c, float x, float* z)
+{
+    return clip_step_scalar<MODE, GENERAL, false, PY> (*c, x, *z);
+}
+template <int MODE, bool GENERAL, bool PY>
+__device__ __forceinline__ float clip_step_r_general (const ClipConst& c, float x, float& z)
+{
+    ClipConst cold = c;
+    float zz = z;
+    const float y = clip_step_r_cold<MODE, GENERAL, PY> (&cold, x, &zz);
+    z = zz;
+    return y;
+}
+template <int MODE, bool GENERAL>
+__device__ __noinline__ void clip_step_recover_cold (const ClipConst* c, float x, float z, float zn, StepTape* tp)
+{
+    clip_step_recover<MODE, GENERAL, false> (*c, x, z, zn, *tp);
+}
+template <int MODE, bool GENERAL>
+__device__ __forceinline__ void clip_step_recover_general (const ClipConst& c, float x, float z, float zn, StepTape& tp)
+{
+    ClipConst cold = c;
+    StepTape t;
+    clip_step_recover_cold<MODE, GENERAL> (&cold, x, z, zn, &t);
+    tp = t;
+}
+
+template <int MODE, bool GENERAL, bool PY>
+__device__ __forceinline__ float clip_step_r (ClipConst& c, const ClipRBase& rb, float x, float r, float& z)
+{
+    clip_set_r<GENERAL> (c, rb, r);
+    if (GENERAL) // N_up != N_down law: the cheap reverse-biased branch wherever this sample's constants allow it
+        return rev_small_ok (c.pair) ? clip_step_scalar<MODE, GENERAL, true, PY> (c, x, z) : clip_step_r_general<MODE, GENERAL, PY> (c, x, z);
+    if (MODE == kModeExact)
+    {
+        if (exact_fast_ok (c.pair))
+        {
+            f1 zz { z };
+            const f1 y = clip_step_exactv<f1, PY> (c, f1 { x }, zz);
+            z = zz.x;
+            return y.x;
+        }
+        return clip_step_r_general<MODE, GENERAL, PY> (c, x, z);
+    }
+    if (rev_small_ok (c.pair)) // omega3's log branch behind a vote of the active lanes, the reverse-biased omega as one exp_approx
+        return clip_step_scalar<MODE, GENERAL, true, PY> (c, x, z);
+    return clip_step_r_general<MODE, GENERAL, PY> (c, x, z);
+}
+
+constexpr int kRStages = 3;
+constexpr int kRStageBytes = 2 * kAdjTileBytes; // x tile (outputs written in place) + r tile, [32 x 16] each: 12 KB per CTA -> 17 CTAs per SM, one wave at 65536 sequences
+
+template <int MODE, bool GENERAL, bool PY>
+__global__ void __launch_bounds__ (kLanes) clipper_forward_r_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmr, const __grid_constant__ CUtensorMap tmy, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T)
+{
+    __shared__ __align__ (1024) uint8_t smem[kRStages * kRStageBytes];
+    __shared__ __align__ (8) uint64_t bar_mem[kRStages];
+    const int lane = threadIdx.x;
+    const int b0 = blockIdx.x * kLanes;
+    const uint32_t tiles = smem_u32 (smem), bars = smem_u32 (bar_mem);
+    if (lane == 0)
+    {
+        tma_prefetch_desc (&tmx);
+        tma_prefetch_desc (&tmr);
+        tma_prefetch_desc (&tmy);
+        for (int s = 0; s < kRStages; ++s)
+            mbar_init (bars + 8 * s, 1);
+        fence_mbar_init ();
+    }
+    __syncwarp ();
+    ClipConst c;
+    ClipRBase rb;
+    clip_setup_r (c, rb, desc, __ldg (params + desc.slot_R), __ldg (params + desc.slot_C), __ldg (params + desc.slot_Is), __ldg (params + desc.slot_nabla));
+    const bool valid = (int64_t) b0 + lane < B;
+    float z = (state != nullptr && valid) ? state[b0 + lane] : 0.0f;
+    const int ntiles = (T + kSeg - 1) / kSeg;
+    auto load = [&] (int i) {
+        const int s = i % kRStages;
+        mbar_expect_tx (bars + 8 * s, kRStageBytes);
+        tma_load_2d (tiles + s * kRStageBytes, &tmx, i * kSeg, b0, bars + 8 * s);
+        tma_load_2d (tiles + s * kRStageBytes + kAdjTileBytes, &tmr, i * kSeg, b0, bars + 8 * s);
+    };
+    if (lane == 0)
+        for (int i = 0; i < kRStages - 1 && i < ntiles; ++i)
+            load (i);
+    for (int i = 0; i < ntiles; ++i)
+    {
+        const uint32_t xt = tiles + (i % kRStages) * kRStageBytes, rt = xt + kAdjTileBytes;
+        mbar_wait (bars + 8 * (i % kRStages), (i / kRStages) & 1);
+        const int nch = min (kSeg / 4, (T - i * kSeg) >> 2);
+        if (ckpt != nullptr && valid)
+            ckpt[(int64_t) i * B + b0 + lane] = z;
+#pragma unroll 2
+        for (int cc = 0; cc < kSeg / 4; ++cc)
+        {
+            if (cc < nch)
+            {
+                const uint32_t addr = chunk64 (xt, lane, cc);
+                const float4 v = lds128 (addr);
+                float4 rv = lds128 (chunk64 (rt, lane, cc));
+                if (! valid)
+                    rv = make_float4 (1.0f, 1.0f, 1.0f, 1.0f); // rows past the batch are zero-filled: keep their arithmetic finite
+                float4 o;
+                o.x = clip_step_r<MODE, GENERAL, PY> (c, rb, v.x, rv.x, z);
+                o.y = clip_step_r<MODE, GENERAL, PY> (c, rb, v.y, rv.y, z);
+                o.z = clip_step_r<MODE, GENERAL, PY> (c, rb, v.z, rv.z, z);
+                o.w = clip_step_r<MODE, GENERAL, PY> (c, rb, v.w, rv.w, z);
+                sts128 (addr, o);
+            }
+        }
+        fence_proxy_async ();
+        __syncwarp ();
+        if (lane == 0)
+        {
+            tma_store_2d (&tmy, i * kSeg, b0, xt);
+            tma_commit ();
+            if (i + kRStages - 1 < ntiles)
+            {
+                tma_wait_read<1> ();
+                load (i + kRStages - 1);
+            }
+        }
+    }
+    if (lane == 0)
+        tma_wait_all<0> ();
+    if (state != nullptr && valid)
+        state[b0 + lane] = z;
+}
+
+template <int MODE, bool GENERAL, bool PY>
+__global__ void __launch_bounds__ (kLanes) clipper_forward_r_direct (const float* __restrict__ x, const float* __restrict__ r, float* __restrict__ y, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state, int64_t B, int T)
+{
+    const int64_t b = (int64_t) blockIdx.x * kLanes + threadIdx.x;
+    if (b >= B)
+        return;
+    ClipConst c;
+    ClipRBase rb;
+    clip_setup_r (c, rb, desc, __ldg (params + desc.slot_R), __ldg (params + desc.slot_C), __ldg (params + desc.slot_Is), __ldg (params + desc.slot_nabla));
+    float z = state != nullptr ? state[b] : 0.0f;
+    const float* xr = x + b * T;
+    const float* rr = r + b * T;
+    float* yr = y + b * T;
+    for (int n = 0; n < T; ++n)
+    {
+        if ((n & (kSeg - 1)) == 0 && ckpt != nullptr)
+            ckpt[(int64_t) (n / kSeg) * B + b] = z;
+        yr[n] = clip_step_r<MODE, GENERAL, PY> (c, rb, __ldg (xr + n), __ldg (rr + n), z);
+    }
+    if (state != nullptr)
+        state[b] = z;
+}
+
+// one checkpoint segment of the reverse sweep with the resistance channel (the scheme of adjoint_segment_impl)
+template <int MODE, bool GENERAL, bool PY, bool TARGET, bool HOMOG, class IO>
+__device__ __forceinline__ void adjoint_segment_r (const ClipConst& c0, const ClipRBase& rb, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc, int n0, int nvalid, int skip, int last)
+{
+    float zs[kSeg + 1];
+    zs[0] = z0;
+#pragma unroll
+    for (int cc = 0; cc < kSeg / 4; ++cc)
+    {
+        const float4 yv = io.y4 (cc);
+        const float ys[4] = { yv.x, yv.y, yv.z, yv.w };
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            if (PY)
+                zs[cc * 4 + k + 1] = fma_ (2.0f, ys[k], -zs[cc * 4 + k]);
+            else
+                zs[cc * 4 + k] = ys[k];
+        }
+    }
+    if (! PY)
+        zs[kSeg] = zend;
+    ClipConst c = c0;
+    float ag = 0.0f, al = 0.0f, ar = 0.0f, av = 0.0f, sse = 0.0f, st2 = 0.0f, hg = 0.0f, hl = 0.0f, hr = 0.0f, hv = 0.0f;
+#pragma unroll
+    for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
+    {
+        if (cc * 4 < nvalid)
+        {
+            const float4 xv = io.x4 (cc), gv = io.g4 (cc), rv = io.r4 (cc);
+            const float xs[4] = { xv.x, xv.y, xv.z, xv.w };
+            const float gs[4] = { gv.x, gv.y, gv.z, gv.w };
+            const float rs[4] = { rv.x, rv.y, rv.z, rv.w };
+#pragma unroll
+            for (int k = 3; k >= 0; --k)
+            {
+                const int idx = cc * 4 + k;
+                if (idx < nvalid)
+                {
+                    float gy = gs[k];
+                    if (TARGET)
+                    {
+                        const bool on = n0 + idx >= skip;
+                        const float yk = PY ? 0.5f * (zs[idx + 1] + zs[idx]) : zs[idx];
+                        gy = on ? yk - gs[k] : 0.0f;
+                        sse = fma_ (gy, gy, sse);
+                        st2 = on ? fma_ (gs[k], gs[k], st2) : st2;
+                    }
+                    if (! PY && idx == last)
+                    {
+                        G = gy; // plugin ordering never observes z[T]
+                        if (HOMOG)
+                            H = 0.0f;
+                    }
+                    else
+                    {
+                        clip_set_r<GENERAL> (c, rb, rs[k]);
+                        StepTape tp;
+                        if (rev_small_ok (c.pair)) // this sample's constants allow the cheap reverse-biased branch (every physical diode)
+                            clip_step_recover<MODE, GENERAL, true> (c, xs[k], zs[idx], zs[idx + 1], tp);
+                        else
+                            clip_step_recover_general<MODE, GENERAL> (c, xs[k], zs[idx], zs[idx + 1], tp);
+                        if (PY)
+                            G = fma_ (0.5f, gy, G);
+                        const float cgg = tp.cg * (c.gamma * c.one_m_gamma), clr = tp.cl * c.Rp;
+                        ag = fma_ (G, cgg, ag);
+                        al = fma_ (G, tp.cl, al);
+                        ar = fma_ (G, clr, ar);
+                        av = fma_ (G, tp.cv, av);
+                        G = fma_ (G, tp.A, PY ? 0.5f * gy : gy);
+                        if (HOMOG)
+                        {
+                            hg = fma_ (H, cgg, hg);
+                            hl = fma_ (H, tp.cl, hl);
+                            hr = fma_ (H, clr, hr);
+                            hv = fma_ (H, tp.cv, hv);
+                            H *= tp.A;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    acc.g += (double) ag;
+    acc.l += (double) al;
+    acc.lr += (double) ar;
+    acc.v += (double) av;
+    if (HOMOG)
+    {
+        acc.hg += (double) hg;
+        acc.hl += (double) hl;
+        acc.hlr += (double) hr;
+        acc.hv += (double) hv;
+    }
+    if (TARGET)
+    {
+        acc.sse += (double) sse;
+        acc.st2 += (double) st2;
+    }
+}
+
+// Four tile streams (x, y, g, r) take 16 KB for a two-slot ring: 13 CTAs per SM, 1924 slots — not enough to hold the 2048
+// CTAs of 65536 sequences at once, and a second wave of full-length CTAs would double the time. The reverse sweep is
+// therefore ALWAYS cut into time chunks (affine maps composed by clipper_adjoint_stitch, as above): many short CTAs
+// balance over the SMs whatever the batch size.
+constexpr int kRAdjStageBytes = 4 * kAdjTileBytes; // x, y, g, r tiles of one 16-sample segment
+
+template <int MODE, bool GENERAL, bool PY, bool TARGET, bool HOMOG>
+__device__ __forceinline__ void adjoint_r_tma_body (const ClipConst& c, const ClipRBase& rb, const CUtensorMap* tmx, const CUtensorMap* tmr, const CUtensorMap* tmy, const CUtensorMap* tmg, uint32_t tiles, uint32_t bars, const float* __restrict__ ckpt, AdjAcc& acc, float& G, float& H, int64_t B, int T, int skip, int lane, int b0, int s0, int s1)
+{
+    const int nseg = s1 - s0;
+    const bool valid = (int64_t) b0 + lane < B;
+    auto fetch = [&] (int k) { // the k-th processed segment is i = s1 - 1 - k
+        const int i = s1 - 1 - k, s = k % kAdjStages;
+        const uint32_t dst = tiles + s * kRAdjStageBytes, bar = bars + 8 * s;
+        mbar_expect_tx (bar, kRAdjStageBytes);
+        tma_load_2d (dst, tmx, i * kSeg, b0, bar);
+        tma_load_2d (dst + kAdjTileBytes, tmy, i * kSeg, b0, bar);
+        tma_load_2d (dst + 2 * kAdjTileBytes, tmg, i * kSeg, b0, bar);
+        tma_load_2d (dst + 3 * kAdjTileBytes, tmr, i * kSeg, b0, bar);
+    };
+    if (lane == 0)
+        for (int k = 0; k < kAdjStages - 1 && k < nseg; ++k)
+            fetch (k);
+    float zend = (! PY && valid && (int64_t) s1 * kSeg < T) ? __ldg (ckpt + (int64_t) s1 * B + b0 + lane) : 0.0f;
+    float znext = valid ? __ldg (ckpt + (int64_t) (s1 - 1) * B + b0 + lane) : 0.0f;
+    for (int k = 0; k < nseg; ++k)
+    {
+        const int i = s1 - 1 - k, s = k % kAdjStages;
+        const float z0 = znext;
+        if (i > s0 && valid)
+            znext = __ldg (ckpt + (int64_t) (i - 1) * B + b0 + lane);
+        if (k + kAdjStages - 1 < nseg)
+        {
+            fence_proxy_async ();
+            __syncwarp ();
+            if (lane == 0)
+                fetch (k + kAdjStages - 1);
+        }
+        mbar_wait (bars + 8 * s, (k / kAdjStages) & 1);
+        const uint32_t base = tiles + s * kRAdjStageBytes;
+        TileIO io { base, base + kAdjTileBytes, base + 2 * kAdjTileBytes, lane, base + 3 * kAdjTileBytes };
+        if (valid) // (rows past the batch hold zero-filled resistances)
+            adjoint_segment_r<MODE, GENERAL, PY, TARGET, HOMOG> (c, rb, io, z0, zend, G, H, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
+        zend = z0;
+    }
+}
+
+template <int MODE, bool GENERAL, bool PY, bool TARGET>
+__global__ void __launch_bounds__ (kLanes) clipper_adjoint_r_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmr, const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg, const float* __restrict__ params, const ClipDesc desc, const float* __restrict__ ckpt, double* __restrict__ partials, float* __restrict__ cmaps, int chunk_segs, int64_t B, int T, int skip)
+{
+    __shared__ __align__ (1024) uint8_t smem[kAdjStages * kRAdjStageBytes];
+    __shared__ __align__ (8) uint64_t bar_mem[kAdjStages];
+    const int lane = threadIdx.x;
+    const int b0 = blockIdx.x * kLanes;
+    const uint32_t tiles = smem_u32 (smem), bars = smem_u32 (bar_mem);
+    if (lane == 0)
+    {
+        for (int s = 0; s < kAdjStages; ++s)
+            mbar_init (bars + 8 * s, 1);
+        fence_mbar_init ();
+    }
+    __syncwarp ();
+    ClipConst c;
+    ClipRBase rb;
+    clip_setup_r (c, rb, desc, __ldg (params + desc.slot_R), __ldg (params + desc.slot_C), __ldg (params + desc.slot_Is), __ldg (params + desc.slot_nabla));
+    AdjAcc acc;
+    float G = 0.0f, H = 1.0f;
+    const int nseg = (T + kSeg - 1) / kSeg;
+    if (gridDim.y == 1)
+    {
+        adjoint_r_tma_body<MODE, GENERAL, PY, TARGET, false> (c, rb, &tmx, &tmr, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, 0, nseg);
+        write_partials_r (acc, partials, blockIdx.x, lane);
+        return;
+    }
+    const int s0 = blockIdx.y * chunk_segs, s1 = min (s0 + chunk_segs, nseg);
+    adjoint_r_tma_body<MODE, GENERAL, PY, TARGET, true> (c, rb, &tmx, &tmr, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, s0, s1);
+    if ((int64_t) b0 + lane < B)
+        write_map (cmaps + (int64_t) blockIdx.y * kMapFloats * B + b0 + lane, B, G, H, acc);
+}
+
+template <int MODE, bool GENERAL, bool PY, bool TARGET>
+__global__ void __launch_bounds__ (kLanes) clipper_adjoint_r_direct (const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ params, const ClipDesc desc, const float* __restrict__ ckpt, double* __restrict__ partials, int64_t B, int T, int skip)
+{
+    const int lane = threadIdx.x;
+    const int64_t b = (int64_t) blockIdx.x * kLanes + lane;
+    ClipConst c;
+    ClipRBase rb;
+    clip_setup_r (c, rb, desc, __ldg (params + desc.slot_R), __ldg (params + desc.slot_C), __ldg (params + desc.slot_Is), __ldg (params + desc.slot_nabla));
+    AdjAcc acc;
+    if (b < B)
+    {
+        const int nseg = (T + kSeg - 1) / kSeg;
+        float G = 0.0f, H = 1.0f, zend = 0.0f;
+        GlobalIO io { x + b * T, y + b * T, g + b * T, nullptr, 0, T, r + b * T };
+        for (int i = nseg - 1; i >= 0; --i)
+        {
+            io.n0 = i * kSeg;
+            const float z0 = __ldg (ckpt + (int64_t) i * B + b);
+            adjoint_segment_r<MODE, GENERAL, PY, TARGET, false> (c, rb, io, z0, zend, G, H, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
+            zend = z0;
+        }
+    }
+    write_partials_r (acc, partials, blockIdx.x, lane);
+}
+
 } // namespace
 
 // ---- one translation unit per (root mode, law) pair: -DDWDF_PART_MODE=0|1 -DDWDF_PART_GENERAL=0|1 -------
@@ -1513,6 +1901,56 @@ cudaError_t clipper_train_part<kM, kG> (bool py, bool use_tma, const ClipTmaMaps
             clipper_train_direct<kM, kG, p><<<grid, kLanes, 0, stream>>> (x, target, y, params, desc, partials, B, (int) T, skip);
     };
     py ? go (std::true_type {}) : go (std::false_type {});
+    return cudaGetLastError ();
+}
+
+template <>
+cudaError_t clipper_forward_r_part<kM, kG> (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* r, float* y, float* ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream)
+{
+    const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
+    auto go = [&] (auto P) {
+        constexpr bool p = decltype (P)::value;
+        if (use_tma)
+            clipper_forward_r_tma<kM, kG, p><<<grid, kLanes, 0, stream>>> (maps->x, maps->r, maps->y, params, desc, ckpt, state, B, (int) T);
+        else
+            clipper_forward_r_direct<kM, kG, p><<<grid, kLanes, 0, stream>>> (x, r, y, params, desc, ckpt, state, B, (int) T);
+    };
+    py ? go (std::true_type {}) : go (std::false_type {});
+    return cudaGetLastError ();
+}
+
+template <>
+cudaError_t clipper_adjoint_r_part<kM, kG> (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* r, const float* y, const float* ckpt, const float* g, bool target, int skip, double* partials, int64_t B, int64_t T, cudaStream_t stream)
+{
+    const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
+    auto go = [&] (auto P, auto TG) {
+        constexpr bool p = decltype (P)::value, tg = decltype (TG)::value;
+        if (use_tma)
+        {
+            // as many chunks as fill the SMs for a small batch; for a batch that needs more than one wave of full-length CTAs,
+            // 8 short chunks per row group so that the waves balance
+            const int nseg = (int) ((T + kSeg - 1) / kSeg);
+            const int resident = resident_ctas (clipper_adjoint_r_tma<kM, kG, p, tg>);
+            const int cap = maps->cmaps != nullptr ? maps->kcap_adj : 1;
+            int K = propose_chunks (resident, grid, nseg / 4 > 0 ? nseg / 4 : 1, cap);
+            if ((int64_t) grid > resident && cap >= 8 && nseg >= 64 && ! (g_clip_opts & kOptNoChunks))
+                K = 8;
+            const int chunk_segs = (nseg + K - 1) / K;
+            K = (nseg + chunk_segs - 1) / chunk_segs;
+            clipper_adjoint_r_tma<kM, kG, p, tg><<<dim3 (grid, (unsigned) K), kLanes, 0, stream>>> (maps->x, maps->r, maps->y, maps->g, params, desc, ckpt, partials, maps->cmaps, chunk_segs, B, (int) T, skip);
+            if (K > 1)
+            {
+                clipper_adjoint_stitch<kM * 2 + (kG ? 1 : 0)><<<grid, kLanes, 0, stream>>> (maps->cmaps, partials, B, K);
+                g_extra_launches.fetch_add (1);
+            }
+        }
+        else
+            clipper_adjoint_r_direct<kM, kG, p, tg><<<grid, kLanes, 0, stream>>> (x, r, y, g, params, desc, ckpt, partials, B, (int) T, skip);
+    };
+    if (py)
+        target ? go (std::true_type {}, std::true_type {}) : go (std::true_type {}, std::false_type {});
+    else
+        target ? go (std::false_type {}, std::true_type {}) : go (std::false_type {}, std::false_type {});
     return cudaGetLastError ();
 }
 

@@ -21,6 +21,7 @@ struct dwdf_program
     std::vector<dwdf_node> nodes;
     dwdf_circuit_desc desc;
     bool is_clipper = false;
+    bool clip_r = false; // the clipper with its source resistance as a per-sample input channel (clipper_pot.py:114-117)
     bool is_neural = false;
     dwdf_mlp_desc mlp {};
     ClipDesc clip {};
@@ -207,7 +208,11 @@ int chunk_cap (int64_t groups, int64_t units)
 }
 int64_t n_fwd_tiles16 (int64_t T) { return (T + 15) / 16; }
 int fwd_chunk_cap (int64_t B, int64_t T) { return T >= 128 ? chunk_cap ((B + 63) / 64, n_fwd_tiles16 (T)) : 1; } // (the one-sequence-per-lane kernel launches twice the groups: its proposal is clamped to this)
-int adj_chunk_cap (int64_t B, int64_t T) { return T >= 128 ? chunk_cap ((B + 31) / 32, (T + 63) / 64) : 1; }
+int adj_chunk_cap (int64_t B, int64_t T)
+{
+    const int k = T >= 128 ? chunk_cap ((B + 31) / 32, (T + 63) / 64) : 1;
+    return (k < 8 && T >= 1024 && ! (g_clip_opts & kOptNoChunks)) ? 8 : k; // (the resistance-channel adjoint balances large batches with 8 chunks)
+}
 constexpr int64_t kNnChunkedMaxB = 16384; // neural root: the network makes every sample ~20x heavier, so lanes stay scarce longer
 size_t partials_bytes (int64_t B) { return ((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256 * 256 + 256; }
 int64_t n_segments (int64_t T) { return (T + kSeg - 1) / kSeg; }
@@ -344,7 +349,7 @@ int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_cir
 
     // the diode clipper: Parallel(P1 = ResistiveVs, P2 = Capacitor) + DiodePair, probe on the capacitor
     const bool clip_shape = d->root_kind == DWDF_ROOT_DIODE_PAIR && n_nodes == 3 && nodes[0].kind == DWDF_RESISTIVE_VS && nodes[1].kind == DWDF_CAPACITOR && nodes[2].kind == DWDF_PARALLEL
-                            && nodes[2].child1 == 0 && nodes[2].child2 == 1 && d->source == 0 && d->probe == 1 && d->r_node < 0 && d->root_mode != DWDF_MODE_APPROX_GOOD;
+                            && nodes[2].child1 == 0 && nodes[2].child2 == 1 && d->source == 0 && d->probe == 1 && (d->r_node < 0 || d->r_node == 0) && d->root_mode != DWDF_MODE_APPROX_GOOD;
     if (clip_shape)
     {
         const int s[4] = { nodes[0].param, nodes[1].param, d->param_Is, d->param_nabla };
@@ -355,6 +360,7 @@ int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_cir
         if (distinct)
         {
             p->is_clipper = true;
+            p->clip_r = d->r_node == 0;
             p->clip = ClipDesc { d->fs, d->Vt, d->n_up, d->n_down, d->newton_tol, d->newton_max_iter, s[0], s[1], s[2], s[3] };
             p->variant = ClipVariant { d->root_mode == DWDF_MODE_EXACT ? kModeExact : kModeApprox, ! (d->n_up == 1.0f && d->n_down == 1.0f), d->ordering == DWDF_ORDER_PYTHON };
         }
@@ -528,7 +534,13 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
         return fail (DWDF_ERR_INVALID, "neural-root programs run through dwdf_forward_neural (they carry a weight vector)");
     if ((prog->desc.r_node >= 0) != (r != nullptr))
         return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
-    if (prog->is_clipper)
+    if (prog->clip_r)
+    {
+        ClipTmaMaps maps;
+        const bool tma = tma_usable (x, y, r, B, T) && make_map (&maps.x, x, B, T, kSeg) && make_map (&maps.y, y, B, T, kSeg) && make_map (&maps.r, r, B, T, kSeg);
+        DWDF_CUDA (launch_clipper_forward_r (prog->variant, tma, &maps, prog->clip, params, x, r, y, z_ckpt, state, B, T, stream));
+    }
+    else if (prog->is_clipper)
     {
         ClipTmaMaps maps;
         const bool tma = tma_usable (x, y, nullptr, B, T) && make_map (&maps.x, x, B, T, kFwdTileSamples) && make_map (&maps.y, y, B, T, kFwdTileSamples);
@@ -594,7 +606,25 @@ static int backward_impl (int raw_only, const dwdf_program* prog, const float* p
     const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
     const double count = (double) B * (double) (T - sk);
     double* partials = (double*) workspace;
-    if (prog->is_clipper)
+    if (prog->clip_r)
+    {
+        if (z_ckpt == nullptr || y == nullptr || r == nullptr)
+            return fail (DWDF_ERR_INVALID, "the clipper adjoint reads the output y, the checkpoints z_ckpt that dwdf_forward wrote and the resistance channel r: one of them is null");
+        if (gx != nullptr)
+            return fail (DWDF_ERR_UNSUPPORTED, "dL/dx with a per-sample resistance channel is not implemented");
+        ClipTmaMaps maps;
+        const bool tma = tma_usable (x, gy_or_target, y, B, T) && ((uintptr_t) r & 15u) == 0 && make_map (&maps.x, x, B, T, kSeg) && make_map (&maps.y, y, B, T, kSeg) && make_map (&maps.g, gy_or_target, B, T, kSeg) && make_map (&maps.r, r, B, T, kSeg);
+        if (tma && adj_chunk_cap (B, T) > 1)
+        {
+            maps.kcap_adj = adj_chunk_cap (B, T);
+            maps.cmaps = (float*) ((char*) workspace + partials_bytes (B));
+        }
+        DWDF_CUDA (launch_clipper_adjoint_r (prog->variant, tma, &maps, prog->clip, params, x, r, y, z_ckpt, gy_or_target, target, sk, partials, B, T, stream));
+        if (raw_only == 2)
+            return fail (DWDF_ERR_UNSUPPORTED, "internal: the fused tail does not cover the resistance channel");
+        DWDF_CUDA (launch_clipper_finalize_r (prog->clip, params, partials, n_groups (B), nullptr, raw_only != 0, target, loss_kind, count, out, stream));
+    }
+    else if (prog->is_clipper)
     {
         if (z_ckpt == nullptr || y == nullptr)
             return fail (DWDF_ERR_INVALID, "the clipper adjoint reads the output y and the checkpoints z_ckpt that dwdf_forward wrote: %s is null", y == nullptr ? "y" : "z_ckpt");
@@ -642,7 +672,9 @@ int dwdf_finalize (const dwdf_program* prog, const float* params, int32_t grad_m
     if (prog == nullptr || params == nullptr || raw_inout == nullptr)
         return fail (DWDF_ERR_INVALID, "null argument");
     const bool target = grad_mode == DWDF_GRAD_TARGET;
-    if (prog->is_clipper)
+    if (prog->clip_r)
+        DWDF_CUDA (launch_clipper_finalize_r (prog->clip, params, nullptr, 0, raw_inout, false, target, loss_kind, 0.0, raw_inout, (cudaStream_t) stream));
+    else if (prog->is_clipper)
         DWDF_CUDA (launch_clipper_finalize (prog->clip, params, nullptr, 0, raw_inout, false, target, loss_kind, 0.0, raw_inout, (cudaStream_t) stream));
     else
         DWDF_CUDA (launch_tree_finalize (prog->tree, params, nullptr, 0, raw_inout, false, target, loss_kind, 0.0, raw_inout, (cudaStream_t) stream));
@@ -657,8 +689,8 @@ static int train_impl (bool raw_only, const dwdf_program* prog, const float* par
         return rc;
     if (target == nullptr || out == nullptr || workspace == nullptr)
         return fail (DWDF_ERR_INVALID, "null argument");
-    if (! prog->is_clipper || r != nullptr)
-        return fail (DWDF_ERR_UNSUPPORTED, "the fused training pass exists for the diode-clipper program only");
+    if (! prog->is_clipper || prog->clip_r || r != nullptr)
+        return fail (DWDF_ERR_UNSUPPORTED, "the fused training pass exists for the diode-clipper program without a resistance channel only");
     if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
         return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
     if (workspace_bytes < dwdf_workspace_bytes (prog, B, T))
@@ -838,7 +870,7 @@ static int train_step_impl (const dwdf_program* prog, const DpPeers& dp, float* 
         return rc;
     g_prof.mark (1, stream);
     const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
-    if (prog->is_clipper)
+    if (prog->is_clipper && ! prog->clip_r)
     { // adjoint -> ONE kernel: reduction of the partials + exchange over peer memory + chain rule + loss + Adam
         if (int rc = backward_impl (2, prog, params, x, r, y, z_ckpt, target, DWDF_GRAD_TARGET, loss_kind, skip, nullptr, out, workspace, workspace_bytes, B, T, stream))
             return rc;
@@ -1014,8 +1046,8 @@ int dwdf_grad_host (const dwdf_program* prog, const float* params_host, const fl
         return rc;
     if (g_host == nullptr || out_host == nullptr)
         return fail (DWDF_ERR_INVALID, "null argument");
-    if (! prog->is_clipper || r_host != nullptr)
-        return fail (DWDF_ERR_UNSUPPORTED, "dwdf_grad_host covers the diode-clipper program; use the device API for other trees");
+    if (! prog->is_clipper || prog->clip_r || r_host != nullptr)
+        return fail (DWDF_ERR_UNSUPPORTED, "dwdf_grad_host covers the diode-clipper program without a resistance channel; use the device API otherwise");
     if (B == 0 || T == 0)
         return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
     std::lock_guard<std::mutex> lock (g_arena.mu);

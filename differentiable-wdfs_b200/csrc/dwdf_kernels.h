@@ -24,7 +24,7 @@ namespace dwdf
 constexpr int kFwdTileSamples = DWDF_FWD_TILE_T;
 constexpr int kSeg = 16; // capacitor-state checkpoint spacing [samples]; also the adjoint's segment
 constexpr int kTimeChunk = 256; // samples per chunk of the neural root's time-parallel kernels
-constexpr int kMapFloatsPerChunk = 10; // clipper adjoint with time chunks: floats per (sequence, chunk)
+constexpr int kMapFloatsPerChunk = 12; // clipper adjoint with time chunks: floats per (sequence, chunk)
 constexpr int kMaxResidentCtas = 148 * 32; // upper bound of one-warp CTAs a B200 holds at once: sizes the time-chunk scratch
 constexpr int kPartialStride = 8; // doubles per sequence-group in the clipper partials buffer
 constexpr int kTreePartialStride = 24; // ... in the tree interpreter partials buffer
@@ -35,7 +35,8 @@ enum : int
     kAccEll = 1, // sum G dz'/d ell,  ell = ln(Rp Is)
     kAccV = 2, // sum G dz'/dV
     kAccSse = 3, // sum (y - target)^2
-    kAccSt2 = 4 // sum target^2
+    kAccSt2 = 4, // sum target^2
+    kAccEllRp = 5 // resistance channel: sum G dz'/d ell Rp[n] (kAccGamma then holds sum G dz'/dgamma gamma (1 - gamma))
 };
 
 // tuning / A-B switches of the clipper kernels (dwdf_set_option); 0 = shipped behaviour
@@ -62,6 +63,7 @@ struct ClipTmaMaps
 {
     CUtensorMap x, y, g; // forward (x, y): 32 x 32 tiles, 128-byte swizzle; adjoint (x, y, g): 16 x 32 tiles, 64-byte swizzle
     CUtensorMap x2, y2; // paired forward: [64 sequences x 32 samples] tiles
+    CUtensorMap r; // per-sample resistance channel (the *_r kernels): same tile shape as x
     bool pair = false; // x2 / y2 are valid and the paired kernel is wanted
     // time chunks (fewer sequences than the SMs hold warps): the launcher proposes up to kcap chunks. Forward scratch zs / ze:
     // kcap_fwd * B floats each; adjoint scratch cmaps: kcap_adj * kMapFloatsPerChunk * B floats. nullptr / 1: no chunks.
@@ -77,6 +79,16 @@ template <int MODE, bool GENERAL>
 cudaError_t clipper_adjoint_part (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* y, const float* ckpt, const float* g, bool target, int skip, float* gx, double* partials, int64_t B, int64_t T, cudaStream_t stream);
 template <int MODE, bool GENERAL>
 cudaError_t clipper_train_part (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* target, int skip, float* y, double* partials, int64_t B, int64_t T, cudaStream_t stream);
+
+template <int MODE, bool GENERAL>
+cudaError_t clipper_forward_r_part (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* r, float* y, float* ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream);
+template <int MODE, bool GENERAL>
+cudaError_t clipper_adjoint_r_part (bool py, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* r, const float* y, const float* ckpt, const float* g, bool target, int skip, double* partials, int64_t B, int64_t T, cudaStream_t stream);
+
+// the same circuit with the source resistance as a per-sample input channel r (clipper_pot.py:114-117); partials carry kAccEllRp too
+cudaError_t launch_clipper_forward_r (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* r, float* y, float* ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream);
+cudaError_t launch_clipper_adjoint_r (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, const float* r, const float* y, const float* ckpt, const float* g, bool target, int64_t skip, double* partials, int64_t B, int64_t T, cudaStream_t stream);
+cudaError_t launch_clipper_finalize_r (const ClipDesc& desc, const float* params, const double* partials, int64_t n_groups, const double* raw_in, bool raw_only, bool target, int loss_kind, double count, double* out, cudaStream_t stream);
 
 cudaError_t launch_clipper_forward (const ClipVariant& v, bool use_tma, const ClipTmaMaps* maps, const ClipDesc& desc, const float* params, const float* x, float* y, float* ckpt, float* state, int64_t B, int64_t T, cudaStream_t stream);
 

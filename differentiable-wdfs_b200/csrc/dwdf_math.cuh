@@ -131,15 +131,16 @@ DWDF_HD float log_approx_pos (float x)
 }
 
 // omega3, omega.h:159-169.
-// WARP (device only): the caller guarantees that all 32 lanes of the warp are converged here; the
-// x >= 8 branch (x - log_approx(x), ~11 instructions) is then skipped when no lane needs it — one
-// vote instead of computing both sides of the select for every sample. Same value either way.
+// WARP (device only): the x >= 8 branch (x - log_approx(x), ~11 instructions) is skipped when no lane of
+// the warp that is active here needs it — one vote instead of computing both sides of the select for
+// every sample. Same value either way (the vote only gates work; a lane that needs the branch always
+// sees its own vote), so the call is legal under divergence.
 template <bool WARP = false>
 DWDF_HD float omega3_approx (float x)
 {
     float y = fma_ (x, fma_ (x, fma_ (x, -1.314293149877800e-3f, 4.775931364975583e-2f), 3.631952663804445e-1f), 6.313183464296682e-1f);
 #if defined(__CUDA_ARCH__)
-    if (! WARP || __any_sync (0xffffffffu, x >= 8.0f))
+    if (! WARP || __any_sync (__activemask (), x >= 8.0f))
 #endif
         y = x < 8.0f ? y : x - log_approx_pos (x);
     y = x < -3.341459552768620f ? 0.0f : y;
@@ -437,6 +438,49 @@ DWDF_HD void clip_setup (ClipConst& c, const ClipDesc& d, float R, float C, floa
     c.one_m_gamma = 1.0f - c.gamma;
     c.two_gamma = 2.0f * c.gamma;
     pair_setup (c.pair, c.Rp, Is, d.Vt, nabla, d.n_up, d.n_down, d.n_iter, d.tol);
+}
+
+// ---- the source resistance as a per-sample input channel -----------------------------------------------
+// clipper_pot.py:114-117 feeds the reference's training batches as (B, T, 2) = (x, R): every sample calls
+// Vs.set_resistance(R[n]) and P1.calc_impedance(), so the adaptor coefficient and the root's port resistance change
+// from sample to sample. ClipRBase holds what does not (capacitor conductance, diode constants); clip_set_r derives the
+// rest for one sample (tf_wdf.py:168-177, wdf_t.h:928-933) on the MUFU pipe: two reciprocals (1 / r, 1 / G; p1R = Gv Rp)
+// and one log2 — which IS the scaled constant the approx root's exponentials take (L log2(e) = log2(Rp Is / V)).
+struct ClipRBase
+{
+    float Gc; // 2 C fs
+    float Is;
+    float ln_up, ln_dn; // ln N_up, ln N_down (general law: ln(Rp Is / (V mu)) = L - ln mu)
+};
+
+DWDF_HD void clip_setup_r (ClipConst& c, ClipRBase& b, const ClipDesc& d, float R0, float C, float Is, float nabla)
+{
+    clip_setup (c, d, R0, C, Is, nabla); // everything that depends on V only (and a valid set for R0)
+    const float Rc = 1.0f / (2.0f * C * d.fs);
+    b.Gc = 1.0f / Rc;
+    b.Is = Is;
+    b.ln_up = logf (d.n_up);
+    b.ln_dn = logf (d.n_down);
+}
+
+template <bool GENERAL>
+DWDF_HD void clip_set_r (ClipConst& c, const ClipRBase& b, float r)
+{
+    const float Gv = rcp (r);
+    c.Rp = rcp (Gv + b.Gc);
+    c.gamma = Gv * c.Rp;
+    c.one_m_gamma = 1.0f - c.gamma;
+    c.two_gamma = 2.0f * c.gamma;
+    PairConst& p = c.pair;
+    p.RIs = c.Rp * b.Is;
+    p.RIs_overV = p.RIs * p.invV;
+    p.Ll2e = lg2_ (p.RIs_overV);
+    p.L = 0.693147180559945f * p.Ll2e;
+    if (GENERAL)
+    {
+        p.L_up = p.L - b.ln_up;
+        p.L_dn = p.L - b.ln_dn;
+    }
 }
 
 // One sample of clipper_pot.py:113-124 / DiodeClipperWDF.cpp:24-29:

@@ -401,7 +401,7 @@ def test_tree_clipper_with_resistance_channel(dwdf, oracle, mode, ordering, oord
     P1 = dwdf.Parallel(Vs, C)
     dp = dwdf.DiodePair(P1, p.Is, p.Vt, p.nabla, mode=mode)
     circ = dwdf.compile_circuit(dp, probe=C, ordering=ordering, r_element=Vs)
-    assert not circ.is_clipper
+    assert circ.is_clipper  # the specialised kernels take the resistance channel (third tile stream, per-sample port constants)
     y = circ.forward(dev(x), r=dev(r)).cpu().numpy()
     nodes = [(RESVS, -1, -1, p.R), (CAPACITOR, -1, -1, p.C), (PARALLEL, 0, 1, 0.0)]
     ref = oracle.tree_run(nodes, p.fs, ROOT_DIODE_PAIR, x, probe=1, source=0, root_par=[float(mode == "exact"), 0, p.Is, p.Vt, p.nabla, 1, 1], ordering=oord, r_in=r, r_node=0)
@@ -726,6 +726,7 @@ def test_tree_adjoint_with_resistance_channel(dwdf, ordering, oord):
     C = dwdf.Capacitor(p.C, p.fs, True)
     dp = dwdf.DiodePair(dwdf.Parallel(Vs, C), p.Is, p.Vt, p.nabla, trainable=True, mode="exact")
     circ = dwdf.compile_circuit(dp, probe=C, ordering=ordering, r_element=Vs)
+    assert circ.is_clipper
     y = circ.forward(dev(x), r=dev(r))
     assert seq_rel_err(y.cpu().numpy(), y_ref.detach().numpy()) < FWD_TOL
     res = circ.backward(target=dev(target), loss="mse+esr", skip=20)
@@ -735,3 +736,60 @@ def test_tree_adjoint_with_resistance_channel(dwdf, ordering, oord):
     assert np.max(np.abs(got / want - 1)) < GRAD_TOL, (got, want)
     assert g[circ.slot(Vs, "R")] == 0.0  # the resistance is an input channel, not a parameter (tf_wdf.py:51-52)
     assert abs(float(res["loss"]) / float(loss) - 1) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+@pytest.mark.parametrize("n_up,n_down", [(1, 1), (1, 2)])
+@pytest.mark.parametrize("B,T", [(100, 1024), (33, 1001), (4096, 256)])
+def test_resistance_channel_kernels(dwdf, oracle, mode, n_up, n_down, B, T):
+    """The reference's training layout on the specialised kernels at larger shapes: TMA tiles (x, r -> y; x, r, y, target ->
+    sums) against the direct-access kernels bit for bit (forward) / to fp64 round-off (reduced sums), ragged T and rows past the
+    last full group, streaming continuation, a resistance that changes from sample to sample, and the oracle's tree executor
+    (calc_impedance every sample) on a sample of rows. Gradients are checked against fp64 autograd in
+    test_tree_adjoint_with_resistance_channel; here they must agree between the two data paths and with a constant-resistance run."""
+    p = ClipperParams(R=45000.0, C=4.7e-9, fs=50000.0, n_up=n_up, n_down=n_down)
+    x = make_inputs(B, T, fs=p.fs, seed=B + T, amp=(0.05, 4.0))
+    rng = np.random.default_rng(B)
+    r = (rng.uniform(1e4, 1e5, (B, 1)) * (1.0 + 0.3 * np.sin(np.arange(T)[None, :] / 37.0))).astype(np.float32)
+    target = (0.5 * np.roll(x, 1, 0)).astype(np.float32)
+    Vs = dwdf.ResistiveVoltageSource(p.R)
+    C = dwdf.Capacitor(p.C, p.fs, True)
+    dp = dwdf.DiodePair(dwdf.Parallel(Vs, C), p.Is, p.Vt, p.nabla, n_up, n_down, trainable=True, mode=mode)
+    circ = dwdf.compile_circuit(dp, probe=C, ordering="python", r_element=Vs)
+    assert circ.is_clipper
+    xd, rd, td = dev(x), dev(r), dev(target)
+    y = circ.forward(xd, r=rd).clone()
+    g = circ.backward(target=td, loss="mse+esr", skip=9)["out"].clone()
+    prev = dwdf.set_tma(False)
+    try:
+        y_direct = circ.forward(xd, r=rd).clone()
+        g_direct = circ.backward(target=td, loss="mse+esr", skip=9)["out"].clone()
+    finally:
+        dwdf.set_tma(prev)
+    assert torch.equal(y, y_direct)
+    assert torch.allclose(g, g_direct, rtol=3e-5, atol=1e-30)  # (the TMA adjoint composes time chunks: equal up to fp32 summation order)
+    assert float(g[circ.slot(Vs, "R")]) == 0.0
+    rows = rng.choice(B, min(B, 24), replace=False)
+    nodes = [(RESVS, -1, -1, p.R), (CAPACITOR, -1, -1, p.C), (PARALLEL, 0, 1, 0.0)]
+    ref = oracle.tree_run(nodes, p.fs, ROOT_DIODE_PAIR, x[rows], probe=1, source=0, root_par=[float(mode == "exact"), 0, p.Is, p.Vt, p.nabla, n_up, n_down], ordering=ORDER_PYTHON, r_in=r[rows], r_node=0)
+    assert seq_rel_err(y[rows].cpu().numpy(), ref) < FWD_TOL
+    # streaming: two blocks == one
+    st = circ.new_state(B)
+    cut = (T // 3) & ~3
+    parts = [circ.process_block(xd[:, a:b].contiguous(), st, r=rd[:, a:b].contiguous()) for a, b in ((0, cut), (cut, T))]
+    circ_pl = circ  # (python ordering streams too: the state is the capacitor's wave)
+    assert torch.equal(torch.cat(parts, 1), y)
+    # a constant resistance channel reproduces the plain clipper with that source resistance (outputs to round-off of the
+    # per-sample constants, gradients w.r.t. C, Is, nF to the fp32 path's accuracy)
+    rc = torch.full_like(xd, 45000.0)
+    yc = circ.forward(xd, r=rc)
+    gc = circ.backward(target=td, loss="mse", skip=9)["grads"].clone()
+    Vs2 = dwdf.ResistiveVoltageSource(45000.0)
+    C2 = dwdf.Capacitor(p.C, p.fs, True)
+    dp2 = dwdf.DiodePair(dwdf.Parallel(Vs2, C2), p.Is, p.Vt, p.nabla, n_up, n_down, trainable=True, mode=mode)
+    plain = dwdf.compile_circuit(dp2, probe=C2, ordering="python")
+    yp = plain.forward(xd)
+    gp = plain.backward(target=td, loss="mse", skip=9)["grads"].clone()
+    assert seq_rel_err(yc.cpu().numpy(), yp.cpu().numpy()) < FWD_TOL
+    for (ca, ea, attr), (cb, eb) in (((circ, C, "C"), (plain, C2)), ((circ, dp, "Is"), (plain, dp2)), ((circ, dp, "nabla"), (plain, dp2))):
+        assert abs(float(gc[ca.slot(ea, attr)]) / float(gp[cb.slot(eb, attr)]) - 1) < GRAD_TOL
