@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DWDF_LIBRARY") or os.path.join(_HERE, "libdwdf.so")  # (DWDF_LIBRARY: a side-by-side build variant, see csrc/Makefile)
 
 # enums of include/dwdf.h
-RESISTOR, CAPACITOR, RESISTIVE_VS, SERIES, PARALLEL, INVERTER = range(6)
-ROOT_IDEAL_VS, ROOT_DIODE_PAIR, ROOT_NEURAL = 0, 1, 2
+RESISTOR, CAPACITOR, RESISTIVE_VS, SERIES, PARALLEL, INVERTER, INDUCTOR, CAPACITOR_ALPHA, INDUCTOR_ALPHA, RESISTIVE_CS, Y_PARAMETER = range(11)
+ROOT_IDEAL_VS, ROOT_DIODE_PAIR, ROOT_NEURAL, ROOT_IDEAL_CS, ROOT_DIODE, ROOT_SWITCH = range(6)
 MODE_APPROX, MODE_EXACT, MODE_APPROX_GOOD = 0, 1, 2
 ORDER_PLUGIN, ORDER_PYTHON = 0, 1
 GRAD_UPSTREAM, GRAD_TARGET = 0, 1
@@ -41,7 +41,7 @@ class CircuitDesc(C.Structure):
     _fields_ = [
         ("root_kind", C.c_int32), ("root_mode", C.c_int32), ("ordering", C.c_int32), ("probe", C.c_int32), ("source", C.c_int32), ("r_node", C.c_int32),
         ("param_Is", C.c_int32), ("param_nabla", C.c_int32), ("n_params", C.c_int32), ("newton_max_iter", C.c_int32),
-        ("fs", C.c_float), ("Vt", C.c_float), ("n_up", C.c_float), ("n_down", C.c_float), ("newton_tol", C.c_float),
+        ("fs", C.c_float), ("Vt", C.c_float), ("n_up", C.c_float), ("n_down", C.c_float), ("newton_tol", C.c_float), ("probe_current", C.c_int32),
     ]
 
 

@@ -23,6 +23,7 @@ struct dwdf_program
     bool is_clipper = false;
     bool clip_r = false; // the clipper with its source resistance as a per-sample input channel (clipper_pot.py:114-117)
     bool is_neural = false;
+    bool differentiable = true; // every node and the root have a reverse-mode implementation
     dwdf_mlp_desc mlp {};
     ClipDesc clip {};
     ClipVariant variant {};
@@ -190,7 +191,10 @@ bool tma_usable (const void* a, const void* b, const void* c, int64_t B, int64_t
 }
 
 // ---- tree validation / lowering ---------------------------------------------------------------------
-bool is_leaf (int k) { return k == DWDF_RESISTOR || k == DWDF_CAPACITOR || k == DWDF_RESISTIVE_VS; }
+bool is_leaf (int k) { return k == DWDF_RESISTOR || k == DWDF_CAPACITOR || k == DWDF_RESISTIVE_VS || k == DWDF_INDUCTOR || k == DWDF_CAPACITOR_ALPHA || k == DWDF_INDUCTOR_ALPHA || k == DWDF_RESISTIVE_CS; }
+int extra_params (int k) { return (k == DWDF_CAPACITOR_ALPHA || k == DWDF_INDUCTOR_ALPHA) ? 1 : (k == DWDF_Y_PARAMETER ? 3 : 0); } // constants kept in the slots after the value
+int states_of (int k) { return (k == DWDF_CAPACITOR || k == DWDF_INDUCTOR) ? 1 : ((k == DWDF_CAPACITOR_ALPHA || k == DWDF_INDUCTOR_ALPHA) ? 2 : 0); }
+bool has_adjoint (int k) { return k <= DWDF_INDUCTOR; } // reverse mode: the wdf_py element set and the inductor
 
 int64_t n_groups (int64_t B) { return (B + 31) / 32; }
 // Time chunks (fewer sequences than the SMs hold warps; clipper_kernels.cu explains the scheme): upper bounds of the
@@ -257,18 +261,17 @@ int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_cir
     for (int i = 0; i < n_nodes; ++i)
     {
         const dwdf_node& n = nodes[i];
-        if (n.kind < DWDF_RESISTOR || n.kind > DWDF_INVERTER)
+        if (n.kind < DWDF_RESISTOR || n.kind > DWDF_Y_PARAMETER)
             return fail (DWDF_ERR_INVALID, "node %d: unknown kind %d", i, n.kind);
-        if (is_leaf (n.kind))
+        if (is_leaf (n.kind) || n.kind == DWDF_Y_PARAMETER)
         {
-            if (n.param < 0 || n.param >= d->n_params)
-                return fail (DWDF_ERR_INVALID, "node %d: leaf parameter slot %d outside [0, %d)", i, n.param, d->n_params);
-            if (n.kind == DWDF_CAPACITOR)
-                ++n_states;
+            if (n.param < 0 || n.param + extra_params (n.kind) >= d->n_params)
+                return fail (DWDF_ERR_INVALID, "node %d: parameter slots %d .. %d outside [0, %d)", i, n.param, n.param + extra_params (n.kind), d->n_params);
+            n_states += states_of (n.kind);
         }
-        else
+        if (! is_leaf (n.kind))
         {
-            const int need = n.kind == DWDF_INVERTER ? 1 : 2;
+            const int need = (n.kind == DWDF_INVERTER || n.kind == DWDF_Y_PARAMETER) ? 1 : 2;
             const int ch[2] = { n.child1, n.child2 };
             for (int k = 0; k < need; ++k)
             {
@@ -287,9 +290,26 @@ int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_cir
         return fail (DWDF_ERR_INVALID, "unknown ordering %d", d->ordering);
     if (d->r_node >= n_nodes || (d->r_node >= 0 && nodes[d->r_node].kind != DWDF_RESISTOR && nodes[d->r_node].kind != DWDF_RESISTIVE_VS))
         return fail (DWDF_ERR_INVALID, "r_node must be a Resistor or ResistiveVoltageSource leaf");
-    if (d->root_kind == DWDF_ROOT_DIODE_PAIR)
+    if (d->probe_current != 0 && d->probe_current != 1)
+        return fail (DWDF_ERR_INVALID, "probe_current is 0 (voltage) or 1 (current)");
+    const bool source_leaf = d->source >= 0 && d->source < n_nodes && (nodes[d->source].kind == DWDF_RESISTIVE_VS || nodes[d->source].kind == DWDF_RESISTIVE_CS);
+    if (d->root_kind == DWDF_ROOT_DIODE || d->root_kind == DWDF_ROOT_SWITCH)
     {
-        if (d->source < 0 || d->source >= n_nodes || nodes[d->source].kind != DWDF_RESISTIVE_VS)
+        if (! source_leaf)
+            return fail (DWDF_ERR_INVALID, "diode / switch circuits are driven through a ResistiveVoltageSource or ResistiveCurrentSource leaf (source = %d)", d->source);
+        if (d->root_kind == DWDF_ROOT_DIODE && (d->param_Is < 0 || d->param_Is >= d->n_params || d->param_nabla < 0 || d->param_nabla >= d->n_params || ! (d->Vt > 0.0f)))
+            return fail (DWDF_ERR_INVALID, "diode parameter slots out of range");
+        if (d->root_kind == DWDF_ROOT_SWITCH && d->root_mode != 0 && d->root_mode != 1)
+            return fail (DWDF_ERR_INVALID, "switch: root_mode is 1 (closed) or 0 (open)");
+    }
+    else if (d->root_kind == DWDF_ROOT_IDEAL_CS)
+    {
+        if (d->source >= 0)
+            return fail (DWDF_ERR_INVALID, "the ideal current source is driven by x[n] itself (source = -1)");
+    }
+    else if (d->root_kind == DWDF_ROOT_DIODE_PAIR)
+    {
+        if (! source_leaf)
             return fail (DWDF_ERR_INVALID, "diode-pair circuits are driven through a ResistiveVoltageSource leaf (source = %d)", d->source);
         if (d->root_mode < DWDF_MODE_APPROX || d->root_mode > DWDF_MODE_APPROX_GOOD)
             return fail (DWDF_ERR_INVALID, "unknown root mode %d", d->root_mode);
@@ -317,6 +337,10 @@ int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_cir
     p->nodes.assign (nodes, nodes + n_nodes);
     p->desc = *d;
     p->n_states = n_states;
+    p->differentiable = d->root_kind == DWDF_ROOT_IDEAL_VS || d->root_kind == DWDF_ROOT_DIODE_PAIR || d->root_kind == DWDF_ROOT_NEURAL;
+    for (int i = 0; i < n_nodes; ++i)
+        p->differentiable = p->differentiable && has_adjoint (nodes[i].kind);
+    p->differentiable = p->differentiable && d->probe_current == 0;
 
     // flat program for the interpreter
     TreeProgram& t = p->tree;
@@ -328,8 +352,14 @@ int dwdf_program_create (const dwdf_node* nodes, int32_t n_nodes, const dwdf_cir
         t.c1[i] = i < n_nodes ? nodes[i].child1 : -1;
         t.c2[i] = i < n_nodes ? nodes[i].child2 : -1;
         t.param[i] = i < n_nodes ? nodes[i].param : -1;
-        t.state_of[i] = (i < n_nodes && nodes[i].kind == DWDF_CAPACITOR) ? st++ : -1;
+        t.state_of[i] = -1;
+        if (i < n_nodes && states_of (nodes[i].kind) > 0)
+        {
+            t.state_of[i] = st;
+            st += states_of (nodes[i].kind);
+        }
     }
+    t.probe_current = d->probe_current;
     t.root_kind = d->root_kind;
     t.root_mode = d->root_mode;
     t.pyorder = d->ordering == DWDF_ORDER_PYTHON;
@@ -602,6 +632,8 @@ static int backward_impl (int raw_only, const dwdf_program* prog, const float* p
         return fail (DWDF_ERR_INVALID, "neural-root programs differentiate through dwdf_backward_neural (the gradient is a weight vector)");
     if (prog->desc.root_kind == DWDF_ROOT_DIODE_PAIR && prog->desc.root_mode == DWDF_MODE_APPROX_GOOD)
         return fail (DWDF_ERR_UNSUPPORTED, "the 'Good' diode law is forward only");
+    if (! prog->differentiable)
+        return fail (DWDF_ERR_UNSUPPORTED, "reverse mode covers the wdf_py element set and the inductor, closed by an ideal voltage source, a diode pair or a neural root; this circuit (alpha-transform / Y-parameter / current-source / diode / switch elements, or a current probe) is forward only");
     const bool target = grad_mode == DWDF_GRAD_TARGET;
     const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
     const double count = (double) B * (double) (T - sk);

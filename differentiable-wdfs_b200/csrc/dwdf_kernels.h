@@ -135,11 +135,11 @@ struct TreeProgram // by-value kernel argument (fits the 4 KB parameter space co
 {
     int n_nodes;
     int kind[16], c1[16], c2[16], param[16];
-    int root_kind, root_mode, pyorder, probe, source, r_node;
+    int root_kind, root_mode, pyorder, probe, probe_current, source, r_node;
     int slot_Is, slot_nabla, n_params, n_iter;
     float fs, Vt, n_up, n_down, tol;
     int n_states;
-    int state_of[16]; // capacitor node -> state index
+    int state_of[16]; // reactive leaf -> (first) state index; alpha-transform leaves own two (z, previous reflected wave)
 };
 
 cudaError_t launch_tree_forward (const TreeProgram& p, const float* params, const float* x, const float* r, float* y, float* state, int64_t B, int64_t T, cudaStream_t stream);

@@ -30,11 +30,12 @@ struct TreeWaves
 };
 struct TreeImp
 {
-    float R[kMaxN], G[kMaxN], p1R[kMaxN];
+    float R[kMaxN], G[kMaxN], p1R[kMaxN]; // p1R doubles as the Y-parameter's coefficient C
+    float ca[kMaxN], cb[kMaxN]; // alpha-transform leaves: a_coef, b_coef; Y-parameter: A, B
 };
 
 // calc_impedance, children before parents: tf_wdf.py:77-78,114-115,139-145,168-177,204-206
-__device__ __forceinline__ void tree_impedance (const TreeProgram& p, const float* __restrict__ val, TreeImp& m)
+__device__ __forceinline__ void tree_impedance (const TreeProgram& p, const float* __restrict__ val, const float (&aux)[3][kMaxN], TreeImp& m)
 {
     for (int i = 0; i < p.n_nodes; ++i)
     {
@@ -50,6 +51,39 @@ __device__ __forceinline__ void tree_impedance (const TreeProgram& p, const floa
                 m.R[i] = 1.0f / (2.0f * val[i] * p.fs);
                 m.G[i] = 1.0f / m.R[i];
                 break;
+            case DWDF_RESISTIVE_CS: // wdf_t.h:809-813
+                m.R[i] = val[i];
+                m.G[i] = 1.0f / m.R[i];
+                break;
+            case DWDF_INDUCTOR: // wdf_t.h:320-324: Z_L = 2 fs L
+                m.R[i] = 2.0f * val[i] * p.fs;
+                m.G[i] = 1.0f / m.R[i];
+                break;
+            case DWDF_CAPACITOR_ALPHA: // wdf_t.h:247-251: 1 / ((1 + alpha) fs C); b_coef, a_coef :205-206
+                m.R[i] = 1.0f / ((1.0f + aux[0][i]) * val[i] * p.fs);
+                m.G[i] = 1.0f / m.R[i];
+                m.cb[i] = (1.0f - aux[0][i]) / 2.0f;
+                m.ca[i] = (1.0f + aux[0][i]) / 2.0f;
+                break;
+            case DWDF_INDUCTOR_ALPHA: // wdf_t.h:411-415: (1 + alpha) fs L
+                m.R[i] = (1.0f + aux[0][i]) * val[i] * p.fs;
+                m.G[i] = 1.0f / m.R[i];
+                m.cb[i] = (1.0f - aux[0][i]) / 2.0f;
+                m.ca[i] = (1.0f + aux[0][i]) / 2.0f;
+                break;
+            case DWDF_Y_PARAMETER: // wdf_t.h:614-627; val = y11, aux = y12, y21, y22
+            {
+                const float y11 = val[i], y12 = aux[0][i], y21 = aux[1][i], y22 = aux[2][i], R1 = m.R[c1];
+                const float den = y22 + R1 * y11 * y22 - R1 * y12 * y21;
+                m.R[i] = (R1 * y11 + 1.0f) / den;
+                m.G[i] = 1.0f / m.R[i];
+                const float rSq = R1 * R1;
+                const float num1A = -y22 * rSq * y11 * y11, num2A = y12 * y21 * rSq * y11;
+                m.ca[i] = (num1A + num2A + y22) / (den * (R1 * y11 + 1.0f)); // A
+                m.cb[i] = -R1 * y12 / (R1 * y11 + 1.0f); // B
+                m.p1R[i] = -y21 / den; // C
+                break;
+            }
             case DWDF_SERIES:
                 m.R[i] = m.R[c1] + m.R[c2];
                 m.G[i] = 1.0f / m.R[i];
@@ -81,7 +115,15 @@ __device__ __forceinline__ float tree_root_pair (const TreeProgram& p, const Pai
     return general ? pair_reflect<kModeApprox, true, true, false> (pc, a, d) : pair_reflect<kModeApprox, false, true, false> (pc, a, d);
 }
 
-// One sample. z: capacitor states by node index (updated). Returns the probe voltage.
+// voltage (a + b) / 2 (tf_wdf.py:8-10, wdf_t.h:1112-1115) or current (a - b) / (2 R) (wdf_t.h:1119-1123) of the probe node
+__device__ __forceinline__ float tree_probe (const TreeProgram& p, const TreeImp& m, const TreeWaves& w)
+{
+    if (p.probe_current)
+        return (w.a[p.probe] - w.b[p.probe]) * (0.5f * m.G[p.probe]);
+    return (w.a[p.probe] + w.b[p.probe]) * 0.5f;
+}
+
+// One sample. z: reactive-element states by node index (updated). Returns the probe value.
 __device__ __forceinline__ float tree_sample (const TreeProgram& p, const TreeImp& m, const PairConst& pc, float x, float* __restrict__ z, TreeWaves& w, PairDeriv* d, float* a_root_out)
 {
     const int top = p.n_nodes - 1;
@@ -92,8 +134,13 @@ __device__ __forceinline__ float tree_sample (const TreeProgram& p, const TreeIm
         switch (p.kind[i])
         {
             case DWDF_RESISTOR: w.b[i] = 0.0f; break;
-            case DWDF_RESISTIVE_VS: w.b[i] = (p.root_kind == DWDF_ROOT_DIODE_PAIR && i == p.source) ? x : 0.0f; break;
+            case DWDF_RESISTIVE_VS: w.b[i] = (i == p.source) ? x : 0.0f; break;
+            case DWDF_RESISTIVE_CS: w.b[i] = (i == p.source) ? m.R[i] * x : 0.0f; break; // wdf_t.h:827-831: b = R Is
             case DWDF_CAPACITOR: w.b[i] = z[i]; break;
+            case DWDF_INDUCTOR: w.b[i] = 0.0f - z[i]; break; // wdf_t.h:334-338
+            case DWDF_CAPACITOR_ALPHA: w.b[i] = m.cb[i] * w.b[i] + m.ca[i] * z[i]; break; // wdf_t.h:262-266 (b on the right is the previous sample's)
+            case DWDF_INDUCTOR_ALPHA: w.b[i] = m.cb[i] * w.b[i] - m.ca[i] * z[i]; break; // wdf_t.h:426-430
+            case DWDF_Y_PARAMETER: w.b[i] = m.p1R[i] * w.b[c1]; break; // wdf_t.h:637-641: b = C port1.b
             case DWDF_SERIES: w.b[i] = 0.0f - (w.b[c1] + w.b[c2]); break;
             case DWDF_PARALLEL:
                 w.bdiff[i] = w.b[c2] - w.b[c1];
@@ -108,13 +155,19 @@ __device__ __forceinline__ float tree_sample (const TreeProgram& p, const TreeIm
     float b_root;
     if (p.root_kind == DWDF_ROOT_IDEAL_VS)
         b_root = 0.0f - a_root + 2.0f * x;
-    else
+    else if (p.root_kind == DWDF_ROOT_DIODE_PAIR)
         b_root = tree_root_pair (p, pc, a_root, d);
+    else if (p.root_kind == DWDF_ROOT_IDEAL_CS)
+        b_root = 2.0f * m.R[top] * x + a_root; // wdf_t.h:777-781: b = 2 R Is + a
+    else if (p.root_kind == DWDF_ROOT_SWITCH)
+        b_root = p.root_mode != 0 ? 0.0f - a_root : a_root; // wdf_t.h:1094-1098 (root_mode: 1 closed, 0 open)
+    else // DWDF_ROOT_DIODE, wdf_t.h:1027-1032 (eq. 10): b = a + 2 R Is - 2 Vt omega4(ln(R Is / Vt) + a / Vt + R Is / Vt)
+        b_root = a_root + 2.0f * pc.RIs - pc.twoV * omega4_approx (pc.L + a_root * pc.invV + pc.RIs_overV);
     if (a_root_out != nullptr)
         *a_root_out = a_root;
     float y = 0.0f;
     if (! p.pyorder)
-        y = (w.a[p.probe] + w.b[p.probe]) * 0.5f; // probe between the sweeps sees the previous incident wave
+        y = tree_probe (p, m, w); // probe between the sweeps sees the previous incident wave
     // down-sweep: incident(), tf_wdf.py:147-151,179-183,208-210,120-122
     w.a[top] = b_root;
     for (int i = top; i >= 0; --i)
@@ -138,24 +191,35 @@ __device__ __forceinline__ float tree_sample (const TreeProgram& p, const TreeIm
                 break;
             }
             case DWDF_INVERTER: w.a[c1] = 0.0f - xin; break;
-            case DWDF_CAPACITOR: z[i] = xin; break;
+            case DWDF_Y_PARAMETER: w.a[c1] = m.ca[i] * w.b[c1] + m.cb[i] * xin; break; // wdf_t.h:630-634: port1.incident(A port1.b + B x)
+            case DWDF_CAPACITOR:
+            case DWDF_INDUCTOR:
+            case DWDF_CAPACITOR_ALPHA:
+            case DWDF_INDUCTOR_ALPHA: z[i] = xin; break;
             default: break;
         }
     }
     if (p.pyorder)
-        y = (w.a[p.probe] + w.b[p.probe]) * 0.5f;
+        y = tree_probe (p, m, w);
     return y;
 }
 
-__device__ __forceinline__ void tree_load_values (const TreeProgram& p, const float* __restrict__ params, float* __restrict__ val)
+// leaf values; elements with more than one constant keep the others in the slots after their value
+// (alpha-transform leaves: alpha; Y-parameter: y12, y21, y22 after y11)
+__device__ __forceinline__ void tree_load_values (const TreeProgram& p, const float* __restrict__ params, float* __restrict__ val, float (&aux)[3][kMaxN])
 {
     for (int i = 0; i < p.n_nodes; ++i)
+    {
         val[i] = p.param[i] >= 0 ? __ldg (params + p.param[i]) : 0.0f;
+        const int extra = (p.kind[i] == DWDF_CAPACITOR_ALPHA || p.kind[i] == DWDF_INDUCTOR_ALPHA) ? 1 : (p.kind[i] == DWDF_Y_PARAMETER ? 3 : 0);
+        for (int k = 0; k < 3; ++k)
+            aux[k][i] = k < extra ? __ldg (params + p.param[i] + 1 + k) : 0.0f;
+    }
 }
 
 __device__ __forceinline__ void tree_pair_setup (const TreeProgram& p, const float* __restrict__ params, float Rp, PairConst& pc)
 {
-    if (p.root_kind == DWDF_ROOT_DIODE_PAIR)
+    if (p.root_kind == DWDF_ROOT_DIODE_PAIR || p.root_kind == DWDF_ROOT_DIODE) // (the single diode shares the constants: V = nDiodes Vt, R Is, ln(R Is / V))
         pair_setup (pc, Rp, __ldg (params + p.slot_Is), p.Vt, __ldg (params + p.slot_nabla), p.n_up, p.n_down, p.n_iter, p.tol);
 }
 
@@ -164,19 +228,23 @@ __global__ void __launch_bounds__ (32) tree_forward (const TreeProgram p, const 
     const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
     if (b >= B)
         return;
-    float val[kMaxN], z[kMaxN];
+    float val[kMaxN], z[kMaxN], aux[3][kMaxN];
     TreeImp m;
     TreeWaves w;
     PairConst pc;
-    tree_load_values (p, params, val);
+    tree_load_values (p, params, val, aux);
     for (int i = 0; i < kMaxN; ++i)
     {
         w.a[i] = w.b[i] = w.bdiff[i] = w.btemp[i] = 0.0f;
         z[i] = (state != nullptr && i < p.n_nodes && p.state_of[i] >= 0) ? state[(int64_t) p.state_of[i] * B + b] : 0.0f;
     }
+    if (state != nullptr)
+        for (int i = 0; i < p.n_nodes; ++i)
+            if (p.kind[i] == DWDF_CAPACITOR_ALPHA || p.kind[i] == DWDF_INDUCTOR_ALPHA)
+                w.b[i] = state[(int64_t) (p.state_of[i] + 1) * B + b]; // alpha-transform leaves also carry their previous reflected wave
     if (state != nullptr && ! p.pyorder)
         w.a[p.probe] = state[(int64_t) p.n_states * B + b]; // streaming: the probe's previous incident wave
-    tree_impedance (p, val, m);
+    tree_impedance (p, val, aux, m);
     tree_pair_setup (p, params, m.R[p.n_nodes - 1], pc);
     const float* xr = x + b * T;
     const float* rr = r != nullptr ? r + b * T : nullptr;
@@ -186,7 +254,7 @@ __global__ void __launch_bounds__ (32) tree_forward (const TreeProgram p, const 
         if (rr != nullptr)
         { // per-sample resistance channel: set_resistance + calc_impedance every sample (clipper_pot.py:114-117)
             val[p.r_node] = __ldg (rr + n);
-            tree_impedance (p, val, m);
+            tree_impedance (p, val, aux, m);
             tree_pair_setup (p, params, m.R[p.n_nodes - 1], pc);
         }
         yr[n] = tree_sample (p, m, pc, __ldg (xr + n), z, w, nullptr, nullptr);
@@ -195,7 +263,11 @@ __global__ void __launch_bounds__ (32) tree_forward (const TreeProgram p, const 
     {
         for (int i = 0; i < p.n_nodes; ++i)
             if (p.state_of[i] >= 0)
+            {
                 state[(int64_t) p.state_of[i] * B + b] = z[i];
+                if (p.kind[i] == DWDF_CAPACITOR_ALPHA || p.kind[i] == DWDF_INDUCTOR_ALPHA)
+                    state[(int64_t) (p.state_of[i] + 1) * B + b] = w.b[i];
+            }
         if (! p.pyorder)
             state[(int64_t) p.n_states * B + b] = w.a[p.probe];
     }
@@ -234,6 +306,9 @@ __device__ __forceinline__ void tree_impedance_adjoint (const TreeProgram& p, co
             case DWDF_CAPACITOR: // R = 1/(2 C fs), G = 1/R
                 gval[i] += (gR[i] + gG[i] * (-1.0f / (m.R[i] * m.R[i]))) * (-m.R[i] / val[i]);
                 break;
+            case DWDF_INDUCTOR: // R = 2 L fs
+                gval[i] += (gR[i] + gG[i] * (-1.0f / (m.R[i] * m.R[i]))) * (m.R[i] / val[i]);
+                break;
             default: // Resistor / ResistiveVoltageSource: R = value, G = 1/R
                 gval[i] += gR[i] + gG[i] * (-1.0f / (m.R[i] * m.R[i]));
                 break;
@@ -255,14 +330,14 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
         acc[k] = 0.0;
     if (b < B)
     {
-        float val[kMaxN], z[kMaxN];
+        float val[kMaxN], z[kMaxN], aux[3][kMaxN];
         TreeImp m;
         TreeWaves w;
         PairConst pc;
-        tree_load_values (p, params, val);
+        tree_load_values (p, params, val, aux);
         for (int i = 0; i < kMaxN; ++i)
             w.a[i] = w.b[i] = w.bdiff[i] = w.btemp[i] = z[i] = 0.0f;
-        tree_impedance (p, val, m);
+        tree_impedance (p, val, aux, m);
         tree_pair_setup (p, params, m.R[top], pc);
         const float* xr = x + b * T;
         const float* gr = g + b * T;
@@ -273,7 +348,7 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
             if (rr != nullptr)
             {
                 val[p.r_node] = __ldg (rr + n);
-                tree_impedance (p, val, m);
+                tree_impedance (p, val, aux, m);
                 tree_pair_setup (p, params, m.R[top], pc);
             }
             for (int i = 0; i <= top; ++i)
@@ -298,7 +373,7 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
             if (rr != nullptr)
             {
                 val[p.r_node] = __ldg (rr + n);
-                tree_impedance (p, val, m);
+                tree_impedance (p, val, aux, m);
                 tree_pair_setup (p, params, m.R[top], pc);
             }
             for (int i = 0; i <= top; ++i)
@@ -322,7 +397,7 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
                 aa[i] = ab[i] = abdiff[i] = abtemp[i] = 0.0f;
             // state hand-over z' = a (Capacitor.incident) and the probe
             for (int i = 0; i <= top; ++i)
-                if (p.kind[i] == DWDF_CAPACITOR)
+                if (p.kind[i] == DWDF_CAPACITOR || p.kind[i] == DWDF_INDUCTOR)
                     aa[i] += gz[i];
             ab[p.probe] += 0.5f * gy;
             if (p.pyorder)
@@ -391,6 +466,7 @@ __global__ void __launch_bounds__ (32) tree_adjoint (const TreeProgram p, const 
                     }
                     case DWDF_INVERTER: ab[c1] -= ab[i]; break;
                     case DWDF_CAPACITOR: gz[i] = ab[i]; break;
+                    case DWDF_INDUCTOR: gz[i] = 0.0f - ab[i]; break; // b = -z
                     default: break;
                 }
             }
@@ -496,6 +572,7 @@ __global__ void __launch_bounds__ (256) tree_finalize (const TreeProgram p, cons
             case DWDF_RESISTOR:
             case DWDF_RESISTIVE_VS: R[i] = v; break;
             case DWDF_CAPACITOR: R[i] = 1.0 / (2.0 * v * (double) p.fs); break;
+            case DWDF_INDUCTOR: R[i] = 2.0 * v * (double) p.fs; break;
             case DWDF_SERIES: R[i] = R[c1] + R[c2]; break;
             case DWDF_PARALLEL: R[i] = 1.0 / (1.0 / R[c1] + 1.0 / R[c2]); break;
             default: R[i] = R[c1]; break;
@@ -549,6 +626,12 @@ __global__ void __launch_bounds__ (256) tree_finalize (const TreeProgram p, cons
             {
                 const double gRt = gR[i] + gG[i] * (-1.0 / (R[i] * R[i]));
                 out[p.param[i]] += alpha * gRt * (-R[i] / (double) params[p.param[i]]);
+                break;
+            }
+            case DWDF_INDUCTOR: // R = 2 L fs, G = 1/R
+            {
+                const double gRt = gR[i] + gG[i] * (-1.0 / (R[i] * R[i]));
+                out[p.param[i]] += alpha * gRt * (R[i] / (double) params[p.param[i]]);
                 break;
             }
             default: // Resistor / ResistiveVoltageSource: R = value, G = 1/R

@@ -35,6 +35,11 @@ def voltage(wdf):
     return (wdf.a + wdf.b) * 0.5
 
 
+def current(wdf):
+    """wdf_t.h:1119-1123: the current through a node, (a - b) / (2 R)"""
+    return (wdf.a - wdf.b) * (0.5 / wdf.R)
+
+
 def _scalar(v, trainable=False):
     t = torch.tensor(float(v), dtype=torch.float32)
     t.requires_grad_(bool(trainable))
@@ -229,6 +234,240 @@ class Inverter(_Element):
 PolarityInverter = Inverter  # wdf_t.h:558
 
 
+# ---- the remaining chowdsp_wdf elements (wdf_t.h): same protocol, C++ constructor signatures ---------------------
+
+class Inductor(_Element):
+    """wdf_t.h:280-348 (InductorT): b = -z, z <- a; R = 2 L FS. Trainable like the Capacitor (reverse mode implemented)."""
+
+    def __init__(self, initial_L, FS, trainable=False):
+        super().__init__()
+        self.trainable = trainable
+        self.FS = FS
+        self.L = _scalar(initial_L, trainable)
+        self.R = torch.tensor(2.0 * float(initial_L) * FS, dtype=torch.float32)
+        self.z = torch.zeros(1)
+
+    def calc_impedance(self):
+        self.R = self.L * (2.0 * self.FS)
+
+    def reset(self):
+        self.z = torch.zeros(1)
+
+    def incident(self, x):
+        self.a = x
+        self.z = self.a
+
+    def reflected(self):
+        self.b = -self.z
+        return self.b
+
+
+class CapacitorAlpha(_Element):
+    """wdf_t.h:190-276 (CapacitorAlphaT): alpha transform, alpha = 1 bilinear ... 0 backward Euler.
+    R = 1 / ((1 + alpha) C FS); b = b_coef b_prev + a_coef z."""
+
+    def __init__(self, initial_C, FS, alpha=1.0):
+        super().__init__()
+        self.FS = FS
+        self.C = _scalar(initial_C)
+        self.alpha = float(alpha)
+        self.z = torch.zeros(1)
+        self.calc_impedance()
+
+    def set_alpha(self, alpha):
+        self.alpha = float(alpha)
+        self.calc_impedance()
+
+    def calc_impedance(self):
+        self.b_coef = (1.0 - self.alpha) / 2.0
+        self.a_coef = (1.0 + self.alpha) / 2.0
+        self.R = torch.reciprocal(self.C * ((1.0 + self.alpha) * self.FS))
+
+    def reset(self):
+        self.z = torch.zeros(1)
+        self.b = torch.zeros(1)
+
+    def incident(self, x):
+        self.a = x
+        self.z = self.a
+
+    def reflected(self):
+        self.b = self.b_coef * self.b + self.a_coef * self.z
+        return self.b
+
+
+class InductorAlpha(_Element):
+    """wdf_t.h:352-444 (InductorAlphaT): R = (1 + alpha) L FS; b = b_coef b_prev - a_coef z."""
+
+    def __init__(self, initial_L, FS, alpha=1.0):
+        super().__init__()
+        self.FS = FS
+        self.L = _scalar(initial_L)
+        self.alpha = float(alpha)
+        self.z = torch.zeros(1)
+        self.calc_impedance()
+
+    def set_alpha(self, alpha):
+        self.alpha = float(alpha)
+        self.calc_impedance()
+
+    def calc_impedance(self):
+        self.b_coef = (1.0 - self.alpha) / 2.0
+        self.a_coef = (1.0 + self.alpha) / 2.0
+        self.R = self.L * ((1.0 + self.alpha) * self.FS)
+
+    def reset(self):
+        self.z = torch.zeros(1)
+        self.b = torch.zeros(1)
+
+    def incident(self, x):
+        self.a = x
+        self.z = self.a
+
+    def reflected(self):
+        self.b = self.b_coef * self.b - self.a_coef * self.z
+        return self.b
+
+
+class ResistiveCurrentSource(_Element):
+    """wdf_t.h:786-846 (ResistiveCurrentSourceT): current source with a parallel resistance, b = R Is."""
+
+    def __init__(self, initial_R=1.0e9):
+        super().__init__()
+        self.R = _scalar(initial_R)
+        self.Is = torch.zeros(1)
+
+    def calc_impedance(self):
+        pass
+
+    def set_current(self, current):
+        self.Is = current
+
+    set_voltage = set_current  # (the compiled path drives whichever source the circuit has with x[n])
+
+    def set_resistance(self, resistance):
+        self.R = resistance
+
+    def incident(self, x):
+        self.a = x
+
+    def reflected(self):
+        self.b = self.R * self.Is * torch.ones_like(self.a) if torch.is_tensor(self.Is) else self.R * float(self.Is) * torch.ones_like(self.a)
+        return self.b
+
+
+class YParameter(_Element):
+    """wdf_t.h:597-654 (YParameterT): two-port described by its short-circuit admittances, port 1 = ``P1``."""
+
+    def __init__(self, P1, y11, y12, y21, y22):
+        super().__init__()
+        self.P1 = P1
+        self.y = (float(y11), float(y12), float(y21), float(y22))
+
+    def calc_impedance(self):
+        self.P1.calc_impedance()
+        y11, y12, y21, y22 = self.y
+        R1 = self.P1.R
+        den = y22 + R1 * y11 * y22 - R1 * y12 * y21
+        self.R = (R1 * y11 + 1.0) / den
+        self.A = (-y22 * R1 * R1 * y11 * y11 + y12 * y21 * R1 * R1 * y11 + y22) / (den * (R1 * y11 + 1.0))
+        self.B = -R1 * y12 / (R1 * y11 + 1.0)
+        self.C = -y21 / den
+
+    def incident(self, x):
+        self.a = x
+        self.P1.incident(self.A * self.P1.b + self.B * x)
+
+    def reflected(self):
+        self.b = self.C * self.P1.reflected()
+        return self.b
+
+
+class IdealCurrentSource(_Element):
+    """wdf_t.h:746-784 (root): b = 2 R Is + a, R = the port resistance of ``next``."""
+
+    def __init__(self, next=None):
+        super().__init__()
+        self.next = next
+        self.Is = torch.zeros(1)
+
+    def set_current(self, current):
+        self.Is = current
+
+    def incident(self, x):
+        self.a = x
+
+    def reflected(self):
+        self.b = 2.0 * self.next.R * self.Is + self.a
+        return self.b
+
+
+class Diode(_Element):
+    """wdf_t.h:987-1072 (DiodeT, root): a single diode, Werner eq. 10 with omega4 (both of the reference's qualities):
+    b = a + 2 R Is - 2 Vt omega4(ln(R Is / Vt) + a / Vt + R Is / Vt), Vt := nDiodes Vt."""
+
+    def __init__(self, next, Is, Vt=25.85e-3, nDiodes=1.0):
+        super().__init__()
+        self.next = next
+        self.Is = _scalar(Is)
+        self.nabla = _scalar(nDiodes)
+        self.Vt = float(Vt)
+
+    def incident(self, x):
+        self.a = x
+
+    def reflected(self):
+        V = self.Vt * self.nabla
+        RIs = self.next.R * self.Is
+        self.b = self.a + 2.0 * RIs - 2.0 * V * omega4_approx(torch.log(RIs / V) + self.a / V + RIs / V)
+        return self.b
+
+
+class Switch(_Element):
+    """wdf_t.h:1076-1106 (SwitchT, root): b = -a closed (short), b = a open."""
+
+    def __init__(self, next=None, closed=True):
+        super().__init__()
+        self.next = next
+        self.closed = bool(closed)
+
+    def set_closed(self, closed):
+        self.closed = bool(closed)
+
+    def incident(self, x):
+        self.a = x
+
+    def reflected(self):
+        self.b = -self.a if self.closed else self.a
+        return self.b
+
+
+def _exp_approx(x):
+    """omega.h:99-116 (exp_approx with pow2_approx :83-92) on float32 tensors"""
+    xp = torch.clamp(x.float() * 1.442695040888963, min=-126.0)
+    l = torch.floor(xp)
+    f = xp - l
+    p = 1.0 + f * (0.6931471805599453 + f * (0.2274112777602189 + f * 0.07944154167983575))
+    return torch.ldexp(p, l.to(torch.int32))
+
+
+def _log_approx(x):
+    """omega.h:49-63 (log_approx with log2_approx :33-42): exponent + cubic on the mantissa"""
+    m, e = torch.frexp(x.float())  # x = m 2^e, m in [0.5, 1)
+    m, e = m * 2.0, (e - 1).float()
+    p = -2.213475204444817 + m * (3.148297929334117 + m * (-1.098865286222744 + m * 0.1640425613334452))
+    return 0.693147180559945 * (e + p)
+
+
+def omega4_approx(x):
+    """omega.h:159-177 (omega3 + one Newton step): the approximation wdft::DiodePairT / DiodeT evaluate"""
+    x = torch.as_tensor(x, dtype=torch.float32)
+    cubic = 6.313183464296682e-1 + x * (3.631952663804445e-1 + x * (4.775931364975583e-2 - x * 1.314293149877800e-3))
+    y = torch.where(x < -3.341459552768620, torch.zeros_like(x), torch.where(x < 8.0, cubic, x - _log_approx(torch.clamp(x, min=1.0))))
+    return y - (y - _exp_approx(x - y)) / (y + 1.0)
+
+
+
 def wright_omega(x: torch.Tensor, iters: int = 3) -> torch.Tensor:
     """Wright omega on the real axis for the imperative API: start from e^x below -2 (the cubic of
     omega.h:160-167 touches zero at -3.34 and is useless as a start near there), the cubic up to 8 and
@@ -253,7 +492,7 @@ class DiodePair(_Element):
     modelled on ``DiodePairT(next, Is, Vt, nDiodes)`` (wdf_t.h:868-872) and ``DiodeConfig``
     (diode_config.py:5-9: ``nabla`` multiplies Vt). ``mode``: 'approx' (omega4, omega.h:172-177),
     'exact' (Wright omega to fp32 round-off) or 'approx_good' (eq. 18, wdf_t.h:907-913) — the mode
-    selects the fused kernels' root; the imperative ``reflected()`` below always evaluates the exact law.
+    selects the fused kernels' root, and the imperative ``reflected()`` below evaluates the same law.
     """
 
     def __init__(self, next, Is, Vt=25.85e-3, nabla=1.0, N_up=1, N_down=1, trainable=False, mode="approx", newton_max_iter=0, newton_tol=0.0):
@@ -282,8 +521,13 @@ class DiodePair(_Element):
         mu0 = torch.where(pos, torch.full_like(a, self.N_down), torch.full_like(a, self.N_up))
         mu1 = torch.where(pos, torch.full_like(a, self.N_up), torch.full_like(a, self.N_down))
         lam = torch.sign(a)
-        w0 = wright_omega(torch.log(k / mu0) + lam * a / (mu0 * V))
-        w1 = wright_omega(torch.log(k / mu1) - lam * a / (mu1 * V))
+        if self.mode == "approx_good":  # eq. 18, wdf_t.h:907-913
+            RIs = self.Is * self.next.R
+            self.b = a + 2 * lam * (RIs - V * omega4_approx(torch.log(k) + lam * a / V + k))
+            return self.b
+        omega = wright_omega if self.mode == "exact" else omega4_approx  # 'approx': what wdft::DiodePairT evaluates (omega.h:172-177)
+        w0 = omega(torch.log(k / mu0) + lam * a / (mu0 * V))
+        w1 = omega(torch.log(k / mu1) - lam * a / (mu1 * V))
         self.b = a - 2 * V * lam * (mu0 * w0 - mu1 * w1)
         return self.b
 
@@ -345,7 +589,8 @@ class DenseRootModel(_Element):
 # ==================================================================================================
 # compiled path
 # ==================================================================================================
-_KIND = {Resistor: L.RESISTOR, Capacitor: L.CAPACITOR, ResistiveVoltageSource: L.RESISTIVE_VS, Series: L.SERIES, Parallel: L.PARALLEL, Inverter: L.INVERTER}
+_KIND = {Resistor: L.RESISTOR, Capacitor: L.CAPACITOR, ResistiveVoltageSource: L.RESISTIVE_VS, Series: L.SERIES, Parallel: L.PARALLEL, Inverter: L.INVERTER, Inductor: L.INDUCTOR,
+         CapacitorAlpha: L.CAPACITOR_ALPHA, InductorAlpha: L.INDUCTOR_ALPHA, ResistiveCurrentSource: L.RESISTIVE_CS, YParameter: L.Y_PARAMETER}
 _MODE = {"approx": L.MODE_APPROX, "exact": L.MODE_EXACT, "approx_good": L.MODE_APPROX_GOOD}
 
 
@@ -380,7 +625,9 @@ class CompiledCircuit:
     to the slot; ``trainable`` lists the slots whose elements were built with ``trainable=True``.
     """
 
-    def __init__(self, root, tree=None, probe=None, ordering="python", r_element=None, device=None, fs=None):
+    def __init__(self, root, tree=None, probe=None, ordering="python", r_element=None, device=None, fs=None, probe_kind="voltage"):
+        if probe_kind not in ("voltage", "current"):
+            raise ValueError("probe_kind is 'voltage' ((a + b) / 2, tf_wdf.py:8-10) or 'current' ((a - b) / (2 R), wdf_t.h:1119-1123)")
         if not torch.cuda.is_available():
             raise RuntimeError("differentiable-wdfs_b200: the compiled path is CUDA-only and no CUDA device is visible (there is no CPU fallback)")
         self.lib = L.lib()
@@ -406,9 +653,28 @@ class CompiledCircuit:
             c1 = c2 = -1
             if kind in (L.SERIES, L.PARALLEL):
                 c1, c2 = visit(e.P1), visit(e.P2)
-            elif kind == L.INVERTER:
+            elif kind in (L.INVERTER, L.Y_PARAMETER):
                 c1 = visit(e.P1)
             slot = -1
+            if kind in (L.INDUCTOR, L.INDUCTOR_ALPHA):
+                slot = len(values)
+                values.append(float(e.L.detach()))
+                self.slots[(id(e), "L")] = slot
+                fs_seen.append(float(e.FS))
+            if kind in (L.CAPACITOR_ALPHA, L.INDUCTOR_ALPHA):
+                if kind == L.CAPACITOR_ALPHA:
+                    slot = len(values)
+                    values.append(float(e.C.detach()))
+                    self.slots[(id(e), "C")] = slot
+                    fs_seen.append(float(e.FS))
+                values.append(float(e.alpha))  # the constants of an element follow its value slot
+            elif kind == L.Y_PARAMETER:
+                slot = len(values)
+                values.extend(e.y)
+            elif kind == L.RESISTIVE_CS:
+                slot = len(values)
+                values.append(float(e.R.detach()) if torch.is_tensor(e.R) else float(e.R))
+                self.slots[(id(e), "R")] = slot
             if kind in (L.RESISTOR, L.RESISTIVE_VS):
                 slot = len(values)
                 values.append(float(e.R.detach()) if torch.is_tensor(e.R) else float(e.R))
@@ -430,6 +696,7 @@ class CompiledCircuit:
             raise ValueError("probe must be an element of the tree (the node whose voltage is the output)")
         d = L.CircuitDesc()
         d.probe = index[id(probe)]
+        d.probe_current = 1 if probe_kind == "current" else 0
         d.ordering = L.ORDER_PYTHON if ordering == "python" else L.ORDER_PLUGIN
         d.source = -1
         d.r_node = index[id(r_element)] if r_element is not None else -1
@@ -438,9 +705,9 @@ class CompiledCircuit:
         if isinstance(root, DiodePair):
             d.root_kind = L.ROOT_DIODE_PAIR
             d.root_mode = _MODE[root.mode]
-            sources = [i for i, e in enumerate(self.elements) if isinstance(e, ResistiveVoltageSource)]
+            sources = [i for i, e in enumerate(self.elements) if isinstance(e, (ResistiveVoltageSource, ResistiveCurrentSource))]
             if len(sources) != 1:
-                raise ValueError("a DiodePair circuit is driven through exactly one ResistiveVoltageSource")
+                raise ValueError("a DiodePair circuit is driven through exactly one ResistiveVoltageSource (or ResistiveCurrentSource)")
             d.source = sources[0]
             d.param_Is = len(values)
             values.append(float(root.Is.detach()))
@@ -452,6 +719,24 @@ class CompiledCircuit:
             d.newton_max_iter, d.newton_tol = root.newton_max_iter, root.newton_tol
         elif isinstance(root, IdealVoltageSource):
             d.root_kind = L.ROOT_IDEAL_VS
+        elif isinstance(root, IdealCurrentSource):
+            d.root_kind = L.ROOT_IDEAL_CS
+        elif isinstance(root, (Diode, Switch)):
+            sources = [i for i, e in enumerate(self.elements) if isinstance(e, (ResistiveVoltageSource, ResistiveCurrentSource))]
+            if len(sources) != 1:
+                raise ValueError("a Diode / Switch circuit is driven through exactly one ResistiveVoltageSource or ResistiveCurrentSource")
+            d.source = sources[0]
+            if isinstance(root, Switch):
+                d.root_kind, d.root_mode = L.ROOT_SWITCH, 1 if root.closed else 0
+            else:
+                d.root_kind = L.ROOT_DIODE
+                d.param_Is = len(values)
+                values.append(float(root.Is.detach()))
+                self.slots[(id(root), "Is")] = d.param_Is
+                d.param_nabla = len(values)
+                values.append(float(root.nabla.detach()))
+                self.slots[(id(root), "nabla")] = d.param_nabla
+                d.Vt = root.Vt
         elif isinstance(root, DenseRootModel):
             d.root_kind = L.ROOT_NEURAL
             sources = [i for i, e in enumerate(self.elements) if isinstance(e, ResistiveVoltageSource)]
@@ -463,7 +748,7 @@ class CompiledCircuit:
                 raise ValueError(f"network {root.sizes} / {root.activations}: the fused kernel runs the reference's shapes, 2 -> H (tanh) x (n+1) -> 1")
             self.mlp = L.MlpDesc(len(hidden) - 1, hidden[0])
         else:
-            raise TypeError("root must be an IdealVoltageSource, a DiodePair or a DenseRootModel")
+            raise TypeError("root must be an IdealVoltageSource, an IdealCurrentSource, a DiodePair, a Diode, a Switch or a DenseRootModel")
         if fs is None:
             if not fs_seen:
                 fs = 48000.0
@@ -736,8 +1021,8 @@ class CompiledCircuit:
             setattr(e, attr, _scalar(float(vals[s]), getattr(e, "trainable", False)))
 
 
-def compile_circuit(root, tree=None, probe=None, ordering="python", r_element=None, device=None, fs=None) -> CompiledCircuit:
-    return CompiledCircuit(root, tree, probe, ordering, r_element, device, fs)
+def compile_circuit(root, tree=None, probe=None, ordering="python", r_element=None, device=None, fs=None, probe_kind="voltage") -> CompiledCircuit:
+    return CompiledCircuit(root, tree, probe, ordering, r_element, device, fs, probe_kind)
 
 
 class AdamWeights:

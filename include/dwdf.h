@@ -55,7 +55,13 @@ enum dwdf_node_kind
     DWDF_RESISTIVE_VS = 2, /* tf_wdf.py:31-59   value = R [ohm]; reflected wave = source voltage     */
     DWDF_SERIES = 3, /* tf_wdf.py:129-155 child1 = P1, child2 = P2                             */
     DWDF_PARALLEL = 4, /* tf_wdf.py:158-192 child1 = P1, child2 = P2                             */
-    DWDF_INVERTER = 5 /* tf_wdf.py:195-214 child1 = P1                                          */
+    DWDF_INVERTER = 5, /* tf_wdf.py:195-214 child1 = P1                                          */
+    /* the remaining chowdsp_wdf one-ports and the two-port (wdf_t.h); forward and streaming everywhere, reverse mode for the inductor */
+    DWDF_INDUCTOR = 6, /* wdf_t.h:280-348   value = L [henry]; port resistance 2 L fs; reflects -z            */
+    DWDF_CAPACITOR_ALPHA = 7, /* wdf_t.h:190-276 value = C, params[param + 1] = alpha (0 backward Euler .. 1 bilinear) */
+    DWDF_INDUCTOR_ALPHA = 8, /* wdf_t.h:352-444  value = L, params[param + 1] = alpha                            */
+    DWDF_RESISTIVE_CS = 9, /* wdf_t.h:786-846   value = R [ohm]; reflected wave = R * source current          */
+    DWDF_Y_PARAMETER = 10 /* wdf_t.h:597-654   child1 = port1; params[param .. param + 3] = y11, y12, y21, y22 */
 };
 
 /* Non-adaptable root closing the tree. */
@@ -63,8 +69,11 @@ enum dwdf_root_kind
 {
     DWDF_ROOT_IDEAL_VS = 0, /* tf_wdf.py:13-28 / wdf_t.h:658-689: b = -a + 2 Vs, Vs = x[n]            */
     DWDF_ROOT_DIODE_PAIR = 1, /* analytic antiparallel diode pair (see dwdf_root_mode)                 */
-    DWDF_ROOT_NEURAL = 2 /* b = -MLP(a, ln Rp): layers.py:42-82 (DenseRootModel), DiodePairNeuralModel.h:62-75;
+    DWDF_ROOT_NEURAL = 2, /* b = -MLP(a, ln Rp): layers.py:42-82 (DenseRootModel), DiodePairNeuralModel.h:62-75;
                             programs of this kind are created by dwdf_program_create_neural                */
+    DWDF_ROOT_IDEAL_CS = 3, /* wdf_t.h:746-784: b = 2 R Is + a, Is = x[n]                                       */
+    DWDF_ROOT_DIODE = 4, /* wdf_t.h:987-1072: single diode, eq. 10 with omega4; param_Is / param_nabla as the pair */
+    DWDF_ROOT_SWITCH = 5 /* wdf_t.h:1076-1106: b = -a closed (root_mode 1), b = a open (root_mode 0)             */
 };
 
 /* How the diode-pair root evaluates the Wright-omega function. */
@@ -100,7 +109,7 @@ typedef struct dwdf_circuit_desc
     int32_t root_mode; /* dwdf_root_mode (diode pair only) */
     int32_t ordering; /* dwdf_ordering */
     int32_t probe; /* node whose voltage (a+b)/2 is the output (tf_wdf.py:8-10) */
-    int32_t source; /* node driven by x[n] (a DWDF_RESISTIVE_VS; ignored for DWDF_ROOT_IDEAL_VS) */
+    int32_t source; /* leaf driven by x[n] (a DWDF_RESISTIVE_VS or DWDF_RESISTIVE_CS); -1 when x[n] drives the root (DWDF_ROOT_IDEAL_VS / _CS) */
     int32_t r_node; /* leaf whose resistance is the per-sample channel `r` (clipper_pot.py:116), or -1 */
     int32_t param_Is; /* parameter slot of the diode saturation current, diode pair only */
     int32_t param_nabla; /* parameter slot of the ideality factor / nDiodes (wdf_t.h:875-882) */
@@ -111,6 +120,7 @@ typedef struct dwdf_circuit_desc
     float n_up; /* diodes in series, "up" branch (diode_config.py:5-9); 1 = symmetric */
     float n_down;
     float newton_tol; /* exact mode: stop refining when |residual| <= tol (0: run all iterations) */
+    int32_t probe_current; /* 0: the output is the probe's voltage (a + b) / 2; 1: its current (a - b) / (2 R) (wdf_t.h:1119-1123) */
 } dwdf_circuit_desc;
 
 typedef struct dwdf_program dwdf_program; /* opaque, immutable after creation, thread-shareable */

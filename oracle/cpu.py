@@ -20,8 +20,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _OUT = os.path.join(_HERE, "_ref")
 
 # enums shared with wdf_oracle.c / ref_harness.cpp
-RESISTOR, CAPACITOR, RESVS, SERIES, PARALLEL, INVERTER = range(6)
-ROOT_IDEAL_VS, ROOT_DIODE_PAIR = 0, 1
+RESISTOR, CAPACITOR, RESVS, SERIES, PARALLEL, INVERTER, INDUCTOR, CAPACITOR_ALPHA, INDUCTOR_ALPHA, RESCS, YPARAM = range(11)
+ROOT_IDEAL_VS, ROOT_DIODE_PAIR, ROOT_IDEAL_CS, ROOT_DIODE, ROOT_SWITCH = 0, 1, 3, 4, 5
 ORDER_PLUGIN, ORDER_PYTHON = 0, 1
 ROOT_APPROX, ROOT_EXACT, ROOT_APPROX_GOOD = 0, 1, 2
 
@@ -105,6 +105,27 @@ class Oracle:
         fn = self.lib.ow_tree_run_f32 if dtype == np.float32 else self.lib.ow_tree_run_f64
         ct = C.c_float if dtype == np.float32 else C.c_double
         rc = fn(C.c_int(len(nodes)), _ptr(kind), _ptr(c1), _ptr(c2), _ptr(val), ct(fs), C.c_int(root_kind), _ptr(rp), C.c_int(source), C.c_int(probe), C.c_int(ordering), C.c_int(r_node), _ptr(x), _ptr(r) if r is not None else None, _ptr(y), C.c_int64(B), C.c_int64(T))
+        assert rc == 0
+        return y
+
+    def tree_run_ext(self, nodes, fs, root_kind, x, probe, source=-1, root_par=None, ordering=ORDER_PYTHON, probe_current=False, dtype=np.float32):
+        """The full chowdsp_wdf element set. nodes: (kind, c1, c2, value[, aux...]) in post-order, aux = alpha for the
+        alpha-transform leaves, (y12, y21, y22) for the Y-parameter (value = y11); x: (B, T)."""
+        x = _np(x, dtype)
+        B, T = x.shape
+        kind = _np([n[0] for n in nodes], np.int32)
+        c1 = _np([n[1] for n in nodes], np.int32)
+        c2 = _np([n[2] for n in nodes], np.int32)
+        val = _np([n[3] for n in nodes], dtype)
+        aux = np.zeros((len(nodes), 3), dtype)
+        for i, n in enumerate(nodes):
+            aux[i, :len(n) - 4] = n[4:]
+        rp = _np(root_par if root_par is not None else [0] * 7, dtype)
+        y = np.empty_like(x)
+        fn = self.lib.ow_tree_run_ext_f32 if dtype == np.float32 else self.lib.ow_tree_run_ext_f64
+        ct = C.c_float if dtype == np.float32 else C.c_double
+        rc = fn(C.c_int(len(nodes)), _ptr(kind), _ptr(c1), _ptr(c2), _ptr(val), _ptr(aux), ct(fs), C.c_int(root_kind), _ptr(rp), C.c_int(source), C.c_int(probe), C.c_int(int(probe_current)), C.c_int(ordering), _ptr(x), _ptr(y),
+                C.c_int64(B), C.c_int64(T))
         assert rc == 0
         return y
 
@@ -209,3 +230,35 @@ class Ref:
 
     def hardware_threads(self) -> int:
         return int(self.lib.ref_hardware_threads())
+
+
+class RefElements:
+    """oracle/_ref/libdwdf_ref_elements.so: the unmodified chowdsp_wdf classes of the remaining elements in the circuits of
+    the reference's own tests (oracle/ref_elements_harness.cpp). One mono signal in, one out."""
+
+    def __init__(self):
+        path = os.path.join(_OUT, "libdwdf_ref_elements.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+
+    def _run(self, fn, x, *args):
+        x = _np(x, np.float32).ravel()
+        y = np.empty_like(x)
+        fn(_ptr(x), _ptr(y), C.c_int64(x.size), *args)
+        return y
+
+    def current_divider(self, x, R1, R2):
+        return self._run(self.lib.ref_el_current_divider, x, C.c_float(R1), C.c_float(R2))
+
+    def current_switch(self, x, R1, Rs, closed):
+        return self._run(self.lib.ref_el_current_switch, x, C.c_float(R1), C.c_float(Rs), C.c_int(int(closed)))
+
+    def rlc_highpass(self, x, fs, R, Cv, L, alpha=-1.0):
+        return self._run(self.lib.ref_el_rlc_highpass, x, C.c_float(fs), C.c_float(R), C.c_float(Cv), C.c_float(L), C.c_float(alpha))
+
+    def y_parameter(self, x, R, y11, y12, y21, y22, probe):
+        return self._run(self.lib.ref_el_y_parameter, x, C.c_float(R), C.c_float(y11), C.c_float(y12), C.c_float(y21), C.c_float(y22), C.c_int(probe))
+
+    def diode(self, x, fs, Rs, Cv, Is, Vt, n_diodes, probe):
+        return self._run(self.lib.ref_el_diode, x, C.c_float(fs), C.c_float(Rs), C.c_float(Cv), C.c_float(Is), C.c_float(Vt), C.c_float(n_diodes), C.c_int(probe))

@@ -30,8 +30,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { OW_RESISTOR = 0, OW_CAPACITOR = 1, OW_RESVS = 2, OW_SERIES = 3, OW_PARALLEL = 4, OW_INVERTER = 5 };
-enum { OW_ROOT_IDEAL_VS = 0, OW_ROOT_DIODE_PAIR = 1 };
+enum { OW_RESISTOR = 0, OW_CAPACITOR = 1, OW_RESVS = 2, OW_SERIES = 3, OW_PARALLEL = 4, OW_INVERTER = 5, OW_INDUCTOR = 6, OW_CAPACITOR_ALPHA = 7, OW_INDUCTOR_ALPHA = 8, OW_RESCS = 9, OW_YPARAM = 10 };
+enum { OW_ROOT_IDEAL_VS = 0, OW_ROOT_DIODE_PAIR = 1, OW_ROOT_IDEAL_CS = 3, OW_ROOT_DIODE = 4, OW_ROOT_SWITCH = 5 };
 enum { OW_ORDER_PLUGIN = 0, OW_ORDER_PYTHON = 1 };
 #define OW_MAX_NODES 64
 #define OW_MAX_THREADS 256

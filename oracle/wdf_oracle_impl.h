@@ -212,6 +212,8 @@ typedef struct
     REAL z; /* Capacitor state (tf_wdf.py:112) */
     REAL Vs; /* source voltage (tf_wdf.py:48-49) */
     REAL p1R, b_diff, b_temp; /* adaptor coefficients / carried temporaries (tf_wdf.py:146,189-190) */
+    REAL aux[3]; /* alpha-transform leaves: alpha; Y-parameter: y12, y21, y22 (value = y11) */
+    REAL cA, cB, cC; /* alpha leaves: a_coef, b_coef (wdf_t.h:205-206); Y-parameter: A, B, C (wdf_t.h:621-626) */
 } SFX (node_t);
 
 static void SFX (calc_impedance) (SFX (node_t) * t, int i, REAL fs)
@@ -228,6 +230,41 @@ static void SFX (calc_impedance) (SFX (node_t) * t, int i, REAL fs)
             n->R = (REAL) 1 / ((REAL) 2 * n->value * fs);
             n->G = (REAL) 1 / n->R;
             break;
+        case OW_RESCS: /* wdf_t.h:809-813 */
+            n->R = n->value;
+            n->G = (REAL) 1 / n->R;
+            break;
+        case OW_INDUCTOR: /* wdf_t.h:320-324 */
+            n->R = (REAL) 2 * n->value * fs;
+            n->G = (REAL) 1 / n->R;
+            break;
+        case OW_CAPACITOR_ALPHA: /* wdf_t.h:247-251, coefficients :205-206 */
+            n->R = (REAL) 1 / (((REAL) 1 + n->aux[0]) * n->value * fs);
+            n->G = (REAL) 1 / n->R;
+            n->cB = ((REAL) 1 - n->aux[0]) / (REAL) 2;
+            n->cA = ((REAL) 1 + n->aux[0]) / (REAL) 2;
+            break;
+        case OW_INDUCTOR_ALPHA: /* wdf_t.h:411-415 */
+            n->R = ((REAL) 1 + n->aux[0]) * n->value * fs;
+            n->G = (REAL) 1 / n->R;
+            n->cB = ((REAL) 1 - n->aux[0]) / (REAL) 2;
+            n->cA = ((REAL) 1 + n->aux[0]) / (REAL) 2;
+            break;
+        case OW_YPARAM: /* wdf_t.h:614-627 */
+        {
+            SFX (calc_impedance) (t, n->c1, fs);
+            REAL y11 = n->value, y12 = n->aux[0], y21 = n->aux[1], y22 = n->aux[2], R1 = t[n->c1].R;
+            REAL den = y22 + R1 * y11 * y22 - R1 * y12 * y21;
+            n->R = (R1 * y11 + (REAL) 1) / den;
+            n->G = (REAL) 1 / n->R;
+            REAL rSq = R1 * R1;
+            REAL num1A = -y22 * rSq * y11 * y11;
+            REAL num2A = y12 * y21 * rSq * y11;
+            n->cA = (num1A + num2A + y22) / (den * (R1 * y11 + (REAL) 1));
+            n->cB = -R1 * y12 / (R1 * y11 + (REAL) 1);
+            n->cC = -y21 / den;
+            break;
+        }
         case OW_SERIES: /* tf_wdf.py:139-145; wdf_t.h:525-530 */
             SFX (calc_impedance) (t, n->c1, fs);
             SFX (calc_impedance) (t, n->c2, fs);
@@ -259,6 +296,11 @@ static REAL SFX (reflected) (SFX (node_t) * t, int i)
         case OW_RESISTOR: n->b = (REAL) 0; break; /* tf_wdf.py:86-88 */
         case OW_RESVS: n->b = n->Vs; break; /* tf_wdf.py:57-59 */
         case OW_CAPACITOR: n->b = n->z; break; /* tf_wdf.py:124-126 */
+        case OW_RESCS: n->b = n->R * n->Vs; break; /* wdf_t.h:827-831 (Vs holds the source current) */
+        case OW_INDUCTOR: n->b = -n->z; break; /* wdf_t.h:334-338 */
+        case OW_CAPACITOR_ALPHA: n->b = n->cB * n->b + n->cA * n->z; break; /* wdf_t.h:262-266 */
+        case OW_INDUCTOR_ALPHA: n->b = n->cB * n->b - n->cA * n->z; break; /* wdf_t.h:426-430 */
+        case OW_YPARAM: n->b = n->cC * SFX (reflected) (t, n->c1); break; /* wdf_t.h:637-641 */
         case OW_SERIES: /* tf_wdf.py:153-155 */
         {
             REAL r1 = SFX (reflected) (t, n->c1);
@@ -289,6 +331,11 @@ static void SFX (incident) (SFX (node_t) * t, int i, REAL x)
         case OW_RESISTOR:
         case OW_RESVS: n->a = x; break; /* tf_wdf.py:83-84, 54-55 */
         case OW_CAPACITOR: n->a = x; n->z = n->a; break; /* tf_wdf.py:120-122 */
+        case OW_RESCS: n->a = x; break; /* wdf_t.h:821-824 */
+        case OW_INDUCTOR: /* wdf_t.h:327-331 */
+        case OW_CAPACITOR_ALPHA: /* wdf_t.h:254-258 */
+        case OW_INDUCTOR_ALPHA: n->a = x; n->z = n->a; break; /* wdf_t.h:418-422 */
+        case OW_YPARAM: n->a = x; SFX (incident) (t, n->c1, n->cA * t[n->c1].b + n->cB * x); break; /* wdf_t.h:630-634 */
         case OW_SERIES: /* tf_wdf.py:147-151 */
         {
             REAL b1 = t[n->c1].b - n->p1R * (x + t[n->c1].b + t[n->c2].b);
@@ -363,6 +410,64 @@ int SFX (ow_tree_run) (int n_nodes, const int* kind, const int* c1, const int* c
             SFX (incident) (t, top, root_b);
             if (ordering != OW_ORDER_PLUGIN)
                 y[s * nT + n] = (t[probe].a + t[probe].b) * (REAL) 0.5;
+        }
+    }
+    return 0;
+}
+
+/* The same executor for the full chowdsp_wdf element set: aux = 3 extra constants per node (alpha; y12, y21, y22),
+ * root kinds OW_ROOT_IDEAL_CS (wdf_t.h:746-784), OW_ROOT_DIODE (:987-1072, eq. 10, always omega4) and OW_ROOT_SWITCH
+ * (:1076-1106; root_par[0] != 0: closed), a ResistiveCurrentSource as the driven leaf, and a current probe
+ * (a - b) / (2 R), wdf_t.h:1119-1123. root_par for the diode: {_, _, Is, Vt, nDiodes}. */
+int SFX (ow_tree_run_ext) (int n_nodes, const int* kind, const int* c1, const int* c2, const REAL* value, const REAL* aux, REAL fs, int root_kind, const REAL* root_par, int source, int probe, int probe_current, int ordering, const REAL* x, REAL* y, int64_t nB, int64_t nT)
+{
+    if (n_nodes <= 0 || n_nodes > OW_MAX_NODES)
+        return 1;
+    SFX (node_t) t[OW_MAX_NODES];
+    const int top = n_nodes - 1;
+    for (int64_t s = 0; s < nB; ++s)
+    {
+        memset (t, 0, sizeof (t));
+        for (int i = 0; i < n_nodes; ++i)
+        {
+            t[i].kind = kind[i];
+            t[i].c1 = c1[i];
+            t[i].c2 = c2[i];
+            t[i].value = value[i];
+            for (int k = 0; k < 3; ++k)
+                t[i].aux[k] = aux[i * 3 + k];
+        }
+        SFX (calc_impedance) (t, top, fs);
+        SFX (pair_t) dp;
+        REAL twoR_Is = 0;
+        if (root_kind == OW_ROOT_DIODE_PAIR)
+            SFX (pair_setup) (&dp, (int) root_par[0], (int) root_par[1], root_par[2], root_par[3], root_par[4], root_par[5], root_par[6], t[top].R);
+        if (root_kind == OW_ROOT_DIODE)
+        { /* wdf_t.h:1003-1010,1047-1052: Vt = nDiodes Vt; twoR_Is, R_Is_overVt, log */
+            SFX (pair_setup) (&dp, 0, 0, root_par[2], root_par[3], root_par[4], (REAL) 1, (REAL) 1, t[top].R);
+            twoR_Is = (REAL) 2 * t[top].R * root_par[2];
+        }
+        for (int64_t n = 0; n < nT; ++n)
+        {
+            REAL xin = x[s * nT + n];
+            if (source >= 0)
+                t[source].Vs = xin;
+            REAL root_a = SFX (reflected) (t, top), root_b;
+            switch (root_kind)
+            {
+                case OW_ROOT_IDEAL_VS: root_b = (REAL) 0 - root_a + (REAL) 2 * xin; break;
+                case OW_ROOT_IDEAL_CS: root_b = (REAL) 2 * t[top].R * xin + root_a; break; /* wdf_t.h:777-781 */
+                case OW_ROOT_SWITCH: root_b = root_par[0] != (REAL) 0 ? -root_a : root_a; break; /* wdf_t.h:1094-1098 */
+                case OW_ROOT_DIODE: root_b = root_a + twoR_Is - dp.twoVt * SFX (omega4) (dp.logR_Is_overVt + root_a * dp.oneOverVt + dp.R_Is_overVt); break; /* wdf_t.h:1027-1032 */
+                default: root_b = SFX (pair_reflect) (&dp, root_a, NULL); break;
+            }
+            #define OW_PROBE() (probe_current ? (t[probe].a - t[probe].b) * ((REAL) 0.5 * t[probe].G) : (t[probe].a + t[probe].b) * (REAL) 0.5)
+            if (ordering == OW_ORDER_PLUGIN)
+                y[s * nT + n] = OW_PROBE ();
+            SFX (incident) (t, top, root_b);
+            if (ordering != OW_ORDER_PLUGIN)
+                y[s * nT + n] = OW_PROBE ();
+            #undef OW_PROBE
         }
     }
     return 0;
