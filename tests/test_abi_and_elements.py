@@ -126,19 +126,21 @@ def test_config1_rc_lowpass_imperative_cpu(dwdf, golden):
         out.append(dwdf.voltage(C1))
     y = torch.stack(out).reshape(-1).detach().numpy()
     assert np.max(np.abs(y - golden["lpf_y_f64"])) < 1e-5 * np.max(np.abs(golden["lpf_y_f64"]))  # fp32 element arithmetic like the reference (tf_wdf.py:72,102)
-    # the same protocol with a diode pair as root (imperative reflected() evaluates the exact law)
-    Vr = dwdf.ResistiveVoltageSource(47000.0)
-    Cc = dwdf.Capacitor(2.2e-9, 48000.0)
-    P1 = dwdf.Parallel(Vr, Cc)
-    dp = dwdf.DiodePair(P1, 4.352e-9, 25.85e-3, 1.906)
-    P1.calc_impedance()
-    xs = torch.from_numpy(golden["clip_x"][:2, :64])
-    ys = []
-    for i in range(xs.shape[1]):  # clipper_pot.py:113-124
-        Vr.set_voltage(xs[:, i:i + 1])
-        dp.incident(P1.reflected())
-        P1.incident(dp.reflected())
-        ys.append(dwdf.voltage(Cc))
-    ys = torch.cat(ys, dim=1).numpy()
-    ref = golden["clip_plugin_exact_python_f32"][:2, :64]
-    assert np.max(np.abs(ys - ref)) < 1e-5 * np.max(np.abs(ref))
+    # the same protocol with a diode pair as root: the imperative reflected() evaluates the law its mode names
+    # ('exact': Wright omega; 'approx': omega4 as wdft::DiodePairT) — against the reference C++'s own outputs for each
+    for mode, key in (("exact", "clip_plugin_exact_python_f32"), ("approx", "clip_plugin_approx_python_f32")):
+        Vr = dwdf.ResistiveVoltageSource(47000.0)
+        Cc = dwdf.Capacitor(2.2e-9, 48000.0)
+        P1 = dwdf.Parallel(Vr, Cc)
+        dp = dwdf.DiodePair(P1, 4.352e-9, 25.85e-3, 1.906, mode=mode)
+        P1.calc_impedance()
+        xs = torch.from_numpy(golden["clip_x"][:2, :64])
+        ys = []
+        for i in range(xs.shape[1]):  # clipper_pot.py:113-124
+            Vr.set_voltage(xs[:, i:i + 1])
+            dp.incident(P1.reflected())
+            P1.incident(dp.reflected())
+            ys.append(dwdf.voltage(Cc))
+        ys = torch.cat(ys, dim=1).numpy()
+        ref = golden[key][:2, :64]
+        assert np.max(np.abs(ys - ref)) < 1e-5 * np.max(np.abs(ref)), mode
