@@ -851,13 +851,13 @@ class CompiledCircuit:
         if self.is_neural:
             ck = self._scratch("_ckpt", self.lib.dwdf_neural_ckpt_bytes(self.handle, B, T)) if keep_for_backward else None
             L.check(self.lib.dwdf_forward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), None, _ptr(ck), B, T, _stream_ptr(self.device)))
-            self._last = (x, r, y, B, T) if keep_for_backward else None
+            self._last = (x, r, y, B, T, y._version) if keep_for_backward else None
             return y
         ck = None
         if keep_for_backward and self.is_clipper and B * T > 0:
             ck = self._scratch("_ckpt", self.lib.dwdf_ckpt_bytes(self.handle, B, T))
         L.check(self.lib.dwdf_forward(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), B, T, _stream_ptr(self.device)))
-        self._last = (x, r, y, B, T) if keep_for_backward else None
+        self._last = (x, r, y, B, T, y._version) if keep_for_backward else None
         return y
 
     def forward_time_major(self, x, r=None):
@@ -867,7 +867,8 @@ class CompiledCircuit:
     @_on_device
     def backward(self, gy=None, target=None, loss="mse", skip=0, want_gx=False, raw=False):
         """Gradients of the last ``forward``: upstream ``gy = dL/dy`` or a fused loss against ``target``.
-        The adjoint kernel reads the output tensor that ``forward`` returned; do not modify it in between.
+        The adjoint kernel recovers the states from the output tensor that ``forward`` returned (no tape, no replay):
+        an in-place torch operation on that tensor between the two calls is detected (version counter) and raises.
 
         Returns a dict with ``grads`` (float64 tensor, one per parameter slot, on the device), ``loss``,
         ``mse``, ``esr`` (0-d device tensors; target mode) and ``gx`` if requested.
@@ -876,7 +877,9 @@ class CompiledCircuit:
             raise RuntimeError("backward() needs a preceding forward(keep_for_backward=True)")
         if (gy is None) == (target is None):
             raise ValueError("give exactly one of gy (upstream gradient) or target (fused loss)")
-        x, r, y, B, T = self._last
+        x, r, y, B, T, y_version = self._last
+        if y._version != y_version:
+            raise RuntimeError("the tensor forward() returned was modified in place before backward(): the adjoint recovers the circuit's states from it (clone it before modifying, or call forward() again)")
         g = gy if gy is not None else target
         self._check_xy(g, "gy/target", (B, T))
         if self.is_neural:
@@ -950,7 +953,7 @@ class CompiledCircuit:
             L.check(self.lib.dwdf_train_step(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(y), _ptr(ck), _ptr(self.out),
                                              _ptr(work), work.numel(), _ptr(o.m), _ptr(o.v), _ptr(o.step_count), 0.0, _ptr(o.lr), float(o.beta_1), float(o.beta_2), float(o.epsilon), _ptr(self.clip_lo),
                                              _ptr(self.clip_hi), B, T, _stream_ptr(self.device)))
-        self._last = (x, None, y, B, T)
+        self._last = (x, None, y, B, T, y._version)
         return self._result(None)
 
     def _result(self, gx):

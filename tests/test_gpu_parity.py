@@ -522,6 +522,24 @@ def test_errors_are_loud(dwdf):
         circ.backward()
 
 
+def test_backward_refuses_a_modified_forward_output(dwdf):
+    """The adjoint recovers the states from the tensor forward() returned: touching it in between is an error, not a
+    silently wrong gradient; a clone may be modified freely."""
+    circ, _ = make_clipper(dwdf)
+    x = dev(make_inputs(40, 256, seed=5))
+    target = torch.zeros_like(x)
+    y = circ.forward(x)
+    y2 = y.clone().mul_(2.0)  # fine: not the tensor the adjoint reads
+    g_ok = circ.backward(target=target)["grads"].clone()
+    y = circ.forward(x)
+    y.mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        circ.backward(target=target)
+    circ.forward(x)
+    assert torch.equal(circ.backward(target=target)["grads"], g_ok)
+    del y2
+
+
 # ---- time chunks (fewer sequences than the SMs hold warps) ------------------------------------------------
 
 @pytest.mark.parametrize("mode", ["approx", "exact"])
