@@ -18,7 +18,7 @@ ROOT_IDEAL_VS, ROOT_DIODE_PAIR, ROOT_NEURAL, ROOT_IDEAL_CS, ROOT_DIODE, ROOT_SWI
 MODE_APPROX, MODE_EXACT, MODE_APPROX_GOOD = 0, 1, 2
 ORDER_PLUGIN, ORDER_PYTHON = 0, 1
 GRAD_UPSTREAM, GRAD_TARGET = 0, 1
-LOSS_MSE, LOSS_MSE_ESR = 0, 1
+LOSS_MSE, LOSS_MSE_ESR, LOSS_MSE_ESR_AS_CALLED = 0, 1, 2
 MAX_PARAMS, MAX_NODES = 16, 16
 OUT_LOSS, OUT_MSE, OUT_ESR, OUT_LEN = 16, 17, 18, 24
 
@@ -30,6 +30,7 @@ SYMBOLS = (
     "dwdf_forward", "dwdf_backward", "dwdf_train_pass", "dwdf_adam_step", "dwdf_forward_host", "dwdf_grad_host", "dwdf_process_block",
     "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_backward_neural", "dwdf_neural_ckpt_bytes", "dwdf_neural_workspace_bytes", "dwdf_adam_step_vec", "dwdf_last_error", "dwdf_build_info", "dwdf_train_step", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option", "dwdf_time_parallel_redone",
     "dwdf_comm_create", "dwdf_comm_handle_bytes", "dwdf_comm_get_handle", "dwdf_comm_connect", "dwdf_comm_set_timeout", "dwdf_comm_destroy", "dwdf_allreduce_sum", "dwdf_train_step_dp", "dwdf_profile_begin", "dwdf_profile_end",
+    "dwdf_backward_neural_raw", "dwdf_finalize_neural", "dwdf_train_step_neural",
 )
 
 
@@ -101,7 +102,10 @@ def lib() -> C.CDLL:
     L.dwdf_mlp_weight_count.restype = sz
     L.dwdf_program_create_neural.argtypes = [C.POINTER(Node), i32, C.POINTER(CircuitDesc), C.POINTER(MlpDesc), C.POINTER(vp)]
     L.dwdf_forward_neural.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
-    L.dwdf_backward_neural.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, vp, sz, i64, i64, vp]
+    L.dwdf_backward_neural.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, vp, vp, sz, i64, i64, vp]
+    L.dwdf_backward_neural_raw.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, sz, i64, i64, vp]
+    L.dwdf_finalize_neural.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.dwdf_train_step_neural.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, sz, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, i64, i64, vp]
     L.dwdf_neural_ckpt_bytes.argtypes = [vp, i64, i64]
     L.dwdf_neural_ckpt_bytes.restype = sz
     L.dwdf_neural_workspace_bytes.argtypes = [vp, i64, i64]

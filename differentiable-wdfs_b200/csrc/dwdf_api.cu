@@ -221,6 +221,33 @@ constexpr int64_t kNnChunkedMaxB = 16384; // neural root: the network makes ever
 size_t partials_bytes (int64_t B) { return ((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256 * 256 + 256; }
 int64_t n_segments (int64_t T) { return (T + kSeg - 1) / kSeg; }
 size_t adj_maps_bytes (int64_t B, int64_t T) { const int k = adj_chunk_cap (B, T); return k > 1 ? (size_t) k * kMapFloatsPerChunk * (size_t) B * sizeof (float) : 0; }
+
+// DWDF_LOSS_MSE_ESR_AS_CALLED (loss_kernels.cu): batch sums over (y, target) -> [summed over ranks] -> dL/dy into scratch. The
+// struct keeps the stream-ordered scratch alive until the caller has enqueued the sweep that reads it.
+struct AsCalledLoss
+{
+    AsyncScratch buf;
+    double* sums = nullptr;
+    float* ybar = nullptr;
+};
+int as_called_prepare (AsCalledLoss& a, const float* y, const float* target, int64_t B, int64_t T, int64_t sk, const DpPeers* dp, cudaStream_t stream)
+{
+    const size_t head = (loss_scratch_doubles (B) * sizeof (double) + 255) / 256 * 256;
+    DWDF_CUDA (a.buf.alloc (head + (size_t) B * (size_t) T * sizeof (float), stream));
+    a.sums = reinterpret_cast<double*> (a.buf.p);
+    a.ybar = reinterpret_cast<float*> (reinterpret_cast<char*> (a.buf.p) + head);
+    DWDF_CUDA (launch_loss_sums (y, target, B, T, (int) sk, a.sums, stream));
+    g_launches.fetch_add (2);
+    if (dp != nullptr && dp->world > 1)
+    {
+        DWDF_CUDA (launch_peer_allreduce (a.sums, 4, *dp, stream));
+        g_launches.fetch_add (1);
+    }
+    DWDF_CUDA (launch_loss_ybar (y, target, B, T, (int) sk, a.sums, a.ybar, stream));
+    g_launches.fetch_add (1);
+    return DWDF_OK;
+}
+bool loss_kind_ok (int32_t k) { return k == DWDF_LOSS_MSE || k == DWDF_LOSS_MSE_ESR || k == DWDF_LOSS_MSE_ESR_AS_CALLED; }
 } // namespace
 
 extern "C" {
@@ -468,8 +495,8 @@ int dwdf_forward_neural (const dwdf_program* prog, const float* params, const fl
     return DWDF_OK;
 }
 
-int dwdf_backward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode,
-                          int32_t loss_kind, int64_t skip, double* grad_w, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream_)
+static int backward_neural_impl (bool raw_only, const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode,
+                                 int32_t loss_kind, int64_t skip, float* gx, double* grad_w, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t) stream_;
     if (int rc = check_batch (prog, params, x, B, T))
@@ -480,10 +507,23 @@ int dwdf_backward_neural (const dwdf_program* prog, const float* params, const f
         return fail (DWDF_ERR_INVALID, "null argument");
     if (grad_mode != DWDF_GRAD_UPSTREAM && grad_mode != DWDF_GRAD_TARGET)
         return fail (DWDF_ERR_INVALID, "unknown grad mode %d", grad_mode);
-    if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
+    if (! loss_kind_ok (loss_kind))
         return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
     if (B == 0 || T == 0)
         return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
+    if (loss_kind == DWDF_LOSS_MSE_ESR_AS_CALLED)
+    { // the reference's loss as its loop calls it: batch sums -> dL/dy -> the same sweep in upstream mode
+        if (grad_mode != DWDF_GRAD_TARGET || raw_only)
+            return fail (DWDF_ERR_INVALID, "DWDF_LOSS_MSE_ESR_AS_CALLED is a fused loss of the whole batch: it needs DWDF_GRAD_TARGET (and has no raw-sum form)");
+        AsCalledLoss a;
+        if (int rc = as_called_prepare (a, y, gy_or_target, B, T, skip < 0 ? 0 : (skip > T ? T : skip), nullptr, stream))
+            return rc;
+        if (int rc = backward_neural_impl (false, prog, params, weights, x, r, y, z_ckpt, a.ybar, DWDF_GRAD_UPSTREAM, DWDF_LOSS_MSE, 0, gx, grad_w, out, workspace, workspace_bytes, B, T, stream_))
+            return rc;
+        DWDF_CUDA (launch_loss_write (a.sums, out, stream));
+        g_launches.fetch_add (1);
+        return DWDF_OK;
+    }
     if (workspace_bytes < dwdf_neural_workspace_bytes (prog, B, T))
         return fail (DWDF_ERR_WORKSPACE, "workspace of %zu bytes, need %zu", workspace_bytes, dwdf_neural_workspace_bytes (prog, B, T));
     if ((prog->desc.r_node >= 0) != (r != nullptr))
@@ -498,9 +538,37 @@ int dwdf_backward_neural (const dwdf_program* prog, const float* params, const f
     const size_t partials_bytes = ((size_t) nn_adjoint_ctas (B, K) * (nw + 8) * sizeof (double) + 255) / 256 * 256;
     float* scratch = K > 1 ? (float*) ((char*) workspace + partials_bytes) : nullptr;
     DWDF_CUDA (launch_nn_adjoint (prog->mlp.hidden, prog->mlp.n_hidden, prog->desc.ordering == DWDF_ORDER_PYTHON, target, x, r, y, gy_or_target, z_ckpt, params, prog->nodes[0].param, prog->nodes[1].param,
-                                  prog->desc.fs, weights, nw, (double*) workspace, (int) sk, B, T, K, scratch, stream));
-    DWDF_CUDA (launch_nn_finalize ((const double*) workspace, nn_adjoint_ctas (B, K), nw, target, loss_kind, (double) B * (double) (T - sk), grad_w, out, stream));
+                                  prog->desc.fs, weights, nw, (double*) workspace, (int) sk, B, T, K, scratch, gx, stream));
+    DWDF_CUDA (launch_nn_reduce ((const double*) workspace, nn_adjoint_ctas (B, K), nw, (double) B * (double) (T - sk), grad_w, out, stream));
     g_launches.fetch_add (K > 1 ? 4 : 2);
+    if (! raw_only)
+    {
+        DWDF_CUDA (launch_nn_scale (nw, target, loss_kind, grad_w, out, stream));
+        g_launches.fetch_add (1);
+    }
+    return DWDF_OK;
+}
+
+int dwdf_backward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode,
+                          int32_t loss_kind, int64_t skip, float* gx, double* grad_w, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
+{
+    return backward_neural_impl (false, prog, params, weights, x, r, y, z_ckpt, gy_or_target, grad_mode, loss_kind, skip, gx, grad_w, out, workspace, workspace_bytes, B, T, stream);
+}
+
+int dwdf_backward_neural_raw (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode,
+                              int64_t skip, float* gx, double* grad_w_raw, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream)
+{
+    return backward_neural_impl (true, prog, params, weights, x, r, y, z_ckpt, gy_or_target, grad_mode, DWDF_LOSS_MSE, skip, gx, grad_w_raw, raw, workspace, workspace_bytes, B, T, stream);
+}
+
+int dwdf_finalize_neural (const dwdf_program* prog, int32_t grad_mode, int32_t loss_kind, double* grad_w_inout, double* raw_inout, void* stream)
+{
+    if (prog == nullptr || ! prog->is_neural || grad_w_inout == nullptr || raw_inout == nullptr)
+        return fail (DWDF_ERR_INVALID, "dwdf_finalize_neural needs a neural-root program, the summed weight gradients and the summed raw block");
+    if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
+        return fail (DWDF_ERR_INVALID, "loss kind %d has no raw-sum form", loss_kind);
+    DWDF_CUDA (launch_nn_scale ((int) dwdf_mlp_weight_count (&prog->mlp), grad_mode == DWDF_GRAD_TARGET, loss_kind, grad_w_inout, raw_inout, (cudaStream_t) stream));
+    g_launches.fetch_add (1);
     return DWDF_OK;
 }
 
@@ -622,7 +690,7 @@ static int backward_impl (int raw_only, const dwdf_program* prog, const float* p
         return fail (DWDF_ERR_INVALID, "null argument");
     if (grad_mode != DWDF_GRAD_UPSTREAM && grad_mode != DWDF_GRAD_TARGET)
         return fail (DWDF_ERR_INVALID, "unknown grad mode %d", grad_mode);
-    if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
+    if (! loss_kind_ok (loss_kind))
         return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
     if (workspace_bytes < dwdf_workspace_bytes (prog, B, T))
         return fail (DWDF_ERR_WORKSPACE, "workspace of %zu bytes, need %zu", workspace_bytes, dwdf_workspace_bytes (prog, B, T));
@@ -630,6 +698,21 @@ static int backward_impl (int raw_only, const dwdf_program* prog, const float* p
         return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
     if (prog->is_neural)
         return fail (DWDF_ERR_INVALID, "neural-root programs differentiate through dwdf_backward_neural (the gradient is a weight vector)");
+    if (loss_kind == DWDF_LOSS_MSE_ESR_AS_CALLED)
+    { // the reference's loss as its loop calls it: batch sums -> dL/dy -> the same sweep in upstream mode
+        if (grad_mode != DWDF_GRAD_TARGET || raw_only != 0)
+            return fail (DWDF_ERR_INVALID, "DWDF_LOSS_MSE_ESR_AS_CALLED is a fused loss of the whole batch: it needs DWDF_GRAD_TARGET (and has no raw-sum form)");
+        if (y == nullptr)
+            return fail (DWDF_ERR_INVALID, "DWDF_LOSS_MSE_ESR_AS_CALLED reads the forward output y: it is null");
+        AsCalledLoss a;
+        if (int rc = as_called_prepare (a, y, gy_or_target, B, T, skip < 0 ? 0 : (skip > T ? T : skip), nullptr, stream))
+            return rc;
+        if (int rc = backward_impl (0, prog, params, x, r, y, z_ckpt, a.ybar, DWDF_GRAD_UPSTREAM, DWDF_LOSS_MSE, 0, gx, out, workspace, workspace_bytes, B, T, stream_))
+            return rc;
+        DWDF_CUDA (launch_loss_write (a.sums, out, stream));
+        g_launches.fetch_add (1);
+        return DWDF_OK;
+    }
     if (prog->desc.root_kind == DWDF_ROOT_DIODE_PAIR && prog->desc.root_mode == DWDF_MODE_APPROX_GOOD)
         return fail (DWDF_ERR_UNSUPPORTED, "the 'Good' diode law is forward only");
     if (! prog->differentiable)
@@ -723,6 +806,8 @@ static int train_impl (bool raw_only, const dwdf_program* prog, const float* par
         return fail (DWDF_ERR_INVALID, "null argument");
     if (! prog->is_clipper || prog->clip_r || r != nullptr)
         return fail (DWDF_ERR_UNSUPPORTED, "the fused training pass exists for the diode-clipper program without a resistance channel only");
+    if (loss_kind == DWDF_LOSS_MSE_ESR_AS_CALLED)
+        return fail (DWDF_ERR_UNSUPPORTED, "DWDF_LOSS_MSE_ESR_AS_CALLED needs the batch's output energy before the gradient sweep: use dwdf_forward + dwdf_backward (or dwdf_train_step), not the one-sweep pass");
     if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
         return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
     if (workspace_bytes < dwdf_workspace_bytes (prog, B, T))
@@ -895,13 +980,34 @@ static int train_step_impl (const dwdf_program* prog, const DpPeers& dp, float* 
 {
     if (B < 1 || T < 1)
         return fail (DWDF_ERR_INVALID, "a training step needs at least one sequence (B = %lld, T = %lld)", (long long) B, (long long) T);
-    if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
+    if (! loss_kind_ok (loss_kind))
         return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
     g_prof.mark (0, stream);
     if (int rc = dwdf_forward (prog, params, x, r, y, z_ckpt, B, T, stream))
         return rc;
     g_prof.mark (1, stream);
     const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
+    if (loss_kind == DWDF_LOSS_MSE_ESR_AS_CALLED)
+    { // batch sums (summed over ranks) -> dL/dy -> reverse sweep in upstream mode -> [exchange of the raw sums] -> chain rule -> Adam
+        AsCalledLoss a;
+        if (int rc = as_called_prepare (a, y, target, B, T, sk, &dp, stream))
+            return rc;
+        if (int rc = backward_impl (dp.world > 1 ? 1 : 0, prog, params, x, r, y, z_ckpt, a.ybar, DWDF_GRAD_UPSTREAM, DWDF_LOSS_MSE, 0, nullptr, out, workspace, workspace_bytes, B, T, stream))
+            return rc;
+        g_prof.mark (2, stream);
+        if (dp.world > 1)
+        {
+            DWDF_CUDA (launch_peer_allreduce (out, DWDF_OUT_LEN, dp, stream));
+            g_launches.fetch_add (1);
+            if (int rc = dwdf_finalize (prog, params, DWDF_GRAD_UPSTREAM, DWDF_LOSS_MSE, out, stream))
+                return rc;
+        }
+        DWDF_CUDA (launch_loss_write (a.sums, out, stream));
+        g_launches.fetch_add (1);
+        int rc = m == nullptr ? DWDF_OK : dwdf_adam_step (params, out, m, v, step, prog->desc.n_params, lr, lr_per_slot, beta1, beta2, eps, 1.0, lo, hi, stream);
+        g_prof.mark (3, stream);
+        return rc;
+    }
     if (prog->is_clipper && ! prog->clip_r)
     { // adjoint -> ONE kernel: reduction of the partials + exchange over peer memory + chain rule + loss + Adam
         if (int rc = backward_impl (2, prog, params, x, r, y, z_ckpt, target, DWDF_GRAD_TARGET, loss_kind, skip, nullptr, out, workspace, workspace_bytes, B, T, stream))
@@ -946,6 +1052,56 @@ int dwdf_train_step_dp (const dwdf_program* prog, const dwdf_comm* comm, float* 
     if (prog == nullptr || ! comm_peers (comm, dp))
         return fail (DWDF_ERR_INVALID, "dwdf_train_step_dp needs a program and a connected communicator");
     return train_step_impl (prog, dp, params, x, r, target, loss_kind, skip, y, z_ckpt, out, workspace, workspace_bytes, m, v, step, lr, lr_per_slot, beta1, beta2, eps, lo, hi, B, T, (cudaStream_t) stream);
+}
+
+// Neural root: one whole training step of clipper_pot.py:246-269 (the trainable variables are the network's kernels and
+// biases) in one call, on this rank's shard when a communicator is given: forward + reverse sweep + fixed-order reduction
+// [+ exchange of the raw weight-gradient sums and the loss sums over peer memory] + loss scale + Adam on the weights.
+int dwdf_train_step_neural (const dwdf_program* prog, const dwdf_comm* comm, const float* params, float* weights, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, float* z_ckpt,
+                            double* grad_w, double* out, void* workspace, size_t workspace_bytes, float* m, float* v, int32_t* step, float lr, float beta1, float beta2, float eps, int64_t B, int64_t T, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t) stream_;
+    if (prog == nullptr || ! prog->is_neural)
+        return fail (DWDF_ERR_INVALID, "dwdf_train_step_neural needs a neural-root program");
+    if (B < 1 || T < 1)
+        return fail (DWDF_ERR_INVALID, "a training step needs at least one sequence (B = %lld, T = %lld)", (long long) B, (long long) T);
+    if (! loss_kind_ok (loss_kind))
+        return fail (DWDF_ERR_INVALID, "unknown loss kind %d", loss_kind);
+    DpPeers dp {};
+    dp.world = 1;
+    if (comm != nullptr && ! comm_peers (comm, dp))
+        return fail (DWDF_ERR_INVALID, "the communicator is not connected (dwdf_comm_connect)");
+    if (int rc = dwdf_forward_neural (prog, params, weights, x, r, y, nullptr, z_ckpt, B, T, stream_))
+        return rc;
+    const int nw = (int) dwdf_mlp_weight_count (&prog->mlp);
+    const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);
+    const bool as_called = loss_kind == DWDF_LOSS_MSE_ESR_AS_CALLED, many = dp.world > 1;
+    AsCalledLoss a;
+    if (as_called)
+        if (int rc = as_called_prepare (a, y, target, B, T, sk, &dp, stream))
+            return rc;
+    if (int rc = backward_neural_impl (many, prog, params, weights, x, r, y, z_ckpt, as_called ? a.ybar : target, as_called ? DWDF_GRAD_UPSTREAM : DWDF_GRAD_TARGET, as_called ? DWDF_LOSS_MSE : loss_kind, as_called ? 0 : skip,
+                                       nullptr, grad_w, out, workspace, workspace_bytes, B, T, stream_))
+        return rc;
+    if (many)
+    {
+        for (int w0 = 0; w0 < nw; w0 += kDpSlotDoubles - 1)
+        {
+            DWDF_CUDA (launch_peer_allreduce (grad_w + w0, nw - w0 < kDpSlotDoubles - 1 ? nw - w0 : kDpSlotDoubles - 1, dp, stream));
+            g_launches.fetch_add (1);
+        }
+        DWDF_CUDA (launch_peer_allreduce (out, DWDF_OUT_LEN, dp, stream));
+        DWDF_CUDA (launch_nn_scale (nw, ! as_called, as_called ? DWDF_LOSS_MSE : loss_kind, grad_w, out, stream));
+        g_launches.fetch_add (2);
+    }
+    if (as_called)
+    {
+        DWDF_CUDA (launch_loss_write (a.sums, out, stream));
+        g_launches.fetch_add (1);
+    }
+    if (m != nullptr)
+        return dwdf_adam_step_vec (weights, grad_w, m, v, step, nw, lr, beta1, beta2, eps, 1.0, stream_);
+    return DWDF_OK;
 }
 
 int dwdf_profile_begin (int32_t max_steps)
@@ -1082,6 +1238,8 @@ int dwdf_grad_host (const dwdf_program* prog, const float* params_host, const fl
         return fail (DWDF_ERR_UNSUPPORTED, "dwdf_grad_host covers the diode-clipper program without a resistance channel; use the device API otherwise");
     if (B == 0 || T == 0)
         return fail (DWDF_ERR_INVALID, "empty batch has no gradient");
+    if (loss_kind != DWDF_LOSS_MSE && loss_kind != DWDF_LOSS_MSE_ESR)
+        return fail (loss_kind == DWDF_LOSS_MSE_ESR_AS_CALLED ? DWDF_ERR_UNSUPPORTED : DWDF_ERR_INVALID, "dwdf_grad_host pipelines the batch in chunks: loss kind %d is not available here (DWDF_LOSS_MSE_ESR_AS_CALLED needs the whole batch's output energy before the sweep; use the device API)", loss_kind);
     std::lock_guard<std::mutex> lock (g_arena.mu);
     const bool target = grad_mode == DWDF_GRAD_TARGET;
     const int64_t sk = skip < 0 ? 0 : (skip > T ? T : skip);

@@ -115,6 +115,12 @@ cudaError_t launch_clipper_finalize_dp (const ClipDesc& desc, float* params, con
                                         float lr, const float* lr_vec, float beta1, float beta2, float eps, const float* lo, const float* hi, cudaStream_t stream);
 cudaError_t launch_peer_allreduce (double* inout, int n, const DpPeers& dp, cudaStream_t stream);
 
+// ---- the reference's loss as its training loop calls it (loss_kernels.cu): sums over (y, target), then dL/dy -------------
+size_t loss_scratch_doubles (int64_t B); // scratch of launch_loss_sums; the sums (sse, sum y^2, sum target^2, count) land in scratch[0 .. 4)
+cudaError_t launch_loss_sums (const float* y, const float* t, int64_t B, int64_t T, int skip, double* scratch, cudaStream_t stream);
+cudaError_t launch_loss_ybar (const float* y, const float* t, int64_t B, int64_t T, int skip, const double* sums, float* ybar, cudaStream_t stream);
+cudaError_t launch_loss_write (const double* sums, double* out, cudaStream_t stream);
+
 cudaError_t launch_adam (float* params, const double* out, float* m, float* v, int32_t* step, int n_params, float lr, const float* lr_vec, float beta1, float beta2, float eps, double grad_scale, const float* lo, const float* hi, cudaStream_t stream);
 
 // ---- neural diode-pair root (inference): clipper tree + b = -MLP(a, ln Rp), hidden width 4 / 8 / 16 ----------
@@ -125,9 +131,11 @@ int nn_time_chunks (int64_t T); // chunks of the time-parallel variant (K > 1 ne
 int64_t nn_ckpt_floats (int64_t B, int64_t T);
 int64_t nn_groups (int64_t B);
 cudaError_t launch_nn_adjoint (int hidden, int n_hidden, bool pyorder, bool target, const float* x, const float* r, const float* y, const float* g, const float* ckpt, const float* params, int slot_R, int slot_C,
-                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, int K, float* scratch, cudaStream_t stream);
+                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, int K, float* scratch, float* gx, cudaStream_t stream);
 int64_t nn_adjoint_ctas (int64_t B, int K);
-cudaError_t launch_nn_finalize (const double* partials, int64_t n_groups, int n_weights, bool target, int loss_kind, double count, double* grad_w, double* out, cudaStream_t stream);
+// partial vectors -> raw sums (grad_w_raw[n_weights]; raw[kAccSse], raw[kAccSt2], raw[23] = count), then raw -> gradients + loss in place
+cudaError_t launch_nn_reduce (const double* partials, int64_t n_groups, int n_weights, double count, double* grad_w_raw, double* raw, cudaStream_t stream);
+cudaError_t launch_nn_scale (int n_weights, bool target, int loss_kind, double* grad_w_inout, double* raw_inout, cudaStream_t stream);
 cudaError_t launch_adam_vec (float* w, const double* gw, float* m, float* v, int32_t* step, int64_t n, float lr, float beta1, float beta2, float eps, double grad_scale, cudaStream_t stream);
 
 // ---- generic tree interpreter -----------------------------------------------------------------

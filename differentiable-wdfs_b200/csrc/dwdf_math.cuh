@@ -9,9 +9,19 @@
 // check the logic against the oracle on a machine without a GPU; the product only ever calls them
 // from kernels.
 #pragma once
+#if defined(__CUDACC_RTC__) // runtime-specialised tree kernels (tree_jit.cu): NVRTC has no host headers
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#ifndef INFINITY
+#define INFINITY __int_as_float (0x7f800000)
+#endif
+#else
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#endif
 
 #if defined(__CUDACC__)
 #define DWDF_HD __host__ __device__ __forceinline__

@@ -1,8 +1,16 @@
 // dwdf_tma.cuh — thin inline-PTX wrappers for the sm_100a async-copy machinery the clipper kernels
 // use: mbarrier, cp.async.bulk.tensor (TMA) 2-D tile loads/stores, proxy fences, bulk-group waits.
 #pragma once
+#if defined(__CUDACC_RTC__) // NVRTC: no host headers; the tensor map is an opaque 128-byte kernel parameter
+struct alignas (64) CUtensorMap_st
+{
+    unsigned long long opaque[16];
+};
+typedef CUtensorMap_st CUtensorMap;
+#else
 #include <cuda.h>
 #include <cstdint>
+#endif
 
 namespace dwdf
 {

@@ -353,7 +353,7 @@ __device__ __forceinline__ void nn_column_pass (const float* __restrict__ mat, c
 template <int H, int NH, bool PY, bool TARGET, int PHASE>
 __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ ckpt,
                                                           const float* __restrict__ params, int slot_R, int slot_C, float fs, const float* __restrict__ weights, int n_weights, double* __restrict__ partials,
-                                                          int skip, int64_t B, int T, int K, float4* __restrict__ pq, const f2* __restrict__ gin)
+                                                          int skip, int64_t B, int T, int K, float4* __restrict__ pq, const f2* __restrict__ gin, float* __restrict__ gx)
 {
     using St = NnStage<H>;
     extern __shared__ __align__ (16) float smem[];
@@ -553,6 +553,14 @@ __global__ void __launch_bounds__ (32) nn_clipper_adjoint (const float* __restri
         // ---- state recurrence: A = (1 - gamma) f'(a) - gamma, f' = -dN/da ---------------------------
         const f2 omg = addv (bc (f2 {}, 1.0f), negv (gamma));
         const f2 A = addv (mulv (omg, negv (dNda)), negv (gamma));
+        if (PHASE != 1 && gx != nullptr && act)
+        { // dL/dx[n] = G dz'/dx, dz'/dx = gamma (1 + f') = gamma (1 - dN/da); plugin ordering never observes z[T]
+            const f2 gxv = last_plugin ? f2 { 0.0f, 0.0f } : mulv (mulv (G, gamma), addv (bc (f2 {}, 1.0f), negv (dNda)));
+            if (validA)
+                gx[rowA * T + n] = gxv.x;
+            if (validB)
+                gx[rowB * T + n] = gxv.y;
+        }
         if (act)
         {
             G = last_plugin ? gy : fmav (G, A, PY ? mulv (bc (f2 {}, 0.5f), gy) : gy);
@@ -649,33 +657,60 @@ __global__ void __launch_bounds__ (128) nn_adjoint_stitch (const float4* __restr
     }
 }
 
-// fixed-order reduction over the warps' partials, loss, and the loss's scale on the gradients
-// (MSE: 2/N; + ESR: clipper_pot.py:148-156 with eps = float64 eps, :145); upstream mode: scale 1.
-__global__ void __launch_bounds__ (256) nn_finalize (const double* __restrict__ partials, int64_t n_groups, int n_weights, int target, int loss_kind, double count, double* __restrict__ grad_w, double* __restrict__ out)
+// Fixed-order reduction over the warps' partial vectors -> RAW sums: grad_w[w] = sum over the batch (before the loss's
+// scale), raw[kAccSse] / raw[kAccSt2] / raw[23] = sse, target energy, samples in the loss — what ranks exchange
+// (dwdf_backward_neural_raw). 64 weights per block, 4 interleaved slices of the groups per weight, combined in slice order.
+__global__ void __launch_bounds__ (256) nn_reduce (const double* __restrict__ partials, int64_t n_groups, int n_weights, double count, double* __restrict__ grad_w, double* __restrict__ raw)
 {
-    __shared__ double sm[2][256];
-    __shared__ double alpha_s;
-    const int tid = threadIdx.x;
+    __shared__ double sm[4][64];
+    __shared__ double sl[2][256];
+    const int tid = threadIdx.x, wl = tid & 63, slice = tid >> 6;
+    const int w = blockIdx.x * 64 + wl;
+    const int64_t stride = n_weights + 8;
+    double sum = 0.0;
+    if (w < n_weights)
+        for (int64_t gidx = slice; gidx < n_groups; gidx += 4)
+            sum += partials[gidx * stride + w];
+    sm[slice][wl] = sum;
+    __syncthreads ();
+    if (slice == 0 && w < n_weights)
+        grad_w[w] = ((sm[0][wl] + sm[1][wl]) + sm[2][wl]) + sm[3][wl];
+    if (blockIdx.x != 0)
+        return;
     double a0 = 0.0, a1 = 0.0;
     for (int64_t gidx = tid; gidx < n_groups; gidx += 256)
     {
-        a0 += partials[gidx * (n_weights + 8) + n_weights];
-        a1 += partials[gidx * (n_weights + 8) + n_weights + 1];
+        a0 += partials[gidx * stride + n_weights];
+        a1 += partials[gidx * stride + n_weights + 1];
     }
-    sm[0][tid] = a0, sm[1][tid] = a1;
+    sl[0][tid] = a0, sl[1][tid] = a1;
     __syncthreads ();
     for (int o = 128; o > 0; o >>= 1)
     {
         if (tid < o)
-            sm[0][tid] += sm[0][tid + o], sm[1][tid] += sm[1][tid + o];
+            sl[0][tid] += sl[0][tid + o], sl[1][tid] += sl[1][tid + o];
         __syncthreads ();
     }
+    if (tid == 0)
+    {
+        for (int k = 0; k < 24; ++k)
+            raw[k] = 0.0;
+        raw[kAccSse] = sl[0][0], raw[kAccSt2] = sl[1][0], raw[23] = count;
+    }
+}
+
+// raw sums (possibly summed over ranks) -> gradients and loss, in place: the loss's scale on the gradients
+// (MSE: 2/N; + ESR: clipper_pot.py:148-156 with eps = float64 eps, :145); upstream mode: scale 1.
+__global__ void __launch_bounds__ (256) nn_scale (int n_weights, int target, int loss_kind, double* __restrict__ grad_w, double* __restrict__ out)
+{
+    __shared__ double alpha_s;
+    const int tid = threadIdx.x;
     if (tid == 0)
     {
         double alpha = 1.0, loss = 0.0, mse = 0.0, esr = 0.0;
         if (target)
         {
-            const double sse = sm[0][0], st2 = sm[1][0], N = count > 0.0 ? count : 1.0;
+            const double sse = out[kAccSse], st2 = out[kAccSt2], N = out[23] > 0.0 ? out[23] : 1.0;
             mse = sse / N;
             alpha = 2.0 / N;
             loss = mse;
@@ -696,12 +731,7 @@ __global__ void __launch_bounds__ (256) nn_finalize (const double* __restrict__ 
     __syncthreads ();
     const double alpha = alpha_s;
     for (int w = tid; w < n_weights; w += 256)
-    {
-        double sum = 0.0;
-        for (int64_t gidx = 0; gidx < n_groups; ++gidx)
-            sum += partials[gidx * (n_weights + 8) + w];
-        grad_w[w] = alpha * sum;
-    }
+        grad_w[w] *= alpha;
 }
 
 // Adam on a weight vector of any length (clipper_pot.py:180,269: Adam(1e-4, beta_1 = 0.5) on the network)
@@ -757,7 +787,7 @@ int64_t nn_adjoint_ctas (int64_t B, int K) { return (((B + 1) / 2) * K + 31) / 3
 // K == 1: one lane per pair (partials: nn_groups(B) vectors). K > 1: time-parallel, two phases; scratch holds
 // ceil(B/2) * K float4 (P, Q) followed by ceil(B/2) * K f2 (incoming G); partials: nn_adjoint_ctas(B, K) vectors.
 cudaError_t launch_nn_adjoint (int hidden, int n_hidden, bool pyorder, bool target, const float* x, const float* r, const float* y, const float* g, const float* ckpt, const float* params, int slot_R, int slot_C,
-                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, int K, float* scratch, cudaStream_t stream)
+                               float fs, const float* weights, int n_weights, double* partials, int skip, int64_t B, int64_t T, int K, float* scratch, float* gx, cudaStream_t stream)
 {
     const int64_t pairs = (B + 1) / 2;
     const unsigned grid = (unsigned) nn_adjoint_ctas (B, K);
@@ -773,12 +803,12 @@ cudaError_t launch_nn_adjoint (int hidden, int n_hidden, bool pyorder, bool targ
         if (e != cudaSuccess)
             return e;
         if (K == 1)
-            full<<<grid, 32, smem, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T, 1, nullptr, nullptr);
+            full<<<grid, 32, smem, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T, 1, nullptr, nullptr, gx);
         else
         {
-            phase1<<<grid, 32, smem_w, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T, K, pq, nullptr);
+            phase1<<<grid, 32, smem_w, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T, K, pq, nullptr, nullptr);
             nn_adjoint_stitch<<<(unsigned) ((pairs + 127) / 128), 128, 0, stream>>> (pq, gin, pairs, K);
-            phase2<<<grid, 32, smem, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T, K, nullptr, gin);
+            phase2<<<grid, 32, smem, stream>>> (x, r, y, g, ckpt, params, slot_R, slot_C, fs, weights, n_weights, partials, skip, B, (int) T, K, nullptr, gin, gx);
         }
         return cudaGetLastError ();
     };
@@ -800,9 +830,15 @@ cudaError_t launch_nn_adjoint (int hidden, int n_hidden, bool pyorder, bool targ
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_nn_finalize (const double* partials, int64_t n_groups, int n_weights, bool target, int loss_kind, double count, double* grad_w, double* out, cudaStream_t stream)
+cudaError_t launch_nn_reduce (const double* partials, int64_t n_groups, int n_weights, double count, double* grad_w_raw, double* raw, cudaStream_t stream)
 {
-    nn_finalize<<<1, 256, 0, stream>>> (partials, n_groups, n_weights, target ? 1 : 0, loss_kind, count, grad_w, out);
+    nn_reduce<<<(unsigned) ((n_weights + 63) / 64), 256, 0, stream>>> (partials, n_groups, n_weights, count, grad_w_raw, raw);
+    return cudaGetLastError ();
+}
+
+cudaError_t launch_nn_scale (int n_weights, bool target, int loss_kind, double* grad_w_inout, double* raw_inout, cudaStream_t stream)
+{
+    nn_scale<<<1, 256, 0, stream>>> (n_weights, target ? 1 : 0, loss_kind, grad_w_inout, raw_inout);
     return cudaGetLastError ();
 }
 

@@ -594,6 +594,20 @@ _KIND = {Resistor: L.RESISTOR, Capacitor: L.CAPACITOR, ResistiveVoltageSource: L
 _MODE = {"approx": L.MODE_APPROX, "exact": L.MODE_EXACT, "approx_good": L.MODE_APPROX_GOOD}
 
 
+_LOSS_KINDS = {"mse": L.LOSS_MSE, "mse+esr": L.LOSS_MSE_ESR, "mse+esr_as_called": L.LOSS_MSE_ESR_AS_CALLED}
+
+
+def _loss_kind(loss: str) -> int:
+    """'mse' (clipper_pot.py:176); 'mse+esr': MSE + the error-to-signal ratio as esr_loss's signature reads, normalised by the
+    TARGET's energy (clipper_pot.py:148-156,177); 'mse+esr_as_called': the same loss as the reference's training loop calls it,
+    ``loss_func(outs, train_Y)`` (clipper_pot.py:248) — the arguments are swapped there, so the energy is the PREDICTION's and
+    has a gradient of its own. The last one is what reproduces the reference's optimisation trajectory."""
+    try:
+        return _LOSS_KINDS[loss]
+    except KeyError:
+        raise ValueError(f"loss must be one of {sorted(_LOSS_KINDS)}, got {loss!r}") from None
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -883,14 +897,18 @@ class CompiledCircuit:
         g = gy if gy is not None else target
         self._check_xy(g, "gy/target", (B, T))
         if self.is_neural:
-            if want_gx or raw:
-                raise NotImplementedError("neural root: dL/dx and raw (pre-all-reduce) sums are not implemented")
             work = self._scratch("_work", self.lib.dwdf_neural_workspace_bytes(self.handle, B, T))
             if getattr(self, "grad_w", None) is None:
                 self.grad_w = torch.zeros(self.weights.numel(), dtype=torch.float64, device=self.device)
-            L.check(self.lib.dwdf_backward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), _ptr(self._ckpt), _ptr(g), L.GRAD_UPSTREAM if gy is not None else L.GRAD_TARGET,
-                                                  L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(self.grad_w), _ptr(self.out), _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
-            res = self._result(None)
+            gx = torch.empty_like(x) if want_gx else None
+            mode = L.GRAD_UPSTREAM if gy is not None else L.GRAD_TARGET
+            if raw:  # this rank's sums, before the loss's scale: all-reduce grad_w and out, then finalize()
+                L.check(self.lib.dwdf_backward_neural_raw(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), _ptr(self._ckpt), _ptr(g), mode, int(skip), _ptr(gx), _ptr(self.grad_w),
+                                                          _ptr(self.out), _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
+            else:
+                L.check(self.lib.dwdf_backward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), _ptr(self._ckpt), _ptr(g), mode, _loss_kind(loss), int(skip), _ptr(gx),
+                                                      _ptr(self.grad_w), _ptr(self.out), _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
+            res = self._result(gx)
             res["grads"] = self.grad_w
             return res
         gx = torch.empty_like(x) if want_gx else None
@@ -902,14 +920,19 @@ class CompiledCircuit:
             L.check(self.lib.dwdf_backward_raw(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), _ptr(g), mode, int(skip), _ptr(gx), _ptr(self.out), _ptr(work), work.numel(), B, T,
                                                _stream_ptr(self.device)))
         else:
-            L.check(self.lib.dwdf_backward(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), _ptr(g), mode, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(gx),
+            L.check(self.lib.dwdf_backward(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), _ptr(g), mode, _loss_kind(loss), int(skip), _ptr(gx),
                                            _ptr(self.out), _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
         return self._result(gx)
 
     @_on_device
     def finalize(self, target=True, loss="mse"):
-        """Turns the (all-reduced) raw sums in ``self.out`` into gradients and loss, in place."""
-        L.check(self.lib.dwdf_finalize(self.handle, _ptr(self.params), L.GRAD_TARGET if target else L.GRAD_UPSTREAM, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, _ptr(self.out),
+        """Turns the (all-reduced) raw sums in ``self.out`` (neural root: and ``self.grad_w``) into gradients and loss, in place."""
+        if self.is_neural:
+            L.check(self.lib.dwdf_finalize_neural(self.handle, L.GRAD_TARGET if target else L.GRAD_UPSTREAM, _loss_kind(loss), _ptr(self.grad_w), _ptr(self.out), _stream_ptr(self.device)))
+            res = self._result(None)
+            res["grads"] = self.grad_w
+            return res
+        L.check(self.lib.dwdf_finalize(self.handle, _ptr(self.params), L.GRAD_TARGET if target else L.GRAD_UPSTREAM, _loss_kind(loss), _ptr(self.out),
                                        _stream_ptr(self.device)))
         return self._result(None)
 
@@ -925,12 +948,12 @@ class CompiledCircuit:
             L.check(self.lib.dwdf_train_pass_raw(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), int(skip), _ptr(y), _ptr(self.out), _ptr(work), work.numel(), B, T,
                                                  _stream_ptr(self.device)))
         else:
-            L.check(self.lib.dwdf_train_pass(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(y), _ptr(self.out),
+            L.check(self.lib.dwdf_train_pass(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), _loss_kind(loss), int(skip), _ptr(y), _ptr(self.out),
                                              _ptr(work), work.numel(), B, T, _stream_ptr(self.device)))
         return self._result(None)
 
     @_on_device
-    def train_step(self, x, target, optimizer: "Adam", loss="mse", skip=0, out=None, comm=None):
+    def train_step(self, x, target, optimizer: "Adam", loss="mse", skip=0, out=None, comm=None, r=None):
         """forward + adjoint (fused loss) + Adam in one library call, nothing synchronises: capturable in a
         ``torch.cuda.CUDAGraph`` and replayable (small batches are launch-bound). Returns the result dict of
         ``backward`` (device tensors, overwritten by the next step). ``comm`` (a ``data_parallel.PeerComm``): x and
@@ -940,17 +963,36 @@ class CompiledCircuit:
         self._check_xy(target, "target", (B, T))
         y = torch.empty_like(x) if out is None else out
         self._check_xy(y, "out", (B, T))
+        if comm is not None and comm.device != self.device:
+            raise ValueError(f"the communicator lives on {comm.device}, the circuit on {self.device}")
+        if self.is_neural:
+            # the network's kernels and biases are the trainable variables (clipper_pot.py:246-269); optimizer: AdamWeights or None
+            if r is not None:
+                self._check_xy(r, "r", (B, T))
+            ck = self._scratch("_ckpt", self.lib.dwdf_neural_ckpt_bytes(self.handle, B, T))
+            work = self._scratch("_work", self.lib.dwdf_neural_workspace_bytes(self.handle, B, T))
+            if getattr(self, "grad_w", None) is None:
+                self.grad_w = torch.zeros(self.weights.numel(), dtype=torch.float64, device=self.device)
+            o = optimizer
+            L.check(self.lib.dwdf_train_step_neural(self.handle, comm.handle if comm is not None else None, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(target), _loss_kind(loss), int(skip), _ptr(y),
+                                                    _ptr(ck), _ptr(self.grad_w), _ptr(self.out), _ptr(work), work.numel(), _ptr(o.m) if o is not None else None, _ptr(o.v) if o is not None else None,
+                                                    _ptr(o.step_count) if o is not None else None, float(o.lr) if o is not None else 0.0, float(o.beta_1) if o is not None else 0.0,
+                                                    float(o.beta_2) if o is not None else 0.0, float(o.epsilon) if o is not None else 0.0, B, T, _stream_ptr(self.device)))
+            self._last = (x, r, y, B, T, y._version)
+            res = self._result(None)
+            res["grads"] = self.grad_w
+            return res
+        if r is not None:
+            raise ValueError("train_step takes the resistance channel for the neural root only; use forward(x, r) + backward for the analytic root")
         ck = self._scratch("_ckpt", self.lib.dwdf_ckpt_bytes(self.handle, B, T))
         work = self._scratch("_work", self.lib.dwdf_workspace_bytes(self.handle, B, T))
         o = optimizer
         if comm is not None:
-            if comm.device != self.device:
-                raise ValueError(f"the communicator lives on {comm.device}, the circuit on {self.device}")
-            L.check(self.lib.dwdf_train_step_dp(self.handle, comm.handle, _ptr(self.params), _ptr(x), None, _ptr(target), L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(y), _ptr(ck), _ptr(self.out),
+            L.check(self.lib.dwdf_train_step_dp(self.handle, comm.handle, _ptr(self.params), _ptr(x), None, _ptr(target), _loss_kind(loss), int(skip), _ptr(y), _ptr(ck), _ptr(self.out),
                                                 _ptr(work), work.numel(), _ptr(o.m), _ptr(o.v), _ptr(o.step_count), 0.0, _ptr(o.lr), float(o.beta_1), float(o.beta_2), float(o.epsilon), _ptr(self.clip_lo),
                                                 _ptr(self.clip_hi), B, T, _stream_ptr(self.device)))
         else:
-            L.check(self.lib.dwdf_train_step(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE, int(skip), _ptr(y), _ptr(ck), _ptr(self.out),
+            L.check(self.lib.dwdf_train_step(self.handle, _ptr(self.params), _ptr(x), None, _ptr(target), _loss_kind(loss), int(skip), _ptr(y), _ptr(ck), _ptr(self.out),
                                              _ptr(work), work.numel(), _ptr(o.m), _ptr(o.v), _ptr(o.step_count), 0.0, _ptr(o.lr), float(o.beta_1), float(o.beta_2), float(o.epsilon), _ptr(self.clip_lo),
                                              _ptr(self.clip_hi), B, T, _stream_ptr(self.device)))
         self._last = (x, None, y, B, T, y._version)
@@ -997,7 +1039,7 @@ class CompiledCircuit:
         if not (torch.is_tensor(out_host) and not out_host.is_cuda and out_host.dtype == torch.float64 and out_host.is_contiguous() and out_host.numel() >= L.OUT_LEN):
             raise ValueError(f"out_host must be a contiguous float64 CPU tensor of at least {L.OUT_LEN} elements")
         p = self._host_params(params_host)
-        L.check(self.lib.dwdf_grad_host(self.handle, _ptr(p), _ptr(x_host), None, _ptr(g_host), L.GRAD_TARGET if target else L.GRAD_UPSTREAM, L.LOSS_MSE_ESR if loss == "mse+esr" else L.LOSS_MSE,
+        L.check(self.lib.dwdf_grad_host(self.handle, _ptr(p), _ptr(x_host), None, _ptr(g_host), L.GRAD_TARGET if target else L.GRAD_UPSTREAM, _loss_kind(loss),
                                         int(skip), _ptr(y_host), _ptr(out_host), B, T))
         return out_host
 

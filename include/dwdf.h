@@ -144,7 +144,13 @@ enum dwdf_grad_mode
 enum dwdf_loss_kind
 {
     DWDF_LOSS_MSE = 0, /* tf.keras.losses.MeanSquaredError, clipper_pot.py:176                   */
-    DWDF_LOSS_MSE_ESR = 1 /* MSE + error-to-signal ratio, clipper_pot.py:148-156,177               */
+    DWDF_LOSS_MSE_ESR = 1, /* MSE + error-to-signal ratio as esr_loss's signature reads (clipper_pot.py:148-156,177):
+                            * sqrt(sum (y - target)^2 / (sum target^2 + eps) / N); fused in the adjoint kernels          */
+    DWDF_LOSS_MSE_ESR_AS_CALLED = 2 /* the same loss AS THE TRAINING LOOP CALLS IT: loss_func(outs, train_Y)
+                            * (clipper_pot.py:248) puts the model output into esr_loss's `target_y` slot, so the energy
+                            * is the PREDICTION's, sum y^2, and contributes its own gradient -esr y / E. Needs the batch
+                            * sums before the sweep: one reduction over (y, target) + one pass writing dL/dy + the reverse
+                            * sweep in upstream mode (DWDF_GRAD_TARGET only; not in dwdf_train_pass / dwdf_grad_host)     */
 };
 
 /* Result block written by dwdf_backward / dwdf_train_step: doubles, device (or host in *_host).
@@ -273,14 +279,23 @@ DWDF_API int dwdf_grad_host (const dwdf_program* prog, const float* params_host,
  * dwdf_backward_neural replaces tape.gradient(loss, model.trainable_variables) (clipper_pot.py:246-269;
  * the trainable variables are the network's kernels and biases): one reverse sweep over (x, y, g), the
  * network differentiated by hand per sample; grad_w receives dL/d(weights) (n_weights doubles, same layout
- * as `weights`), out[DWDF_OUT_LOSS / _MSE / _ESR] the fused loss. Implemented for the reference's shapes
+ * as `weights`), out[DWDF_OUT_LOSS / _MSE / _ESR] the fused loss, gx (NULL or (B, T) floats) dL/dx. Implemented for the reference's shapes
  * 2xH (H = 4, 8, 16) and 4xH (H = 4, 8). dwdf_adam_step_vec: Adam on a vector of any length. */
 DWDF_API size_t dwdf_mlp_weight_count (const dwdf_mlp_desc* mlp);
 DWDF_API int dwdf_program_create_neural (const dwdf_node* nodes, int32_t n_nodes, const dwdf_circuit_desc* desc, const dwdf_mlp_desc* mlp, dwdf_program** out);
 DWDF_API size_t dwdf_neural_ckpt_bytes (const dwdf_program* prog, int64_t B, int64_t T);
 DWDF_API size_t dwdf_neural_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T);
 DWDF_API int dwdf_forward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, float* y, float* state, float* z_ckpt, int64_t B, int64_t T, void* stream);
-DWDF_API int dwdf_backward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, double* grad_w, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+DWDF_API int dwdf_backward_neural (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* grad_w, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+/* Multi-GPU split, as dwdf_backward_raw / dwdf_finalize for the analytic root: the *_raw variant stops after the fixed-order
+ * batch reduction (grad_w_raw = unscaled sums over this rank's sequences, raw = the loss sums with raw[23] = samples in the
+ * loss); ranks sum both vectors (dwdf_allreduce_sum) and dwdf_finalize_neural applies the loss's scale in place.
+ * dwdf_train_step_neural is the whole step of clipper_pot.py:246-269 on the network's weights in one call: forward + reverse
+ * sweep + reduction [+ the exchange when `comm` is not NULL: x / target are then this rank's shard] + loss + Adam (m == NULL
+ * skips the update). Nothing synchronises with the host. */
+DWDF_API int dwdf_backward_neural_raw (const dwdf_program* prog, const float* params, const float* weights, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int64_t skip, float* gx, double* grad_w_raw, double* raw, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+DWDF_API int dwdf_finalize_neural (const dwdf_program* prog, int32_t grad_mode, int32_t loss_kind, double* grad_w_inout, double* raw_inout, void* stream);
+DWDF_API int dwdf_train_step_neural (const dwdf_program* prog, const dwdf_comm* comm, const float* params, float* weights, const float* x, const float* r, const float* target, int32_t loss_kind, int64_t skip, float* y, float* z_ckpt, double* grad_w, double* out, void* workspace, size_t workspace_bytes, float* m, float* v, int32_t* step, float lr, float beta1, float beta2, float eps, int64_t B, int64_t T, void* stream);
 DWDF_API int dwdf_adam_step_vec (float* w, const double* grad, float* m, float* v, int32_t* step, int64_t n, float lr, float beta1, float beta2, float eps, double grad_scale, void* stream);
 
 /* Streaming twin of DiodeClipperWDF::{prepare, process} (DiodeClipperWDF.cpp:3-30): like

@@ -66,15 +66,15 @@ def nn_clipper_forward(x, weights, sizes, fs, R, C, ordering=ORDER_PYTHON, r=Non
     return y
 
 
-def nn_clipper_grad_torch(x, target, weights, sizes, fs, R, C, ordering=ORDER_PYTHON, r=None, loss="mse", skip=0, gy=None):
+def nn_clipper_grad_torch(x, target, weights, sizes, fs, R, C, ordering=ORDER_PYTHON, r=None, loss="mse", skip=0, gy=None, want_gx=False):
     """Gradient oracle: the same recurrence in fp64 PyTorch, differentiated by autograd (what tf.GradientTape
     does for clipper_pot.py:246-269; trainable variables = the network's kernels and biases, :268).
     Loss: MSE [+ ESR, clipper_pot.py:148-156,177] on samples >= skip (:232,248), or sum(gy * y) when gy is given.
-    Returns dict(y, loss, mse, esr, grad_w (flat, same layout as weights))."""
+    Returns dict(y, loss, mse, esr, grad_w (flat, same layout as weights)[, gx = dL/dx])."""
     import torch
 
     dt = torch.float64
-    xt = torch.as_tensor(np.asarray(x), dtype=dt)
+    xt = torch.tensor(np.asarray(x, np.float64), dtype=dt, requires_grad=bool(want_gx))
     B, T = xt.shape
     w = torch.tensor(np.asarray(weights, np.float64), dtype=dt, requires_grad=True)
     layers, k = [], 0
@@ -122,4 +122,6 @@ def nn_clipper_grad_torch(x, target, weights, sizes, fs, R, C, ordering=ORDER_PY
         out.update(loss=float(L.detach()), mse=float(mse.detach()), esr=float(esr.detach()))
     L.backward()
     out["grad_w"] = w.grad.numpy().copy()
+    if want_gx:
+        out["gx"] = xt.grad.numpy().copy()
     return out

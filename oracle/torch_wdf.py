@@ -326,7 +326,10 @@ def clipper_forward(x, p: _cpu.ClipperParams = _cpu.ClipperParams(), mode="exact
 
 
 def mse_esr_loss(target, pred, with_esr=True):
-    """clipper_pot.py:141-156,176-177: MeanSquaredError + esr_loss (eps = float64 eps, :145)."""
+    """clipper_pot.py:141-156,176-177: MeanSquaredError + esr_loss (eps = float64 eps, :145), arguments in esr_loss's own
+    order: the energy is the FIRST argument's. The reference's training loop calls ``loss_func(outs, train_Y)`` (:248), i.e.
+    with the model output first — ``mse_esr_loss(outs, train_Y)`` restates that call (DWDF_LOSS_MSE_ESR_AS_CALLED),
+    ``mse_esr_loss(train_Y, outs)`` the textbook error-to-signal ratio (DWDF_LOSS_MSE_ESR)."""
     mse = torch.mean((target - pred) ** 2)
     if not with_esr:
         return mse

@@ -77,7 +77,7 @@ def _worker(rank, world, port, B, T, steps, loss, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B,T,loss", [(8192, 512, "mse"), (333, 1024, "mse+esr")])
+@pytest.mark.parametrize("B,T,loss", [(8192, 512, "mse"), (333, 1024, "mse+esr"), (200, 512, "mse+esr_as_called")])
 def test_two_rank_sharded_step_equals_unsharded(B, T, loss):
     import torch.multiprocessing as mp
 
@@ -105,3 +105,78 @@ def test_two_rank_sharded_step_equals_unsharded(B, T, loss):
     want = np.arange(700, dtype=np.float64) * 3
     np.testing.assert_array_equal(v0, want)
     np.testing.assert_array_equal(v1, want)
+
+
+def _worker_nn(rank, world, port, B, T, steps, loss, q):
+    import importlib
+    import os as _os
+
+    import torch.distributed as dist
+
+    from conftest import GOLDEN, make_inputs
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dwdf = importlib.import_module("differentiable-wdfs_b200")
+    device = torch.device("cuda", rank % torch.cuda.device_count())
+    torch.cuda.set_device(device)
+    nnv = np.load(_os.path.join(GOLDEN, "nn_vectors.npz"))
+    mj = dwdf.model_io.json_from_weights(nnv["2x8_weights"], [int(v) for v in nnv["2x8_sizes"]])
+
+    def build():
+        Vs = dwdf.ResistiveVoltageSource(47000.0)
+        Cc = dwdf.Capacitor(2.2e-9, 48000.0)
+        circ = dwdf.compile_circuit(dwdf.DenseRootModel(mj), tree=dwdf.Parallel(Vs, Cc), probe=Cc, ordering="python", device=device)
+        return circ, dwdf.AdamWeights(circ, lr=1e-3, beta_1=0.5)
+
+    x = make_inputs(B, T, seed=78)
+    target = (0.5 * np.tanh(2.0 * x)).astype(np.float32)
+    lo, hi = dwdf.shard_rows(B, world, rank)
+    xs, ts = torch.from_numpy(x[lo:hi]).to(device), torch.from_numpy(target[lo:hi]).to(device)
+    comm = dwdf.PeerComm(device)
+    circ, opt = build()
+    hist = []
+    for _ in range(steps):
+        res = circ.train_step(xs, ts, opt, loss=loss, skip=20, comm=comm)
+        hist.append((res["out"][16:19].cpu().numpy().copy(), res["grads"].cpu().numpy().copy(), circ.weights.cpu().numpy().copy()))
+    torch.cuda.synchronize()
+    ref = None
+    if rank == 0:
+        c1, o1 = build()
+        xa, ta = torch.from_numpy(x).to(device), torch.from_numpy(target).to(device)
+        ref = []
+        for _ in range(steps):
+            r1 = c1.train_step(xa, ta, o1, loss=loss, skip=20)
+            ref.append((r1["out"][16:19].cpu().numpy().copy(), r1["grads"].cpu().numpy().copy(), c1.weights.cpu().numpy().copy()))
+    q.put((rank, hist, ref))
+    dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("loss", ["mse+esr", "mse+esr_as_called"])
+def test_two_rank_neural_root_step_equals_unsharded(loss):
+    """The root the reference actually trains (clipper_pot.py:246-269: the network's weights), sharded over two ranks: raw
+    weight-gradient sums and loss sums exchanged over peer memory inside dwdf_train_step_neural."""
+    import torch.multiprocessing as mp
+
+    world, steps, B, T = 2, 3, 50, 400
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_nn, args=(r, world, port, B, T, steps, loss, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=300) for _ in range(world)], key=lambda o: o[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, h0, ref), (_, h1, _) = out
+    for s in range(steps):
+        for k in range(3):
+            np.testing.assert_array_equal(h0[s][k], h1[s][k])  # identical bits on both ranks
+        np.testing.assert_allclose(h0[s][0], ref[s][0], rtol=1e-6)
+        scale = np.max(np.abs(ref[s][1]))
+        assert np.max(np.abs(h0[s][1] - ref[s][1])) < 3e-5 * scale
+        np.testing.assert_allclose(h0[s][2], ref[s][2], rtol=2e-5, atol=1e-7)

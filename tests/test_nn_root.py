@@ -239,3 +239,55 @@ def test_time_parallel_adjoint_equals_serial(dwdf, nnv, name, ordering):
     assert np.max(np.abs(g_tp - g_se)) < 2e-5 * np.max(np.abs(g_se)) and abs(l_tp / l_se - 1) < 1e-5
     ref = nn.nn_clipper_grad_torch(xn, target, w, sizes, 48000.0, 47000.0, 2.2e-9, order, loss="mse+esr", skip=50)
     assert np.max(np.abs(g_tp - ref["grad_w"])) < NN_GRAD_TOL * np.max(np.abs(ref["grad_w"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ordering,order", [("plugin", nn.ORDER_PLUGIN), ("python", nn.ORDER_PYTHON)])
+@pytest.mark.parametrize("with_r", [False, True])
+@pytest.mark.parametrize("T", [150, 1100], ids=["one_lane_per_pair", "time_parallel"])
+def test_dl_dx_against_autograd(dwdf, nnv, ordering, order, with_r, T):
+    """dL/dx of the neural-root circuit (what tape.gradient would feed to a layer in front of the clipper) against
+    fp64 autograd, on both adjoint kernels (the long sequences run the two-phase time-parallel one)."""
+    B = 6
+    x = make_inputs(B, T, seed=33)
+    gy = np.random.default_rng(5).standard_normal((B, T)).astype(np.float32)
+    r = None
+    if with_r:
+        r = (np.random.default_rng(6).uniform(1e4, 1e5, (B, 1)) * np.ones((1, T))).astype(np.float32)
+        r[:, T // 3:] *= 1.5
+    w, sizes = nnv["2x8_weights"], [int(v) for v in nnv["2x8_sizes"]]
+    circ = make_circuit(dwdf, model_json(dwdf, nnv, "2x8"), ordering, with_r=with_r)
+    circ.forward(torch.from_numpy(x).cuda(), r=None if r is None else torch.from_numpy(r).cuda())
+    res = circ.backward(gy=torch.from_numpy(gy).cuda(), want_gx=True)
+    ref = nn.nn_clipper_grad_torch(x, None, w, sizes, 48000.0, 47000.0, 2.2e-9, order, r=r, gy=gy, want_gx=True)
+    gx = res["gx"].cpu().numpy()
+    assert np.max(np.abs(gx - ref["gx"])) < 1e-4 * np.max(np.abs(ref["gx"]))
+    assert np.max(np.abs(res["grads"].cpu().numpy() - ref["grad_w"])) < NN_GRAD_TOL * np.max(np.abs(ref["grad_w"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("loss", ["mse", "mse+esr"])
+def test_raw_sums_finalize_and_one_call_step(dwdf, nnv, loss):
+    """The multi-GPU split (raw sums -> [all-reduce] -> finalize) equals the fused call, and dwdf_train_step_neural equals
+    forward + backward + Adam on the weights."""
+    x = torch.from_numpy(make_inputs(40, 300, seed=41)).cuda()
+    target = (0.6 * torch.tanh(2.0 * x)).contiguous()
+    mj = model_json(dwdf, nnv, "2x8")
+    a = make_circuit(dwdf, mj, "python")
+    a.forward(x)
+    ra = a.backward(target=target, loss=loss, skip=50)
+    ga, outa = ra["grads"].clone(), ra["out"].clone()
+    b = make_circuit(dwdf, mj, "python")
+    b.forward(x)
+    b.backward(target=target, skip=50, raw=True)
+    assert float(b.out[23]) == 40 * 250
+    rb = b.finalize(target=True, loss=loss)
+    assert torch.equal(rb["grads"], ga) and torch.equal(rb["out"][16:19], outa[16:19])
+    # one-call step
+    opt_a = dwdf.AdamWeights(a, lr=1e-3, beta_1=0.5)
+    opt_a.apply()
+    c = make_circuit(dwdf, mj, "python")
+    opt_c = dwdf.AdamWeights(c, lr=1e-3, beta_1=0.5)
+    rc = c.train_step(x, target, opt_c, loss=loss, skip=50)
+    assert torch.equal(rc["grads"], ga) and torch.equal(rc["out"][16:19], outa[16:19])
+    assert torch.equal(c.weights, a.weights) and int(opt_c.step_count) == 1
