@@ -321,10 +321,37 @@ def other_paths(torch, dwdf, device, x, target):
                 out[f"neural_root_{name}_fwd_bwd"] = {"value": xs.numel() / timed(lambda: fwd_bwd(cn, xs, ts), reps=2), "unit": UNIT, "B": b, "T": T}
                 if name == "2x16":  # the reference's largest network at the headline batch (one lane per pair of sequences)
                     out["neural_root_2x16_fwd_bwd_B65536"] = {"value": x.numel() / timed(lambda: fwd_bwd(cn, x, target), reps=2), "unit": UNIT, "B": x.shape[0], "T": T}
-        # the generic tree interpreter on lpf.py's circuit (IdealVoltageSource root, Inverter(Series(R, C)), probe C)
-        R1, C1 = dwdf.Resistor(1000.0, True), dwdf.Capacitor(1.0e-6, FS, True)
-        ct = dwdf.compile_circuit(dwdf.IdealVoltageSource(), tree=dwdf.Inverter(dwdf.Series(R1, C1)), probe=C1, device=device)
-        out["tree_interpreter_rc_lowpass_fwd_bwd"] = {"value": x.numel() / timed(lambda: fwd_bwd(ct, x, target), reps=2), "unit": UNIT, "B": x.shape[0], "T": T}
+        # tree programs. lpf.py's circuit (IdealVoltageSource root, Inverter(Series(R, C)), probe C) and the plugin's HPF clipper
+        # (HPFDiodeClipper.h:25-37: Parallel(R, Series(Vs, C)) + DiodePair): run-time specialised kernels (dwdf_program_specialize:
+        # generated straight-line source, NVRTC, TMA tiles, no tape) and, on a slice, the node-list interpreter beside them
+        try:
+            def lpf():
+                R1, C1 = dwdf.Resistor(1000.0, True), dwdf.Capacitor(1.0e-6, FS, True)
+                return dwdf.compile_circuit(dwdf.IdealVoltageSource(), tree=dwdf.Inverter(dwdf.Series(R1, C1)), probe=C1, device=device)
+
+            def hpf(mode):
+                Vs, Ch, Rh = dwdf.ResistiveVoltageSource(4700.0, True), dwdf.Capacitor(2.2e-9, FS, True), dwdf.Resistor(47000.0, True)
+                dph = dwdf.DiodePair(dwdf.Parallel(Rh, dwdf.Series(Vs, Ch)), 4.352e-9, 25.85e-3, 1.906, trainable=True, mode=mode)
+                return dwdf.compile_circuit(dph, probe=Ch, ordering="plugin", device=device)
+
+            xi, ti = x[:4096].contiguous(), target[:4096].contiguous()
+            for key, make in (("rc_lowpass", lpf), ("hpf_clipper_approx", lambda: hpf("approx")), ("hpf_clipper_exact", lambda: hpf("exact"))):
+                ct = make()
+                t0 = time.perf_counter()
+                spec = ct.specialize(quiet=True)
+                t_spec = time.perf_counter() - t0
+                entry = {"unit": UNIT, "B": x.shape[0], "T": T, "specialised": bool(spec), "specialise_s": t_spec}
+                if spec:
+                    entry["forward"] = x.numel() / timed(lambda: ct.forward(x, keep_for_backward=False), reps=2)
+                    entry["value"] = x.numel() / timed(lambda: fwd_bwd(ct, x, target), reps=2)
+                    entry["what"] = "forward + reverse mode (fused MSE), specialised kernels; 'forward' = inference alone"
+                ci = make()
+                ci._specialize_error = RuntimeError("interpreter wanted")  # keep this copy on the node-list interpreter
+                entry["interpreter_value"] = xi.numel() / timed(lambda: fwd_bwd(ci, xi, ti), reps=1)
+                entry["interpreter_B"] = int(xi.shape[0])
+                out[f"tree_{key}_fwd_bwd"] = entry
+        except Exception as e:
+            out["tree_error"] = repr(e)
     except Exception as e:  # the headline line must not depend on these
         out["error"] = repr(e)
     return out

@@ -31,6 +31,7 @@ SYMBOLS = (
     "dwdf_backward_raw", "dwdf_train_pass_raw", "dwdf_finalize", "dwdf_mlp_weight_count", "dwdf_program_create_neural", "dwdf_forward_neural", "dwdf_backward_neural", "dwdf_neural_ckpt_bytes", "dwdf_neural_workspace_bytes", "dwdf_adam_step_vec", "dwdf_last_error", "dwdf_build_info", "dwdf_train_step", "dwdf_launch_count", "dwdf_set_tma", "dwdf_set_option", "dwdf_time_parallel_redone",
     "dwdf_comm_create", "dwdf_comm_handle_bytes", "dwdf_comm_get_handle", "dwdf_comm_connect", "dwdf_comm_set_timeout", "dwdf_comm_destroy", "dwdf_allreduce_sum", "dwdf_train_step_dp", "dwdf_profile_begin", "dwdf_profile_end",
     "dwdf_backward_neural_raw", "dwdf_finalize_neural", "dwdf_train_step_neural",
+    "dwdf_program_specialize", "dwdf_program_is_specialized", "dwdf_program_specialized_source",
 )
 
 
@@ -73,6 +74,10 @@ def lib() -> C.CDLL:
     L.dwdf_program_destroy.argtypes = [vp]
     L.dwdf_program_is_clipper.argtypes = [vp]
     L.dwdf_program_n_states.argtypes = [vp]
+    L.dwdf_program_specialize.argtypes = [vp]
+    L.dwdf_program_is_specialized.argtypes = [vp]
+    L.dwdf_program_specialized_source.argtypes = [vp, i32, C.c_char_p, sz]
+    L.dwdf_program_specialized_source.restype = sz
     L.dwdf_ckpt_bytes.argtypes = [vp, i64, i64]
     L.dwdf_ckpt_bytes.restype = sz
     L.dwdf_workspace_bytes.argtypes = [vp, i64, i64]

@@ -3,6 +3,7 @@
 // the extern "C" surface of include/dwdf.h. No torch, no Python: plain C++ over the CUDA runtime.
 #include "../../include/dwdf.h"
 #include "dwdf_kernels.h"
+#include "tree_jit.h"
 
 #include <atomic>
 #include <cstdarg>
@@ -29,6 +30,8 @@ struct dwdf_program
     ClipVariant variant {};
     TreeProgram tree {};
     int n_states = 0;
+    TreeJit* jit = nullptr; // run-time specialised kernels of a tree program (dwdf_program_specialize), else the interpreter
+    ~dwdf_program () { tree_jit_destroy (jit); }
 };
 
 namespace
@@ -590,12 +593,60 @@ int dwdf_program_destroy (dwdf_program* prog)
 int dwdf_program_is_clipper (const dwdf_program* prog) { return prog != nullptr && prog->is_clipper ? 1 : 0; }
 int dwdf_program_n_states (const dwdf_program* prog) { return prog == nullptr ? 0 : ((prog->is_clipper || prog->is_neural) ? 1 : prog->n_states + 1); }
 
+// ---- run-time specialisation of tree programs (tree_jit.cu) ------------------------------------------------------------
+int dwdf_program_specialize (dwdf_program* prog)
+{
+    if (prog == nullptr)
+        return fail (DWDF_ERR_INVALID, "null argument");
+    if (prog->jit != nullptr)
+        return DWDF_OK;
+    if (prog->is_clipper || prog->is_neural)
+        return fail (DWDF_ERR_UNSUPPORTED, "the program already runs on kernels written for its circuit (diode clipper / neural root)");
+    std::string err;
+    TreeJit* j = tree_jit_create (prog->tree, err);
+    if (j == nullptr)
+        return fail (DWDF_ERR_UNSUPPORTED, "%s", err.c_str ());
+    if (! tree_jit_load (j, err))
+    {
+        tree_jit_destroy (j);
+        return fail (DWDF_ERR_CUDA, "%s", err.c_str ());
+    }
+    prog->jit = j;
+    return DWDF_OK;
+}
+
+int dwdf_program_is_specialized (const dwdf_program* prog) { return prog != nullptr && prog->jit != nullptr ? 1 : 0; }
+
+size_t dwdf_program_specialized_source (const dwdf_program* prog, int32_t part, char* buf, size_t capacity)
+{
+    if (prog == nullptr || prog->is_clipper || prog->is_neural || part < 0 || part > 2)
+        return 0;
+    std::string src;
+    if (part == 0)
+    {
+        if (! tree_jit_supported (prog->tree))
+            return 0;
+        src = tree_jit_full_source (prog->tree);
+    }
+    else
+        src = tree_jit_header (part - 1);
+    if (buf != nullptr && capacity > 0)
+    {
+        const size_t n = src.size () < capacity - 1 ? src.size () : capacity - 1;
+        std::memcpy (buf, src.data (), n);
+        buf[n] = '\0';
+    }
+    return src.size () + 1;
+}
+
 size_t dwdf_ckpt_bytes (const dwdf_program* prog, int64_t B, int64_t T)
 {
     if (prog == nullptr || B <= 0 || T <= 0)
         return 0;
     if (prog->is_clipper)
         return (size_t) (n_segments (T) * B) * sizeof (float);
+    if (prog->jit != nullptr) // specialised tree: every state (and the probe's incident wave) at each segment start
+        return (size_t) (n_segments (T) * B) * (size_t) (prog->n_states + 1) * sizeof (float);
     return 16; // the interpreter's adjoint keeps its own tape in the workspace
 }
 
@@ -606,7 +657,7 @@ size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
     size_t bytes = partials_bytes (B);
     if (prog->is_clipper)
         bytes += adj_maps_bytes (B, T); // affine maps of the adjoint's time chunks (small batches)
-    if (! prog->is_clipper) // per-sample tape of the interpreter adjoint: (n_states + 1) floats per sample
+    if (! prog->is_clipper && prog->jit == nullptr) // per-sample tape of the interpreter adjoint: (n_states + 1) floats per sample (the specialised kernels keep none)
         bytes += (size_t) B * (size_t) T * (size_t) (prog->n_states + 1) * sizeof (float);
     return bytes;
 }
@@ -660,6 +711,14 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
                 z_ckpt = scratch.p + 2 * zfloats;
         }
         DWDF_CUDA (launch_clipper_forward (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, state, B, T, stream));
+    }
+    else if (prog->jit != nullptr)
+    { // run-time specialised kernels (tree_jit.cu): TMA tiles when the rows allow it, else a lane walks its own row
+        CUtensorMap mx, my;
+        const bool tma = tma_usable (x, y, nullptr, B, T) && make_map (&mx, x, B, T, 32) && make_map (&my, y, B, T, 32);
+        std::string err;
+        if (! tree_jit_forward (prog->jit, tma ? &mx : nullptr, tma ? &my : nullptr, params, x, y, z_ckpt, state, B, T, stream, err))
+            return fail (DWDF_ERR_CUDA, "specialised tree kernel: %s", err.c_str ());
     }
     else
     {
@@ -764,8 +823,21 @@ static int backward_impl (int raw_only, const dwdf_program* prog, const float* p
             return fail (DWDF_ERR_UNSUPPORTED, "dL/dx is available for the diode-clipper program only");
         if ((prog->desc.r_node >= 0) != (r != nullptr))
             return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
-        float* tape = (float*) ((char*) workspace + (((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256) * 256);
-        DWDF_CUDA (launch_tree_adjoint (prog->tree, params, x, r, gy_or_target, target, sk, partials, tape, B, T, stream));
+        if (prog->jit != nullptr)
+        { // specialised reverse sweep: no tape; replays 16-sample segments from the checkpoints the specialised forward wrote
+            if (z_ckpt == nullptr)
+                return fail (DWDF_ERR_INVALID, "a specialised tree program differentiates from the checkpoints of dwdf_forward (z_ckpt, dwdf_ckpt_bytes): z_ckpt is null");
+            CUtensorMap mx, mg;
+            const bool tma = tma_usable (x, gy_or_target, nullptr, B, T) && make_map (&mx, x, B, T, kSeg) && make_map (&mg, gy_or_target, B, T, kSeg);
+            std::string err;
+            if (! tree_jit_adjoint (prog->jit, tma ? &mx : nullptr, tma ? &mg : nullptr, params, x, gy_or_target, z_ckpt, target, (int) sk, partials, B, T, stream, err))
+                return fail (DWDF_ERR_CUDA, "specialised tree kernel: %s", err.c_str ());
+        }
+        else
+        {
+            float* tape = (float*) ((char*) workspace + (((size_t) n_groups (B) * kTreePartialStride * sizeof (double) + 255) / 256) * 256);
+            DWDF_CUDA (launch_tree_adjoint (prog->tree, params, x, r, gy_or_target, target, sk, partials, tape, B, T, stream));
+        }
         DWDF_CUDA (launch_tree_finalize (prog->tree, params, partials, n_groups (B), nullptr, raw_only != 0, target, loss_kind, count, out, stream));
     }
     g_launches.fetch_add (2);

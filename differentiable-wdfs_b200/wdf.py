@@ -787,6 +787,8 @@ class CompiledCircuit:
                 L.check(self.lib.dwdf_program_create(arr, len(nodes), C.byref(d), C.byref(handle)))
         self.handle = handle
         self.is_clipper = bool(self.lib.dwdf_program_is_clipper(handle))
+        self.is_specialized = False  # tree programs: run-time specialised kernels instead of the interpreter (specialize())
+        self._specialize_error = None
         self.n_states = int(self.lib.dwdf_program_n_states(handle))
         self.params = torch.tensor(values, dtype=torch.float32, device=self.device)
         self.trainable = sorted(s for (eid, _), s in self.slots.items() if getattr(self._owner(eid), "trainable", False))
@@ -823,6 +825,36 @@ class CompiledCircuit:
 
     def slot(self, element, attr) -> int:
         return self.slots[(id(element), attr)]
+
+    # ---- run-time specialisation of tree programs ----------------------------------------------------
+    AUTO_SPECIALIZE_SAMPLES = 1 << 20  # forward() / train_step() specialise a tree program on their own from this batch size on
+
+    @_on_device
+    def specialize(self, quiet=False) -> bool:
+        """Generates, compiles (NVRTC, about a second) and loads kernels written for THIS circuit (dwdf_program_specialize):
+        straight-line wave arithmetic with every state in registers, TMA-tiled data movement, reverse mode without a tape.
+        Trees the specialiser does not cover (alpha-transform / Y-parameter / current-source elements, diode / switch roots,
+        current probe, resistance channel) keep running on the interpreter: returns False (or raises unless ``quiet``)."""
+        if self.is_specialized:
+            return True
+        if self.is_clipper or self.is_neural:
+            return False
+        if self._specialize_error is None:
+            try:
+                L.check(self.lib.dwdf_program_specialize(self.handle))
+                self.is_specialized = True
+                self._last = None  # a forward pass of the interpreter left no checkpoints for the specialised reverse sweep
+                self._ckpt = self._work = None
+                return True
+            except L.DwdfError as e:
+                self._specialize_error = e
+        if not quiet:
+            raise self._specialize_error
+        return False
+
+    def _maybe_specialize(self, B, T):
+        if not (self.is_clipper or self.is_neural or self.is_specialized) and self._specialize_error is None and B * T >= self.AUTO_SPECIALIZE_SAMPLES:
+            self.specialize(quiet=True)
 
     # ---- buffers -------------------------------------------------------------------------------
     def _check_xy(self, x, name="x", shape=None):
@@ -867,8 +899,9 @@ class CompiledCircuit:
             L.check(self.lib.dwdf_forward_neural(self.handle, _ptr(self.params), _ptr(self.weights), _ptr(x), _ptr(r), _ptr(y), None, _ptr(ck), B, T, _stream_ptr(self.device)))
             self._last = (x, r, y, B, T, y._version) if keep_for_backward else None
             return y
+        self._maybe_specialize(B, T)
         ck = None
-        if keep_for_backward and self.is_clipper and B * T > 0:
+        if keep_for_backward and (self.is_clipper or self.is_specialized) and B * T > 0:
             ck = self._scratch("_ckpt", self.lib.dwdf_ckpt_bytes(self.handle, B, T))
         L.check(self.lib.dwdf_forward(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), B, T, _stream_ptr(self.device)))
         self._last = (x, r, y, B, T, y._version) if keep_for_backward else None
@@ -914,7 +947,7 @@ class CompiledCircuit:
         gx = torch.empty_like(x) if want_gx else None
         nbytes = self.lib.dwdf_workspace_bytes(self.handle, B, T)
         work = self._scratch("_work", nbytes)
-        ck = self._ckpt if self.is_clipper else None
+        ck = self._ckpt if (self.is_clipper or self.is_specialized) else None
         mode = L.GRAD_UPSTREAM if gy is not None else L.GRAD_TARGET
         if raw:
             L.check(self.lib.dwdf_backward_raw(self.handle, _ptr(self.params), _ptr(x), _ptr(r), _ptr(y), _ptr(ck), _ptr(g), mode, int(skip), _ptr(gx), _ptr(self.out), _ptr(work), work.numel(), B, T,
@@ -984,6 +1017,7 @@ class CompiledCircuit:
             return res
         if r is not None:
             raise ValueError("train_step takes the resistance channel for the neural root only; use forward(x, r) + backward for the analytic root")
+        self._maybe_specialize(B, T)
         ck = self._scratch("_ckpt", self.lib.dwdf_ckpt_bytes(self.handle, B, T))
         work = self._scratch("_work", self.lib.dwdf_workspace_bytes(self.handle, B, T))
         o = optimizer

@@ -175,6 +175,22 @@ DWDF_API int dwdf_program_destroy (dwdf_program* prog);
 /* 1 if the program runs on the specialised diode-clipper kernels, 0 if on the tree interpreter. */
 DWDF_API int dwdf_program_is_clipper (const dwdf_program* prog);
 
+/* Run-time specialisation of a tree program (any tree that is not the diode clipper). The interpreter sweeps a node list
+ * per sample; dwdf_program_specialize instead generates straight-line CUDA source for THIS circuit (one scalar per wave,
+ * the reverse-mode step derived node by node), compiles it with NVRTC for sm_100a and loads it: the same entry points
+ * then run TMA-tiled kernels with every state in registers, and reverse mode keeps no tape (16-sample segments replayed
+ * from state checkpoints that dwdf_forward writes to z_ckpt; dwdf_ckpt_bytes / dwdf_workspace_bytes change accordingly, so
+ * query them after specialising, and run dwdf_forward again before dwdf_backward). Covers Resistor, ResistiveVoltageSource,
+ * Capacitor, Inductor, Series, Parallel, Inverter with an IdealVoltageSource or DiodePair root and a voltage probe, no
+ * resistance channel; DWDF_ERR_UNSUPPORTED otherwise (or without libnvrtc) and the program stays on the interpreter.
+ * Compiles for about a second; not to be called concurrently with launches of the same program or inside a stream capture.
+ * dwdf_program_specialized_source: the text handed to NVRTC (part 0: generated circuit code + kernel skeleton; 1, 2: the
+ * two embedded headers it includes, dwdf_math.cuh and dwdf_tma.cuh); returns the size needed including the terminator
+ * (0: not a specialisable tree) and copies at most `capacity` bytes. Needs no device: the CPU test-suite compiles it. */
+DWDF_API int dwdf_program_specialize (dwdf_program* prog);
+DWDF_API int dwdf_program_is_specialized (const dwdf_program* prog);
+DWDF_API size_t dwdf_program_specialized_source (const dwdf_program* prog, int32_t part, char* buf, size_t capacity);
+
 /* Floats of streaming state per sequence for dwdf_process_block: 1 for the diode-clipper program
  * (its capacitor), number of capacitors + 1 (the probe's last incident wave) for other trees. */
 DWDF_API int dwdf_program_n_states (const dwdf_program* prog);
