@@ -43,8 +43,13 @@ BYTES_FWD, BYTES_ADJ = 8, 8
 # measured DRAM traffic per sample (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at
 # B = 65536, T = 4096; the file named in TRAFFIC_SOURCE). The adjoint also reads the forward output y (4 B/sample):
 # that read replaces the replay of the forward recurrence.
-TRAFFIC_FWD, TRAFFIC_ADJ = 2.166901e9 / (65536 * 4096), 3.293523e9 / (65536 * 4096)
-TRAFFIC_SOURCE = "ncu --set full, profiles/r01_d_ncu_full_summary.txt (bytes per sample x samples per launch)"
+TRAFFIC_FWD, TRAFFIC_ADJ = (1.073804e9 + 1.093476e9) / (65536 * 4096), (3.289196e9 + 0.003737e9) / (65536 * 4096)
+TRAFFIC_SOURCE = "ncu --set full, round 2: profiles/r02_c_ncu_forward_summary.txt, profiles/r02_d_ncu_adjoint_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch at 65536 x 4096)"
+# fp32 side of the roofline (op-counted algorithmic flops per sample; the roof is the MEASURED FFMA issue rate,
+# tools/micro/ffma2_bench.cu on this pool's B200: 120.8 fma lanes/clk/SM x 2 x 148 SMs x 1.965 GHz)
+FLOPS = {"approx": (70, 130), "exact": (190, 260)}  # (forward, adjoint)
+FP32_PEAK_TFLOPS = 70.3
+FP32_PEAK_SOURCE = "measured FFMA / FFMA2 issue rate, profiles/r02_d_ffma2_microbench.txt (nominal 128 lanes/clk/SM: 74.4)"
 
 
 def measured_peak_gbs():
@@ -370,6 +375,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the brief timings of the other paths (exact root, small batches, neural root)")
+    ap.add_argument("--opts", type=int, default=0, help="development: dwdf_set_option bits for A/B timing (0 = shipped behaviour; recorded in config when set)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -379,6 +385,8 @@ def main():
     import torch.distributed as dist
 
     dwdf = importlib.import_module("differentiable-wdfs_b200")
+    if args.opts:
+        dwdf.set_option(args.opts)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -585,6 +593,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": dom_traffic * B * T if (args.mode == "approx" and B == 65536) else None, "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": dom_bytes, "kernel_ms": dom_ms, "timing": f"CUDA events at the kernel boundaries inside the timed region, mean of {n_prof} steps (dwdf_profile_begin/_end)",
+                         "fp32": {"what": "second roof (SURVEY.md §8d): algorithmic flops per sample / kernel time against the measured fp32 FMA issue rate; pipe utilisations from ncu are in profiles/r02_*_ncu_*_summary.txt",
+                                  "algorithmic_flops_per_sample": {"forward": FLOPS[args.mode][0], "adjoint": FLOPS[args.mode][1]}, "peak_TFLOPs": FP32_PEAK_TFLOPS, "peak_source": FP32_PEAK_SOURCE,
+                                  "kernel_TFLOPs": (FLOPS[args.mode][1] if dom == "clipper_adjoint_tma" else FLOPS[args.mode][0]) * B * T / (dom_ms * 1e-3) / 1e12 if dom_ms else None,
+                                  "kernel_frac": (FLOPS[args.mode][1] if dom == "clipper_adjoint_tma" else FLOPS[args.mode][0]) * B * T / (dom_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS if dom_ms else None,
+                                  "step_TFLOPs": sum(FLOPS[args.mode]) * B * T / ((fwd_ms + adj_ms + tail_ms) * 1e-3) / 1e12 if n_prof else None,
+                                  "step_frac": sum(FLOPS[args.mode]) * B * T / ((fwd_ms + adj_ms + tail_ms) * 1e-3) / 1e12 / FP32_PEAK_TFLOPS if n_prof else None},
                          "step": {"forward_ms": fwd_ms, "adjoint_ms": adj_ms, "tail_ms": tail_ms, "bytes_per_sample": BYTES_FWD + BYTES_ADJ,
                                   "achieved_GBs": step_bytes / ((fwd_ms + adj_ms + tail_ms) * 1e-3) / 1e9 if n_prof else None,
                                   "frac": step_bytes / ((fwd_ms + adj_ms + tail_ms) * 1e-3) / 1e9 / peak if n_prof else None}},

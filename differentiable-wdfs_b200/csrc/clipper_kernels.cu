@@ -143,21 +143,23 @@ struct ChunkPlan
     int Wt; // warm-up tiles
 };
 
-__device__ __forceinline__ int warmup_samples_raw (const ClipConst& c)
+__device__ __forceinline__ int warmup_samples_raw (const ClipConst& c, int opts)
 {
     // off-state contraction per sample: dz'/dz = 1 - 2 gamma (f' = 1). (1 - 2 gamma)^W <= 1e-13: far enough below
-    // one ulp of a quiet signal that the speculated and the true trajectory have merged bit for bit
+    // one ulp of a quiet signal that the speculated and the true trajectory have merged bit for bit. (A/B switches:
+    // 1e-10 / 1e-8 — shorter warm-ups, more chunks for the verification pass to repair; the result is the same bits.)
     const float rho = fmaxf (fabsf (1.0f - 2.0f * c.gamma), 0.5f);
-    const float w = -29.9f / logf (fminf (rho, 0.999999f));
+    const float lnthr = (opts & kOptWarm8) ? 18.4f : ((opts & kOptWarm10) ? 23.0f : 29.9f);
+    const float w = -lnthr / logf (fminf (rho, 0.999999f));
     return (int) fminf (w, 1.0e6f);
 }
 
-__device__ __forceinline__ ChunkPlan plan_chunks (const ClipConst& c, int ntiles, int kmax)
+__device__ __forceinline__ ChunkPlan plan_chunks (const ClipConst& c, int ntiles, int kmax, int opts)
 {
     ChunkPlan p { ntiles, 1, 0 };
     if (kmax > 1)
     {
-        p.Wt = (warmup_samples_raw (c) + kFwdTileT - 1) / kFwdTileT;
+        p.Wt = (warmup_samples_raw (c, opts) + kFwdTileT - 1) / kFwdTileT;
         p.chunk = min (max ((ntiles + kmax - 1) / kmax, max (p.Wt, 1)), ntiles); // the warm-up at most doubles a chunk's work
         p.K = (ntiles + p.chunk - 1) / p.chunk;
     }
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_con
     ClipConst c;
     load_consts (c, desc, params);
     const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
-    const ChunkPlan pl = plan_chunks (c, ntiles, gridDim.y);
+    const ChunkPlan pl = plan_chunks (c, ntiles, gridDim.y, opts);
     const int k = blockIdx.y;
     if (k >= pl.K)
         return;
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __gri
     ClipConst c;
     load_consts (c, desc, params);
     const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
-    const ChunkPlan pl = plan_chunks (c, ntiles, gridDim.y);
+    const ChunkPlan pl = plan_chunks (c, ntiles, gridDim.y, opts);
     const int k = blockIdx.y;
     if (k >= pl.K)
         return;
@@ -879,16 +881,32 @@ __global__ void __launch_bounds__ (kLanes) clipper_adjoint_stitch (const float* 
     if (b < B)
     {
         double G = 0.0;
-        for (int k = K - 1; k >= 0; --k)
+        constexpr int kAhead = 4; // maps of four chunks are loaded before the (serial, fp64) composition touches them: the lane's own loads are all there is to overlap
+        for (int k0 = K - 1; k0 >= 0; k0 -= kAhead)
         {
-            const float* o = cmaps + (int64_t) k * kMapFloats * B + b;
-            acc.g += (double) o[2 * B] + G * (double) o[6 * B];
-            acc.l += (double) o[3 * B] + G * (double) o[7 * B];
-            acc.v += (double) o[4 * B] + G * (double) o[8 * B];
-            acc.lr += (double) o[5 * B] + G * (double) o[9 * B];
-            acc.sse += (double) o[10 * B];
-            acc.st2 += (double) o[11 * B];
-            G = (double) o[0] * G + (double) o[B];
+            float v[kAhead][kMapFloats];
+#pragma unroll
+            for (int j = 0; j < kAhead; ++j)
+            {
+                const float* o = cmaps + (int64_t) max (k0 - j, 0) * kMapFloats * B + b;
+#pragma unroll
+                for (int f = 0; f < kMapFloats; ++f)
+                    v[j][f] = __ldg (o + (int64_t) f * B);
+            }
+#pragma unroll
+            for (int j = 0; j < kAhead; ++j)
+            {
+                if (k0 - j < 0)
+                    break;
+                const float* o = v[j];
+                acc.g += (double) o[2] + G * (double) o[6];
+                acc.l += (double) o[3] + G * (double) o[7];
+                acc.v += (double) o[4] + G * (double) o[8];
+                acc.lr += (double) o[5] + G * (double) o[9];
+                acc.sse += (double) o[10];
+                acc.st2 += (double) o[11];
+                G = (double) o[0] * G + (double) o[1];
+            }
         }
     }
     write_partials_r (acc, partials, blockIdx.x, lane);
@@ -1002,14 +1020,14 @@ __device__ __forceinline__ bool redo_until_merged (const ClipConst& c, const flo
 // two-sequences-per-lane kernel (whose choice of step for out-of-range parameters this kernel has to repeat).
 template <int MODE, bool GENERAL, bool PY>
 __global__ void __launch_bounds__ (128) clipper_forward_stitch (const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state,
-                                                               const float* __restrict__ zs, const float* __restrict__ ze, int64_t B, int T, int kmax, int pair, int* __restrict__ redone)
+                                                               const float* __restrict__ zs, const float* __restrict__ ze, int64_t B, int T, int kmax, int pair, int* __restrict__ redone, int opts)
 {
     const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B)
         return;
     ClipConst c;
     load_consts (c, desc, params);
-    const ChunkPlan pl = plan_chunks (c, (T + kFwdTileT - 1) / kFwdTileT, kmax);
+    const ChunkPlan pl = plan_chunks (c, (T + kFwdTileT - 1) / kFwdTileT, kmax, opts);
     const int K = pl.K;
     if (K <= 1)
         return; // one chunk after all (long circuit memory): the forward kernel has written the state itself
@@ -1815,6 +1833,7 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
 {
     const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
     const int ntiles = (int) ((T + kFwdTileT - 1) / kFwdTileT);
+    const int opts = g_clip_opts.load (); // read once: the forward kernel and its verification pass must make the same chunk plan
     auto go = [&] (auto P) {
         constexpr bool p = decltype (P)::value;
         if (! use_tma)
@@ -1829,20 +1848,20 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
             {
                 const unsigned groups = (unsigned) ((B + kPairRows - 1) / kPairRows);
                 const int kmax = propose_chunks (resident_ctas (clipper_forward_pair_tma<kM, p>), groups, ntiles, cap);
-                clipper_forward_pair_tma<kM, p><<<dim3 (groups, (unsigned) kmax), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, g_clip_opts);
+                clipper_forward_pair_tma<kM, p><<<dim3 (groups, (unsigned) kmax), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, opts);
                 if (kmax > 1)
                 {
-                    clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 1, maps->redone);
+                    clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 1, maps->redone, opts);
                     g_extra_launches.fetch_add (1);
                 }
                 return;
             }
         }
         const int kmax = propose_chunks (resident_ctas (clipper_forward_tma<kM, kG, p>), grid, ntiles, cap);
-        clipper_forward_tma<kM, kG, p><<<dim3 (grid, (unsigned) kmax), kLanes, 0, stream>>> (maps->x, maps->y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, g_clip_opts);
+        clipper_forward_tma<kM, kG, p><<<dim3 (grid, (unsigned) kmax), kLanes, 0, stream>>> (maps->x, maps->y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, opts);
         if (kmax > 1)
         {
-            clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 0, maps->redone);
+            clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 0, maps->redone, opts);
             g_extra_launches.fetch_add (1);
         }
     };

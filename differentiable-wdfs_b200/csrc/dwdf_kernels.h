@@ -46,6 +46,7 @@ enum : int
     kOptNoPair = 2, // forward, approx: one sequence per lane instead of the packed-fp32x2 pair kernel
     kOptNoChunks = 8, // never use the time-parallel kernels
     kOptForceChunks = 16, // use them whatever the batch size (crossover measurements)
+    kOptWarm10 = 64, kOptWarm8 = 128, // time-chunk warm-up until the off-state decay is 1e-10 / 1e-8 instead of 1e-13 (shorter warm-up, more repairs)
     kOptL2Prefetch = 4 // cp.async.bulk.prefetch.tensor L2 run-ahead (measured: slower — forward 0.47 -> 0.58 ms, adjoint 0.63 -> 0.94 ms; off)
 };
 extern std::atomic<int> g_clip_opts; // diagnostic switches (dwdf_set_option); read once per launch

@@ -203,6 +203,22 @@ def test_train_pass_equals_forward_backward(dwdf, oracle, tma, mode, ordering, o
         assert seq_rel_err(y2.cpu().numpy(), y1.cpu().numpy()) < 2e-6
 
 
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+def test_train_step_engines_agree(dwdf, oracle, mode):
+    """train_step(engine="tangent") — the one-sweep kernel behind the same call — takes the same Adam steps as the reverse-mode engine."""
+    p = ClipperParams()
+    x = dev(make_inputs(128, 512, seed=12))
+    target = dev(oracle.clipper_forward(x.cpu().numpy(), perturbed(p), exact=True))
+    runs = []
+    for engine in ("adjoint", "tangent"):
+        circ, _ = make_clipper(dwdf, p, mode, "python")
+        opt = dwdf.Adam(circ, lr={s: 1e-3 * float(circ.params[s]) for s in range(circ.n_params)}, beta_1=0.5)
+        losses = [float(circ.train_step(x, target, opt, loss="mse+esr", skip=50, engine=engine)["loss"]) for _ in range(4)]
+        runs.append((losses, circ.params.clone()))
+    assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5) and runs[0][0][-1] < runs[0][0][0]
+    assert torch.allclose(runs[0][1], runs[1][1], rtol=1e-5, atol=0)
+
+
 @pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
 @pytest.mark.parametrize("B,T,amp", [(101, 520, (2.0, 10.0)), (64, 64, (0.05, 1.0)), (33, 36, (0.5, 6.0))])
 def test_train_pass_packed_kernel(dwdf, oracle, ordering, oord, B, T, amp):
