@@ -36,5 +36,41 @@ dwdf.set_option(prev)
 R1 = dwdf.Resistor(1000.0, True); C1 = dwdf.Capacitor(1.0e-6, 48000.0, True)
 ct = dwdf.compile_circuit(dwdf.IdealVoltageSource(), tree=dwdf.Inverter(dwdf.Series(R1, C1)), probe=C1)
 y = ct.forward(x); ct.backward(target=(0.5 * y).contiguous())
+# ---- round 2 ----------------------------------------------------------------------------------------------------------
+# time chunks as a grid dimension (forced), the as-called loss composition, the resistance-channel kernels, train_step
+prev = dwdf.set_option(16)
+for mode in ("approx", "exact"):
+    Vs = dwdf.ResistiveVoltageSource(47000.0, True); Cc = dwdf.Capacitor(2.2e-9, 48000.0, True)
+    dp = dwdf.DiodePair(dwdf.Parallel(Vs, Cc), 4.352e-9, 25.85e-3, 1.906, trainable=True, mode=mode)
+    circ = dwdf.compile_circuit(dp, probe=Cc)
+    xc = torch.from_numpy((rng.standard_normal((70, 2048)) * 0.5).astype(np.float32)).cuda()
+    yc = circ.forward(xc); circ.backward(target=(0.5 * yc).contiguous(), loss="mse+esr_as_called", skip=8)
+    opt = dwdf.Adam(circ, lr=1e-6)
+    circ.train_step(xc, (0.5 * yc).contiguous(), opt, loss="mse+esr", skip=8)
+    circ.train_step(xc, (0.5 * yc).contiguous(), opt, loss="mse", engine="tangent")
+    Vr = dwdf.ResistiveVoltageSource(47000.0); Cr = dwdf.Capacitor(2.2e-9, 48000.0, True)
+    dr = dwdf.DiodePair(dwdf.Parallel(Vr, Cr), 4.352e-9, 25.85e-3, 1.906, trainable=True, mode=mode)
+    cr = dwdf.compile_circuit(dr, probe=Cr, r_element=Vr)
+    for Bq, Tq in ((70, 2048), (5, 37)):
+        xr = torch.from_numpy((rng.standard_normal((Bq, Tq)) * 0.5).astype(np.float32)).cuda()
+        rr = torch.full_like(xr, 47000.0); rr[::2] = 10000.0
+        yr = cr.forward(xr, r=rr); cr.backward(target=(0.5 * yr).contiguous(), loss="mse")
+dwdf.set_option(prev)
+# neural root: dL/dx, raw sums + finalize, the one-call step, the as-called loss
+yn = cn.forward(x); cn.backward(gy=torch.ones_like(x), want_gx=True)
+cn.forward(x); cn.backward(target=(0.5 * yn).contiguous(), raw=True); cn.finalize(target=True, loss="mse+esr")
+cn.train_step(x, (0.5 * yn).contiguous(), dwdf.AdamWeights(cn, lr=1e-4), loss="mse+esr_as_called", skip=5)
+# run-time specialised tree programs: TMA kernels (aligned) and the direct twins (ragged), linear and diode roots, both orderings
+for ordering in ("python", "plugin"):
+    for mode in (None, "approx", "exact"):
+        Rt = dwdf.Resistor(47000.0, True); Vt_ = dwdf.ResistiveVoltageSource(4700.0, True); Ct = dwdf.Capacitor(2.2e-9, 48000.0, True)
+        top = dwdf.Parallel(Rt, dwdf.Series(Vt_, Ct))
+        root = dwdf.IdealVoltageSource() if mode is None else dwdf.DiodePair(top, 4.352e-9, 25.85e-3, 1.906, trainable=True, mode=mode)
+        cj = dwdf.compile_circuit(root, tree=top, probe=Ct, ordering=ordering)
+        assert cj.specialize()
+        for Bq, Tq in ((70, 256), (33, 203)):
+            xj = torch.from_numpy((rng.standard_normal((Bq, Tq)) * 0.5).astype(np.float32)).cuda()
+            yj = cj.forward(xj); cj.backward(target=(0.5 * yj).contiguous(), loss="mse+esr", skip=3)
+            st = cj.new_state(Bq); cj.process_block(xj, st)
 torch.cuda.synchronize()
 print("sanitize smoke done")
