@@ -1198,7 +1198,7 @@ constexpr int kTrainPairTileBytes = kPairRows * kSeg * 4; // 4 KB
 constexpr int kTrainPairStageBytes = 2 * kTrainPairTileBytes;
 constexpr int kTrainPairStages = 3;
 
-template <bool PY>
+template <int MODE, bool PY>
 struct TrainStateV
 {
     f2 z { 0.0f, 0.0f }, hz { 0.0f, 0.0f }, sg { 0.0f, 0.0f }, sl { 0.0f, 0.0f }, sv { 0.0f, 0.0f };
@@ -1206,7 +1206,11 @@ struct TrainStateV
     __device__ __forceinline__ f2 step (const ClipConst& c, f2 x, f2 t, bool onA, bool onB, f2& umax)
     {
         StepTapeV<f2> tp;
-        const f2 y = clip_step_fastv_impl<f2, PY, true> (c, x, z, hz, umax, &tp);
+        f2 y;
+        if (MODE == kModeExact)
+            y = clip_step_exact_tapev<f2, PY> (c, x, z, tp);
+        else
+            y = clip_step_fastv_impl<f2, PY, true> (c, x, z, hz, umax, &tp);
         const f2 e { onA ? y.x - t.x : 0.0f, onB ? y.y - t.y : 0.0f };
         const f2 tm { onA ? t.x : 0.0f, onB ? t.y : 0.0f };
         const f2 ng = fmav (tp.A, sg, tp.cg), nl = fmav (tp.A, sl, tp.cl), nv = fmav (tp.A, sv, tp.cv);
@@ -1229,14 +1233,14 @@ struct TrainStateV
         return y;
     }
     // one element (0: .x, 1: .y) as the scalar state of the general step, and back
-    __device__ __forceinline__ TrainState<kModeApprox, false, false, PY> get (int k) const
+    __device__ __forceinline__ TrainState<MODE, false, false, PY> get (int k) const
     {
-        TrainState<kModeApprox, false, false, PY> s;
+        TrainState<MODE, false, false, PY> s;
         s.z = k ? z.y : z.x, s.sg = k ? sg.y : sg.x, s.sl = k ? sl.y : sl.x, s.sv = k ? sv.y : sv.x;
         s.ag = k ? ag.y : ag.x, s.al = k ? al.y : al.x, s.av = k ? av.y : av.x, s.sse = k ? sse.y : sse.x, s.st2 = k ? st2.y : st2.x;
         return s;
     }
-    __device__ __forceinline__ void put (int k, const TrainState<kModeApprox, false, false, PY>& s)
+    __device__ __forceinline__ void put (int k, const TrainState<MODE, false, false, PY>& s)
     {
         if (k)
             z.y = s.z, hz.y = 0.5f * s.z, sg.y = s.sg, sl.y = s.sl, sv.y = s.sv, ag.y = s.ag, al.y = s.al, av.y = s.av, sse.y = s.sse, st2.y = s.st2;
@@ -1254,7 +1258,7 @@ struct TrainStateV
     }
 };
 
-template <bool PY>
+template <int MODE, bool PY>
 __global__ void __launch_bounds__ (kLanes) clipper_train_pair_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmt, const __grid_constant__ CUtensorMap tmy, const int want_y, const float* __restrict__ params, const ClipDesc desc, double* __restrict__ partials, int64_t B, int T, int skip, int n_groups)
 {
     __shared__ __align__ (1024) uint8_t smem[kTrainPairStages * kTrainPairStageBytes];
@@ -1274,7 +1278,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_train_pair_tma (const __grid_
     ClipConst c;
     load_consts (c, desc, params);
     const bool validA = (int64_t) b0 + lane < B, validB = (int64_t) b0 + kLanes + lane < B;
-    const bool fast = fast_ok (c.pair.L); // warp-uniform
+    const bool fast = MODE == kModeExact ? exact_fast_ok (c.pair) : fast_ok (c.pair.L); // warp-uniform
     const int ntiles = (T + kSeg - 1) / kSeg;
     auto load_stage = [&] (int j) {
         const int sj = j % kTrainPairStages;
@@ -1285,7 +1289,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_train_pair_tma (const __grid_
     if (lane == 0)
         for (int s = 0; s < kTrainPairStages - 1 && s < ntiles; ++s)
             load_stage (s);
-    TrainStateV<PY> st;
+    TrainStateV<MODE, PY> st;
     AdjAcc acc;
     for (int i = 0; i < ntiles; ++i)
     {
@@ -1305,7 +1309,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_train_pair_tma (const __grid_
                 const float tga[4] = { ta.x, ta.y, ta.z, ta.w }, tgb[4] = { tb.x, tb.y, tb.z, tb.w };
                 const int n = i * kSeg + cc * 4;
                 float oa[4], ob[4];
-                const TrainStateV<PY> saved = st;
+                const TrainStateV<MODE, PY> saved = st;
                 f2 um { -1.0e30f, -1.0e30f };
                 if (fast)
                 {
@@ -1319,7 +1323,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_train_pair_tma (const __grid_
                 }
                 // an instance that crossed omega3's log branch in this chunk (or parameters outside the fast path's range):
                 // that instance's four samples again, the general way, from the state it had before the chunk
-                const bool redoA = ! fast || um.x >= kFastLoud, redoB = ! fast || um.y >= kFastLoud;
+                const bool redoA = ! fast || (MODE != kModeExact && um.x >= kFastLoud), redoB = ! fast || (MODE != kModeExact && um.y >= kFastLoud);
                 if (redoA || redoB)
                 {
 #pragma unroll
@@ -1906,11 +1910,11 @@ cudaError_t clipper_train_part<kM, kG> (bool py, bool use_tma, const ClipTmaMaps
     const unsigned grid = (unsigned) ((B + kLanes - 1) / kLanes);
     auto go = [&] (auto P) {
         constexpr bool p = decltype (P)::value;
-        if constexpr (kM == kModeApprox && ! kG)
+        if constexpr ((kM == kModeApprox || kM == kModeExact) && ! kG)
         {
             if (use_tma && maps[0].pair)
             {
-                clipper_train_pair_tma<p><<<(unsigned) ((B + kPairRows - 1) / kPairRows), kLanes, 0, stream>>> (maps[0].x2, maps[0].y2, maps[1].y2, y != nullptr ? 1 : 0, params, desc, partials, B, (int) T, skip, (int) ((B + kLanes - 1) / kLanes));
+                clipper_train_pair_tma<kM, p><<<(unsigned) ((B + kPairRows - 1) / kPairRows), kLanes, 0, stream>>> (maps[0].x2, maps[0].y2, maps[1].y2, y != nullptr ? 1 : 0, params, desc, partials, B, (int) T, skip, (int) ((B + kLanes - 1) / kLanes));
                 return;
             }
         }

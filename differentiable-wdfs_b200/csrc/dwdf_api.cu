@@ -894,8 +894,8 @@ static int train_impl (bool raw_only, const dwdf_program* prog, const float* par
         tma = make_map (&maps[1].y, y, B, T, 32);
     else if (tma)
         maps[1].y = maps[0].y;
-    // approx root, symmetric pair, more than a warp's worth of sequences: two sequences per lane, [64 x 16] tiles of x, target (and y)
-    if (tma && prog->variant.mode == kModeApprox && ! prog->variant.general && B > 32 && ! (g_clip_opts & kOptNoPair))
+    // symmetric pair (approx or exact root), more than a warp's worth of sequences: two sequences per lane, [64 x 16] tiles of x, target (and y)
+    if (tma && (prog->variant.mode == kModeApprox || prog->variant.mode == kModeExact) && ! prog->variant.general && B > 32 && ! (g_clip_opts & kOptNoPair))
     {
         maps[0].pair = make_map (&maps[0].x2, x, B, T, kSeg, 64) && make_map (&maps[0].y2, target, B, T, kSeg, 64) && (y == nullptr || make_map (&maps[1].y2, y, B, T, kSeg, 64));
         if (maps[0].pair && y == nullptr)

@@ -863,6 +863,34 @@ DWDF_HD V clip_step_exactv (const ClipConst& c, V x, V& z)
     return y;
 }
 
+// The same step with its linearisation (the one-sweep tangent pass on the exact root): w0 and w1 are at hand, so the tape costs
+// two reciprocals and a dozen FMAs on top of the forward step. Output and state bit-identical to clip_step_exactv.
+template <class V, bool PYORDER>
+DWDF_HD V clip_step_exact_tapev (const ClipConst& c, V x, V& z, StepTapeV<V>& tp)
+{
+    const PairConst& p = c.pair;
+    const V xz = addv (x, negv (z));
+    const V a = fmav (bc (V {}, c.gamma), xz, z);
+    const V aa = absv (a);
+    const V w0 = opaque (omega_exact1v (fmav (aa, bc (V {}, p.invV), bc (V {}, p.L))));
+    const V w1 = opaque (omega_exact_lowv (fmav (aa, bc (V {}, -p.invV), bc (V {}, p.L))));
+    const V b = fmav (bc (V {}, -p.twoV), xor_signv (addv (w0, negv (w1)), a), a);
+    const V zn = fmav (bc (V {}, c.gamma), xz, b);
+    const V y = PYORDER ? mulv (bc (V {}, 0.5f), addv (zn, z)) : z;
+    z = zn;
+    const V wp0 = mulv (w0, rcpv (addv (w0, bc (V {}, 1.0f))));
+    const V wp1 = mulv (w1, rcpv (addv (w1, bc (V {}, 1.0f))));
+    const V S1 = addv (wp0, wp1);
+    const V M1 = xor_signv (addv (wp0, negv (wp1)), a);
+    const V fp1 = fmav (bc (V {}, -2.0f), S1, bc (V {}, 2.0f)); // f'(a) + 1
+    tp.A = fmav (fp1, bc (V {}, c.one_m_gamma), bc (V {}, -1.0f));
+    tp.cg = mulv (xz, fp1);
+    tp.cl = mulv (bc (V {}, -p.twoV), M1);
+    const V ww = xor_signv (fmav (w0, wp0, negv (mulv (w1, wp1))), a);
+    tp.cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, mulv (bc (V {}, -2.0f), ww));
+    return y;
+}
+
 // MODE kModeApprox: fast-path parameters (lsmall_ok(L)); kModeExact: rev_small_ok (the reverse-biased argument stays
 // in TOMS-917's x <= -2 region, and so does the forward-biased one wherever it is evaluated directly)
 template <class V, int MODE = kModeApprox>

@@ -221,14 +221,15 @@ def test_train_step_engines_agree(dwdf, oracle, mode):
 
 @pytest.mark.parametrize("ordering,oord", [("plugin", ORDER_PLUGIN), ("python", ORDER_PYTHON)])
 @pytest.mark.parametrize("B,T,amp", [(101, 520, (2.0, 10.0)), (64, 64, (0.05, 1.0)), (33, 36, (0.5, 6.0))])
-def test_train_pass_packed_kernel(dwdf, oracle, ordering, oord, B, T, amp):
-    """The fused pass on two sequences per lane (approx root): loud inputs (instances that cross omega3's log branch
-    are redone the general way, state and tangents included), odd row counts, partial last tiles, skip inside a tile —
+@pytest.mark.parametrize("mode", ["approx", "exact"])
+def test_train_pass_packed_kernel(dwdf, oracle, ordering, oord, B, T, amp, mode):
+    """The fused pass on two sequences per lane (approx and exact root): loud inputs (approx: instances that cross omega3's
+    log branch are redone the general way, state and tangents included), odd row counts, partial last tiles, skip inside a tile —
     loss and gradients against forward + adjoint and against the fp64 oracle, outputs against the forward kernel."""
     p = ClipperParams()
     x = make_inputs(B, T, seed=91, amp=amp)
     target = oracle.clipper_forward(x, perturbed(p), exact=True, ordering=oord)
-    circ, order = make_clipper(dwdf, p, "approx", ordering)
+    circ, order = make_clipper(dwdf, p, mode, ordering)
     y1 = circ.forward(dev(x))
     a = circ.backward(target=dev(target), loss="mse+esr", skip=7)
     ga, la = a["grads"].clone(), float(a["loss"])
@@ -238,7 +239,7 @@ def test_train_pass_packed_kernel(dwdf, oracle, ordering, oord, B, T, amp):
     assert abs(la / float(b["loss"]) - 1) < 1e-5
     assert seq_rel_err(y2.cpu().numpy(), y1.cpu().numpy()) < 2e-6
     if amp[1] <= 6.0:  # (hard-driven diodes make dz'/dz -> -1: the sums are ill-conditioned in fp32, the fuzz tests bound those by their condition)
-        ref = oracle.clipper_grad(x, target, p, exact=False, ordering=oord, mode="target", loss="mse+esr", skip=7, dtype=np.float64)
+        ref = oracle.clipper_grad(x, target, p, exact=(mode == "exact"), ordering=oord, mode="target", loss="mse+esr", skip=7, dtype=np.float64)
         g = b["grads"].cpu().numpy()[order]
         assert np.max(np.abs(g / ref["grads"] - 1.0)) < GRAD_TOL, (g, ref["grads"])
     prev = dwdf.set_option(2)  # kOptNoPair: the one-sequence-per-lane kernel
