@@ -785,7 +785,18 @@ void tree_jit_destroy (TreeJit* j)
 {
     if (j == nullptr)
         return;
-    // modules are left to their contexts (unloading needs the owning context current; a program is destroyed from any thread)
+    // a module lives in its device's primary context: make that device current for the unload, then put the caller's back
+    if (! j->modules.empty () && driver ().ok)
+    {
+        int prev = -1;
+        const bool have_prev = cudaGetDevice (&prev) == cudaSuccess;
+        for (auto& dm : j->modules)
+            if (dm.second.mod != nullptr && cudaSetDevice (dm.first) == cudaSuccess)
+                (void) driver ().ModuleUnload (dm.second.mod);
+        if (have_prev)
+            (void) cudaSetDevice (prev);
+        (void) cudaGetLastError ();
+    }
     delete j;
 }
 

@@ -11,4 +11,9 @@ the checker or the timed CPU baseline, never as the product path. The product pa
 * ``oracle.torch_wdf`` line-for-line torch restatement of ``wdf_py/lib/tf_wdf.py`` (TensorFlow 2.5
                        is not installable here) + an analytic DiodePair root; gradient oracle via
                        ``torch.autograd`` and the stand-in for the wdf_py TensorFlow CPU path.
+* ``oracle.nn``        numpy / torch restatement of the neural-root clipper (``layers.py``, ``clipper_pot.py:94-127``).
+* ``oracle/shim_tf``   a minimal ``tensorflow`` look-alike on torch, so that ``tests/golden/make_golden_py_reference.py``
+                       can execute the UNMODIFIED reference Python sources and record their outputs and
+                       ``tape.gradient`` results (``tests/golden/py_reference_vectors.npz``): what pins the two
+                       restatements above, and the kernels, to the reference's own code — gradients included.
 """

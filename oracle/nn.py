@@ -119,6 +119,10 @@ def nn_clipper_grad_torch(x, target, weights, sizes, fs, R, C, ordering=ORDER_PY
         if loss == "mse+esr":
             esr = torch.sqrt((e * e).sum() / ((tt * tt).sum() + 2.220446049250313e-16) / N)  # clipper_pot.py:145,148-156
             L = mse + esr
+        elif loss == "mse+esr_as_called":  # loss_func(outs, train_Y), clipper_pot.py:248: the energy is the model output's
+            yy = y[:, skip:]
+            esr = torch.sqrt((e * e).sum() / ((yy * yy).sum() + 2.220446049250313e-16) / N)
+            L = mse + esr
         out.update(loss=float(L.detach()), mse=float(mse.detach()), esr=float(esr.detach()))
     L.backward()
     out["grad_w"] = w.grad.numpy().copy()
