@@ -2,6 +2,7 @@
 // clipper_kernels.cu), plus the two tiny single-block kernels of a training step: the fixed-order
 // finalize (reduction, chain rule, loss) and Adam.
 #include "dwdf_kernels.h"
+#include "dwdf_tma.cuh"
 
 namespace dwdf
 {
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__ (256) clipper_finalize_dp (const ClipDesc desc
     __shared__ unsigned long long epoch_sm;
     __shared__ int timed_out;
     const int tid = threadIdx.x;
+    grid_dependency_wait (); // (a programmatic dependent of the adjoint pass)
     reduce_partials (sm, partials, n_groups);
     if (tid == 0)
     {
@@ -396,8 +398,8 @@ cudaError_t launch_clipper_finalize (const ClipDesc& desc, const float* params, 
 cudaError_t launch_clipper_finalize_dp (const ClipDesc& desc, float* params, const double* partials, int64_t n_groups, bool target, int loss_kind, double count, double* out, const DpPeers& dp, float* m, float* v, int32_t* step, int n_params,
                                         float lr, const float* lr_vec, float beta1, float beta2, float eps, const float* lo, const float* hi, cudaStream_t stream)
 {
-    clipper_finalize_dp<<<1, 256, 0, stream>>> (desc, params, partials, n_groups, target ? 1 : 0, loss_kind, count, out, dp, m, v, step, n_params, lr, lr_vec, beta1, beta2, eps, lo, hi);
-    return cudaGetLastError ();
+    return launch_dependent (! (g_clip_opts & kOptNoPdl), clipper_finalize_dp, dim3 (1), dim3 (256), stream, desc, params, partials, n_groups, target ? 1 : 0, loss_kind, count, out, dp, m, v, step, n_params, lr, lr_vec, beta1, beta2, eps, lo,
+                             hi);
 }
 
 cudaError_t launch_peer_allreduce (double* inout, int n, const DpPeers& dp, cudaStream_t stream)

@@ -847,6 +847,7 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid
         fence_mbar_init ();
     }
     __syncwarp ();
+    grid_dependency_wait (); // everything above overlaps the tail of the forward pass when launched as its programmatic dependent
     ClipConst c;
     load_consts (c, desc, params);
     AdjAcc acc;
@@ -875,6 +876,7 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid
 template <int PART> // (one instance per translation unit of this file)
 __global__ void __launch_bounds__ (kLanes) clipper_adjoint_stitch (const float* __restrict__ cmaps, double* __restrict__ partials, int64_t B, int K)
 {
+    grid_dependency_wait ();
     const int lane = threadIdx.x;
     const int64_t b = (int64_t) blockIdx.x * kLanes + lane;
     AdjAcc acc;
@@ -1022,6 +1024,7 @@ template <int MODE, bool GENERAL, bool PY>
 __global__ void __launch_bounds__ (128) clipper_forward_stitch (const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params, const ClipDesc desc, float* __restrict__ ckpt, float* __restrict__ state,
                                                                const float* __restrict__ zs, const float* __restrict__ ze, int64_t B, int T, int kmax, int pair, int* __restrict__ redone, int opts)
 {
+    grid_dependency_wait (); // (launched as a programmatic dependent of the forward kernel)
     const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B)
         return;
@@ -1855,7 +1858,7 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
                 clipper_forward_pair_tma<kM, p><<<dim3 (groups, (unsigned) kmax), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, opts);
                 if (kmax > 1)
                 {
-                    clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 1, maps->redone, opts);
+                    launch_dependent (! (opts & kOptNoPdl), clipper_forward_stitch<kM, kG, p>, dim3 ((unsigned) ((B + 127) / 128)), dim3 (128), stream, x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 1, maps->redone, opts);
                     g_extra_launches.fetch_add (1);
                 }
                 return;
@@ -1865,7 +1868,7 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
         clipper_forward_tma<kM, kG, p><<<dim3 (grid, (unsigned) kmax), kLanes, 0, stream>>> (maps->x, maps->y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, opts);
         if (kmax > 1)
         {
-            clipper_forward_stitch<kM, kG, p><<<(unsigned) ((B + 127) / 128), 128, 0, stream>>> (x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 0, maps->redone, opts);
+            launch_dependent (! (opts & kOptNoPdl), clipper_forward_stitch<kM, kG, p>, dim3 ((unsigned) ((B + 127) / 128)), dim3 (128), stream, x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 0, maps->redone, opts);
             g_extra_launches.fetch_add (1);
         }
     };
@@ -1885,10 +1888,12 @@ cudaError_t clipper_adjoint_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
             int K = propose_chunks (resident_ctas (clipper_adjoint_tma<kM, kG, p, tg>), grid, nseg / 4 > 0 ? nseg / 4 : 1, maps->cmaps != nullptr ? maps->kcap_adj : 1); // chunks of at least 4 segments
             const int chunk_segs = (nseg + K - 1) / K;
             K = (nseg + chunk_segs - 1) / chunk_segs;
-            clipper_adjoint_tma<kM, kG, p, tg><<<dim3 (grid, (unsigned) K), kLanes, 0, stream>>> (maps->x, maps->y, maps->g, params, desc, ckpt, partials, maps->cmaps, chunk_segs, B, (int) T, skip, g_clip_opts);
+            const int opts = g_clip_opts.load ();
+            const bool pdl = ! (opts & kOptNoPdl);
+            launch_dependent (pdl, clipper_adjoint_tma<kM, kG, p, tg>, dim3 (grid, (unsigned) K), dim3 (kLanes), stream, maps->x, maps->y, maps->g, params, desc, ckpt, partials, maps->cmaps, chunk_segs, B, (int) T, skip, opts);
             if (K > 1)
             {
-                clipper_adjoint_stitch<kM * 2 + (kG ? 1 : 0)><<<grid, kLanes, 0, stream>>> (maps->cmaps, partials, B, K);
+                launch_dependent (pdl, clipper_adjoint_stitch<kM * 2 + (kG ? 1 : 0)>, dim3 (grid), dim3 (kLanes), stream, (const float*) maps->cmaps, partials, B, K);
                 g_extra_launches.fetch_add (1);
             }
         }

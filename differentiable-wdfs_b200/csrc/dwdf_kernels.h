@@ -47,8 +47,27 @@ enum : int
     kOptNoChunks = 8, // never use the time-parallel kernels
     kOptForceChunks = 16, // use them whatever the batch size (crossover measurements)
     kOptWarm10 = 64, kOptWarm8 = 128, // time-chunk warm-up until the off-state decay is 1e-10 / 1e-8 instead of 1e-13 (shorter warm-up, more repairs)
+    kOptNoPdl = 256, // no programmatic dependent launches
     kOptL2Prefetch = 4 // cp.async.bulk.prefetch.tensor L2 run-ahead (measured: slower — forward 0.47 -> 0.58 ms, adjoint 0.63 -> 0.94 ms; off)
 };
+// Launch `kernel` as a programmatic dependent of whatever precedes it in `stream` (the kernel calls grid_dependency_wait()
+// before it touches anything a predecessor wrote): the short kernels of a small-batch training step hide their launch latency
+// behind the kernel before them. kOptNoPdl: plain launches (A/B).
+template <class... KArgs, class... Args>
+cudaError_t launch_dependent (bool pdl, void (*kernel) (KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
+{
+    cudaLaunchConfig_t cfg {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx (&cfg, kernel, KArgs (args)...);
+}
 extern std::atomic<int> g_clip_opts; // diagnostic switches (dwdf_set_option); read once per launch
 extern std::atomic<int64_t> g_extra_launches; // kernels the launchers add on their own (the time-chunk stitch passes)
 

@@ -15,6 +15,11 @@ typedef CUtensorMap_st CUtensorMap;
 namespace dwdf
 {
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start before
+// its predecessor in the stream has finished (its launch latency and prologue overlap the predecessor's tail); this waits until
+// the predecessor has completed and its memory operations are visible. A no-op for a normally launched kernel.
+__device__ __forceinline__ void grid_dependency_wait () { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32 (const void* p) { return (uint32_t) __cvta_generic_to_shared (p); }
 
 __device__ __forceinline__ void mbar_init (uint32_t bar, uint32_t count)
