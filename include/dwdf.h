@@ -328,9 +328,11 @@ DWDF_API int64_t dwdf_launch_count (void);
 /* Selects the data-movement path of the clipper kernels: 1 = TMA tiles (default when usable),
  * 0 = direct global loads. Returns the previous value. For tests and A/B timing. */
 DWDF_API int dwdf_set_tma (int enable);
-/* Kernel-variant switches for A/B timing. bit 0: forward approx root evaluated sample by sample
- * (no packed fast step); bit 1: one sequence per lane instead of the packed-fp32x2 pair kernel;
- * bit 2: TMA L2 prefetch run-ahead; bit 3: never use the time-parallel (small-batch) kernels.
+/* Kernel-variant switches for A/B timing (bit values). 1: forward approx root evaluated sample by sample
+ * (no packed fast step); 2: one sequence per lane instead of the packed-fp32x2 pair kernels; 4: TMA L2 prefetch
+ * run-ahead; 8: never use time chunks (small batches run one lane per sequence over the whole T); 16: use time
+ * chunks whatever the batch size; 64 / 128: time-chunk warm-up until the off-state decay is 1e-10 / 1e-8 instead
+ * of 1e-13 (same bits out: the verification pass repairs more chunks); 256: no programmatic dependent launches.
  * 0 = shipped behaviour. Returns the previous bits. */
 DWDF_API int dwdf_set_option (int bits);
 /* Diagnostics: chunks the time-parallel forward kernels (small batches) had to recompute so far because

@@ -158,7 +158,7 @@ def test_swapped_clipper_against_the_clipper_oracle(dwdf, oracle, mode, ordering
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("DWDF_FUZZ_N5", "16"))))
 def test_random_trees_specialised_equal_interpreter(dwdf, oracle, seed):
     """Random trees (tests/test_gpu_fuzz.py's generator): the specialised kernels against the interpreter — output, fused-loss
     gradients, upstream gradients, streaming in blocks — on aligned shapes (TMA kernels) and ragged ones (direct twins)."""
