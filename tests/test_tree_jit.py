@@ -162,6 +162,7 @@ def test_swapped_clipper_against_the_clipper_oracle(dwdf, oracle, mode, ordering
 def test_random_trees_specialised_equal_interpreter(dwdf, oracle, seed):
     """Random trees (tests/test_gpu_fuzz.py's generator): the specialised kernels against the interpreter — output, fused-loss
     gradients, upstream gradients, streaming in blocks — on aligned shapes (TMA kernels) and ragged ones (direct twins)."""
+    from oracle.cpu import ROOT_DIODE_PAIR, ROOT_IDEAL_VS
     from test_gpu_fuzz import _random_tree
 
     outs = []
@@ -197,13 +198,27 @@ def test_random_trees_specialised_equal_interpreter(dwdf, oracle, seed):
         vals = circ.params.cpu().numpy().astype(np.float64)
         outs.append((y.cpu().numpy(), gt, lt, gu, parts.cpu().numpy(), vals))
     (y0, gt0, l0, gu0, s0, vals), (y1, gt1, l1, gu1, s1, _) = outs
-    scale = np.maximum(np.max(np.abs(y0), axis=1, keepdims=True), 1e-6)
-    assert np.max(np.abs(y1 - y0) / scale) < 5e-6
-    assert np.max(np.abs(s1 - y1) / scale) < 5e-6  # streaming in two blocks = one long block
-    assert abs(l1 / l0 - 1) < 1e-5
+    # the circuit's own conditioning in fp32 (as tests/test_gpu_fuzz.py measures it): the oracle's tree executor in fp32 against fp64.
+    # Two fp32 evaluations that differ only in where the compiler contracts a product into an FMA differ by about that much.
+    oord = ORDER_PLUGIN if ordering == "plugin" else ORDER_PYTHON
+    if diode:
+        source = [i for i, e in enumerate(elems) if isinstance(e, dwdf.ResistiveVoltageSource)][0]
+        args = dict(root_kind=ROOT_DIODE_PAIR, source=source, root_par=[float(mode == "exact"), 0, p.Is, p.Vt, p.nabla, 1, 1])
+    else:
+        args = dict(root_kind=ROOT_IDEAL_VS, source=-1, root_par=None)
+    ref32 = oracle.tree_run(nodes, fs, args["root_kind"], x, probe=probe, source=args["source"], root_par=args["root_par"], ordering=oord)
+    ref64 = oracle.tree_run(nodes, fs, args["root_kind"], x, probe=probe, source=args["source"], root_par=args["root_par"], ordering=oord, dtype=np.float64)
+    scale = np.maximum(np.max(np.abs(ref64), axis=1, keepdims=True), 1e-3 * np.max(np.abs(x), axis=1, keepdims=True) + 1e-30)
+    cond = float(np.max(np.abs(ref32 - ref64) / scale))
+    tol = max(5e-6, 5.0 * cond)
+    assert np.max(np.abs(y1 - ref64) / scale) < max(1e-5, 5.0 * cond), (nodes, probe, cond)  # the interpreter's own bar
+    assert np.max(np.abs(y1 - y0) / scale) < tol, (nodes, probe, cond)
+    assert np.max(np.abs(s1 - y1) / scale) < tol  # streaming in two blocks = one long block
+    assert abs(l1 / l0 - 1) < max(1e-5, 20.0 * cond)
+    gtol = max(5e-4, 200.0 * cond)
     for a, b in ((gt0, gt1), (gu0, gu1)):
         a, b = a[: len(vals)] * vals, b[: len(vals)] * vals  # d/d ln(value): comparable across ohms, farads, amperes
-        assert np.max(np.abs(a - b)) < 5e-4 * np.max(np.abs(a)) + 1e-12, (a, b)
+        assert np.max(np.abs(a - b)) < gtol * np.max(np.abs(a)) + 1e-12, (a, b, cond)
 
 
 @pytest.mark.gpu
