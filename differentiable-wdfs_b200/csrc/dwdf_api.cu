@@ -30,8 +30,11 @@ struct dwdf_program
     ClipVariant variant {};
     TreeProgram tree {};
     int n_states = 0;
-    TreeJit* jit = nullptr; // run-time specialised kernels of a tree program (dwdf_program_specialize), else the interpreter
-    ~dwdf_program () { tree_jit_destroy (jit); }
+    // run-time specialised kernels of a tree program (dwdf_program_specialize), else the interpreter. Published once, fully built,
+    // with release / acquire ordering: a launch on another thread sees either none or a complete one
+    std::atomic<TreeJit*> jit { nullptr };
+    std::mutex jit_mu;
+    ~dwdf_program () { tree_jit_destroy (jit.load ()); }
 };
 
 namespace
@@ -598,10 +601,11 @@ int dwdf_program_specialize (dwdf_program* prog)
 {
     if (prog == nullptr)
         return fail (DWDF_ERR_INVALID, "null argument");
-    if (prog->jit != nullptr)
-        return DWDF_OK;
     if (prog->is_clipper || prog->is_neural)
         return fail (DWDF_ERR_UNSUPPORTED, "the program already runs on kernels written for its circuit (diode clipper / neural root)");
+    std::lock_guard<std::mutex> lock (prog->jit_mu);
+    if (prog->jit.load () != nullptr)
+        return DWDF_OK;
     std::string err;
     TreeJit* j = tree_jit_create (prog->tree, err);
     if (j == nullptr)
@@ -611,11 +615,11 @@ int dwdf_program_specialize (dwdf_program* prog)
         tree_jit_destroy (j);
         return fail (DWDF_ERR_CUDA, "%s", err.c_str ());
     }
-    prog->jit = j;
+    prog->jit.store (j, std::memory_order_release);
     return DWDF_OK;
 }
 
-int dwdf_program_is_specialized (const dwdf_program* prog) { return prog != nullptr && prog->jit != nullptr ? 1 : 0; }
+int dwdf_program_is_specialized (const dwdf_program* prog) { return prog != nullptr && prog->jit.load () != nullptr ? 1 : 0; }
 
 size_t dwdf_program_specialized_source (const dwdf_program* prog, int32_t part, char* buf, size_t capacity)
 {
@@ -645,7 +649,7 @@ size_t dwdf_ckpt_bytes (const dwdf_program* prog, int64_t B, int64_t T)
         return 0;
     if (prog->is_clipper)
         return (size_t) (n_segments (T) * B) * sizeof (float);
-    if (prog->jit != nullptr) // specialised tree: every state (and the probe's incident wave) at each segment start
+    if (prog->jit.load () != nullptr) // specialised tree: every state (and the probe's incident wave) at each segment start
         return (size_t) (n_segments (T) * B) * (size_t) (prog->n_states + 1) * sizeof (float);
     return 16; // the interpreter's adjoint keeps its own tape in the workspace
 }
@@ -657,7 +661,7 @@ size_t dwdf_workspace_bytes (const dwdf_program* prog, int64_t B, int64_t T)
     size_t bytes = partials_bytes (B);
     if (prog->is_clipper)
         bytes += adj_maps_bytes (B, T); // affine maps of the adjoint's time chunks (small batches)
-    if (! prog->is_clipper && prog->jit == nullptr) // per-sample tape of the interpreter adjoint: (n_states + 1) floats per sample (the specialised kernels keep none)
+    if (! prog->is_clipper && prog->jit.load () == nullptr) // per-sample tape of the interpreter adjoint: (n_states + 1) floats per sample (the specialised kernels keep none)
         bytes += (size_t) B * (size_t) T * (size_t) (prog->n_states + 1) * sizeof (float);
     return bytes;
 }
@@ -712,12 +716,12 @@ static int forward_impl (const dwdf_program* prog, const float* params, const fl
         }
         DWDF_CUDA (launch_clipper_forward (prog->variant, tma, &maps, prog->clip, params, x, y, z_ckpt, state, B, T, stream));
     }
-    else if (prog->jit != nullptr)
+    else if (TreeJit* jit = prog->jit.load (std::memory_order_acquire))
     { // run-time specialised kernels (tree_jit.cu): TMA tiles when the rows allow it, else a lane walks its own row
         CUtensorMap mx, my;
         const bool tma = tma_usable (x, y, nullptr, B, T) && make_map (&mx, x, B, T, 32) && make_map (&my, y, B, T, 32);
         std::string err;
-        if (! tree_jit_forward (prog->jit, tma ? &mx : nullptr, tma ? &my : nullptr, params, x, y, z_ckpt, state, B, T, stream, err))
+        if (! tree_jit_forward (jit, tma ? &mx : nullptr, tma ? &my : nullptr, params, x, y, z_ckpt, state, B, T, stream, err))
             return fail (DWDF_ERR_CUDA, "specialised tree kernel: %s", err.c_str ());
     }
     else
@@ -823,14 +827,14 @@ static int backward_impl (int raw_only, const dwdf_program* prog, const float* p
             return fail (DWDF_ERR_UNSUPPORTED, "dL/dx is available for the diode-clipper program only");
         if ((prog->desc.r_node >= 0) != (r != nullptr))
             return fail (DWDF_ERR_INVALID, "the per-sample resistance channel must be given exactly when the program has an r_node");
-        if (prog->jit != nullptr)
+        if (TreeJit* jit = prog->jit.load (std::memory_order_acquire))
         { // specialised reverse sweep: no tape; replays 16-sample segments from the checkpoints the specialised forward wrote
             if (z_ckpt == nullptr)
                 return fail (DWDF_ERR_INVALID, "a specialised tree program differentiates from the checkpoints of dwdf_forward (z_ckpt, dwdf_ckpt_bytes): z_ckpt is null");
             CUtensorMap mx, mg;
             const bool tma = tma_usable (x, gy_or_target, nullptr, B, T) && make_map (&mx, x, B, T, kSeg) && make_map (&mg, gy_or_target, B, T, kSeg);
             std::string err;
-            if (! tree_jit_adjoint (prog->jit, tma ? &mx : nullptr, tma ? &mg : nullptr, params, x, gy_or_target, z_ckpt, target, (int) sk, partials, B, T, stream, err))
+            if (! tree_jit_adjoint (jit, tma ? &mx : nullptr, tma ? &mg : nullptr, params, x, gy_or_target, z_ckpt, target, (int) sk, partials, B, T, stream, err))
                 return fail (DWDF_ERR_CUDA, "specialised tree kernel: %s", err.c_str ());
         }
         else

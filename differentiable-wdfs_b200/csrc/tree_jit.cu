@@ -10,8 +10,8 @@
 //     shared-memory ring, results written in place (the data movement of the diode-clipper kernels); all states
 //     in registers; state checkpoints every 16 samples for the reverse sweep;
 //   * reverse mode: NO tape. Segments of 16 samples, last to first: reload the segment's checkpoint, replay the 16
-//     samples keeping only each sample's start states (registers), then walk the segment backwards, recomputing a
-//     sample's waves from its start state and applying the adjoint of every adaptor equation. Reads x and the target
+//     samples keeping each sample's start states and the root's derivative pieces, then walk the segment backwards,
+//     recomputing a sample's (linear) waves from its start state and applying the adjoint of every adaptor equation. Reads x and the target
 //     (or dL/dy): 8 B/sample, the algorithmic minimum. Same partial-sum layout as tree_adjoint, so tree_finalize
 //     (fixed-order reduction, chain rule through calc_impedance) is shared;
 //   * direct-global-access twins of both kernels for ragged T / unaligned rows.
@@ -82,7 +82,8 @@ const char* pair_mode (const TreeProgram& p) { return p.root_mode == DWDF_MODE_E
 const char* pair_general (const TreeProgram& p) { return (p.n_up == 1.0f && p.n_down == 1.0f) ? "false" : "true"; }
 
 // reflected(): children before parents (tf_wdf.py:57-59,86-88,124-126,153-155,185-192,212-214), then the root
-void emit_up_and_root (Gen& g, const TreeProgram& p, bool deriv)
+// root: 0 = forward only, 1 = with the derivative pieces, recorded in `rec` (the reverse sweep's replay), 2 = taken from `rec`
+void emit_up_and_root (Gen& g, const TreeProgram& p, int root)
 {
     const int top = p.n_nodes - 1;
     for (int i = 0; i <= top; ++i)
@@ -106,10 +107,18 @@ void emit_up_and_root (Gen& g, const TreeProgram& p, bool deriv)
     g.f ("    const float a_root = b%d;\n", top);
     if (p.root_kind == DWDF_ROOT_IDEAL_VS)
         g.f ("    const float b_root = 0.0f - a_root + 2.0f * x;\n"); // tf_wdf.py:23-28
+    else if (root == 2)
+        g.f ("    const float b_root = rec.b;\n    const PairDeriv d { rec.S1, rec.M1, rec.dV };\n    (void) a_root;\n");
     else if (p.root_mode == DWDF_MODE_APPROX_GOOD)
         g.f ("    const float b_root = pair_reflect<kModeApproxGood, false, false, false> (c.pc, a_root, nullptr);\n");
+    else if (root == 1)
+    {
+        g.f ("    PairDeriv d { 0.0f, 0.0f, 0.0f };\n");
+        g.f ("    const float b_root = pair_reflect<%s, %s, true, false> (c.pc, a_root, &d);\n", pair_mode (p), pair_general (p));
+        g.f ("    rec.b = b_root, rec.S1 = d.S1, rec.M1 = d.M1, rec.dV = d.dV;\n");
+    }
     else
-        g.f ("    const float b_root = pair_reflect<%s, %s, %s, false> (c.pc, a_root, %s);\n", pair_mode (p), pair_general (p), deriv ? "true" : "false", deriv ? "&d" : "nullptr");
+        g.f ("    const float b_root = pair_reflect<%s, %s, false, false> (c.pc, a_root, nullptr);\n", pair_mode (p), pair_general (p));
 }
 
 // incident(): parents before children (tf_wdf.py:147-151,179-183,208-210,120-122); reactive leaves hand their state on in zn[]
@@ -201,20 +210,27 @@ std::string tree_jit_generate (const TreeProgram& p)
              hexf (p.tol).c_str ());
     g.f ("}\n\n");
     // ---- one sample: root.incident(tree.reflected()); tree.incident(root.reflected()); y = voltage(probe)
-    g.f ("__device__ __forceinline__ float jit_step (const JC& c, float x, float (&z)[kNS1])\n{\n    float zn[kNS1];\n");
-    emit_up_and_root (g, p, false);
-    emit_down (g, p, true);
-    if (p.pyorder)
-        g.f ("    const float y = (a%d + b%d) * 0.5f;\n", p.probe, p.probe); // probe after tree.incident (clipper_pot.py:113-124)
-    else
-        g.f ("    const float y = (z[kNS] + b%d) * 0.5f;\n", p.probe); // probe between the sweeps (DiodeClipperWDF.cpp:22-29): the previous incident wave
-    g.f ("    zn[kNS] = a%d;\n", p.probe);
-    g.f ("#pragma unroll\n    for (int k = 0; k < kNS1; ++k)\n        z[k] = zn[k];\n    return y;\n}\n\n");
+    g.f ("struct JRec\n{\n    float b, S1, M1, dV; // the root's reflected wave and derivative pieces of one sample (diode-pair root)\n};\n");
+    for (int rec = 0; rec < 2; ++rec)
+    {
+        if (rec == 0)
+            g.f ("__device__ __forceinline__ float jit_step (const JC& c, float x, float (&z)[kNS1])\n{\n    float zn[kNS1];\n");
+        else // the reverse sweep's replay: the same sample, keeping what the adjoint of the root needs
+            g.f ("__device__ __forceinline__ float jit_step_rec (const JC& c, float x, float (&z)[kNS1], JRec& rec)\n{\n    float zn[kNS1];\n    (void) rec;\n");
+        emit_up_and_root (g, p, rec);
+        emit_down (g, p, true);
+        if (p.pyorder)
+            g.f ("    const float y = (a%d + b%d) * 0.5f;\n", p.probe, p.probe); // probe after tree.incident (clipper_pot.py:113-124)
+        else
+            g.f ("    const float y = (z[kNS] + b%d) * 0.5f;\n", p.probe); // probe between the sweeps (DiodeClipperWDF.cpp:22-29): the previous incident wave
+        g.f ("    zn[kNS] = a%d;\n", p.probe);
+        g.f ("#pragma unroll\n    for (int k = 0; k < kNS1; ++k)\n        z[k] = zn[k];\n    return y;\n}\n\n");
+    }
     // ---- reverse mode of one sample: waves recomputed from the sample's start state, then the adjoint of every equation.
     // gz: in = dL/d(states handed to the next sample), out = dL/d(states this sample started from).
-    g.f ("__device__ __forceinline__ void jit_step_adj (const JC& c, float x, const float (&z)[kNS1], float gy, float (&gz)[kNS1], float (&pf)[kNP], float& fl, float& fv)\n{\n");
-    g.f ("    PairDeriv d { 0.0f, 0.0f, 0.0f };\n    (void) d;\n");
-    emit_up_and_root (g, p, true);
+    g.f ("__device__ __forceinline__ void jit_step_adj (const JC& c, float x, const float (&z)[kNS1], const JRec& rec, float gy, float (&gz)[kNS1], float (&pf)[kNP], float& fl, float& fv)\n{\n");
+    g.f ("    (void) rec;\n");
+    emit_up_and_root (g, p, 2);
     emit_down (g, p, false);
     for (int i = 0; i <= top; ++i)
     {
@@ -448,6 +464,7 @@ template <bool UNROLL, class IO>
 __device__ __forceinline__ void jit_adjoint_segment (const JC& c, const IO& io, const float (&z0)[kNS1], float (&gz)[kNS1], int n0, int T, int skip, int target, JitAcc& acc)
 {
     float zs[kSeg][kNS1], ys[kSeg], xs[kSeg];
+    JRec rs[kSeg];
     float z[kNS1];
 #pragma unroll
     for (int k = 0; k < kNS1; ++k)
@@ -463,7 +480,7 @@ __device__ __forceinline__ void jit_adjoint_segment (const JC& c, const IO& io, 
 #pragma unroll
             for (int q = 0; q < kNS1; ++q)
                 zs[s][q] = z[q];
-            ys[s] = jit_step (c, x4[k], z);
+            ys[s] = jit_step_rec (c, x4[k], z, rs[s]);
         }
     };
     float pf[kNP], fl = 0.0f, fv = 0.0f, fsse = 0.0f, fst2 = 0.0f;
@@ -488,7 +505,7 @@ __device__ __forceinline__ void jit_adjoint_segment (const JC& c, const IO& io, 
                     fsse = fma_ (gy, gy, fsse);
                     fst2 = on ? fma_ (t, t, fst2) : fst2;
                 }
-                jit_step_adj (c, xs[s], zs[s], gy, gz, pf, fl, fv);
+                jit_step_adj (c, xs[s], zs[s], rs[s], gy, gz, pf, fl, fv);
             }
         }
     };

@@ -183,7 +183,8 @@ DWDF_API int dwdf_program_is_clipper (const dwdf_program* prog);
  * query them after specialising, and run dwdf_forward again before dwdf_backward). Covers Resistor, ResistiveVoltageSource,
  * Capacitor, Inductor, Series, Parallel, Inverter with an IdealVoltageSource or DiodePair root and a voltage probe, no
  * resistance channel; DWDF_ERR_UNSUPPORTED otherwise (or without libnvrtc) and the program stays on the interpreter.
- * Compiles for about a second; not to be called concurrently with launches of the same program or inside a stream capture.
+ * Compiles for about a second (serialised per program; launches on other threads keep using the interpreter until the
+ * specialised kernels are published); not inside a stream capture.
  * dwdf_program_specialized_source: the text handed to NVRTC (part 0: generated circuit code + kernel skeleton; 1, 2: the
  * two embedded headers it includes, dwdf_math.cuh and dwdf_tma.cuh); returns the size needed including the terminator
  * (0: not a specialisable tree) and copies at most `capacity` bytes. Needs no device: the CPU test-suite compiles it. */
