@@ -505,8 +505,12 @@ def main():
         dist.barrier()  # every rank enters the timed region together (rank 0 has just started the clock sampler)
         torch.cuda.synchronize()
     profiled = world == 1 or comm is not None
+    # per-phase CUDA events (for the roofline block) on the FIRST tenth of the timed steps only: an event record between two kernels
+    # costs nothing at 65536 sequences per GPU but ~4 us per boundary on a 200 us step (it also defeats the programmatic dependent
+    # launches), i.e. 8 % of an 8-GPU shard's step — measured with tools/graph_step_bench.py
+    n_prof_steps = max(1, min(args.steps, max(10, args.steps // 10)))
     if profiled:
-        dwdf._lib.profile_begin(args.steps)
+        dwdf._lib.profile_begin(n_prof_steps)
     t_beg.record()
     for i in range(args.steps):
         step()
@@ -600,7 +604,7 @@ def main():
                        "parallelism": f"dp{world}: sequences sharded, one exchange of 24 doubles per step ({exchange})"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": dom_traffic * B * T if (args.mode == "approx" and B == 65536) else None, "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
-                         "algorithmic_bytes_per_sample": dom_bytes, "kernel_ms": dom_ms, "timing": f"CUDA events at the kernel boundaries inside the timed region, mean of {n_prof} steps (dwdf_profile_begin/_end)",
+                         "algorithmic_bytes_per_sample": dom_bytes, "kernel_ms": dom_ms, "timing": f"CUDA events at the kernel boundaries inside the timed region, mean of its first {n_prof} steps (dwdf_profile_begin/_end)",
                          "fp32": {"what": "second roof (SURVEY.md §8d): algorithmic flops per sample / kernel time against the measured fp32 FMA issue rate; pipe utilisations from ncu are in profiles/r02_*_ncu_*_summary.txt",
                                   "algorithmic_flops_per_sample": {"forward": FLOPS[args.mode][0], "adjoint": FLOPS[args.mode][1]}, "peak_TFLOPs": FP32_PEAK_TFLOPS, "peak_source": FP32_PEAK_SOURCE,
                                   "kernel_TFLOPs": (FLOPS[args.mode][1] if dom == "clipper_adjoint_tma" else FLOPS[args.mode][0]) * B * T / (dom_ms * 1e-3) / 1e12 if dom_ms else None,
