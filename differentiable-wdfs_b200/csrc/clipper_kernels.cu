@@ -273,6 +273,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_tma (const __grid_con
     __shared__ __align__ (8) uint64_t bar_mem[kFwdStages];
     const int lane = threadIdx.x;
     const int b0 = blockIdx.x * kLanes;
+    grid_dependency_wait (); // (a programmatic dependent of the previous step's tail kernel, which updates the parameters)
     ClipConst c;
     load_consts (c, desc, params);
     const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __gri
     __shared__ __align__ (8) uint64_t bar_mem[kFwdStages];
     const int lane = threadIdx.x;
     const int b0 = blockIdx.x * kPairRows;
+    grid_dependency_wait (); // (a programmatic dependent of the previous step's tail kernel, which updates the parameters)
     ClipConst c;
     load_consts (c, desc, params);
     const int ntiles = (T + kFwdTileT - 1) / kFwdTileT;
@@ -1855,7 +1857,7 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
             {
                 const unsigned groups = (unsigned) ((B + kPairRows - 1) / kPairRows);
                 const int kmax = propose_chunks (resident_ctas (clipper_forward_pair_tma<kM, p>), groups, ntiles, cap);
-                clipper_forward_pair_tma<kM, p><<<dim3 (groups, (unsigned) kmax), kLanes, 0, stream>>> (maps->x2, maps->y2, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, opts);
+                launch_dependent (! (opts & kOptNoPdl), clipper_forward_pair_tma<kM, p>, dim3 (groups, (unsigned) kmax), dim3 (kLanes), stream, maps->x2, maps->y2, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, opts);
                 if (kmax > 1)
                 {
                     launch_dependent (! (opts & kOptNoPdl), clipper_forward_stitch<kM, kG, p>, dim3 ((unsigned) ((B + 127) / 128)), dim3 (128), stream, x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 1, maps->redone, opts);
@@ -1865,7 +1867,7 @@ cudaError_t clipper_forward_part<kM, kG> (bool py, bool use_tma, const ClipTmaMa
             }
         }
         const int kmax = propose_chunks (resident_ctas (clipper_forward_tma<kM, kG, p>), grid, ntiles, cap);
-        clipper_forward_tma<kM, kG, p><<<dim3 (grid, (unsigned) kmax), kLanes, 0, stream>>> (maps->x, maps->y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, opts);
+        launch_dependent (! (opts & kOptNoPdl), clipper_forward_tma<kM, kG, p>, dim3 (grid, (unsigned) kmax), dim3 (kLanes), stream, maps->x, maps->y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, opts);
         if (kmax > 1)
         {
             launch_dependent (! (opts & kOptNoPdl), clipper_forward_stitch<kM, kG, p>, dim3 ((unsigned) ((B + 127) / 128)), dim3 (128), stream, x, y, params, desc, ckpt, state, maps->zs, maps->ze, B, (int) T, kmax, 0, maps->redone, opts);
