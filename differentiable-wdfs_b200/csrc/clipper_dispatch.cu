@@ -211,19 +211,19 @@ __global__ void adam_kernel (float* __restrict__ params, const double* __restric
 // message is pure latency, so instead of a library all-reduce between two tiny kernels, the reduction kernel does the
 // exchange itself through NVLink peer memory: every rank owns a MAILBOX (device memory its peers map with CUDA IPC),
 // with one slot per sender and epoch parity. A step's kernel
-//     1. writes its vector into slot[my rank] of EVERY rank's mailbox (remote stores, then a system-scope release of
-//        the slot's epoch flag),
-//     2. waits until all slots of its OWN mailbox carry this epoch (system-scope acquire loads, local memory),
+//     1. writes its vector into slot[my rank] of EVERY rank's mailbox as self-validating 8-byte words (epoch tag | half a
+//        double: peer_allreduce below), plain remote stores, no fence,
+//     2. polls the slots of its OWN mailbox (local memory) until every word carries this epoch's tag,
 //     3. sums the slots in rank order — every rank adds the same numbers in the same order, so the results (and
 //        after Adam the parameters) are bit-identical on all ranks without a broadcast.
-// Slots alternate with the epoch's parity: a rank can only be one epoch ahead of a peer (it needs that peer's flag of
+// Slots alternate with the epoch's parity: a rank can only be one epoch ahead of a peer (it needs that peer's words of
 // the current epoch to finish), so the slot it writes next is never one a peer is still reading. A peer that never
 // arrives is reported after a timeout (the result block is filled with NaN) instead of hanging the GPU.
-__device__ __forceinline__ void st_release_sys (unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ unsigned long long ld_acquire_sys (const unsigned long long* p)
+__device__ __forceinline__ void st_relaxed_sys (unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys (const unsigned long long* p)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns ()
@@ -235,51 +235,65 @@ __device__ __forceinline__ unsigned long long global_timer_ns ()
 
 // vals[0..n) (shared or global memory of this block) <- sum over ranks. All 256 threads of the single block call it.
 // Returns false on timeout (some thread saw a peer missing); the caller decides what to report.
+// Wire format: every double travels as two 8-byte words {epoch tag (high 32 bits) | half of the double (low 32 bits)}. An
+// 8-byte store is atomic on NVLink, so a word whose tag equals this epoch IS its data: no fence between payload and flag, no
+// separate flag round trip — the exchange costs one one-way trip plus the skew between the ranks. (Tag 0 = the zeroed mailbox.)
+constexpr int kDpChunk = 64; // doubles received per round: kDpMaxWorld x 2 x kDpChunk halves staged in shared memory
 __device__ __forceinline__ bool peer_allreduce (double* vals, int n, const DpPeers& dp, unsigned long long epoch, int* timed_out_sm)
 {
+    __shared__ unsigned int halves[kDpMaxWorld][2 * kDpChunk];
     const int tid = threadIdx.x;
-    const size_t slot_bytes = (size_t) kDpSlotDoubles * sizeof (double);
+    const unsigned long long tag = (epoch & 0xffffffffull) << 32;
+    const size_t slot_bytes = (size_t) kDpSlotDoubles * 2 * sizeof (unsigned long long);
     const size_t parity_off = (size_t) (epoch & 1ull) * dp.world * slot_bytes;
+    // send: my 2 n words into slot[my rank] of every rank's mailbox (my own included)
     for (int p = 0; p < dp.world; ++p)
     {
-        double* dst = reinterpret_cast<double*> (dp.mailbox[p] + parity_off + (size_t) dp.rank * slot_bytes);
-        for (int i = tid; i < n; i += blockDim.x)
-            dst[i] = vals[i];
-    }
-    __threadfence_system ();
-    __syncthreads ();
-    if (tid < dp.world)
-    {
-        st_release_sys (reinterpret_cast<unsigned long long*> (dp.mailbox[tid] + parity_off + (size_t) dp.rank * slot_bytes) + (kDpSlotDoubles - 1), epoch);
-        const unsigned long long* flag = reinterpret_cast<const unsigned long long*> (dp.mailbox[dp.rank] + parity_off + (size_t) tid * slot_bytes) + (kDpSlotDoubles - 1);
-        const unsigned long long t0 = global_timer_ns ();
-        while (ld_acquire_sys (flag) != epoch)
+        unsigned long long* dst = reinterpret_cast<unsigned long long*> (dp.mailbox[p] + parity_off + (size_t) dp.rank * slot_bytes);
+        for (int w = tid; w < 2 * n; w += blockDim.x)
         {
-            if (global_timer_ns () - t0 > dp.timeout_ns)
-            {
-                *timed_out_sm = 1;
-                break;
-            }
+            const unsigned long long bits = (unsigned long long) __double_as_longlong (vals[w >> 1]);
+            st_relaxed_sys (dst + w, tag | ((w & 1) ? (bits >> 32) : (bits & 0xffffffffull)));
         }
     }
-    __syncthreads ();
-    const bool ok = *timed_out_sm == 0;
-    for (int i = tid; i < n; i += blockDim.x)
+    __syncthreads (); // every word of vals has been read before the sums overwrite it
+    const unsigned long long t0 = global_timer_ns ();
+    for (int c0 = 0; c0 < n; c0 += kDpChunk)
     {
-        double s = 0.0;
-        for (int p = 0; p < dp.world; ++p)
-            s += reinterpret_cast<const volatile double*> (dp.mailbox[dp.rank] + parity_off + (size_t) p * slot_bytes)[i];
-        vals[i] = ok ? s : __longlong_as_double (0x7ff8000000000000ll);
+        const int nc = min (kDpChunk, n - c0);
+        // receive: all threads poll the words of this round in parallel (local memory: the peers' stores land here)
+        for (int k = tid; k < dp.world * 2 * nc; k += blockDim.x)
+        {
+            const int p = k / (2 * nc), w = k % (2 * nc);
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*> (dp.mailbox[dp.rank] + parity_off + (size_t) p * slot_bytes) + 2 * c0 + w;
+            unsigned long long v;
+            while (((v = ld_relaxed_sys (src)) & 0xffffffff00000000ull) != tag)
+                if (global_timer_ns () - t0 > dp.timeout_ns)
+                {
+                    *timed_out_sm = 1;
+                    break;
+                }
+            halves[p][w] = (unsigned int) v;
+        }
+        __syncthreads ();
+        const bool ok = *timed_out_sm == 0;
+        for (int i = tid; i < nc; i += blockDim.x)
+        { // summed in rank order: every rank adds the same numbers in the same order
+            double sum = 0.0;
+            for (int p = 0; p < dp.world; ++p)
+                sum += __longlong_as_double ((long long) (((unsigned long long) halves[p][2 * i + 1] << 32) | halves[p][2 * i]));
+            vals[c0 + i] = ok ? sum : __longlong_as_double (0x7ff8000000000000ll);
+        }
+        __syncthreads ();
     }
-    __syncthreads ();
-    return ok;
+    return *timed_out_sm == 0;
 }
 
 __device__ __forceinline__ unsigned long long next_epoch (const DpPeers& dp, unsigned long long* epoch_sm)
 {
     if (threadIdx.x == 0)
     {
-        unsigned long long* ctr = reinterpret_cast<unsigned long long*> (dp.mailbox[dp.rank] + (size_t) 2 * dp.world * kDpSlotDoubles * sizeof (double));
+        unsigned long long* ctr = reinterpret_cast<unsigned long long*> (dp.mailbox[dp.rank] + (size_t) 2 * dp.world * kDpSlotDoubles * 2 * sizeof (unsigned long long));
         *epoch_sm = *ctr + 1;
         *ctr = *epoch_sm;
     }

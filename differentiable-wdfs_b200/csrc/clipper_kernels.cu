@@ -145,11 +145,12 @@ struct ChunkPlan
 
 __device__ __forceinline__ int warmup_samples_raw (const ClipConst& c, int opts)
 {
-    // off-state contraction per sample: dz'/dz = 1 - 2 gamma (f' = 1). (1 - 2 gamma)^W <= 1e-13: far enough below
-    // one ulp of a quiet signal that the speculated and the true trajectory have merged bit for bit. (A/B switches:
-    // 1e-10 / 1e-8 — shorter warm-ups, more chunks for the verification pass to repair; the result is the same bits.)
+    // off-state contraction per sample: dz'/dz = 1 - 2 gamma (f' = 1). (1 - 2 gamma)^W <= 1e-10: below one ulp of the
+    // state by the end of the warm-up, so the speculated and the true trajectory have merged bit for bit in all but a
+    // few chunks in ten thousand (measured: 24 of 81920 at config 5's shard; 0 at 1e-13, 5064 at 1e-8), and those few the
+    // verification pass repairs — the result is the same bits whatever the threshold. (A/B switches: 1e-13, 1e-8.)
     const float rho = fmaxf (fabsf (1.0f - 2.0f * c.gamma), 0.5f);
-    const float lnthr = (opts & kOptWarm8) ? 18.4f : ((opts & kOptWarm10) ? 23.0f : 29.9f);
+    const float lnthr = (opts & kOptWarm8) ? 18.4f : ((opts & kOptWarm13) ? 29.9f : 23.0f);
     const float w = -lnthr / logf (fminf (rho, 0.999999f));
     return (int) fminf (w, 1.0e6f);
 }

@@ -46,7 +46,7 @@ enum : int
     kOptNoPair = 2, // forward, approx: one sequence per lane instead of the packed-fp32x2 pair kernel
     kOptNoChunks = 8, // never use the time-parallel kernels
     kOptForceChunks = 16, // use them whatever the batch size (crossover measurements)
-    kOptWarm10 = 64, kOptWarm8 = 128, // time-chunk warm-up until the off-state decay is 1e-10 / 1e-8 instead of 1e-13 (shorter warm-up, more repairs)
+    kOptWarm13 = 64, kOptWarm8 = 128, // time-chunk warm-up until the off-state decay is 1e-13 / 1e-8 instead of 1e-10 (longer: no repairs; shorter: many)
     kOptNoPdl = 256, // no programmatic dependent launches
     kOptL2Prefetch = 4 // cp.async.bulk.prefetch.tensor L2 run-ahead (measured: slower — forward 0.47 -> 0.58 ms, adjoint 0.63 -> 0.94 ms; off)
 };
@@ -123,14 +123,14 @@ cudaError_t launch_clipper_finalize (const ClipDesc& desc, const float* params, 
 
 // ---- multi-GPU exchange over peer memory (clipper_dispatch.cu explains the protocol) ----------------------------
 constexpr int kDpMaxWorld = 16; // ranks of one node
-constexpr int kDpSlotDoubles = 2048; // doubles per mailbox slot; the last one is the slot's epoch flag
+constexpr int kDpSlotDoubles = 2048; // doubles per mailbox slot (16 bytes each on the wire: two tagged 8-byte words)
 struct DpPeers // by-value kernel argument
 {
     int rank, world;
     unsigned long long timeout_ns;
     char* mailbox[kDpMaxWorld]; // every rank's mailbox as mapped into this process; mailbox[rank] is this rank's own
 };
-inline size_t dp_mailbox_bytes (int world) { return (size_t) 2 * world * kDpSlotDoubles * sizeof (double) + 256; } // two parities x world slots, then the epoch counter
+inline size_t dp_mailbox_bytes (int world) { return (size_t) 2 * world * kDpSlotDoubles * 2 * sizeof (unsigned long long) + 256; } // two parities x world slots, then the epoch counter
 cudaError_t launch_clipper_finalize_dp (const ClipDesc& desc, float* params, const double* partials, int64_t n_groups, bool target, int loss_kind, double count, double* out, const DpPeers& dp, float* m, float* v, int32_t* step, int n_params,
                                         float lr, const float* lr_vec, float beta1, float beta2, float eps, const float* lo, const float* hi, cudaStream_t stream);
 cudaError_t launch_peer_allreduce (double* inout, int n, const DpPeers& dp, cudaStream_t stream);

@@ -251,8 +251,9 @@ DWDF_API int dwdf_train_step (const dwdf_program* prog, float* params, const flo
  * over GPUs with no data-path collective, and a training step exchanges ONE small vector (the DWDF_OUT_LEN raw sums; the
  * weight-gradient vector for the neural root). That message is pure latency, so the exchange runs INSIDE the step's
  * reduction kernel over NVLink peer memory instead of as a library collective between two tiny kernels: every rank owns a
- * mailbox (device memory, mapped by its peers with CUDA IPC); a step writes its vector into its slot of every mailbox,
- * waits for all slots of its own, and sums them in rank order (bit-identical results on every rank, no broadcast).
+ * mailbox (device memory, mapped by its peers with CUDA IPC); a step writes its vector into its slot of every mailbox as
+ * self-validating 8-byte words (epoch tag + half a double: no fence, no separate flag), polls the slots of its own until
+ * every word carries the epoch, and sums them in rank order (bit-identical results on every rank, no broadcast).
  *   dwdf_comm_create      allocates this rank's mailbox on the CURRENT device
  *   dwdf_comm_get_handle  the mailbox's CUDA IPC handle (dwdf_comm_handle_bytes() bytes), to be gathered by the launcher
  *                         (torch.distributed / MPI / a file — any out-of-band channel)
@@ -332,8 +333,8 @@ DWDF_API int dwdf_set_tma (int enable);
 /* Kernel-variant switches for A/B timing (bit values). 1: forward approx root evaluated sample by sample
  * (no packed fast step); 2: one sequence per lane instead of the packed-fp32x2 pair kernels; 4: TMA L2 prefetch
  * run-ahead; 8: never use time chunks (small batches run one lane per sequence over the whole T); 16: use time
- * chunks whatever the batch size; 64 / 128: time-chunk warm-up until the off-state decay is 1e-10 / 1e-8 instead
- * of 1e-13 (same bits out: the verification pass repairs more chunks); 256: no programmatic dependent launches.
+ * chunks whatever the batch size; 64 / 128: time-chunk warm-up until the off-state decay is 1e-13 / 1e-8 instead
+ * of 1e-10 (same bits out: the verification pass repairs what the speculation missed); 256: no programmatic dependent launches.
  * 0 = shipped behaviour. Returns the previous bits. */
 DWDF_API int dwdf_set_option (int bits);
 /* Diagnostics: chunks the time-parallel forward kernels (small batches) had to recompute so far because
