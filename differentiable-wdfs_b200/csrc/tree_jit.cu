@@ -15,9 +15,10 @@
 //     (or dL/dy): 8 B/sample, the algorithmic minimum. Same partial-sum layout as tree_adjoint, so tree_finalize
 //     (fixed-order reduction, chain rule through calc_impedance) is shared;
 //   * direct-global-access twins of both kernels for ragged T / unaligned rows.
-// Covered: Resistor, ResistiveVoltageSource, Capacitor, Inductor, Series, Parallel, Inverter; roots IdealVoltageSource
-// and DiodePair (every law and mode); voltage probe; both probe orderings. Everything else (alpha-transform leaves,
-// Y-parameter, current sources, diode / switch roots, current probe, per-sample resistance channel) stays on the
+// Covered: every element and root of the interpreter (Resistor, Capacitor, Inductor, alpha-transform C / L, resistive and
+// ideal voltage / current sources, Series, Parallel, Inverter, Y-parameter; diode pair of every law and mode, single diode,
+// switch), voltage or current probe, both probe orderings; reverse mode where the interpreter has it (the wdf_py elements and
+// the inductor, ideal-voltage-source or diode-pair root, voltage probe). Only the per-sample resistance channel stays on the
 // interpreter. NVRTC is loaded with dlopen: without it dwdf_program_specialize reports DWDF_ERR_UNSUPPORTED and the
 // program keeps running on the interpreter (still on the GPU — there is no CPU path anywhere).
 #include "dwdf_kernels.h"
@@ -78,6 +79,18 @@ int adaptor_slot (const TreeProgram& p, int i)
     return j;
 }
 
+bool is_alpha (int k) { return k == DWDF_CAPACITOR_ALPHA || k == DWDF_INDUCTOR_ALPHA; }
+// reverse mode exists for the wdf_py element set and the inductor, closed by an ideal voltage source or a diode pair, voltage probe
+bool jit_differentiable (const TreeProgram& p)
+{
+    if (p.probe_current != 0 || (p.root_kind != DWDF_ROOT_IDEAL_VS && p.root_kind != DWDF_ROOT_DIODE_PAIR))
+        return false;
+    for (int i = 0; i < p.n_nodes; ++i)
+        if (p.kind[i] > DWDF_INDUCTOR)
+            return false;
+    return true;
+}
+
 const char* pair_mode (const TreeProgram& p) { return p.root_mode == DWDF_MODE_EXACT ? "kModeExact" : (p.root_mode == DWDF_MODE_APPROX_GOOD ? "kModeApproxGood" : "kModeApprox"); }
 const char* pair_general (const TreeProgram& p) { return (p.n_up == 1.0f && p.n_down == 1.0f) ? "false" : "true"; }
 
@@ -95,6 +108,15 @@ void emit_up_and_root (Gen& g, const TreeProgram& p, int root)
             case DWDF_RESISTIVE_VS: g.f ("    const float b%d = %s;\n", i, i == p.source ? "x" : "0.0f"); break;
             case DWDF_CAPACITOR: g.f ("    const float b%d = z[%d];\n", i, p.state_of[i]); break;
             case DWDF_INDUCTOR: g.f ("    const float b%d = 0.0f - z[%d];\n", i, p.state_of[i]); break; // wdf_t.h:334-338
+            case DWDF_RESISTIVE_CS: // wdf_t.h:827-831: b = R Is
+                if (i == p.source)
+                    g.f ("    const float b%d = c.R[%d] * x;\n", i, i);
+                else
+                    g.f ("    const float b%d = 0.0f;\n", i);
+                break;
+            case DWDF_CAPACITOR_ALPHA: g.f ("    const float b%d = c.cb[%d] * z[%d] + c.ca[%d] * z[%d];\n", i, i, p.state_of[i] + 1, i, p.state_of[i]); break; // wdf_t.h:262-266 (z[s + 1]: the previous reflected wave)
+            case DWDF_INDUCTOR_ALPHA: g.f ("    const float b%d = c.cb[%d] * z[%d] - c.ca[%d] * z[%d];\n", i, i, p.state_of[i] + 1, i, p.state_of[i]); break; // wdf_t.h:426-430
+            case DWDF_Y_PARAMETER: g.f ("    const float b%d = c.cc[%d] * b%d;\n", i, i, c1); break; // wdf_t.h:637-641: b = C port1.b
             case DWDF_SERIES: g.f ("    const float b%d = 0.0f - (b%d + b%d);\n", i, c1, c2); break;
             case DWDF_PARALLEL:
                 g.f ("    const float bd%d = b%d - b%d;\n", i, c2, c1);
@@ -107,6 +129,12 @@ void emit_up_and_root (Gen& g, const TreeProgram& p, int root)
     g.f ("    const float a_root = b%d;\n", top);
     if (p.root_kind == DWDF_ROOT_IDEAL_VS)
         g.f ("    const float b_root = 0.0f - a_root + 2.0f * x;\n"); // tf_wdf.py:23-28
+    else if (p.root_kind == DWDF_ROOT_IDEAL_CS)
+        g.f ("    const float b_root = 2.0f * c.R[%d] * x + a_root;\n", top); // wdf_t.h:777-781: b = 2 R Is + a
+    else if (p.root_kind == DWDF_ROOT_SWITCH)
+        g.f ("    const float b_root = %s;\n", p.root_mode != 0 ? "0.0f - a_root" : "a_root"); // wdf_t.h:1094-1098 (closed: -a, open: a)
+    else if (p.root_kind == DWDF_ROOT_DIODE) // wdf_t.h:1027-1032 (eq. 10): b = a + 2 R Is - 2 Vt omega4(ln(R Is / Vt) + a / Vt + R Is / Vt)
+        g.f ("    const float b_root = a_root + 2.0f * c.pc.RIs - c.pc.twoV * omega4_approx (c.pc.L + a_root * c.pc.invV + c.pc.RIs_overV);\n");
     else if (root == 2)
         g.f ("    const float b_root = rec.b;\n    const PairDeriv d { rec.S1, rec.M1, rec.dV };\n    (void) a_root;\n");
     else if (p.root_mode == DWDF_MODE_APPROX_GOOD)
@@ -142,10 +170,16 @@ void emit_down (Gen& g, const TreeProgram& p, bool states)
                 g.f ("    const float a%d = t%d;\n", c2, i);
                 break;
             case DWDF_INVERTER: g.f ("    const float a%d = 0.0f - a%d;\n", c1, i); break;
+            case DWDF_Y_PARAMETER: g.f ("    const float a%d = c.ca[%d] * b%d + c.cb[%d] * a%d;\n", c1, i, c1, i, i); break; // wdf_t.h:630-634: port1.incident(A port1.b + B x)
             case DWDF_CAPACITOR:
             case DWDF_INDUCTOR:
                 if (states)
                     g.f ("    zn[%d] = a%d;\n", p.state_of[i], i);
+                break;
+            case DWDF_CAPACITOR_ALPHA:
+            case DWDF_INDUCTOR_ALPHA:
+                if (states)
+                    g.f ("    zn[%d] = a%d;\n    zn[%d] = b%d;\n", p.state_of[i], i, p.state_of[i] + 1, i);
                 break;
             default: break;
         }
@@ -156,16 +190,14 @@ void emit_down (Gen& g, const TreeProgram& p, bool states)
 
 bool tree_jit_supported (const TreeProgram& p)
 {
-    if (p.n_nodes < 1 || p.n_nodes > 16 || p.probe_current != 0 || p.r_node >= 0)
+    // every element and root of the interpreter; only the per-sample resistance channel (calc_impedance every sample) stays there
+    if (p.n_nodes < 1 || p.n_nodes > 16 || p.r_node >= 0)
         return false;
-    if (p.root_kind != DWDF_ROOT_IDEAL_VS && p.root_kind != DWDF_ROOT_DIODE_PAIR)
+    if (p.root_kind != DWDF_ROOT_IDEAL_VS && p.root_kind != DWDF_ROOT_DIODE_PAIR && p.root_kind != DWDF_ROOT_IDEAL_CS && p.root_kind != DWDF_ROOT_DIODE && p.root_kind != DWDF_ROOT_SWITCH)
         return false;
     for (int i = 0; i < p.n_nodes; ++i)
-    {
-        const int k = p.kind[i];
-        if (k != DWDF_RESISTOR && k != DWDF_RESISTIVE_VS && k != DWDF_CAPACITOR && k != DWDF_INDUCTOR && k != DWDF_SERIES && k != DWDF_PARALLEL && k != DWDF_INVERTER)
+        if (p.kind[i] < DWDF_RESISTOR || p.kind[i] > DWDF_Y_PARAMETER)
             return false;
-    }
     return true;
 }
 
@@ -183,7 +215,8 @@ std::string tree_jit_generate (const TreeProgram& p)
     g.f ("constexpr int kNS = %d, kNS1 = kNS + 1; // reactive states, + the probe's previous incident wave (plugin ordering reads it)\n", p.n_states);
     g.f ("constexpr int kNP = %d, kNPreal = %d; // adaptor coefficients (p1R): one gradient accumulator each\n", n_adapt > 0 ? n_adapt : 1, n_adapt);
     g.f ("constexpr bool kUnrollSegment = %s; // a diode root is too much code to unroll 16 samples of\n", diode ? "false" : "true");
-    g.f ("struct JC\n{\n    float p[kNP];\n    PairConst pc;\n};\n");
+    g.f ("constexpr int kNN = %d; // nodes\n", p.n_nodes);
+    g.f ("struct JC\n{\n    float p[kNP]; // adaptor coefficients p1R\n    float R[kNN], ca[kNN], cb[kNN], cc[kNN]; // port resistances; alpha-transform a_coef / b_coef, Y-parameter A / B / C\n    float Gprobe;\n    PairConst pc;\n};\n");
     // ---- constants: calc_impedance, children before parents (tf_wdf.py:77-78,114-115,139-145,168-177,204-206)
     g.f ("__device__ __forceinline__ void jit_consts (const float* __restrict__ params, JC& c)\n{\n    const float fs = %s;\n    c.p[0] = 0.0f;\n", hexf (p.fs).c_str ());
     for (int i = 0; i <= top; ++i)
@@ -201,33 +234,76 @@ std::string tree_jit_generate (const TreeProgram& p)
             case DWDF_PARALLEL:
                 g.f ("    const float G%d = G%d + G%d, R%d = 1.0f / G%d;\n    c.p[%d] = G%d / G%d;\n", i, c1, c2, i, i, adaptor_slot (p, i), c1, i);
                 break;
+            case DWDF_RESISTIVE_CS: g.f ("    const float R%d = __ldg (params + %d), G%d = 1.0f / R%d;\n", i, p.param[i], i, i); break; // wdf_t.h:809-813
+            case DWDF_CAPACITOR_ALPHA: // wdf_t.h:247-251: 1 / ((1 + alpha) fs C); b_coef, a_coef :205-206
+                g.f ("    const float al%d = __ldg (params + %d);\n", i, p.param[i] + 1);
+                g.f ("    const float R%d = 1.0f / ((1.0f + al%d) * __ldg (params + %d) * fs), G%d = 1.0f / R%d;\n", i, i, p.param[i], i, i);
+                g.f ("    c.cb[%d] = (1.0f - al%d) / 2.0f;\n    c.ca[%d] = (1.0f + al%d) / 2.0f;\n", i, i, i, i);
+                break;
+            case DWDF_INDUCTOR_ALPHA: // wdf_t.h:411-415: (1 + alpha) fs L
+                g.f ("    const float al%d = __ldg (params + %d);\n", i, p.param[i] + 1);
+                g.f ("    const float R%d = (1.0f + al%d) * __ldg (params + %d) * fs, G%d = 1.0f / R%d;\n", i, i, p.param[i], i, i);
+                g.f ("    c.cb[%d] = (1.0f - al%d) / 2.0f;\n    c.ca[%d] = (1.0f + al%d) / 2.0f;\n", i, i, i, i);
+                break;
+            case DWDF_Y_PARAMETER: // wdf_t.h:614-627
+                g.f ("    const float y11_%d = __ldg (params + %d), y12_%d = __ldg (params + %d), y21_%d = __ldg (params + %d), y22_%d = __ldg (params + %d);\n", i, p.param[i], i, p.param[i] + 1, i, p.param[i] + 2, i,
+                     p.param[i] + 3);
+                g.f ("    const float den%d = y22_%d + R%d * y11_%d * y22_%d - R%d * y12_%d * y21_%d;\n", i, i, c1, i, i, c1, i, i);
+                g.f ("    const float R%d = (R%d * y11_%d + 1.0f) / den%d, G%d = 1.0f / R%d;\n", i, c1, i, i, i, i);
+                g.f ("    const float rSq%d = R%d * R%d;\n", i, c1, c1);
+                g.f ("    const float n1A%d = -y22_%d * rSq%d * y11_%d * y11_%d, n2A%d = y12_%d * y21_%d * rSq%d * y11_%d;\n", i, i, i, i, i, i, i, i, i, i);
+                g.f ("    c.ca[%d] = (n1A%d + n2A%d + y22_%d) / (den%d * (R%d * y11_%d + 1.0f));\n", i, i, i, i, i, c1, i);
+                g.f ("    c.cb[%d] = -R%d * y12_%d / (R%d * y11_%d + 1.0f);\n    c.cc[%d] = -y21_%d / den%d;\n", i, c1, i, c1, i, i, i, i);
+                break;
             default: g.f ("    const float R%d = R%d, G%d = 1.0f / R%d;\n", i, c1, i, i); break;
         }
+        g.f ("    c.R[%d] = R%d;\n    (void) G%d;\n", i, i, i);
     }
-    g.f ("    (void) fs;\n    (void) G%d;\n", top);
-    if (diode)
+    g.f ("    (void) fs;\n    c.Gprobe = G%d;\n", p.probe);
+    if (diode || p.root_kind == DWDF_ROOT_DIODE)
         g.f ("    pair_setup (c.pc, R%d, __ldg (params + %d), %s, __ldg (params + %d), %s, %s, %d, %s);\n", top, p.slot_Is, hexf (p.Vt).c_str (), p.slot_nabla, hexf (p.n_up).c_str (), hexf (p.n_down).c_str (), p.n_iter,
              hexf (p.tol).c_str ());
     g.f ("}\n\n");
     // ---- one sample: root.incident(tree.reflected()); tree.incident(root.reflected()); y = voltage(probe)
     g.f ("struct JRec\n{\n    float b, S1, M1, dV; // the root's reflected wave and derivative pieces of one sample (diode-pair root)\n};\n");
+    const bool differentiable = jit_differentiable (p);
     for (int rec = 0; rec < 2; ++rec)
     {
+        if (rec == 1 && ! differentiable)
+        { // forward-only circuit: reverse mode is refused at the API (the kernels of the skeleton still have to compile)
+            g.f ("__device__ __forceinline__ float jit_step_rec (const JC& c, float x, float (&z)[kNS1], JRec&) { return jit_step (c, x, z); }\n\n");
+            break;
+        }
         if (rec == 0)
             g.f ("__device__ __forceinline__ float jit_step (const JC& c, float x, float (&z)[kNS1])\n{\n    float zn[kNS1];\n");
         else // the reverse sweep's replay: the same sample, keeping what the adjoint of the root needs
             g.f ("__device__ __forceinline__ float jit_step_rec (const JC& c, float x, float (&z)[kNS1], JRec& rec)\n{\n    float zn[kNS1];\n    (void) rec;\n");
         emit_up_and_root (g, p, rec);
         emit_down (g, p, true);
-        if (p.pyorder)
-            g.f ("    const float y = (a%d + b%d) * 0.5f;\n", p.probe, p.probe); // probe after tree.incident (clipper_pot.py:113-124)
-        else
-            g.f ("    const float y = (z[kNS] + b%d) * 0.5f;\n", p.probe); // probe between the sweeps (DiodeClipperWDF.cpp:22-29): the previous incident wave
+        // probe after tree.incident (clipper_pot.py:113-124) or between the sweeps (DiodeClipperWDF.cpp:22-29: the previous incident
+        // wave); voltage (a + b) / 2 (tf_wdf.py:8-10) or current (a - b) / (2 R) (wdf_t.h:1119-1123)
+        {
+            char ap[32];
+            if (p.pyorder)
+                snprintf (ap, sizeof (ap), "a%d", p.probe);
+            else
+                snprintf (ap, sizeof (ap), "z[kNS]");
+            if (p.probe_current)
+                g.f ("    const float y = (%s - b%d) * (0.5f * c.Gprobe);\n", ap, p.probe);
+            else
+                g.f ("    const float y = (%s + b%d) * 0.5f;\n", ap, p.probe);
+        }
         g.f ("    zn[kNS] = a%d;\n", p.probe);
         g.f ("#pragma unroll\n    for (int k = 0; k < kNS1; ++k)\n        z[k] = zn[k];\n    return y;\n}\n\n");
     }
     // ---- reverse mode of one sample: waves recomputed from the sample's start state, then the adjoint of every equation.
     // gz: in = dL/d(states handed to the next sample), out = dL/d(states this sample started from).
+    if (! differentiable)
+    {
+        g.f ("__device__ __forceinline__ void jit_step_adj (const JC&, float, const float (&)[kNS1], const JRec&, float, float (&)[kNS1], float (&)[kNP], float&, float&) {}\n\n");
+        g.f ("__device__ __forceinline__ int jit_pf_node (int) { return 0; }\n} // namespace dwdf\n\n");
+        return g.s;
+    }
     g.f ("__device__ __forceinline__ void jit_step_adj (const JC& c, float x, const float (&z)[kNS1], const JRec& rec, float gy, float (&gz)[kNS1], float (&pf)[kNP], float& fl, float& fv)\n{\n");
     g.f ("    (void) rec;\n");
     emit_up_and_root (g, p, 2);
@@ -770,8 +846,11 @@ TreeJit* tree_jit_create (const TreeProgram& p, std::string& err)
         delete j;
         return nullptr;
     }
-    const char* opts[] = { "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo" };
-    const int rc = rt.CompileProgram (prog, 3, opts);
+    // --fmad=false: the generated wave arithmetic is evaluated as written, one rounding per operation like the reference's own
+    // (where the compiler contracts a product into an FMA on one sweep and not on the other, an open switch is no longer exactly
+    // silent); dwdf_math.cuh spells out the FMAs it wants (fma_), so the roots are unaffected
+    const char* opts[] = { "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--fmad=false" };
+    const int rc = rt.CompileProgram (prog, 4, opts);
     if (rc != 0)
     {
         size_t n = 0;

@@ -180,9 +180,9 @@ DWDF_API int dwdf_program_is_clipper (const dwdf_program* prog);
  * the reverse-mode step derived node by node), compiles it with NVRTC for sm_100a and loads it: the same entry points
  * then run TMA-tiled kernels with every state in registers, and reverse mode keeps no tape (16-sample segments replayed
  * from state checkpoints that dwdf_forward writes to z_ckpt; dwdf_ckpt_bytes / dwdf_workspace_bytes change accordingly, so
- * query them after specialising, and run dwdf_forward again before dwdf_backward). Covers Resistor, ResistiveVoltageSource,
- * Capacitor, Inductor, Series, Parallel, Inverter with an IdealVoltageSource or DiodePair root and a voltage probe, no
- * resistance channel; DWDF_ERR_UNSUPPORTED otherwise (or without libnvrtc) and the program stays on the interpreter.
+ * query them after specialising, and run dwdf_forward again before dwdf_backward). Covers every element, root and probe of the
+ * interpreter (reverse mode where the interpreter has it) except a per-sample resistance channel: DWDF_ERR_UNSUPPORTED then (or
+ * without libnvrtc) and the program stays on the interpreter.
  * Compiles for about a second (serialised per program; launches on other threads keep using the interpreter until the
  * specialised kernels are published); not inside a stream capture.
  * dwdf_program_specialized_source: the text handed to NVRTC (part 0: generated circuit code + kernel skeleton; 1, 2: the

@@ -56,7 +56,7 @@ def test_generated_source_compiles_for_sm_100a(dwdf, name):
     main, hm, ht = _source(lib, h, 0), _source(lib, h, 1), _source(lib, h, 2)
     assert b"jit_step_adj" in main and b"jit_tree_adjoint_tma" in main and b"pair_reflect" in hm and b"tma_load_2d" in ht
     err, prog = nvrtc.nvrtcCreateProgram(main, b"dwdf_tree_jit.cu", 2, [hm, ht], [b"dwdf_math.cuh", b"dwdf_tma.cuh"])
-    opts = [b"--gpu-architecture=sm_100a", b"-std=c++17"]
+    opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"--fmad=false"]
     (err,) = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
     _, nlog = nvrtc.nvrtcGetProgramLogSize(prog)
     log = b" " * nlog
@@ -71,18 +71,25 @@ def test_unsupported_circuits_say_so(dwdf):
     L = dwdf._lib
     lib = L.lib()
     h = C.c_void_p()
-    # the diode clipper has its own kernels; a resistance channel and a current probe stay on the interpreter
+    # the diode clipper has its own kernels; a per-sample resistance channel stays on the interpreter
     clip = (L.Node * 3)(L.Node(L.RESISTIVE_VS, -1, -1, 0), L.Node(L.CAPACITOR, -1, -1, 1), L.Node(L.PARALLEL, 0, 1, -1))
     d = _desc(L, root_kind=L.ROOT_DIODE_PAIR, probe=1, source=0, param_Is=2, param_nabla=3, n_params=4)
     assert lib.dwdf_program_create(clip, 3, C.byref(d), C.byref(h)) == 0
     assert lib.dwdf_program_specialized_source(h, 0, None, 0) == 0 and lib.dwdf_program_specialize(h) == 2
     lib.dwdf_program_destroy(h)
     swapped = (L.Node * 3)(L.Node(L.CAPACITOR, -1, -1, 0), L.Node(L.RESISTIVE_VS, -1, -1, 1), L.Node(L.PARALLEL, 0, 1, -1))
-    for kw in (dict(r_node=1), dict(probe_current=1)):
-        d = _desc(L, root_kind=L.ROOT_DIODE_PAIR, probe=0, source=1, param_Is=2, param_nabla=3, n_params=4, **kw)
-        assert lib.dwdf_program_create(swapped, 3, C.byref(d), C.byref(h)) == 0, lib.dwdf_last_error()
-        assert lib.dwdf_program_specialized_source(h, 0, None, 0) == 0
-        lib.dwdf_program_destroy(h)
+    d = _desc(L, root_kind=L.ROOT_DIODE_PAIR, probe=0, source=1, param_Is=2, param_nabla=3, n_params=4, r_node=1)
+    assert lib.dwdf_program_create(swapped, 3, C.byref(d), C.byref(h)) == 0, lib.dwdf_last_error()
+    assert lib.dwdf_program_specialized_source(h, 0, None, 0) == 0
+    lib.dwdf_program_destroy(h)
+    # a current probe is forward only: the generated source carries a stub for the reverse-mode step
+    d = _desc(L, root_kind=L.ROOT_DIODE_PAIR, probe=0, source=1, param_Is=2, param_nabla=3, n_params=4, probe_current=1)
+    assert lib.dwdf_program_create(swapped, 3, C.byref(d), C.byref(h)) == 0, lib.dwdf_last_error()
+    n = lib.dwdf_program_specialized_source(h, 0, None, 0)
+    buf = C.create_string_buffer(n)
+    lib.dwdf_program_specialized_source(h, 0, buf, n)
+    assert b"c.Gprobe" in buf.value and b"jit_step_adj (const JC&, float" in buf.value
+    lib.dwdf_program_destroy(h)
 
 
 # ---- GPU -----------------------------------------------------------------------------------------------------------
