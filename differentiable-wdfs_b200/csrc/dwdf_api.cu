@@ -260,7 +260,7 @@ extern "C" {
 static int check_batch (const dwdf_program* prog, const void* params, const void* x, int64_t B, int64_t T);
 
 const char* dwdf_last_error (void) { return g_err; }
-const char* dwdf_build_info (void) { return "libdwdf v3 sm_100a cuda-12.9 tma+mbarrier fp32x2 no-cpu-fallback"; }
+const char* dwdf_build_info (void) { return "libdwdf v4 sm_100a cuda-12.9 tma+mbarrier fp32x2 nvrtc-specialiser no-cpu-fallback"; }
 int64_t dwdf_launch_count (void) { return g_launches.load () + g_extra_launches.load (); }
 int dwdf_set_tma (int enable) { return g_use_tma.exchange (enable ? 1 : 0); }
 int64_t dwdf_time_parallel_redone (void)
