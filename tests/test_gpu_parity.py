@@ -621,6 +621,29 @@ def test_time_chunks_shapes_state_and_misses(dwdf, oracle, B, T, n_up, n_down):
             assert seq_rel_err(y1.cpu().numpy(), oracle.clipper_forward(x, p)) < FWD_TOL
 
 
+@pytest.mark.parametrize("opts", [64, 128, 256, 64 + 256])
+def test_option_switches_do_not_change_the_result(dwdf, opts):
+    """Warm-up length of the time chunks (1e-13 / 1e-8 instead of 1e-10) and plain instead of programmatic dependent launches:
+    the forward output is the same bits, the training step the same numbers."""
+    p = ClipperParams()
+    x = dev(make_inputs(300, 2048, seed=44, amp=(0.05, 6.0)))
+    target = (0.5 * torch.tanh(x)).contiguous()
+    outs = []
+    for o in (0, opts):
+        prev = dwdf.set_option(o)
+        try:
+            circ, _ = make_clipper(dwdf, p, "approx", "python")
+            opt = dwdf.Adam(circ, lr={s: 1e-3 * float(circ.params[s]) for s in range(circ.n_params)}, beta_1=0.5)
+            y = circ.forward(x).clone()
+            for _ in range(3):
+                res = circ.train_step(x, target, opt, loss="mse+esr", skip=9)
+            outs.append((y, res["out"].clone(), circ.params.clone()))
+        finally:
+            dwdf.set_option(prev)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.allclose(outs[0][1][:19], outs[1][1][:19], rtol=1e-9, atol=0) and torch.allclose(outs[0][2], outs[1][2], rtol=1e-7, atol=0)
+
+
 def test_time_chunk_misses_are_recomputed(dwdf):
     """Hard-driven inputs keep the diodes conducting through a chunk's warm-up in a way the speculation (which starts
     from z = 0) cannot always reproduce to the bit; the verification pass must catch every such chunk. The recompute
