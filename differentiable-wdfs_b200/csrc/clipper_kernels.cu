@@ -38,7 +38,10 @@ constexpr int kTrainTileT = 32; // fused one-sequence-per-lane training pass
 constexpr int kTrainTileBytes = kLanes * kTrainTileT * 4;
 constexpr int kAdjTileT = kSeg; // samples per adjoint tile = one checkpoint segment (64-byte rows)
 constexpr int kAdjTileBytes = kLanes * kAdjTileT * 4; // 2 KB
-constexpr int kAdjStages = 2;
+constexpr int kAdjStages = 2; // x, y, g tiles per slot
+constexpr int kAdjStagesFromY = 3; // y, g tiles per slot (the exact root's sweep, which never reads x): same 12 KB
+constexpr int kAdjMaxStages = 3;
+constexpr int kAdjSmemBytes = kAdjStages * 3 * kAdjTileBytes;
 constexpr int kAdjL2Ahead = 4; // segments the L2 prefetch runs ahead of the shared-memory ring
 
 // 16-byte chunk `c` (4 samples) of row `lane` inside a swizzled tile
@@ -534,12 +537,17 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
         zs[kSeg] = zend;
     float ag = 0.0f, al = 0.0f, av = 0.0f, sse = 0.0f, st2 = 0.0f, hg = 0.0f, hl = 0.0f, hv = 0.0f;
     const float gxk = c.gamma / c.one_m_gamma; // dz'/dx = gamma (f'+1) = (A + 1) gamma / (1 - gamma)
+    constexpr bool FROMY = RecoverFromY<MODE, GENERAL, LSMALL>::value; // the linearisation from (y, z) alone: x is never read
+    const float inv_gamma = FROMY ? rcp (c.gamma) : 0.0f;
 #pragma unroll
     for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
     {
         if (FULL || cc * 4 < nvalid)
         {
-            const float4 xv = io.x4 (cc), gv = io.g4 (cc);
+            float4 xv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+            if (! FROMY)
+                xv = io.x4 (cc);
+            const float4 gv = io.g4 (cc);
             const float xs[4] = { xv.x, xv.y, xv.z, xv.w };
             const float gs[4] = { gv.x, gv.y, gv.z, gv.w };
             float gxs[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
@@ -567,7 +575,14 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
                     else
                     {
                         StepTape tp;
-                        clip_step_recover<MODE, GENERAL, LSMALL> (c, xs[k], zs[idx], zs[idx + 1], tp);
+                        if (FROMY)
+                        {
+                            StepTapeV<f1> tv;
+                            clip_step_recover_yv<f1> (c, inv_gamma, f1 { 0.5f * (zs[idx + 1] + zs[idx]) }, f1 { zs[idx] }, tv);
+                            tp.A = tv.A.x, tp.cg = tv.cg.x, tp.cl = tv.cl.x, tp.cv = tv.cv.x;
+                        }
+                        else
+                            clip_step_recover<MODE, GENERAL, LSMALL> (c, xs[k], zs[idx], zs[idx + 1], tp);
                         if (PY)
                             G = fma_ (0.5f, gy, G); // y[n] = (z[n+1] + z[n]) / 2
                         ag = fma_ (G, tp.cg, ag);
@@ -646,12 +661,17 @@ __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& i
         zn2[NP - 1].y = zend;
     f2 ag { 0.0f, 0.0f }, al { 0.0f, 0.0f }, av { 0.0f, 0.0f }, sse { 0.0f, 0.0f }, st2 { 0.0f, 0.0f };
     f2 hg { 0.0f, 0.0f }, hl { 0.0f, 0.0f }, hv { 0.0f, 0.0f };
+    constexpr bool FROMY = RecoverFromY<MODE, false, true>::value; // exact root: the linearisation from (y, z) alone, x is never read
+    const float inv_gamma = FROMY ? rcp (c.gamma) : 0.0f;
 #pragma unroll
     for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
     {
-        const float4 xv = io.x4 (cc), gv = io.g4 (cc);
+        float4 xv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+        if (! FROMY)
+            xv = io.x4 (cc);
+        const float4 gv = io.g4 (cc);
         float4 yv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-        if (TARGET)
+        if (TARGET || (FROMY && PY))
             yv = io.y4 (cc);
 #pragma unroll
         for (int h = 1; h >= 0; --h)
@@ -660,11 +680,14 @@ __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& i
             const f2 x2 = h ? f2 { xv.z, xv.w } : f2 { xv.x, xv.y };
             const f2 g2 = h ? f2 { gv.z, gv.w } : f2 { gv.x, gv.y };
             StepTapeV<f2> tp;
-            clip_step_recoverv<f2, MODE> (c, x2, z2[p], zn2[p], tp);
+            const f2 y2 = h ? f2 { yv.z, yv.w } : f2 { yv.x, yv.y };
+            if (FROMY) // the diode voltage of the step: the stored output itself (python ordering) or (z + z') / 2
+                clip_step_recover_yv<f2> (c, inv_gamma, PY ? y2 : mulv (bc (f2 {}, 0.5f), addv (z2[p], zn2[p])), z2[p], tp);
+            else
+                clip_step_recoverv<f2, MODE> (c, x2, z2[p], zn2[p], tp);
             f2 gy = g2;
             if (TARGET)
             {
-                const f2 y2 = h ? f2 { yv.z, yv.w } : f2 { yv.x, yv.y };
                 gy = addv (y2, negv (g2));
                 sse = fmav (gy, gy, sse);
                 st2 = fmav (g2, g2, st2);
@@ -771,29 +794,36 @@ __device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUte
 {
     const int nseg = s1 - s0; // of this chunk
     const bool valid = (int64_t) b0 + lane < B;
-    constexpr int kStageBytes = 3 * kAdjTileBytes;
+    // the exact root's sweep never reads x (clip_step_recover_yv): two tiles per segment, and the shared memory the x tiles
+    // would take becomes a third ring slot
+    constexpr bool FROMY = RecoverFromY<MODE, GENERAL, LSMALL>::value;
+    constexpr int kStages = FROMY ? kAdjStagesFromY : kAdjStages;
+    constexpr int kStageBytes = (FROMY ? 2 : 3) * kAdjTileBytes;
+    static_assert (kStages * kStageBytes <= kAdjSmemBytes && kStages <= kAdjMaxStages, "ring fits the kernel's shared memory");
     auto prefetch = [&] (int k) { // HBM -> L2, kAdjL2Ahead segments ahead of the ring
         const int i = s1 - 1 - k;
-        tma_prefetch_l2_2d (tmx, i * kSeg, b0);
+        if (! FROMY)
+            tma_prefetch_l2_2d (tmx, i * kSeg, b0);
         tma_prefetch_l2_2d (tmy, i * kSeg, b0);
         tma_prefetch_l2_2d (tmg, i * kSeg, b0);
     };
     auto fetch = [&] (int k) { // the k-th processed segment is i = s1 - 1 - k
         if (k + kAdjL2Ahead < nseg && l2_ahead)
             prefetch (k + kAdjL2Ahead);
-        const int i = s1 - 1 - k, s = k % kAdjStages;
+        const int i = s1 - 1 - k, s = k % kStages;
         const uint32_t dst = tiles + s * kStageBytes, bar = bars + 8 * s;
         mbar_expect_tx (bar, kStageBytes);
-        tma_load_2d (dst, tmx, i * kSeg, b0, bar);
-        tma_load_2d (dst + kAdjTileBytes, tmy, i * kSeg, b0, bar);
-        tma_load_2d (dst + 2 * kAdjTileBytes, tmg, i * kSeg, b0, bar);
+        if (! FROMY)
+            tma_load_2d (dst + 2 * kAdjTileBytes, tmx, i * kSeg, b0, bar);
+        tma_load_2d (dst, tmy, i * kSeg, b0, bar);
+        tma_load_2d (dst + kAdjTileBytes, tmg, i * kSeg, b0, bar);
     };
     if (lane == 0)
     {
         if (l2_ahead)
             for (int k = 1; k < kAdjL2Ahead && k < nseg; ++k)
                 prefetch (k);
-        for (int k = 0; k < kAdjStages - 1 && k < nseg; ++k)
+        for (int k = 0; k < kStages - 1 && k < nseg; ++k)
             fetch (k);
     }
     // plugin ordering: the state after a segment = the checkpoint of the next one (nothing depends on it past the sequence's end)
@@ -802,19 +832,19 @@ __device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUte
     for (int k = 0; k < nseg; ++k)
     {
         const int i = s1 - 1 - k;
-        const int s = k % kAdjStages;
+        const int s = k % kStages;
         const float z0 = znext;
         if (i > s0 && valid)
             znext = __ldg (ckpt + (int64_t) (i - 1) * B + b0 + lane); // in flight while this segment is processed
-        if (k + kAdjStages - 1 < nseg)
+        if (k + kStages - 1 < nseg)
         { // refill the slot the previous segment was read from
             fence_proxy_async ();
             __syncwarp ();
             if (lane == 0)
-                fetch (k + kAdjStages - 1);
+                fetch (k + kStages - 1);
         }
-        mbar_wait (bars + 8 * s, (k / kAdjStages) & 1);
-        TileIO io { tiles + s * kStageBytes, tiles + s * kStageBytes + kAdjTileBytes, tiles + s * kStageBytes + 2 * kAdjTileBytes, lane };
+        mbar_wait (bars + 8 * s, (k / kStages) & 1);
+        TileIO io { tiles + s * kStageBytes + 2 * kAdjTileBytes, tiles + s * kStageBytes, tiles + s * kStageBytes + kAdjTileBytes, lane }; // (x tile: only where it is loaded)
         adjoint_segment<MODE, GENERAL, LSMALL, PY, TARGET, false, HOMOG> (c, io, z0, zend, G, H, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
         zend = z0;
     }
@@ -835,8 +865,8 @@ __device__ __forceinline__ void write_map (float* __restrict__ o, int64_t B, flo
 template <int MODE, bool GENERAL, bool PY, bool TARGET>
 __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmg, const float* __restrict__ params, const ClipDesc desc, const float* __restrict__ ckpt, double* __restrict__ partials, float* __restrict__ cmaps, int chunk_segs, int64_t B, int T, int skip, int opts)
 {
-    __shared__ __align__ (1024) uint8_t smem[kAdjStages * 3 * kAdjTileBytes];
-    __shared__ __align__ (8) uint64_t bar_mem[kAdjStages];
+    __shared__ __align__ (1024) uint8_t smem[kAdjSmemBytes];
+    __shared__ __align__ (8) uint64_t bar_mem[kAdjMaxStages];
     const int lane = threadIdx.x;
     const int b0 = blockIdx.x * kLanes;
     const uint32_t tiles = smem_u32 (smem), bars = smem_u32 (bar_mem);
@@ -845,7 +875,7 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid
         tma_prefetch_desc (&tmx);
         tma_prefetch_desc (&tmy);
         tma_prefetch_desc (&tmg);
-        for (int s = 0; s < kAdjStages; ++s)
+        for (int s = 0; s < kAdjMaxStages; ++s)
             mbar_init (bars + 8 * s, 1);
         fence_mbar_init ();
     }

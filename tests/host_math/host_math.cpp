@@ -120,10 +120,12 @@ extern "C" void hm_clipper (int mode, int general, int pyorder, float fs, float 
 // The adjoint's way (clipper_kernels.cu adjoint_segment): forward once for y, then a reverse sweep that
 // recovers the states from y (re-anchored every 16 samples at a checkpoint) and each step's
 // linearisation with clip_step_recover. acc as in hm_clipper.
-template <int MODE, bool GENERAL, bool LSMALL, bool PY>
+// FROMY: the hot variants' step, clip_step_recover_yv — the linearisation from (y, z) alone, x never read.
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool FROMY = false>
 static void recover_run (const ClipConst& c, const float* x, const float* g, float* y, double* acc, int64_t B, int64_t T)
 {
     constexpr int SEG = 16;
+    const float inv_gamma = 1.0f / c.gamma;
     std::vector<float> ck ((size_t) ((T + SEG - 1) / SEG)), zs ((size_t) T + 1);
     for (int64_t s = 0; s < B; ++s)
     {
@@ -158,7 +160,15 @@ static void recover_run (const ClipConst& c, const float* x, const float* g, flo
             if (PY && (n + 1) % SEG == 0)
                 zn = std::fmaf (2.0f, y[s * T + n], -zs[(size_t) n]); // within-segment reconstruction, not the next checkpoint
             StepTape tp;
-            clip_step_recover<MODE, GENERAL, LSMALL> (c, x[s * T + n], zs[(size_t) n], zn, tp);
+            if (FROMY)
+            {
+                StepTapeV<f1> tv;
+                const float v = PY ? y[s * T + n] : 0.5f * (zs[(size_t) n] + zn);
+                clip_step_recover_yv<f1> (c, inv_gamma, f1 { v }, f1 { zs[(size_t) n] }, tv);
+                tp.A = tv.A.x, tp.cg = tv.cg.x, tp.cl = tv.cl.x, tp.cv = tv.cv.x;
+            }
+            else
+                clip_step_recover<MODE, GENERAL, LSMALL> (c, x[s * T + n], zs[(size_t) n], zn, tp);
             if (PY) G += 0.5 * gy;
             acc[0] += G * tp.cg;
             acc[1] += G * tp.cl;
@@ -187,6 +197,21 @@ extern "C" void hm_clipper_recover (int mode, int general, int pyorder, float fs
         else RUN (kModeExact, false, false);
     }
 #undef RUN
+}
+
+// symmetric pair, rev_small_ok parameters only (returns 1 otherwise): the reverse sweep that never reads x
+extern "C" int hm_clipper_recover_y (int mode, int pyorder, float fs, float R, float C, float Is, float Vt, float nabla, const float* x, const float* g, float* y, double* acc, int64_t B, int64_t T)
+{
+    ClipDesc d { fs, Vt, 1.0f, 1.0f, 0.0f, 1, 0, 1, 2, 3 };
+    ClipConst c;
+    clip_setup (c, d, R, C, Is, nabla);
+    if (! rev_small_ok (c.pair))
+        return 1;
+    if (mode == kModeApprox)
+        pyorder ? recover_run<kModeApprox, false, true, true, true> (c, x, g, y, acc, B, T) : recover_run<kModeApprox, false, true, false, true> (c, x, g, y, acc, B, T);
+    else
+        pyorder ? recover_run<kModeExact, false, true, true, true> (c, x, g, y, acc, B, T) : recover_run<kModeExact, false, true, false, true> (c, x, g, y, acc, B, T);
+    return 0;
 }
 
 // The forward kernels' fast path exactly as clipper_kernels.cu arranges it: clip_chunk_fastv on 4-sample

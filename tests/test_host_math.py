@@ -247,3 +247,54 @@ def test_adjoint_sums_of_a_quiet_signal(hm, oracle, mode, n_up, n_down, recover)
     _, acc = clip(hm, mode, 1, p, x, gy, recover=recover)
     ref = oracle.clipper_grad(x, gy, p, exact=bool(mode), ordering=ORDER_PYTHON, mode="upstream", dtype=np.float64)
     assert np.max(np.abs(acc / ref["raw"][:3] - 1)) < 1e-4, acc / ref["raw"][:3] - 1
+
+
+def clip_from_y(hm, mode, py, p, x, g):
+    x = np.ascontiguousarray(x, np.float32)
+    g = np.ascontiguousarray(g, np.float32)
+    y = np.empty_like(x)
+    acc = np.zeros(3)
+    rc = hm.hm_clipper_recover_y(C.c_int(mode), C.c_int(py), C.c_float(p.fs), C.c_float(p.R), C.c_float(p.C), C.c_float(p.Is), C.c_float(p.Vt), C.c_float(p.nabla), P(x), P(g), P(y), P(acc),
+                                 C.c_int64(x.shape[0]), C.c_int64(x.shape[1]))
+    assert rc == 0
+    return y, acc
+
+
+@pytest.mark.parametrize("py,oord", [(0, ORDER_PLUGIN), (1, ORDER_PYTHON)])
+@pytest.mark.parametrize("amp", [(0.001, 0.02), (0.1, 2.0), (3.0, 10.0)])
+def test_step_recover_from_output_alone(hm, oracle, py, oord, amp):
+    """clip_step_recover_yv — the step of the exact root's reverse sweep: states AND linearisation from the forward
+    output, x never read (a + b = 2 v, the omegas explicit in the diode voltage) — gives the replayed tape's sums and the
+    fp64 oracle's, from signals that never open the diodes to +-10 V, both probe orderings, T not a multiple of 16."""
+    p = ClipperParams()
+    x = make_inputs(8, 1000, seed=6, amp=amp)
+    g = np.random.default_rng(6).standard_normal(x.shape).astype(np.float32)
+    _, acc = clip_from_y(hm, 1, py, p, x, g)
+    _, acc0 = clip(hm, 1, py, p, x, g)
+    assert np.max(np.abs(acc / acc0 - 1)) < 2e-5, acc / acc0 - 1
+    ref = oracle.clipper_grad(x, g, p, exact=True, ordering=oord, mode="upstream", dtype=np.float64)
+    assert np.max(np.abs(acc / ref["raw"][:3] - 1)) < 2e-5, (acc / ref["raw"][:3] - 1, acc0 / ref["raw"][:3] - 1)
+
+
+def test_step_recover_from_output_is_not_for_the_approx_root(hm, oracle):
+    """Why the approx root's reverse sweep keeps reading x: omega4's own error (~1e-3 w0) is exponentiated when a is
+    recovered from the diode voltage, and the sums leave the gradient bar (5e-4) by an order of magnitude."""
+    p = ClipperParams()
+    x = make_inputs(8, 1000, seed=6, amp=(0.1, 2.0))
+    g = np.random.default_rng(6).standard_normal(x.shape).astype(np.float32)
+    _, acc = clip_from_y(hm, 0, 1, p, x, g)
+    ref = oracle.clipper_grad(x, g, p, exact=False, ordering=ORDER_PYTHON, mode="upstream", dtype=np.float64)
+    assert 2e-3 < np.max(np.abs(acc / ref["raw"][:3] - 1)) < 0.2
+
+
+@pytest.mark.parametrize("params", [dict(fs=48000.0, R=9778.8, C=2.8895e-07, Is=3.6248e-11, nabla=1.0321),  # diodes never conduct (L = -17)
+                                    dict(fs=96000.0, R=866000.0, C=5.5e-9, Is=1.3e-12, nabla=1.9),  # gamma = 1e-3
+                                    dict(R=1.0e6, C=1.0e-9, Is=8.0e-8, nabla=1.0),  # k = Rp Is / V = 0.032: the lsmall boundary
+                                    dict(R=180.0, C=1.0e-6, Is=1.0e-15, nabla=2.0)])
+def test_step_recover_from_output_parameter_corners(hm, oracle, params):
+    p = ClipperParams(**params)
+    x = make_inputs(4, 600, fs=p.fs, seed=475)
+    gy = np.random.default_rng(475).standard_normal(x.shape).astype(np.float32)
+    _, acc = clip_from_y(hm, 1, 1, p, x, gy)
+    ref = oracle.clipper_grad(x, gy, p, exact=True, ordering=ORDER_PYTHON, mode="upstream", dtype=np.float64)
+    assert np.max(np.abs(acc / ref["raw"][:3] - 1)) < 1e-4, acc / ref["raw"][:3] - 1
