@@ -514,7 +514,8 @@ struct AdjAcc
 //   sequence's last — the common case, free of per-sample predicates.
 //   HOMOG (time chunks): the chunk does not know its incoming adjoint, so next to the particular solution G (sources,
 //   G_in = 0) it carries the homogeneous one H (no sources, G_in = 1) and the parameter sums weighted with it.
-template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, bool FULL, bool HOMOG, class IO>
+//   FROMY (exact root, symmetric pair, fromy_ok parameters): the linearisation comes from (y, z) alone, x is never read.
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, bool FULL, bool HOMOG, bool FROMY, class IO>
 __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc, int n0, int nvalid, int skip, int last)
 {
     float zs[kSeg + 1];
@@ -537,7 +538,6 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
         zs[kSeg] = zend;
     float ag = 0.0f, al = 0.0f, av = 0.0f, sse = 0.0f, st2 = 0.0f, hg = 0.0f, hl = 0.0f, hv = 0.0f;
     const float gxk = c.gamma / c.one_m_gamma; // dz'/dx = gamma (f'+1) = (A + 1) gamma / (1 - gamma)
-    constexpr bool FROMY = RecoverFromY<MODE, GENERAL, LSMALL>::value; // the linearisation from (y, z) alone: x is never read
     const float inv_gamma = FROMY ? rcp (c.gamma) : 0.0f;
 #pragma unroll
     for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
@@ -577,9 +577,10 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
                         StepTape tp;
                         if (FROMY)
                         {
-                            StepTapeV<f1> tv;
-                            clip_step_recover_yv<f1> (c, inv_gamma, f1 { 0.5f * (zs[idx + 1] + zs[idx]) }, f1 { zs[idx] }, tv);
-                            tp.A = tv.A.x, tp.cg = tv.cg.x, tp.cl = tv.cl.x, tp.cv = tv.cv.x;
+                            StepTapeY<f1> ty;
+                            clip_step_recover_yv<f1> (c, f1 { 0.5f * (zs[idx + 1] + zs[idx]) }, f1 { zs[idx] }, ty);
+                            tp.A = ty.A.x;
+                            from_y_scale (c, inv_gamma, ty.cg.x, ty.m1.x, ty.as.x, ty.ww.x, tp.cg, tp.cl, tp.cv);
                         }
                         else
                             clip_step_recover<MODE, GENERAL, LSMALL> (c, xs[k], zs[idx], zs[idx + 1], tp);
@@ -621,13 +622,134 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
     }
 }
 
+// The common segment of the exact root's sweep when the parameters allow clip_step_recover_yv (fromy_ok): pairs of consecutive
+// samples in packed fp32x2 as below, but x is never read — the step's diode voltage is the stored output itself (python
+// ordering) or (z + z')/2 — and the tape comes back unscaled: four running sums, the constant factors once per segment.
+// Python ordering carries 2 G (the halves of y = (z' + z)/2 would cost a multiply per pair; powers of two scale exactly).
+template <bool PY, bool TARGET, bool HOMOG, class IO>
+__device__ __forceinline__ void adjoint_segment_pairs_from_y (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc)
+{
+    constexpr int NP = kSeg / 2;
+    f2 z2[NP]; // (z[2p], z[2p+1])
+    f2 v2[PY ? 1 : NP]; // plugin ordering: the diode voltages (z[n] + z[n+1]) / 2
+    float zc = z0;
+#pragma unroll
+    for (int cc = 0; cc < kSeg / 4; ++cc)
+    {
+        const float4 yv = io.y4 (cc);
+        const float ys[4] = { yv.x, yv.y, yv.z, yv.w };
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+        {
+            const int p = cc * 2 + h;
+            if (PY)
+            { // z[n+1] = 2 y[n] - z[n]
+                z2[p].x = zc;
+                z2[p].y = fma_ (2.0f, ys[2 * h], -zc);
+                zc = fma_ (2.0f, ys[2 * h + 1], -z2[p].y);
+            }
+            else
+            { // y[n] = z[n]
+                z2[p] = f2 { ys[2 * h], ys[2 * h + 1] };
+                v2[p].x = 0.5f * (ys[2 * h] + ys[2 * h + 1]);
+                if (p > 0)
+                    v2[p - 1].y = 0.5f * (z2[p - 1].y + ys[2 * h]);
+            }
+        }
+    }
+    if (! PY)
+        v2[NP - 1].y = 0.5f * (z2[NP - 1].y + zend);
+    f2 sg { 0.0f, 0.0f }, sm { 0.0f, 0.0f }, sa { 0.0f, 0.0f }, sw { 0.0f, 0.0f }, sse { 0.0f, 0.0f }, st2 { 0.0f, 0.0f };
+    f2 hg { 0.0f, 0.0f }, hm { 0.0f, 0.0f }, ha { 0.0f, 0.0f }, hw { 0.0f, 0.0f };
+    float Gs = PY ? 2.0f * G : G; // python ordering: 2 G
+#pragma unroll
+    for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
+    {
+        const float4 gv = io.g4 (cc);
+        float4 yv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+        if (TARGET || PY)
+            yv = io.y4 (cc);
+#pragma unroll
+        for (int h = 1; h >= 0; --h)
+        {
+            const int p = cc * 2 + h;
+            const f2 g2 = h ? f2 { gv.z, gv.w } : f2 { gv.x, gv.y };
+            const f2 y2 = h ? f2 { yv.z, yv.w } : f2 { yv.x, yv.y };
+            StepTapeY<f2> tp;
+            clip_step_recover_yv<f2> (c, PY ? y2 : v2[PY ? 0 : p], z2[p], tp);
+            f2 gy = g2;
+            if (TARGET)
+            {
+                gy = addv (y2, negv (g2));
+                sse = fmav (gy, gy, sse);
+                st2 = fmav (g2, g2, st2);
+            }
+            f2 Gm; // (python ordering: twice) the adjoint of z[n+1] each sample's parameter terms are weighted with
+            if (PY)
+            {
+                Gm.y = Gs + gy.y;
+                Gs = fma_ (Gm.y, tp.A.y, gy.y);
+                Gm.x = Gs + gy.x;
+                Gs = fma_ (Gm.x, tp.A.x, gy.x);
+            }
+            else
+            {
+                Gm.y = Gs;
+                Gs = fma_ (Gs, tp.A.y, gy.y);
+                Gm.x = Gs;
+                Gs = fma_ (Gs, tp.A.x, gy.x);
+            }
+            sg = fmav (Gm, tp.cg, sg);
+            sm = fmav (Gm, tp.m1, sm);
+            sa = fmav (Gm, tp.as, sa);
+            sw = fmav (Gm, tp.ww, sw);
+            if (HOMOG)
+            { // the homogeneous solution has no sources: each sample's terms are weighted with H before its own step
+                f2 Hm;
+                Hm.y = H;
+                H *= tp.A.y;
+                Hm.x = H;
+                H *= tp.A.x;
+                hg = fmav (Hm, tp.cg, hg);
+                hm = fmav (Hm, tp.m1, hm);
+                ha = fmav (Hm, tp.as, ha);
+                hw = fmav (Hm, tp.ww, hw);
+            }
+        }
+    }
+    const float half = PY ? 0.5f : 1.0f, inv_gamma = rcp (c.gamma);
+    G = half * Gs;
+    float ag, al, av;
+    from_y_scale (c, inv_gamma, half * (sg.x + sg.y), half * (sm.x + sm.y), half * (sa.x + sa.y), half * (sw.x + sw.y), ag, al, av);
+    acc.g += (double) ag;
+    acc.l += (double) al;
+    acc.v += (double) av;
+    if (HOMOG)
+    {
+        from_y_scale (c, inv_gamma, hg.x + hg.y, hm.x + hm.y, ha.x + ha.y, hw.x + hw.y, ag, al, av);
+        acc.hg += (double) ag;
+        acc.hl += (double) al;
+        acc.hv += (double) av;
+    }
+    if (TARGET)
+    {
+        acc.sse += (double) (sse.x + sse.y);
+        acc.st2 += (double) (st2.x + st2.y);
+    }
+}
+
 // The common segment (all kSeg samples valid, inside the loss, not the sequence's end) of the hot variant
 // (approx root, symmetric pair, fast-path parameters) on pairs of consecutive samples in packed fp32x2:
 // 8 pair-steps of clip_step_recoverv<f2> instead of 16 scalar ones; only the state reconstruction
 // (one FMA per sample) and the adjoint recurrence (two FMAs per sample) run per element.
-template <int MODE, bool PY, bool TARGET, bool HOMOG, class IO>
+template <int MODE, bool PY, bool TARGET, bool HOMOG, bool FROMY, class IO>
 __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc)
 {
+    if (FROMY)
+    {
+        adjoint_segment_pairs_from_y<PY, TARGET, HOMOG> (c, io, z0, zend, G, H, acc);
+        return;
+    }
     constexpr int NP = kSeg / 2;
     f2 z2[NP], zn2[NP]; // (z[2p], z[2p+1]) and (z[2p+1], z[2p+2])
     float zc = z0;
@@ -661,17 +783,12 @@ __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& i
         zn2[NP - 1].y = zend;
     f2 ag { 0.0f, 0.0f }, al { 0.0f, 0.0f }, av { 0.0f, 0.0f }, sse { 0.0f, 0.0f }, st2 { 0.0f, 0.0f };
     f2 hg { 0.0f, 0.0f }, hl { 0.0f, 0.0f }, hv { 0.0f, 0.0f };
-    constexpr bool FROMY = RecoverFromY<MODE, false, true>::value; // exact root: the linearisation from (y, z) alone, x is never read
-    const float inv_gamma = FROMY ? rcp (c.gamma) : 0.0f;
 #pragma unroll
     for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
     {
-        float4 xv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-        if (! FROMY)
-            xv = io.x4 (cc);
-        const float4 gv = io.g4 (cc);
+        const float4 xv = io.x4 (cc), gv = io.g4 (cc);
         float4 yv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-        if (TARGET || (FROMY && PY))
+        if (TARGET)
             yv = io.y4 (cc);
 #pragma unroll
         for (int h = 1; h >= 0; --h)
@@ -680,14 +797,11 @@ __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& i
             const f2 x2 = h ? f2 { xv.z, xv.w } : f2 { xv.x, xv.y };
             const f2 g2 = h ? f2 { gv.z, gv.w } : f2 { gv.x, gv.y };
             StepTapeV<f2> tp;
-            const f2 y2 = h ? f2 { yv.z, yv.w } : f2 { yv.x, yv.y };
-            if (FROMY) // the diode voltage of the step: the stored output itself (python ordering) or (z + z') / 2
-                clip_step_recover_yv<f2> (c, inv_gamma, PY ? y2 : mulv (bc (f2 {}, 0.5f), addv (z2[p], zn2[p])), z2[p], tp);
-            else
-                clip_step_recoverv<f2, MODE> (c, x2, z2[p], zn2[p], tp);
+            clip_step_recoverv<f2, MODE> (c, x2, z2[p], zn2[p], tp);
             f2 gy = g2;
             if (TARGET)
             {
+                const f2 y2 = h ? f2 { yv.z, yv.w } : f2 { yv.x, yv.y };
                 gy = addv (y2, negv (g2));
                 sse = fmav (gy, gy, sse);
                 st2 = fmav (g2, g2, st2);
@@ -740,19 +854,23 @@ __device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& i
     }
 }
 
-template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, bool HOMOG, class IO>
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, bool HOMOG, bool FROMY, class IO>
 __device__ __forceinline__ void adjoint_segment (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc, int n0, int nvalid, int skip, int last)
 {
+    static_assert (! FROMY || (MODE == kModeExact && ! GENERAL && LSMALL), "clip_step_recover_yv: exact root, symmetric pair, fromy_ok parameters");
     if (nvalid == kSeg && n0 >= skip && (PY || last >= kSeg))
     {
         if ((MODE == kModeApprox || MODE == kModeExact) && ! GENERAL && LSMALL && ! WANT_GX)
-            adjoint_segment_pairs<MODE, PY, TARGET, HOMOG> (c, io, z0, zend, G, H, acc);
+            adjoint_segment_pairs<MODE, PY, TARGET, HOMOG, FROMY> (c, io, z0, zend, G, H, acc);
         else
-            adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, true, HOMOG> (c, io, z0, zend, G, H, acc, n0, nvalid, skip, last);
+            adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, true, HOMOG, FROMY> (c, io, z0, zend, G, H, acc, n0, nvalid, skip, last);
     }
     else
-        adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, false, HOMOG> (c, io, z0, zend, G, H, acc, n0, nvalid, skip, last);
+        adjoint_segment_impl<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, false, HOMOG, FROMY> (c, io, z0, zend, G, H, acc, n0, nvalid, skip, last);
 }
+// which sweeps run from the output alone: decided once per launch from the parameters
+template <int MODE, bool GENERAL>
+__device__ __forceinline__ bool sweep_from_y (const ClipConst& c) { return MODE == kModeExact && ! GENERAL && fromy_ok (c.pair); }
 
 __device__ __forceinline__ void write_partials (AdjAcc& acc, double* __restrict__ partials, int group, int lane)
 {
@@ -789,14 +907,13 @@ struct TileIO
 };
 
 // Segments [s0, s1) of the rows starting at b0, last to first.
-template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool HOMOG>
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool HOMOG, bool FROMY = false>
 __device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUtensorMap* tmx, const CUtensorMap* tmy, const CUtensorMap* tmg, uint32_t tiles, uint32_t bars, const float* __restrict__ ckpt, AdjAcc& acc, float& G, float& H, int64_t B, int T, int skip, int lane, int b0, int s0, int s1, bool l2_ahead)
 {
     const int nseg = s1 - s0; // of this chunk
     const bool valid = (int64_t) b0 + lane < B;
     // the exact root's sweep never reads x (clip_step_recover_yv): two tiles per segment, and the shared memory the x tiles
     // would take becomes a third ring slot
-    constexpr bool FROMY = RecoverFromY<MODE, GENERAL, LSMALL>::value;
     constexpr int kStages = FROMY ? kAdjStagesFromY : kAdjStages;
     constexpr int kStageBytes = (FROMY ? 2 : 3) * kAdjTileBytes;
     static_assert (kStages * kStageBytes <= kAdjSmemBytes && kStages <= kAdjMaxStages, "ring fits the kernel's shared memory");
@@ -845,7 +962,7 @@ __device__ __forceinline__ void adjoint_tma_body (const ClipConst& c, const CUte
         }
         mbar_wait (bars + 8 * s, (k / kStages) & 1);
         TileIO io { tiles + s * kStageBytes + 2 * kAdjTileBytes, tiles + s * kStageBytes, tiles + s * kStageBytes + kAdjTileBytes, lane }; // (x tile: only where it is loaded)
-        adjoint_segment<MODE, GENERAL, LSMALL, PY, TARGET, false, HOMOG> (c, io, z0, zend, G, H, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
+        adjoint_segment<MODE, GENERAL, LSMALL, PY, TARGET, false, HOMOG, FROMY> (c, io, z0, zend, G, H, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
         zend = z0;
     }
 }
@@ -889,6 +1006,13 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid
     const bool l2 = (opts & kOptL2Prefetch) != 0;
     if (gridDim.y == 1)
     {
+        if constexpr (MODE == kModeExact && ! GENERAL)
+            if (sweep_from_y<MODE, GENERAL> (c))
+            {
+                adjoint_tma_body<MODE, GENERAL, true, PY, TARGET, false, true> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, 0, nseg, l2);
+                write_partials (acc, partials, blockIdx.x, lane);
+                return;
+            }
         if (rev_small_ok (c.pair))
             adjoint_tma_body<MODE, GENERAL, true, PY, TARGET, false> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, 0, nseg, l2);
         else
@@ -897,7 +1021,16 @@ __global__ void __launch_bounds__ (kLanes, 16) clipper_adjoint_tma (const __grid
         return;
     }
     const int s0 = blockIdx.y * chunk_segs, s1 = min (s0 + chunk_segs, nseg);
-    if (rev_small_ok (c.pair))
+    bool done = false;
+    if constexpr (MODE == kModeExact && ! GENERAL)
+        if (sweep_from_y<MODE, GENERAL> (c))
+        {
+            adjoint_tma_body<MODE, GENERAL, true, PY, TARGET, true, true> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, s0, s1, l2);
+            done = true;
+        }
+    if (done)
+        ;
+    else if (rev_small_ok (c.pair))
         adjoint_tma_body<MODE, GENERAL, true, PY, TARGET, true> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, s0, s1, l2);
     else
         adjoint_tma_body<MODE, GENERAL, false, PY, TARGET, true> (c, &tmx, &tmy, &tmg, tiles, bars, ckpt, acc, G, H, B, T, skip, lane, b0, s0, s1, l2);
@@ -977,7 +1110,7 @@ struct GlobalIO
     }
 };
 
-template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX>
+template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool TARGET, bool WANT_GX, bool FROMY = false>
 __device__ __forceinline__ void adjoint_direct_body (const ClipConst& c, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g, float* __restrict__ gx, const float* __restrict__ ckpt, AdjAcc& acc, int64_t B, int64_t b, int T, int skip)
 {
     const int nseg = (T + kSeg - 1) / kSeg;
@@ -987,7 +1120,7 @@ __device__ __forceinline__ void adjoint_direct_body (const ClipConst& c, const f
     {
         io.n0 = i * kSeg;
         const float z0 = __ldg (ckpt + (int64_t) i * B + b);
-        adjoint_segment<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, false> (c, io, z0, zend, G, H, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
+        adjoint_segment<MODE, GENERAL, LSMALL, PY, TARGET, WANT_GX, false, FROMY> (c, io, z0, zend, G, H, acc, i * kSeg, min (kSeg, T - i * kSeg), skip, T - 1 - i * kSeg);
         zend = z0;
     }
 }
@@ -1002,7 +1135,16 @@ __global__ void __launch_bounds__ (kLanes, 12) clipper_adjoint_direct (const flo
     AdjAcc acc;
     if (b < B)
     {
-        if (rev_small_ok (c.pair))
+        bool done = false;
+        if constexpr (MODE == kModeExact && ! GENERAL)
+            if (sweep_from_y<MODE, GENERAL> (c))
+            {
+                adjoint_direct_body<MODE, GENERAL, true, PY, TARGET, WANT_GX, true> (c, x, y, g, gx, ckpt, acc, B, b, T, skip);
+                done = true;
+            }
+        if (done)
+            ;
+        else if (rev_small_ok (c.pair))
             adjoint_direct_body<MODE, GENERAL, true, PY, TARGET, WANT_GX> (c, x, y, g, gx, ckpt, acc, B, b, T, skip);
         else
             adjoint_direct_body<MODE, GENERAL, false, PY, TARGET, WANT_GX> (c, x, y, g, gx, ckpt, acc, B, b, T, skip);

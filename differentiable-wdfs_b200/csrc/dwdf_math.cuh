@@ -930,59 +930,68 @@ DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V
     tp.cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, mulv (bc (V {}, -2.0f), ww));
 }
 
-// The same linearisation from the forward OUTPUT ALONE — the reverse sweep of the exact root (symmetric pair, rev_small_ok
+// The same linearisation from the forward OUTPUT ALONE — the reverse sweep of the exact root (symmetric pair, fromy_ok
 // parameters) reads y and the target and never touches x again: 8 bytes per sample instead of 12.
 // The two step equations a = z + t, b = z' - t (t = gamma (x - z)) give a + b = z + z' = 2 v, the diode voltage — in the
 // python ordering that IS the stored output y[n] — and the root's law b = a - 2 V lambda (w0 - w1) gives a - b. With
 // w + ln w = u (Wright omega) and a = v + V lambda (w0 - w1) the two omegas become explicit in v:
-//     w0 = E exp(-w1),  w1 = W exp(-w0),   E = k e^{|v|/V},  W = k e^{-|v|/V},  k = Rp Is / V = e^L
-// (w0 w1 <= k^2 < 1.3e-3 under lsmall_ok: one fixed-point round from w0 ~ E leaves a relative error of k^3). Everything the
-// tape needs follows: x - z = (v - z + V lambda delta) / gamma with delta = w0 - w1, f'(a) from S1 = w0' + w1' as before,
+//     w0 = E exp(-w1),  w1 = W exp(-w0),   E = k e^{|v|/V},  W = k e^{-|v|/V},  k = Rp Is / V = e^L.
+// fromy_ok asks for k < e^-6 (every diode of diode_config.py at any clipper impedance: k ~ 1e-4): then w1 <= k, w0 w1 <= k^2 <
+// 6.2e-6, and first order in w1 is fp32-exact:  w1 = W exp(-E),  w0 = E (1 - w1),  1 / (1 + w1) = 1 - w1.
+// Everything the tape needs follows: gamma (x - z) = v - z + V lambda delta with delta = w0 - w1, f'(a) from S1 = w0' + w1',
 //     M1 = lambda delta r0 r1,   lambda (w0 w0' - w1 w1') = M1 (w0 + w1 + w0 w1),   r = 1 / (1 + w).
 // While the diodes are off (|v| < V / 8) delta = w0 - w1 would cancel (dL/dIs of a quiet signal is the sum of exactly these
-// terms), so there it is k 2 sinh(|v|/V) (1 + w0 w1 / 2) with the sinh as its odd series (next terms: k^3, (|v|/V)^6 / 5040).
+// terms), so there it is k 2 sinh(|v|/V) with the sinh as its odd series (neglected: k^2 / 2, (|v|/V)^6 / 5040).
 // Three MUFU.EX2 and one MUFU.RCP per sample and no omega evaluation (clip_step_recoverv<exact>: four EX2, four RCP).
+// The tape comes back UNSCALED (StepTapeY): the sweep accumulates G cg, G m1, G as, G ww and applies the constant factors
+// once per segment (from_y_scale).
 // EXACT ROOT ONLY. Recovering a from v is ill-conditioned by 1 + w0 (a conducting diode pins its voltage), which fp32's
 // resolution of v survives (sums within 7e-6 of the fp64 oracle at +-10 V) but the approx root's own error does not:
 // omega4 misses omega by up to ~1e-3 w0, that miss is exponentiated on the way back (w0 e^{-(omega4 - omega)}), and the
 // sums drift by 1e-3 ... 2e-2 from the oracle's (measured, tests/test_host_math.py) — the approx root's sweep keeps reading x.
-// v: the step's diode voltage (z + z')/2; z: the state before the step. (v, z) -> (A, cg, cl, cv) as in clip_step_recover.
+// (Repairing it takes one omega4 evaluation per sample, w0~ = w0 + (omega4(c + w0) - w0)(1 + w0) with c = ln E - w1: more
+// issue slots than the 4 bytes cost.)
 template <class V>
-DWDF_HD void clip_step_recover_yv (const ClipConst& c, float inv_gamma, V v, V z, StepTapeV<V>& tp)
+struct StepTapeY
+{
+    V A; // dz'/dz
+    V cg; // dz'/dgamma * gamma / 2
+    V m1; // dz'/d ell / (-2 V)
+    V as, ww; // dz'/dV = (2 / V) as - 2 ww
+};
+DWDF_HD bool fromy_ok (const PairConst& c) { return rev_small_ok (c) && c.L < -6.0f; }
+// v: the step's diode voltage (z + z')/2; z: the state before the step.
+template <class V>
+DWDF_HD void clip_step_recover_yv (const ClipConst& c, V v, V z, StepTapeY<V>& tp)
 {
     const PairConst& p = c.pair;
     const V one = bc (V {}, 1.0f);
     const V av = absv (v);
     const V E = ex2v (fmav (av, bc (V {}, p.invVl2e), bc (V {}, p.Ll2e)));
     const V W = ex2v (fmav (av, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e)));
-    const V X = ex2v (mulv (E, bc (V {}, -kLog2e)));
-    const V w1a = mulv (W, X); // W exp(-E)
-    const V w1 = fmav (mulv (w1a, E), w1a, w1a); // W exp(-w0) with w0 = E (1 - w1)
-    const V w0 = mulv (E, fmav (w1, fmav (bc (V {}, 0.5f), w1, bc (V {}, -1.0f)), one)); // E exp(-w1), w1 < 0.04
+    const V w1 = mulv (W, ex2v (mulv (E, bc (V {}, -kLog2e)))); // W exp(-E)
+    const V w0 = fmav (negv (E), w1, E); // E (1 - w1)
     const V r0 = rcpv (addv (w0, one));
-    const V r1 = fmav (negv (w1), fmav (negv (w1), fmav (negv (w1), one, one), one), one); // 1 / (1 + w1) = 1 - w1 + w1^2 - w1^3
-    const V wp0 = mulv (w0, r0), wp1 = mulv (w1, r1);
+    const V wp0 = mulv (w0, r0), wp1 = fmav (negv (w1), w1, w1);
     const V S1 = addv (wp0, wp1);
     const V q = mulv (av, bc (V {}, p.invV)), q2 = mulv (q, q);
     const V sh = mulv (mulv (q, bc (V {}, 2.0f * p.RIs_overV)), fmav (q2, fmav (q2, bc (V {}, 1.0f / 120.0f), bc (V {}, 1.0f / 6.0f)), one)); // k 2 sinh q
-    const V dq = mulv (sh, fmav (mulv (bc (V {}, 0.5f), w0), w1, one));
-    const V ld = xor_signv (select_below (dq, addv (w0, negv (w1)), q, 0.125f), v); // lambda (w0 - w1)
-    const V M1 = mulv (mulv (ld, r0), r1);
-    const V ww = mulv (M1, fmav (w0, w1, addv (w0, w1)));
-    const V a = fmav (bc (V {}, p.V), ld, v);
-    const V xz = mulv (fmav (bc (V {}, p.V), ld, addv (v, negv (z))), bc (V {}, inv_gamma));
-    const V fp1 = fmav (bc (V {}, -2.0f), S1, bc (V {}, 2.0f)); // f'(a) + 1
-    tp.A = fmav (fp1, bc (V {}, c.one_m_gamma), bc (V {}, -1.0f));
-    tp.cg = mulv (xz, fp1);
-    tp.cl = mulv (bc (V {}, -p.twoV), M1);
-    tp.cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, mulv (bc (V {}, -2.0f), ww));
+    const V ld = xor_signv (select_below (sh, addv (w0, negv (w1)), q, 0.125f), v); // lambda (w0 - w1)
+    const V t = mulv (ld, r0);
+    tp.m1 = fmav (negv (t), w1, t); // lambda delta r0 (1 - w1)
+    tp.ww = mulv (tp.m1, fmav (w0, w1, addv (w0, w1)));
+    const V xzg = fmav (bc (V {}, p.V), ld, addv (v, negv (z))); // gamma (x - z)
+    tp.A = fmav (S1, bc (V {}, -2.0f * c.one_m_gamma), bc (V {}, c.one_m_gamma - c.gamma)); // (f' + 1)(1 - gamma) - 1,  f' + 1 = 2 - 2 S1
+    tp.cg = fmav (negv (S1), xzg, xzg);
+    tp.as = mulv (fmav (bc (V {}, p.V), ld, v), S1);
 }
-// which reverse sweeps take it: decided per (variant, parameters), the same for every segment kind of a launch
-template <int MODE, bool GENERAL, bool LSMALL>
-struct RecoverFromY
+// sums of G cg, G m1, G as, G ww over a segment -> the sums of G dz'/dgamma, G dz'/d ell, G dz'/dV
+DWDF_HD void from_y_scale (const ClipConst& c, float inv_gamma, float sg, float sm, float sas, float sww, float& g, float& l, float& v)
 {
-    static constexpr bool value = MODE == kModeExact && ! GENERAL && LSMALL;
-};
+    g = 2.0f * inv_gamma * sg;
+    l = -c.pair.twoV * sm;
+    v = fma_ (2.0f * c.pair.invV, sas, -2.0f * sww);
+}
 
 // The forward step every kernel calls. Exact root, symmetric pair, rev_small_ok parameters, one FSC iteration: the
 // V-form step (so that the packed two-sequences-per-lane kernel and the one-per-lane kernels agree bit for bit).

@@ -162,10 +162,11 @@ static void recover_run (const ClipConst& c, const float* x, const float* g, flo
             StepTape tp;
             if (FROMY)
             {
-                StepTapeV<f1> tv;
+                StepTapeY<f1> ty;
                 const float v = PY ? y[s * T + n] : 0.5f * (zs[(size_t) n] + zn);
-                clip_step_recover_yv<f1> (c, inv_gamma, f1 { v }, f1 { zs[(size_t) n] }, tv);
-                tp.A = tv.A.x, tp.cg = tv.cg.x, tp.cl = tv.cl.x, tp.cv = tv.cv.x;
+                clip_step_recover_yv<f1> (c, f1 { v }, f1 { zs[(size_t) n] }, ty);
+                tp.A = ty.A.x;
+                from_y_scale (c, inv_gamma, ty.cg.x, ty.m1.x, ty.as.x, ty.ww.x, tp.cg, tp.cl, tp.cv);
             }
             else
                 clip_step_recover<MODE, GENERAL, LSMALL> (c, x[s * T + n], zs[(size_t) n], zn, tp);
@@ -199,13 +200,13 @@ extern "C" void hm_clipper_recover (int mode, int general, int pyorder, float fs
 #undef RUN
 }
 
-// symmetric pair, rev_small_ok parameters only (returns 1 otherwise): the reverse sweep that never reads x
+// symmetric pair, fromy_ok parameters only (returns 1 otherwise): the reverse sweep that never reads x
 extern "C" int hm_clipper_recover_y (int mode, int pyorder, float fs, float R, float C, float Is, float Vt, float nabla, const float* x, const float* g, float* y, double* acc, int64_t B, int64_t T)
 {
     ClipDesc d { fs, Vt, 1.0f, 1.0f, 0.0f, 1, 0, 1, 2, 3 };
     ClipConst c;
     clip_setup (c, d, R, C, Is, nabla);
-    if (! rev_small_ok (c.pair))
+    if (! fromy_ok (c.pair))
         return 1;
     if (mode == kModeApprox)
         pyorder ? recover_run<kModeApprox, false, true, true, true> (c, x, g, y, acc, B, T) : recover_run<kModeApprox, false, true, false, true> (c, x, g, y, acc, B, T);

@@ -289,7 +289,7 @@ def test_step_recover_from_output_is_not_for_the_approx_root(hm, oracle):
 
 @pytest.mark.parametrize("params", [dict(fs=48000.0, R=9778.8, C=2.8895e-07, Is=3.6248e-11, nabla=1.0321),  # diodes never conduct (L = -17)
                                     dict(fs=96000.0, R=866000.0, C=5.5e-9, Is=1.3e-12, nabla=1.9),  # gamma = 1e-3
-                                    dict(R=1.0e6, C=1.0e-9, Is=8.0e-8, nabla=1.0),  # k = Rp Is / V = 0.032: the lsmall boundary
+                                    dict(R=1.0e6, C=1.0e-9, Is=6.0e-9, nabla=1.0),  # k = Rp Is / V = 2.4e-3: the fromy_ok boundary (e^-6)
                                     dict(R=180.0, C=1.0e-6, Is=1.0e-15, nabla=2.0)])
 def test_step_recover_from_output_parameter_corners(hm, oracle, params):
     p = ClipperParams(**params)
