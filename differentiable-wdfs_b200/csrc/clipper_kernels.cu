@@ -580,7 +580,7 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
                             StepTapeY<f1> ty;
                             clip_step_recover_yv<f1> (c, f1 { 0.5f * (zs[idx + 1] + zs[idx]) }, f1 { zs[idx] }, ty);
                             tp.A = ty.A.x;
-                            from_y_scale (c, inv_gamma, ty.cg.x, ty.m1.x, ty.as.x, ty.ww.x, tp.cg, tp.cl, tp.cv);
+                            tape_scale (c, inv_gamma, ty.cg.x, ty.m1.x, ty.as.x, ty.ww.x, tp.cg, tp.cl, tp.cv);
                         }
                         else
                             clip_step_recover<MODE, GENERAL, LSMALL> (c, xs[k], zs[idx], zs[idx + 1], tp);
@@ -622,16 +622,21 @@ __device__ __forceinline__ void adjoint_segment_impl (const ClipConst& c, IO& io
     }
 }
 
-// The common segment of the exact root's sweep when the parameters allow clip_step_recover_yv (fromy_ok): pairs of consecutive
-// samples in packed fp32x2 as below, but x is never read — the step's diode voltage is the stored output itself (python
-// ordering) or (z + z')/2 — and the tape comes back unscaled: four running sums, the constant factors once per segment.
-// Python ordering carries 2 G (the halves of y = (z' + z)/2 would cost a multiply per pair; powers of two scale exactly).
-template <bool PY, bool TARGET, bool HOMOG, class IO>
-__device__ __forceinline__ void adjoint_segment_pairs_from_y (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc)
+// The common segment (all kSeg samples valid, inside the loss, not the sequence's end) of the hot variants (approx or exact
+// root, symmetric pair, fast-path parameters) on pairs of consecutive samples in packed fp32x2: 8 pair-steps instead of 16
+// scalar ones; only the state reconstruction (one FMA per sample) and the adjoint recurrence (two FMAs per sample) run per
+// element. The tape comes back unscaled: four running sums, the constant factors once per segment (tape_scale). Python
+// ordering carries 2 G (the halves of y = (z' + z)/2 would cost a multiply per pair; powers of two scale exactly).
+//   FROMY (exact root, fromy_ok parameters): x is never read — clip_step_recover_yv takes the step's diode voltage, which is
+//   the stored output itself (python ordering) or (z + z')/2.
+template <int MODE, bool PY, bool TARGET, bool HOMOG, bool FROMY, class IO>
+__device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc)
 {
     constexpr int NP = kSeg / 2;
+    constexpr bool VOLT = FROMY && ! PY;
     f2 z2[NP]; // (z[2p], z[2p+1])
-    f2 v2[PY ? 1 : NP]; // plugin ordering: the diode voltages (z[n] + z[n+1]) / 2
+    f2 zn2[FROMY ? 1 : NP]; // (z[2p+1], z[2p+2]): the x-reading step's second end point
+    f2 v2[VOLT ? NP : 1]; // plugin ordering, from the output alone: the diode voltages (z[n] + z[n+1]) / 2
     float zc = z0;
 #pragma unroll
     for (int cc = 0; cc < kSeg / 4; ++cc)
@@ -647,36 +652,56 @@ __device__ __forceinline__ void adjoint_segment_pairs_from_y (const ClipConst& c
                 z2[p].x = zc;
                 z2[p].y = fma_ (2.0f, ys[2 * h], -zc);
                 zc = fma_ (2.0f, ys[2 * h + 1], -z2[p].y);
+                if (! FROMY)
+                    zn2[FROMY ? 0 : p] = f2 { z2[p].y, zc };
             }
             else
             { // y[n] = z[n]
                 z2[p] = f2 { ys[2 * h], ys[2 * h + 1] };
-                v2[p].x = 0.5f * (ys[2 * h] + ys[2 * h + 1]);
-                if (p > 0)
-                    v2[p - 1].y = 0.5f * (z2[p - 1].y + ys[2 * h]);
+                if (VOLT)
+                {
+                    v2[VOLT ? p : 0].x = 0.5f * (ys[2 * h] + ys[2 * h + 1]);
+                    if (p > 0)
+                        v2[VOLT ? p - 1 : 0].y = 0.5f * (z2[p - 1].y + ys[2 * h]);
+                }
+                else if (! FROMY)
+                {
+                    zn2[FROMY ? 0 : p].x = ys[2 * h + 1];
+                    if (p > 0)
+                        zn2[FROMY ? 0 : p - 1].y = ys[2 * h];
+                }
             }
         }
     }
-    if (! PY)
-        v2[NP - 1].y = 0.5f * (z2[NP - 1].y + zend);
+    if (VOLT)
+        v2[VOLT ? NP - 1 : 0].y = 0.5f * (z2[NP - 1].y + zend);
+    else if (! PY)
+        zn2[FROMY ? 0 : NP - 1].y = zend;
     f2 sg { 0.0f, 0.0f }, sm { 0.0f, 0.0f }, sa { 0.0f, 0.0f }, sw { 0.0f, 0.0f }, sse { 0.0f, 0.0f }, st2 { 0.0f, 0.0f };
     f2 hg { 0.0f, 0.0f }, hm { 0.0f, 0.0f }, ha { 0.0f, 0.0f }, hw { 0.0f, 0.0f };
     float Gs = PY ? 2.0f * G : G; // python ordering: 2 G
 #pragma unroll
     for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
     {
+        float4 xv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+        if (! FROMY)
+            xv = io.x4 (cc);
         const float4 gv = io.g4 (cc);
         float4 yv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-        if (TARGET || PY)
+        if (TARGET || (FROMY && PY))
             yv = io.y4 (cc);
 #pragma unroll
         for (int h = 1; h >= 0; --h)
         {
             const int p = cc * 2 + h;
+            const f2 x2 = h ? f2 { xv.z, xv.w } : f2 { xv.x, xv.y };
             const f2 g2 = h ? f2 { gv.z, gv.w } : f2 { gv.x, gv.y };
             const f2 y2 = h ? f2 { yv.z, yv.w } : f2 { yv.x, yv.y };
             StepTapeY<f2> tp;
-            clip_step_recover_yv<f2> (c, PY ? y2 : v2[PY ? 0 : p], z2[p], tp);
+            if (FROMY)
+                clip_step_recover_yv<f2> (c, PY ? y2 : v2[VOLT ? p : 0], z2[p], tp);
+            else
+                clip_step_recoverv<f2, MODE> (c, x2, z2[p], zn2[FROMY ? 0 : p], tp);
             f2 gy = g2;
             if (TARGET)
             {
@@ -717,135 +742,19 @@ __device__ __forceinline__ void adjoint_segment_pairs_from_y (const ClipConst& c
             }
         }
     }
-    const float half = PY ? 0.5f : 1.0f, inv_gamma = rcp (c.gamma);
+    const float half = PY ? 0.5f : 1.0f, inv_gamma = FROMY ? rcp (c.gamma) : 1.0f;
     G = half * Gs;
     float ag, al, av;
-    from_y_scale (c, inv_gamma, half * (sg.x + sg.y), half * (sm.x + sm.y), half * (sa.x + sa.y), half * (sw.x + sw.y), ag, al, av);
+    tape_scale (c, inv_gamma, half * (sg.x + sg.y), half * (sm.x + sm.y), half * (sa.x + sa.y), half * (sw.x + sw.y), ag, al, av);
     acc.g += (double) ag;
     acc.l += (double) al;
     acc.v += (double) av;
     if (HOMOG)
     {
-        from_y_scale (c, inv_gamma, hg.x + hg.y, hm.x + hm.y, ha.x + ha.y, hw.x + hw.y, ag, al, av);
+        tape_scale (c, inv_gamma, hg.x + hg.y, hm.x + hm.y, ha.x + ha.y, hw.x + hw.y, ag, al, av);
         acc.hg += (double) ag;
         acc.hl += (double) al;
         acc.hv += (double) av;
-    }
-    if (TARGET)
-    {
-        acc.sse += (double) (sse.x + sse.y);
-        acc.st2 += (double) (st2.x + st2.y);
-    }
-}
-
-// The common segment (all kSeg samples valid, inside the loss, not the sequence's end) of the hot variant
-// (approx root, symmetric pair, fast-path parameters) on pairs of consecutive samples in packed fp32x2:
-// 8 pair-steps of clip_step_recoverv<f2> instead of 16 scalar ones; only the state reconstruction
-// (one FMA per sample) and the adjoint recurrence (two FMAs per sample) run per element.
-template <int MODE, bool PY, bool TARGET, bool HOMOG, bool FROMY, class IO>
-__device__ __forceinline__ void adjoint_segment_pairs (const ClipConst& c, IO& io, float z0, float zend, float& G, float& H, AdjAcc& acc)
-{
-    if (FROMY)
-    {
-        adjoint_segment_pairs_from_y<PY, TARGET, HOMOG> (c, io, z0, zend, G, H, acc);
-        return;
-    }
-    constexpr int NP = kSeg / 2;
-    f2 z2[NP], zn2[NP]; // (z[2p], z[2p+1]) and (z[2p+1], z[2p+2])
-    float zc = z0;
-#pragma unroll
-    for (int cc = 0; cc < kSeg / 4; ++cc)
-    {
-        const float4 yv = io.y4 (cc);
-        const float ys[4] = { yv.x, yv.y, yv.z, yv.w };
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-        {
-            const int p = cc * 2 + h;
-            if (PY)
-            { // z[n+1] = 2 y[n] - z[n]
-                z2[p].x = zc;
-                zn2[p].x = fma_ (2.0f, ys[2 * h], -zc);
-                z2[p].y = zn2[p].x;
-                zn2[p].y = fma_ (2.0f, ys[2 * h + 1], -z2[p].y);
-                zc = zn2[p].y;
-            }
-            else
-            { // y[n] = z[n]
-                z2[p] = f2 { ys[2 * h], ys[2 * h + 1] };
-                zn2[p].x = ys[2 * h + 1];
-                if (p > 0)
-                    zn2[p - 1].y = ys[2 * h];
-            }
-        }
-    }
-    if (! PY)
-        zn2[NP - 1].y = zend;
-    f2 ag { 0.0f, 0.0f }, al { 0.0f, 0.0f }, av { 0.0f, 0.0f }, sse { 0.0f, 0.0f }, st2 { 0.0f, 0.0f };
-    f2 hg { 0.0f, 0.0f }, hl { 0.0f, 0.0f }, hv { 0.0f, 0.0f };
-#pragma unroll
-    for (int cc = kSeg / 4 - 1; cc >= 0; --cc)
-    {
-        const float4 xv = io.x4 (cc), gv = io.g4 (cc);
-        float4 yv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-        if (TARGET)
-            yv = io.y4 (cc);
-#pragma unroll
-        for (int h = 1; h >= 0; --h)
-        {
-            const int p = cc * 2 + h;
-            const f2 x2 = h ? f2 { xv.z, xv.w } : f2 { xv.x, xv.y };
-            const f2 g2 = h ? f2 { gv.z, gv.w } : f2 { gv.x, gv.y };
-            StepTapeV<f2> tp;
-            clip_step_recoverv<f2, MODE> (c, x2, z2[p], zn2[p], tp);
-            f2 gy = g2;
-            if (TARGET)
-            {
-                const f2 y2 = h ? f2 { yv.z, yv.w } : f2 { yv.x, yv.y };
-                gy = addv (y2, negv (g2));
-                sse = fmav (gy, gy, sse);
-                st2 = fmav (g2, g2, st2);
-            }
-            const f2 he = PY ? mulv (bc (f2 {}, 0.5f), gy) : gy;
-            f2 Gm; // the adjoint of z[n+1] each sample's parameter terms are weighted with
-            if (PY)
-            {
-                Gm.y = G + he.y;
-                G = fma_ (Gm.y, tp.A.y, he.y);
-                Gm.x = G + he.x;
-                G = fma_ (Gm.x, tp.A.x, he.x);
-            }
-            else
-            {
-                Gm.y = G;
-                G = fma_ (G, tp.A.y, he.y);
-                Gm.x = G;
-                G = fma_ (G, tp.A.x, he.x);
-            }
-            ag = fmav (Gm, tp.cg, ag);
-            al = fmav (Gm, tp.cl, al);
-            av = fmav (Gm, tp.cv, av);
-            if (HOMOG)
-            { // the homogeneous solution has no sources: each sample's terms are weighted with H before its own step
-                f2 Hm;
-                Hm.y = H;
-                H *= tp.A.y;
-                Hm.x = H;
-                H *= tp.A.x;
-                hg = fmav (Hm, tp.cg, hg);
-                hl = fmav (Hm, tp.cl, hl);
-                hv = fmav (Hm, tp.cv, hv);
-            }
-        }
-    }
-    acc.g += (double) (ag.x + ag.y);
-    acc.l += (double) (al.x + al.y);
-    acc.v += (double) (av.x + av.y);
-    if (HOMOG)
-    {
-        acc.hg += (double) (hg.x + hg.y);
-        acc.hl += (double) (hl.x + hl.y);
-        acc.hv += (double) (hv.x + hv.y);
     }
     if (TARGET)
     {

@@ -184,7 +184,7 @@ DWDF_HD bool lsmall_ok (float L) { return L < kOmega3Zero && L > -87.0f; }
 // calls) and selected, then one common FSC iteration.
 //   x <= -2      w = e^x s with s the root of  s = exp(-e^x s)  — the same equation divided by e^x, all
 //                terms O(1): the residual x - w - ln(w) of the original form cancels catastrophically in
-//                fp32 here. Series in e^x (toms917.cpp:240-248) + one Newton step; no FSC needed.
+//                fp32 here. The series in e^x (toms917.cpp:240-248) as a degree-6 fit of W(E)/E; no refinement needed.
 //   -2 < x <= 1+pi  series about x = 1 (toms917.cpp:253-261), one FSC iteration
 //   else            asymptotic series in ln(x) (toms917.cpp:290-296), one FSC iteration
 // Measured against scipy.special.wrightomega on [-60, 300]: <= 3.5e-7 relative after ONE iteration
@@ -231,17 +231,20 @@ DWDF_HD float fsc_step (float w, float r)
     return fma_ (w, e, w);
 }
 
-// omega(x) for x <= -2 (any x: the value is only meaningful there)
+// omega(x) for x <= -2 (any x: the value is only meaningful there): w = E s(E), E = e^x <= e^-2, s = W(E) / E the root of
+// s = exp(-E s). TOMS-917 starts from the series 1 - E + 3/2 E^2 - 8/3 E^3 + 125/24 E^4 (toms917.cpp:240-248) and refines; here s
+// is its degree-6 Chebyshev fit on [0, e^-2] (1.9e-9 from W(E)/E, constant term exactly 1) and nothing is refined: six FMAs
+// and the one MUFU.EX2 of E, where series + Newton step took two more MUFU ops per evaluation (the exact root's forward
+// pass is bound by the MUFU pipe: 59 % busy at 10 per sample, profiles/r01_e_ncu_exact_packed_summary.txt).
+constexpr float kOmLow1 = -0.999998602f, kOmLow2 = 1.49982983f, kOmLow3 = -2.65880158f, kOmLow4 = 5.03137976f, kOmLow5 = -8.66441333f, kOmLow6 = 9.14379624f;
 DWDF_HD float omega_exact_low (float x)
 {
-    // (explicit mul_/add_/fma_: the forward-biased and the reverse-biased branch evaluate this at the same
+    // (explicit mul_/fma_: the forward-biased and the reverse-biased branch evaluate this at the same
     //  argument when a == 0 and must then cancel exactly — silence in, silence out)
     const float E = exp_nonpos (fminf (x, 0.0f));
     const float Ec = fminf (E, 0.1353352832f);
-    const float sig = mul_ (Ec, fma_ (Ec, fma_ (Ec, fma_ (Ec, 5.2083333333333333f, -2.6666666666666667f), 1.5f), -1.0f));
-    const float s = add_ (1.0f, sig);
-    const float ex = ex2_ (mul_ (-1.442695040888963f, mul_ (Ec, s)));
-    return mul_ (E, fma_ (-add_ (s, -ex), rcp (fma_ (Ec, ex, 1.0f)), s));
+    const float s = fma_ (Ec, fma_ (Ec, fma_ (Ec, fma_ (Ec, fma_ (Ec, fma_ (Ec, kOmLow6, kOmLow5), kOmLow4), kOmLow3), kOmLow2), kOmLow1), 1.0f);
+    return mul_ (E, s);
 }
 
 DWDF_HD float omega_exact (float x, int n_iter, float tol)
@@ -802,9 +805,8 @@ DWDF_HD V omega_exact_lowv (V x)
 {
     const V E = exp_nonposv (minv (x, 0.0f));
     const V Ec = minv (E, 0.1353352832f);
-    const V s = fmav (Ec, fmav (Ec, fmav (Ec, fmav (Ec, bc (V {}, 5.2083333333333333f), bc (V {}, -2.6666666666666667f)), bc (V {}, 1.5f)), bc (V {}, -1.0f)), bc (V {}, 1.0f));
-    const V ex = ex2v (mulv (bc (V {}, -1.442695040888963f), mulv (Ec, s)));
-    return mulv (E, fmav (negv (addv (s, negv (ex))), rcpv (fmav (Ec, ex, bc (V {}, 1.0f))), s));
+    const V s = fmav (Ec, fmav (Ec, fmav (Ec, fmav (Ec, fmav (Ec, fmav (Ec, bc (V {}, kOmLow6), bc (V {}, kOmLow5)), bc (V {}, kOmLow4)), bc (V {}, kOmLow3)), bc (V {}, kOmLow2)), bc (V {}, kOmLow1)), bc (V {}, 1.0f));
+    return mulv (E, s);
 }
 
 DWDF_HD f1 lg2v (f1 a) { return f1 { lg2_ (a.x) }; }
@@ -891,10 +893,29 @@ DWDF_HD V clip_step_exact_tapev (const ClipConst& c, V x, V& z, StepTapeV<V>& tp
     return y;
 }
 
+// The reverse sweep's tape, UNSCALED: the sweep accumulates G cg, G m1, G as, G ww over a segment and applies the constant
+// factors once (tape_scale) instead of once per sample.
+template <class V>
+struct StepTapeY
+{
+    V A; // dz'/dz
+    V cg; // dz'/dgamma / 2  (clip_step_recover_yv: times gamma)
+    V m1; // dz'/d ell / (-2 V)
+    V as, ww; // dz'/dV = (2 / V) as - 2 ww
+};
+// sums of G cg, G m1, G as, G ww over a segment -> the sums of G dz'/dgamma, G dz'/d ell, G dz'/dV
+// (inv_gamma: 1 / gamma for clip_step_recover_yv's sums, 1 for clip_step_recoverv's)
+DWDF_HD void tape_scale (const ClipConst& c, float inv_gamma, float sg, float sm, float sas, float sww, float& g, float& l, float& v)
+{
+    g = 2.0f * inv_gamma * sg;
+    l = -c.pair.twoV * sm;
+    v = fma_ (2.0f * c.pair.invV, sas, -2.0f * sww);
+}
+
 // MODE kModeApprox: fast-path parameters (lsmall_ok(L)); kModeExact: rev_small_ok (the reverse-biased argument stays
 // in TOMS-917's x <= -2 region, and so does the forward-biased one wherever it is evaluated directly)
 template <class V, int MODE = kModeApprox>
-DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V>& tp)
+DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeY<V>& tp)
 {
     const PairConst& p = c.pair;
     const V xz = addv (x, negv (z));
@@ -914,20 +935,19 @@ DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V
     {
         w1 = exp_approx_scaledv (clamp_exp_arg (fmav (aa, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e))));
         w0 = fmav (xor_signv (d, a), bc (V {}, p.inv2V), w1);
-        // diode still off (u0 < kOmega3Zero): omega4 = exp_approx there, taken directly (see clip_step_recover)
+        // diode still off (u0 < kOmega3Zero): omega4 = exp_approx there, taken directly (see clip_step_recover);
+        // its argument is at least L log2(e) > -126 under lsmall_ok: no clamp
         const V us = fmav (aa, bc (V {}, p.invVl2e), bc (V {}, p.Ll2e));
-        w0 = select_below (exp_approx_scaledv (clamp_exp_arg (us)), w0, us, kOmega3Zero * kLog2e);
+        w0 = select_below (exp_approx_scaledv (us), w0, us, kOmega3Zero * kLog2e);
     }
     const V wp0 = mulv (w0, rcpv (addv (w0, bc (V {}, 1.0f))));
     const V wp1 = mulv (w1, rcpv (addv (w1, bc (V {}, 1.0f))));
     const V S1 = addv (wp0, wp1);
-    const V M1 = xor_signv (addv (wp0, negv (wp1)), a);
-    const V fp1 = fmav (bc (V {}, -2.0f), S1, bc (V {}, 2.0f)); // f'(a) + 1
-    tp.A = fmav (fp1, bc (V {}, c.one_m_gamma), bc (V {}, -1.0f));
-    tp.cg = mulv (xz, fp1);
-    tp.cl = mulv (bc (V {}, -p.twoV), M1);
-    const V ww = xor_signv (fmav (w0, wp0, negv (mulv (w1, wp1))), a); // lambda (w0 w0' - w1 w1'): the cancellation-free form of pair_deriv
-    tp.cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, mulv (bc (V {}, -2.0f), ww));
+    tp.m1 = xor_signv (addv (wp0, negv (wp1)), a);
+    tp.A = fmav (S1, bc (V {}, -2.0f * c.one_m_gamma), bc (V {}, c.one_m_gamma - c.gamma)); // (f' + 1)(1 - gamma) - 1,  f' + 1 = 2 - 2 S1
+    tp.cg = fmav (negv (S1), xz, xz); // (x - z)(f' + 1) / 2
+    tp.as = mulv (a, S1);
+    tp.ww = xor_signv (fmav (w0, wp0, negv (mulv (w1, wp1))), a); // lambda (w0 w0' - w1 w1'): the cancellation-free form of pair_deriv
 }
 
 // The same linearisation from the forward OUTPUT ALONE — the reverse sweep of the exact root (symmetric pair, fromy_ok
@@ -944,21 +964,13 @@ DWDF_HD void clip_step_recoverv (const ClipConst& c, V x, V z, V zn, StepTapeV<V
 // terms), so there it is k 2 sinh(|v|/V) with the sinh as its odd series (neglected: k^2 / 2, (|v|/V)^6 / 5040).
 // Three MUFU.EX2 and one MUFU.RCP per sample and no omega evaluation (clip_step_recoverv<exact>: four EX2, four RCP).
 // The tape comes back UNSCALED (StepTapeY): the sweep accumulates G cg, G m1, G as, G ww and applies the constant factors
-// once per segment (from_y_scale).
+// once per segment (tape_scale).
 // EXACT ROOT ONLY. Recovering a from v is ill-conditioned by 1 + w0 (a conducting diode pins its voltage), which fp32's
 // resolution of v survives (sums within 7e-6 of the fp64 oracle at +-10 V) but the approx root's own error does not:
 // omega4 misses omega by up to ~1e-3 w0, that miss is exponentiated on the way back (w0 e^{-(omega4 - omega)}), and the
 // sums drift by 1e-3 ... 2e-2 from the oracle's (measured, tests/test_host_math.py) — the approx root's sweep keeps reading x.
 // (Repairing it takes one omega4 evaluation per sample, w0~ = w0 + (omega4(c + w0) - w0)(1 + w0) with c = ln E - w1: more
 // issue slots than the 4 bytes cost.)
-template <class V>
-struct StepTapeY
-{
-    V A; // dz'/dz
-    V cg; // dz'/dgamma * gamma / 2
-    V m1; // dz'/d ell / (-2 V)
-    V as, ww; // dz'/dV = (2 / V) as - 2 ww
-};
 DWDF_HD bool fromy_ok (const PairConst& c) { return rev_small_ok (c) && c.L < -6.0f; }
 // v: the step's diode voltage (z + z')/2; z: the state before the step.
 template <class V>
@@ -985,14 +997,6 @@ DWDF_HD void clip_step_recover_yv (const ClipConst& c, V v, V z, StepTapeY<V>& t
     tp.cg = fmav (negv (S1), xzg, xzg);
     tp.as = mulv (fmav (bc (V {}, p.V), ld, v), S1);
 }
-// sums of G cg, G m1, G as, G ww over a segment -> the sums of G dz'/dgamma, G dz'/d ell, G dz'/dV
-DWDF_HD void from_y_scale (const ClipConst& c, float inv_gamma, float sg, float sm, float sas, float sww, float& g, float& l, float& v)
-{
-    g = 2.0f * inv_gamma * sg;
-    l = -c.pair.twoV * sm;
-    v = fma_ (2.0f * c.pair.invV, sas, -2.0f * sww);
-}
-
 // The forward step every kernel calls. Exact root, symmetric pair, rev_small_ok parameters, one FSC iteration: the
 // V-form step (so that the packed two-sequences-per-lane kernel and the one-per-lane kernels agree bit for bit).
 template <int MODE, bool GENERAL, bool LSMALL, bool PYORDER>

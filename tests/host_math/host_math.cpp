@@ -166,7 +166,7 @@ static void recover_run (const ClipConst& c, const float* x, const float* g, flo
                 const float v = PY ? y[s * T + n] : 0.5f * (zs[(size_t) n] + zn);
                 clip_step_recover_yv<f1> (c, f1 { v }, f1 { zs[(size_t) n] }, ty);
                 tp.A = ty.A.x;
-                from_y_scale (c, inv_gamma, ty.cg.x, ty.m1.x, ty.as.x, ty.ww.x, tp.cg, tp.cl, tp.cv);
+                tape_scale (c, inv_gamma, ty.cg.x, ty.m1.x, ty.as.x, ty.ww.x, tp.cg, tp.cl, tp.cv);
             }
             else
                 clip_step_recover<MODE, GENERAL, LSMALL> (c, x[s * T + n], zs[(size_t) n], zn, tp);
@@ -326,9 +326,11 @@ static void recover_pairs_run (const ClipConst& c, const float* x, const float* 
 {
     for (int64_t i = 0; i + 1 < n; i += 2)
     {
-        StepTapeV<f2> tp;
+        StepTapeY<f2> tp; // unscaled: tape_scale applies the constant factors (the sweep does it once per segment)
         clip_step_recoverv<f2, MODE> (c, f2 { x[i], x[i + 1] }, f2 { z[i], z[i + 1] }, f2 { zn[i], zn[i + 1] }, tp);
-        const float pk[2][4] = { { tp.A.x, tp.cg.x, tp.cl.x, tp.cv.x }, { tp.A.y, tp.cg.y, tp.cl.y, tp.cv.y } };
+        float pk[2][4] = { { tp.A.x, 0, 0, 0 }, { tp.A.y, 0, 0, 0 } };
+        tape_scale (c, 1.0f, tp.cg.x, tp.m1.x, tp.as.x, tp.ww.x, pk[0][1], pk[0][2], pk[0][3]);
+        tape_scale (c, 1.0f, tp.cg.y, tp.m1.y, tp.as.y, tp.ww.y, pk[1][1], pk[1][2], pk[1][3]);
         for (int k = 0; k < 2; ++k)
         {
             StepTape ts;
@@ -363,9 +365,11 @@ extern "C" int hm_recover_pairs (float fs, float R, float C, float Is, float Vt,
         return 1;
     for (int64_t i = 0; i + 1 < n; i += 2)
     {
-        StepTapeV<f2> tp;
+        StepTapeY<f2> tp;
         clip_step_recoverv<f2> (c, f2 { x[i], x[i + 1] }, f2 { z[i], z[i + 1] }, f2 { zn[i], zn[i + 1] }, tp);
-        const float pk[2][4] = { { tp.A.x, tp.cg.x, tp.cl.x, tp.cv.x }, { tp.A.y, tp.cg.y, tp.cl.y, tp.cv.y } };
+        float pk[2][4] = { { tp.A.x, 0, 0, 0 }, { tp.A.y, 0, 0, 0 } };
+        tape_scale (c, 1.0f, tp.cg.x, tp.m1.x, tp.as.x, tp.ww.x, pk[0][1], pk[0][2], pk[0][3]);
+        tape_scale (c, 1.0f, tp.cg.y, tp.m1.y, tp.as.y, tp.ww.y, pk[1][1], pk[1][2], pk[1][3]);
         for (int k = 0; k < 2; ++k)
         {
             StepTape ts;
