@@ -41,13 +41,18 @@ UNIT = "samples/s"
 # algorithmic bytes per sample: forward reads x, writes y; adjoint re-reads x, reads target
 BYTES_FWD, BYTES_ADJ = 8, 8
 # measured DRAM traffic per sample (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at
-# B = 65536, T = 4096; the file named in TRAFFIC_SOURCE). The adjoint also reads the forward output y (4 B/sample):
-# that read replaces the replay of the forward recurrence.
-TRAFFIC_FWD, TRAFFIC_ADJ = (1.073804e9 + 1.093476e9) / (65536 * 4096), (3.289196e9 + 0.003737e9) / (65536 * 4096)
-TRAFFIC_SOURCE = "ncu --set full, round 2: profiles/r02_c_ncu_forward_summary.txt, profiles/r02_d_ncu_adjoint_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch at 65536 x 4096)"
+# B = 65536, T = 4096; the files named in TRAFFIC_SOURCE). Approx root: the adjoint also reads the forward output y
+# (4 B/sample) — that read replaces the replay of the forward recurrence. Exact root: the adjoint reads y and
+# the target only (clip_step_recover_yv: states and linearisation from the output alone), traffic = algorithmic.
+TRAFFIC = {"approx": ((1.073804e9 + 1.093476e9) / (65536 * 4096), (3.289196e9 + 0.003737e9) / (65536 * 4096)),
+           "exact": ((1.073811e9 + 1.099483e9) / (65536 * 4096), (2.214953e9 + 0.003812e9) / (65536 * 4096))}
+TRAFFIC_SOURCE = ("ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum per launch at 65536 x 4096): approx root profiles/r02_c_ncu_forward_summary.txt, "
+                  "profiles/r02_d_ncu_adjoint_summary.txt; exact root profiles/r01_e_ncu_exact_packed_summary.txt (forward), profiles/r02_s_ncu_exact_adjoint_summary.txt")
 # fp32 side of the roofline (op-counted algorithmic flops per sample; the roof is the MEASURED FFMA issue rate,
 # tools/micro/ffma2_bench.cu on this pool's B200: 120.8 fma lanes/clk/SM x 2 x 148 SMs x 1.965 GHz)
-FLOPS = {"approx": (70, 130), "exact": (190, 260)}  # (forward, adjoint)
+# (forward, adjoint). Exact root, end of round 2: the forward's x <= -2 region lost its Newton step (190 -> 155) and the
+# adjoint no longer evaluates an omega at all (260 -> 95), counted op by op from the shipped step functions like the others
+FLOPS = {"approx": (70, 130), "exact": (155, 95)}
 FP32_PEAK_TFLOPS = 70.3
 FP32_PEAK_SOURCE = "measured FFMA / FFMA2 issue rate, profiles/r02_d_ffma2_microbench.txt (nominal 128 lanes/clk/SM: 74.4)"
 
@@ -591,7 +596,8 @@ def main():
         peak, peak_src = measured_peak_gbs()
         pair = args.mode in ("approx", "exact")
         dom = "clipper_adjoint_tma" if adj_ms >= fwd_ms else ("clipper_forward_pair_tma" if pair else "clipper_forward_tma")
-        dom_ms, dom_bytes, dom_traffic = (adj_ms, BYTES_ADJ, TRAFFIC_ADJ) if adj_ms >= fwd_ms else (fwd_ms, BYTES_FWD, TRAFFIC_FWD)
+        traffic_fwd, traffic_adj = TRAFFIC[args.mode]
+        dom_ms, dom_bytes, dom_traffic = (adj_ms, BYTES_ADJ, traffic_adj) if adj_ms >= fwd_ms else (fwd_ms, BYTES_FWD, traffic_fwd)
         achieved = B * T * dom_bytes / (dom_ms * 1e-3) / 1e9 if n_prof else None
         step_bytes = B * T * (BYTES_FWD + BYTES_ADJ)
         line = {
@@ -603,7 +609,7 @@ def main():
                        "l2": f"inputs larger than L2 ({3 * B * T * 4 / 2**20:.0f} MiB working set per GPU against 126 MB, no flush needed)",
                        "parallelism": f"dp{world}: sequences sharded, one exchange of 24 doubles per step ({exchange})"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                         "traffic": dom_traffic * B * T if (args.mode == "approx" and B == 65536) else None, "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
+                         "traffic": dom_traffic * B * T if B == 65536 else None, "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": dom_bytes, "kernel_ms": dom_ms, "timing": f"CUDA events at the kernel boundaries inside the timed region, mean of its first {n_prof} steps (dwdf_profile_begin/_end)",
                          "fp32": {"what": "second roof (SURVEY.md §8d): algorithmic flops per sample / kernel time against the measured fp32 FMA issue rate; pipe utilisations from ncu are in profiles/r02_*_ncu_*_summary.txt",
                                   "algorithmic_flops_per_sample": {"forward": FLOPS[args.mode][0], "adjoint": FLOPS[args.mode][1]}, "peak_TFLOPs": FP32_PEAK_TFLOPS, "peak_source": FP32_PEAK_SOURCE,

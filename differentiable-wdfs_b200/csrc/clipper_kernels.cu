@@ -42,7 +42,10 @@ constexpr int kAdjStages = 2; // x, y, g tiles per slot
 constexpr int kAdjStagesFromY = 3; // y, g tiles per slot (the exact root's sweep, which never reads x): same 12 KB
 constexpr int kAdjMaxStages = 3;
 constexpr int kAdjSmemBytes = kAdjStages * 3 * kAdjTileBytes;
-constexpr int kAdjL2Ahead = 4; // segments the L2 prefetch runs ahead of the shared-memory ring
+#ifndef DWDF_ADJ_L2_AHEAD
+#define DWDF_ADJ_L2_AHEAD 4
+#endif
+constexpr int kAdjL2Ahead = DWDF_ADJ_L2_AHEAD; // segments the L2 prefetch runs ahead of the shared-memory ring
 
 // 16-byte chunk `c` (4 samples) of row `lane` inside a swizzled tile
 __device__ __forceinline__ uint32_t chunk128 (uint32_t tile, int lane, int c) { return tile + lane * 128 + ((c ^ (lane & 7)) << 4); } // CU_TENSOR_MAP_SWIZZLE_128B
