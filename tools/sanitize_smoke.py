@@ -72,5 +72,19 @@ for ordering in ("python", "plugin"):
             xj = torch.from_numpy((rng.standard_normal((Bq, Tq)) * 0.5).astype(np.float32)).cuda()
             yj = cj.forward(xj); cj.backward(target=(0.5 * yj).contiguous(), loss="mse+esr", skip=3)
             st = cj.new_state(Bq); cj.process_block(xj, st)
+# ---- round 2, last session: the exact root's reverse sweep from the output alone (two-tile ring slots, three of them), both
+# probe orderings, one chunk and forced time chunks, and the x-reading sweep above the fromy_ok switch (Is = 4e-8)
+for ordering in ("python", "plugin"):
+    for Is in (4.352e-9, 4.0e-8):
+        Vs = dwdf.ResistiveVoltageSource(47000.0, True); Cc = dwdf.Capacitor(2.2e-9, 48000.0, True)
+        dp = dwdf.DiodePair(dwdf.Parallel(Vs, Cc), Is, 25.85e-3, 1.906, trainable=True, mode="exact")
+        circ = dwdf.compile_circuit(dp, probe=Cc, ordering=ordering)
+        for force in (0, 16):
+            prev = dwdf.set_option(force)
+            for Bq, Tq in ((70, 1024), (33, 203)):
+                xq = torch.from_numpy((rng.standard_normal((Bq, Tq)) * 0.5).astype(np.float32)).cuda()
+                yq = circ.forward(xq); circ.backward(target=(0.5 * yq).contiguous(), loss="mse+esr", skip=8)
+                circ.forward(xq); circ.backward(gy=torch.ones_like(xq), want_gx=True)
+            dwdf.set_option(prev)
 torch.cuda.synchronize()
 print("sanitize smoke done")
