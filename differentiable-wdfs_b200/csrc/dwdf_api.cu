@@ -5,6 +5,7 @@
 #include "dwdf_kernels.h"
 #include "tree_jit.h"
 
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -158,6 +159,7 @@ int cuda_fail (cudaError_t e, const char* what)
     } while (0)
 
 // ---- TMA descriptors ----------------------------------------------------------------------------
+constexpr int kDefaultL2Promotion = 256; // measured at 65536 x 4096 (approx root): forward 0.462 ms at 128 B (or none) -> 0.434 ms at 256 B (the next tile of every row arrives in L2 with the current one); the reverse sweep is indifferent to 128 / 256 / none (0.66 ms) and takes 1.12 ms at 64 B
 PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder ()
 {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = [] () -> PFN_cuTensorMapEncodeTiled_v12000 {
@@ -183,7 +185,13 @@ bool make_map (CUtensorMap* m, const float* base, int64_t B, int64_t T, int tile
     const cuuint32_t box[2] = { (cuuint32_t) tile_t, (cuuint32_t) rows };
     const cuuint32_t estr[2] = { 1, 1 };
     const CUtensorMapSwizzle sw = tile_t == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    return enc (m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*> (base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    // L2 fetch granularity of a tile's row segments. Development switch DWDF_L2_PROMOTION = 0 / 64 / 128 / 256 (read once).
+    static const CUtensorMapL2promotion promo = [] {
+        const char* e = std::getenv ("DWDF_L2_PROMOTION");
+        const int v = e != nullptr ? std::atoi (e) : kDefaultL2Promotion;
+        return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
+    return enc (m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*> (base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool tma_usable (const void* a, const void* b, const void* c, int64_t B, int64_t T)
