@@ -167,8 +167,26 @@ __device__ __forceinline__ ChunkPlan plan_chunks (const ClipConst& c, int ntiles
     if (kmax > 1)
     {
         p.Wt = (warmup_samples_raw (c, opts) + kFwdTileT - 1) / kFwdTileT;
-        p.chunk = min (max ((ntiles + kmax - 1) / kmax, max (p.Wt, 1)), ntiles); // the warm-up at most doubles a chunk's work
-        p.K = (ntiles + p.chunk - 1) / p.chunk;
+        // Chunks never get shorter than their warm-up (it at most doubles a chunk's work). From ~1000 resident CTAs on the pass
+        // runs at the machine's throughput, not at a chunk's latency (B = 32768 in 2 chunks and 65536 in one take the same
+        // time per tile), so among the chunk counts that keep at least three quarters of the proposed wave the one with the
+        // least total work wins: K (chunk) + (K - 1) Wt tiles per row group (B = 8192, 4 warm-up tiles: 8 chunks of 16 tiles
+        // = 156 instead of 10 of 13 = 166).
+        const int cmin = max (p.Wt, 1);
+        int best = 0x7fffffff;
+        // (proposals above 32 chunks mean a handful of row groups: there cmin decides, one candidate is enough)
+        for (int k = kmax > 32 ? kmax : max ((3 * kmax + 3) / 4, 1); k <= kmax; ++k)
+        {
+            const int chunk = min (max ((ntiles + k - 1) / k, cmin), ntiles);
+            const int K = (ntiles + chunk - 1) / chunk;
+            const int work = K * chunk + (K - 1) * p.Wt;
+            if (work <= best) // ties: the larger count
+            {
+                best = work;
+                p.chunk = chunk;
+                p.K = K;
+            }
+        }
     }
     return p;
 }
