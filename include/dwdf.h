@@ -215,7 +215,9 @@ DWDF_API int dwdf_forward (const dwdf_program* prog, const float* params, const 
  * `z_ckpt` — and carries the adjoint of the capacitor state backwards. `skip` leading samples are
  * excluded from the fused loss (clipper_pot.py:232,248). `gx` is NULL or receives dL/dx. `out`
  * receives the DWDF_OUT_LEN doubles described above, already reduced over the batch in a fixed
- * order (bit-reproducible). Programs on the tree interpreter ignore `y` and `z_ckpt` (may be NULL). */
+ * order (bit-reproducible). Programs on the tree interpreter ignore `y` and `z_ckpt` (may be NULL).
+ * Exact (TOMS-917) root with a symmetric pair: the sweep takes each step's linearisation from `y` alone and does
+ * not read `x` (DESIGN.md 4a'); the argument is still validated like the others. */
 DWDF_API int dwdf_backward (const dwdf_program* prog, const float* params, const float* x, const float* r, const float* y, const float* z_ckpt, const float* gy_or_target, int32_t grad_mode, int32_t loss_kind, int64_t skip, float* gx, double* out, void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
 
 /* Fused training pass (forward + loss + parameter gradients in ONE sweep, by propagating the
