@@ -64,16 +64,6 @@ DWDF_HD float rcp (float x)
     return 1.0f / x;
 #endif
 }
-// correctly rounded reciprocal (MUFU.RCP + two FMAs): where a MUFU result's last-bit bias would be integrated by a long
-// circuit memory (see omega4_approx)
-DWDF_HD float rcp_rn (float x)
-{
-#if defined(__CUDA_ARCH__)
-    return __frcp_rn (x);
-#else
-    return 1.0f / x;
-#endif
-}
 // x + y rounded toward -inf (FADD.RM)
 DWDF_HD float add_rd (float x, float y)
 {
@@ -169,16 +159,12 @@ DWDF_HD float omega3_approx (float x)
 
 // omega4, omega.h:172-177: omega3 + one Newton step on  w - exp(x - w).
 // FAST: WARP as above, and the caller guarantees x * log2(e) >= -126 (no clamp in exp_approx).
-// The general form (FAST = false: the N_up != N_down law, parameters outside the packed paths' range, tree programs) rounds
-// every operation where the reference rounds it: no FMA contraction, a correctly rounded reciprocal (see also log_setup).
 template <bool FAST = false>
 DWDF_HD float omega4_approx (float x)
 {
     const float y = omega3_approx<FAST> (x);
     const float e = exp_approx_scaled<! FAST> (1.442695040888963f * (x - y));
-    if (FAST)
-        return y - (y - e) * rcp (y + 1.0f);
-    return add_ (y, -mul_ (add_ (y, -e), rcp_rn (add_ (y, 1.0f)))); // every operation rounded where omega.h:172-177 rounds it
+    return y - (y - e) * rcp (y + 1.0f);
 }
 
 constexpr float kOmega3Zero = -3.341459552768620f; // below this omega3 == 0 and omega4(x) == exp_approx(x)
@@ -314,7 +300,7 @@ struct PairConst
 // law uses TWO such constants, one per branch; an ulp of imbalance between them (5e-7 of L) is a constant offset of the
 // reflected wave — every sample, the same sign — which a circuit with a memory of thousands of samples (gamma ~ 1e-4)
 // integrates into 1.1 … 1.3e-5 of the output's peak (3 of 8000 random circuits of the end-of-round-2 sweep; the same source
-// built for the host, with libm's logf, agrees with the reference to 3e-7). Once per thread and launch.
+// built for the host, with libm's logf, agrees with the reference to 3e-7). Once per thread and launch, two-constant law only.
 DWDF_HD float log_setup (float x)
 {
 #if defined(__CUDA_ARCH__)
@@ -331,14 +317,16 @@ DWDF_HD void pair_setup (PairConst& c, float Rp, float Is, float Vt, float nabla
     c.invV = 1.0f / c.V;
     c.RIs = Rp * Is;
     c.RIs_overV = c.RIs * c.invV;
-    c.L = log_setup (c.RIs_overV);
+    // (a symmetric pair uses ONE constant for both branches, its last ulp cancels: the hot kernels keep logf)
+    const bool two_constants = n_up != n_down;
+    c.L = two_constants ? log_setup (c.RIs_overV) : logf (c.RIs_overV);
     c.Ll2e = kLog2e * c.L;
     c.invVl2e = kLog2e * c.invV;
     c.inv2V = 0.5f * c.invV;
     c.n_up = n_up;
     c.n_dn = n_down;
-    c.L_up = log_setup (c.RIs_overV / n_up);
-    c.L_dn = log_setup (c.RIs_overV / n_down);
+    c.L_up = two_constants ? log_setup (c.RIs_overV / n_up) : logf (c.RIs_overV / n_up);
+    c.L_dn = two_constants ? log_setup (c.RIs_overV / n_down) : logf (c.RIs_overV / n_down);
     c.inv_up = 1.0f / (n_up * c.V);
     c.inv_dn = 1.0f / (n_down * c.V);
     c.rn_up = 1.0f / n_up;
@@ -424,9 +412,9 @@ DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
         mu0 = pos ? c.n_dn : c.n_up;
         mu1 = pos ? c.n_up : c.n_dn;
         const float l0 = pos ? c.L_dn : c.L_up, l1 = pos ? c.L_up : c.L_dn;
-        const float q0 = mul_ (aa, pos ? c.inv_dn : c.inv_up), q1 = mul_ (aa, pos ? c.inv_up : c.inv_dn); // (no contraction: see omega4_approx)
-        w0 = root_omega<MODE> (c, add_ (l0, q0));
-        w1 = root_omega_rev<MODE, LSMALL> (c, add_ (l1, -q1));
+        const float q0 = aa * (pos ? c.inv_dn : c.inv_up), q1 = aa * (pos ? c.inv_up : c.inv_dn);
+        w0 = root_omega<MODE> (c, l0 + q0);
+        w1 = root_omega_rev<MODE, LSMALL> (c, l1 - q1);
         const float s = a == 0.0f ? 0.0f : copysignf (c.twoV, a); // 2 V lambda, lambda = signum(a) (signum.h:5-9; 0 at a == 0)
         b = fma_ (-s, fma_ (mu0, w0, -(mu1 * w1)), a);
     }
@@ -439,9 +427,9 @@ DWDF_HD float pair_reflect (const PairConst& c, float a, PairDeriv* d)
         }
         else
         {
-            const float q = mul_ (aa, c.invV);
-            w0 = root_omega<MODE> (c, add_ (c.L, q));
-            w1 = root_omega_rev<MODE, LSMALL> (c, add_ (c.L, -q));
+            const float q = aa * c.invV;
+            w0 = root_omega<MODE> (c, c.L + q);
+            w1 = root_omega_rev<MODE, LSMALL> (c, c.L - q);
         }
         // a == 0 makes both branches the same computation, w0 - w1 == 0 and b == a: signum's zero needs no select
         b = fma_ (-c.twoV, xor_sign (w0 - w1, a), a);
@@ -534,10 +522,10 @@ DWDF_HD float clip_step (const ClipConst& c, float x, float& z); // defined at t
 template <int MODE, bool GENERAL, bool LSMALL, bool PYORDER>
 DWDF_HD float clip_step_scalar (const ClipConst& c, float x, float& z)
 {
-    const float t = mul_ (-c.gamma, add_ (z, -x)); // each operation rounded as the reference rounds it (tf_wdf.py:185-192): no contraction
-    const float a = add_ (z, t);
+    const float t = -c.gamma * (z - x);
+    const float a = z + t;
     const float b = pair_reflect<MODE, GENERAL, false, LSMALL> (c.pair, a, nullptr);
-    const float zn = add_ (b, t);
+    const float zn = b + t;
     const float y = PYORDER ? 0.5f * (zn + z) : z;
     z = zn;
     return y;
