@@ -68,54 +68,59 @@ __device__ __forceinline__ double warp_sum (double v)
 // =================================================================================================
 // forward
 // =================================================================================================
-// One 4-sample chunk of one sequence (V = f1) or of two (V = f2) the forward kernels' way: fast step, and
-// the instances that crossed omega3's log branch redone the general way (a per-lane branch: rare, and it
-// keeps every sequence's result independent of its neighbours in the warp).
+// One 4-sample chunk of one sequence (V = f1) or of two (V = f2) the forward kernels' way: the plain fast step, and a chunk
+// in which an instance crossed omega3's log branch (|a| > ~0.78 V for the 1N4148 clipper) again with the LOUD step — both
+// packed; an element below the branch gets the same bits from either (dwdf_math.cuh), so neither the redo nor the shortcut
+// below shows in any sequence's output, whatever its neighbour in the lane does.
+// Both decisions are taken by a vote of the warp's active lanes, never per lane (the lanes of a warp sit at different phases
+// of different signals: a per-lane branch would make the warp run both steps for every chunk): if any lane's chunk is loud,
+// all redo theirs with the LOUD step. `hint` is what the caller keeps between the chunks of its rows — whether the previous
+// vote was "loud"; the next chunk then goes straight to the LOUD step, so that a loud passage costs one evaluation per
+// chunk, not two. Since the two steps give a quiet instance the same bits, the votes never show in any output.
 template <bool PY>
-__device__ __forceinline__ float4 forward_chunk (const ClipConst& c, float4 v, float& z)
+__device__ __forceinline__ float4 forward_chunk (const ClipConst& c, float4 v, float& z, bool& hint)
 {
     const f1 x[4] = { { v.x }, { v.y }, { v.z }, { v.w } };
     f1 o[4], zz { z }, um { -1.0e30f };
-    clip_chunk_fastv<f1, PY> (c, x, zz, o, um);
-    float4 r = make_float4 (o[0].x, o[1].x, o[2].x, o[3].x);
-    if (um.x >= kFastLoud)
+    const unsigned active = __activemask ();
+    if (! hint)
     {
-        const float xs[4] = { v.x, v.y, v.z, v.w };
-        float os[4];
-        clip_chunk_general<PY> (c, xs, z, os);
-        return make_float4 (os[0], os[1], os[2], os[3]);
+        clip_chunk_fastv<f1, PY> (c, x, zz, o, um);
+        hint = __any_sync (active, um.x >= kFastLoud) != 0;
+        if (! hint)
+        {
+            z = zz.x;
+            return make_float4 (o[0].x, o[1].x, o[2].x, o[3].x);
+        }
+        zz.x = z;
+        um.x = -1.0e30f;
     }
+    clip_chunk_loudv<f1, PY> (c, x, zz, o, um);
+    hint = __any_sync (active, um.x >= kFastLoud) != 0;
     z = zz.x;
-    return r;
+    return make_float4 (o[0].x, o[1].x, o[2].x, o[3].x);
 }
 template <bool PY>
-__device__ __forceinline__ void forward_chunk2 (const ClipConst& c, float4 va, float4 vb, f2& z, float4& oa, float4& ob)
+__device__ __forceinline__ void forward_chunk2 (const ClipConst& c, float4 va, float4 vb, f2& z, float4& oa, float4& ob, bool& hint)
 {
     const f2 x[4] = { { va.x, vb.x }, { va.y, vb.y }, { va.z, vb.z }, { va.w, vb.w } };
     f2 o[4], zz = z, um { -1.0e30f, -1.0e30f };
-    clip_chunk_fastv<f2, PY> (c, x, zz, o, um);
+    const unsigned active = __activemask ();
+    bool redo = hint;
+    if (! hint)
+    {
+        clip_chunk_fastv<f2, PY> (c, x, zz, o, um);
+        redo = __any_sync (active, fmaxf (um.x, um.y) >= kFastLoud) != 0;
+    }
+    if (redo)
+    {
+        zz = z;
+        um = f2 { -1.0e30f, -1.0e30f };
+        clip_chunk_loudv<f2, PY> (c, x, zz, o, um);
+        hint = __any_sync (active, fmaxf (um.x, um.y) >= kFastLoud) != 0;
+    }
     oa = make_float4 (o[0].x, o[1].x, o[2].x, o[3].x);
     ob = make_float4 (o[0].y, o[1].y, o[2].y, o[3].y);
-    if (fmaxf (um.x, um.y) >= kFastLoud)
-    {
-        float os[4];
-        if (um.x >= kFastLoud)
-        {
-            const float xs[4] = { va.x, va.y, va.z, va.w };
-            float za = z.x;
-            clip_chunk_general<PY> (c, xs, za, os);
-            oa = make_float4 (os[0], os[1], os[2], os[3]);
-            zz.x = za;
-        }
-        if (um.y >= kFastLoud)
-        {
-            const float xs[4] = { vb.x, vb.y, vb.z, vb.w };
-            float zb = z.y;
-            clip_chunk_general<PY> (c, xs, zb, os);
-            ob = make_float4 (os[0], os[1], os[2], os[3]);
-            zz.y = zb;
-        }
-    }
     z = zz;
 }
 
@@ -251,6 +256,7 @@ template <int MODE, bool GENERAL, bool LSMALL, bool PY, bool FAST = true>
 __device__ __forceinline__ void forward_tma_body (const ClipConst& c, const FwdRing<kLanes>& ring, int t0, float* __restrict__ ckpt, float* __restrict__ zs_k, float& z, int64_t B, int T, int lane, bool valid)
 {
     ring.prologue (lane);
+    bool loud_hint = false; // forward_chunk: was the previous chunk of this row loud (never changes a result)
     for (int i = ring.f0; i < ring.t1; ++i)
     {
         const int j = i - ring.f0;
@@ -272,7 +278,7 @@ __device__ __forceinline__ void forward_tma_body (const ClipConst& c, const FwdR
                 const float4 v = lds128 (addr);
                 float4 o;
                 if (MODE == kModeApprox && ! GENERAL && LSMALL && FAST)
-                    o = forward_chunk<PY> (c, v, z);
+                    o = forward_chunk<PY> (c, v, z, loud_hint);
                 else
                 {
                     o.x = clip_step<MODE, GENERAL, LSMALL, PY> (c, v.x, z);
@@ -377,6 +383,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __gri
     }
     __syncwarp ();
     const int t0 = k * pl.chunk;
+    bool loud_hint = false; // forward_chunk2: was the previous chunk of this lane's rows loud (never changes a result)
     const FwdRing<kPairRows> ring { tiles, bars, &tmx, &tmy, b0, max (t0 - pl.Wt, 0), min (t0 + pl.chunk, ntiles) };
     const int64_t rowA = (int64_t) b0 + lane, rowB = rowA + kLanes;
     const bool validA = rowA < B, validB = rowB < B;
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_forward_pair_tma (const __gri
                         ob = make_float4 (o[0].y, o[1].y, o[2].y, o[3].y);
                     }
                     else
-                        forward_chunk2<PY> (c, va, vb, z, oa, ob);
+                        forward_chunk2<PY> (c, va, vb, z, oa, ob, loud_hint);
                 }
                 else
                 { // parameters outside the packed path's range: the general step, one instance after the other
@@ -471,13 +478,14 @@ template <int MODE, bool GENERAL, bool LSMALL, bool PY>
 __device__ __forceinline__ void forward_direct_body (const ClipConst& c, const float* __restrict__ xr, float* __restrict__ yr, float* __restrict__ ckpt, float& z, int64_t B, int64_t b, int T, bool valid)
 {
     int n = 0;
+    bool loud_hint = false;
     if (MODE == kModeApprox && ! GENERAL && LSMALL)
     { // same arithmetic as the TMA kernels (bit-identical per sequence): fast chunks of 4 samples
         for (; n + 4 <= T; n += 4)
         {
             if ((n & (kSeg - 1)) == 0 && ckpt != nullptr && valid)
                 ckpt[(int64_t) (n / kSeg) * B + b] = z;
-            const float4 o = forward_chunk<PY> (c, make_float4 (__ldg (xr + n), __ldg (xr + n + 1), __ldg (xr + n + 2), __ldg (xr + n + 3)), z);
+            const float4 o = forward_chunk<PY> (c, make_float4 (__ldg (xr + n), __ldg (xr + n + 1), __ldg (xr + n + 2), __ldg (xr + n + 3)), z, loud_hint);
             if (valid)
                 yr[n] = o.x, yr[n + 1] = o.y, yr[n + 2] = o.z, yr[n + 3] = o.w;
         }
@@ -1090,7 +1098,10 @@ template <int MODE, bool GENERAL, bool LSMALL, bool PY>
 __device__ __forceinline__ float4 chunk4 (const ClipConst& c, float4 v, float& z)
 {
     if (MODE == kModeApprox && ! GENERAL && LSMALL)
-        return forward_chunk<PY> (c, v, z);
+    {
+        bool hint = false; // (the verification pass redoes single chunks)
+        return forward_chunk<PY> (c, v, z, hint);
+    }
     float4 o;
     o.x = clip_step<MODE, GENERAL, (MODE != kModeApprox || GENERAL) && LSMALL, PY> (c, v.x, z);
     o.y = clip_step<MODE, GENERAL, (MODE != kModeApprox || GENERAL) && LSMALL, PY> (c, v.y, z);

@@ -600,6 +600,24 @@ DWDF_HD f2 sub_in (f2 x, f2 z) { return f2 { add_ (x.x, -z.x), add_ (x.y, -z.y) 
 DWDF_HD f1 add_out (f1 a, f1 b) { return f1 { a.x + b.x }; }
 DWDF_HD f2 add_out (f2 a, f2 b) { return f2 { a.x + b.x, a.y + b.y }; }
 
+DWDF_HD f1 select_below (f1 lo, f1 hi, f1 u, float thr) { return f1 { u.x < thr ? lo.x : hi.x }; }
+DWDF_HD f2 select_below (f2 lo, f2 hi, f2 u, float thr) { return f2 { u.x < thr ? lo.x : hi.x, u.y < thr ? lo.y : hi.y }; }
+DWDF_HD f1 clamp_exp_arg (f1 a) { return f1 { fmaxf (a.x, -126.0f) }; }
+DWDF_HD f2 clamp_exp_arg (f2 a) { return f2 { fmaxf (a.x, -126.0f), fmaxf (a.y, -126.0f) }; }
+// log_approx_pos over V (omega.h:49-63): mantissa and exponent per element (bit operations), the cubic and the sum packed
+DWDF_HD f1 mant12 (f1 a) { return f1 { i2f ((f2i (a.x) & 0x007fffff) | 0x3f800000) }; }
+DWDF_HD f2 mant12 (f2 a) { return f2 { i2f ((f2i (a.x) & 0x007fffff) | 0x3f800000), i2f ((f2i (a.y) & 0x007fffff) | 0x3f800000) }; }
+DWDF_HD f1 expo_magic (f1 a) { return f1 { i2f ((f2i (a.x) >> 23) | 0x4b000000) }; }
+DWDF_HD f2 expo_magic (f2 a) { return f2 { i2f ((f2i (a.x) >> 23) | 0x4b000000), i2f ((f2i (a.y) >> 23) | 0x4b000000) }; }
+template <class V>
+DWDF_HD V log_approx_posv (V x)
+{
+    const V m = mant12 (x);
+    const V e = addv (expo_magic (x), bc (V {}, -8388735.0f));
+    const V pl = fmav (m, fmav (m, fmav (m, bc (V {}, 0.1640425613334452f), bc (V {}, -1.098865286222744f)), bc (V {}, 3.148297929334117f)), bc (V {}, -2.213475204444817f));
+    return mulv (bc (V {}, 0.693147180559945f), addv (e, pl));
+}
+
 DWDF_HD bool fast_ok (float L) { return lsmall_ok (L) && L > -39.0f; }
 constexpr float kFastLoud = 8.0f * kLog2e; // omega3's log branch starts at u0 = 8, i.e. here in the scaled argument
 
@@ -621,7 +639,13 @@ struct StepTapeV;
 template <class V>
 DWDF_HD void fast_step_tape (const ClipConst& c, V xz, V a, V w0, V w1, StepTapeV<V>* tp);
 // TAPE: also the step's linearisation (A, cg, cl, cv as in clip_step_tape), for the fused forward-mode training pass
-template <class V, bool PY, bool TAPE>
+// LOUD: the same step with omega3's x >= 8 branch (x - log_approx(x), omega.h:165) selected per element and the reverse-biased
+// exponential's argument clamped — what a loud chunk is redone with, still two instances per lane in packed registers. For an
+// element below the branch every operation and operand is the one of the plain step (the select keeps the cubic, the clamp
+// does not act), so its result is the same bits: which of the two ran never shows in a sequence's output.
+template <class V>
+DWDF_HD V log_approx_posv (V x);
+template <class V, bool PY, bool TAPE, bool LOUD = false>
 DWDF_HD V clip_step_fastv_impl (const ClipConst& c, V x, V& z, V& hz, V& umax, StepTapeV<V>* tp)
 {
     const PairConst& p = c.pair;
@@ -633,12 +657,18 @@ DWDF_HD V clip_step_fastv_impl (const ClipConst& c, V x, V& z, V& hz, V& umax, S
     const V a2z = fmav (bc (V {}, c.two_gamma), xz, z); // a + gamma (x - z)
     const V aa = absv (a);
     const V us = fmav (aa, bc (V {}, p.invVl2e), bc (V {}, p.Ll2e)); // u0 log2(e), u0 = L + |a| / V
-    const V w1 = exp_approx_scaledv (fmav (aa, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e))); // omega4(L - |a|/V) = exp_approx
+    const V u1s = fmav (aa, bc (V {}, -p.invVl2e), bc (V {}, p.Ll2e));
+    const V w1 = exp_approx_scaledv (LOUD ? clamp_exp_arg (u1s) : u1s); // omega4(L - |a|/V) = exp_approx
     umax = maxv (umax, us);
     // omega3 below 8 (omega.h:160-167) in the scaled argument; exact 0 below the cubic's root (silence in, silence out)
     constexpr float i1 = 1.0f / kLog2e, i2 = i1 * i1, i3 = i2 * i1;
     V y = fmav (us, fmav (us, fmav (us, bc (V {}, -1.314293149877800e-3f * i3), bc (V {}, 4.775931364975583e-2f * i2)), bc (V {}, 3.631952663804445e-1f * i1)), bc (V {}, 6.313183464296682e-1f));
     y = zero_below (y, us, kOmega3Zero * kLog2e);
+    if (LOUD)
+    {
+        const V u0 = mulv (us, bc (V {}, i1)); // u0 = L + |a| / V
+        y = select_below (y, addv (u0, negv (log_approx_posv (maxv (u0, bc (V {}, 1.0f))))), us, kFastLoud);
+    }
     const V r = rcpv (addv (y, bc (V {}, 1.0f)));
     const V q = fmav (negv (y), r, y); // y (1 - r)
     const V e = exp_approx_scaledv (fmav (y, bc (V {}, -kLog2e), us));
@@ -668,7 +698,16 @@ DWDF_HD void clip_chunk_fastv (const ClipConst& c, const V (&x)[4], V& z, V (&o)
     for (int k = 0; k < 4; ++k)
         o[k] = clip_step_fastv<V, PY> (c, x[k], z, hz, umax);
 }
-// ... and the general way (omega3's log branch included), one instance: the redo of a loud chunk
+// ... and a loud chunk's redo: the same four samples through the LOUD step
+template <class V, bool PY>
+DWDF_HD void clip_chunk_loudv (const ClipConst& c, const V (&x)[4], V& z, V (&o)[4], V& umax)
+{
+    V hz = mulv (bc (V {}, 0.5f), z);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        o[k] = clip_step_fastv_impl<V, PY, false, true> (c, x[k], z, hz, umax, nullptr);
+}
+// ... and the general way (omega3's log branch included), one instance: parameters outside the packed paths' range
 template <bool PY>
 DWDF_HD void clip_chunk_general (const ClipConst& c, const float (&x)[4], float& z, float (&o)[4]);
 
@@ -780,10 +819,6 @@ DWDF_HD void fast_step_tape (const ClipConst& c, V xz, V a, V w0, V w1, StepTape
     const V ww = xor_signv (fmav (w0, wp0, negv (mulv (w1, wp1))), a);
     tp->cv = fmav (mulv (a, bc (V {}, 2.0f * p.invV)), S1, mulv (bc (V {}, -2.0f), ww));
 }
-DWDF_HD f1 select_below (f1 lo, f1 hi, f1 u, float thr) { return f1 { u.x < thr ? lo.x : hi.x }; }
-DWDF_HD f2 select_below (f2 lo, f2 hi, f2 u, float thr) { return f2 { u.x < thr ? lo.x : hi.x, u.y < thr ? lo.y : hi.y }; }
-DWDF_HD f1 clamp_exp_arg (f1 a) { return f1 { fmaxf (a.x, -126.0f) }; }
-DWDF_HD f2 clamp_exp_arg (f2 a) { return f2 { fmaxf (a.x, -126.0f), fmaxf (a.y, -126.0f) }; }
 // The packed intrinsics (__fmul2_rn, __fadd2_rn) ARE contracted into FFMA2 by the compiler where a product feeds a sum
 // (the scalar __fmul_rn / __fadd_rn never are), so V-form code that must agree bit for bit between V = f1 and V = f2
 // spells every fused multiply-add out as fmav and never adds a bare product; where a product must be subtracted

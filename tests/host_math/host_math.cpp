@@ -223,10 +223,12 @@ template <class V, bool PY>
 static void fastv_run (const ClipConst& c, const float* x, float* y, int64_t* fallbacks, int64_t B, int64_t T)
 {
     constexpr int W = sizeof (V) / sizeof (float);
+    int64_t mismatches = 0;
     for (int64_t s = 0; s < B; s += W)
     {
         int64_t row[2] = { s, s + 1 < B ? s + 1 : s };
         float z[2] = { 0.0f, 0.0f };
+        bool hint = false;
         int64_t n = 0;
         for (; n + 4 <= T; n += 4)
         {
@@ -238,32 +240,41 @@ static void fastv_run (const ClipConst& c, const float* x, float* y, int64_t* fa
             for (int k = 0; k < 4; ++k)
                 for (int w = 0; w < W; ++w)
                     ((float*) &xv[k])[w] = x[row[w] * T + n + k];
-            clip_chunk_fastv<V, PY> (c, xv, zz, ov, um);
+            // the kernels' scheme (clipper_kernels.cu forward_chunk / forward_chunk2): the plain fast step, and a chunk with a
+            // loud instance again with the LOUD step (packed, both instances); a chunk after a loud one goes
+            // straight to the LOUD step. An instance below the branch must get the same bits from either: checked here on
+            // every chunk (mismatches are reported through *fallbacks as a negative count).
+            bool ahead = hint, loud = false; // hint: the previous chunk of these rows was loud
+            V zf = zz, of[4];
+            clip_chunk_fastv<V, PY> (c, xv, zf, of, um);
+            for (int w = 0; w < W; ++w)
+                loud = loud || up[w] >= kFastLoud;
+            V zl = zz, ol[4], uml;
+            for (int w = 0; w < W; ++w)
+                ((float*) &uml)[w] = -1.0e30f;
+            clip_chunk_loudv<V, PY> (c, xv, zl, ol, uml); // (always evaluated here, for the bit check)
             for (int w = 0; w < W; ++w)
             {
-                if (up[w] >= kFastLoud)
-                {
-                    float xs[4], os[4];
+                const bool inst_loud = up[w] >= kFastLoud;
+                if (! inst_loud)
                     for (int k = 0; k < 4; ++k)
-                        xs[k] = x[row[w] * T + n + k];
-                    clip_chunk_general<PY> (c, xs, z[w], os);
-                    for (int k = 0; k < 4; ++k)
-                        y[row[w] * T + n + k] = os[k];
-                    if (fallbacks)
-                        ++*fallbacks;
-                }
-                else
-                {
-                    z[w] = zp[w];
-                    for (int k = 0; k < 4; ++k)
-                        y[row[w] * T + n + k] = ((float*) &ov[k])[w];
-                }
+                        if (std::memcmp (&((float*) &of[k])[w], &((float*) &ol[k])[w], 4) != 0 || std::memcmp (&((float*) &zf)[w], &((float*) &zl)[w], 4) != 0)
+                            ++mismatches;
+                const bool use_loud = ahead || loud;
+                z[w] = use_loud ? ((float*) &zl)[w] : ((float*) &zf)[w];
+                for (int k = 0; k < 4; ++k)
+                    y[row[w] * T + n + k] = use_loud ? ((float*) &ol[k])[w] : ((float*) &of[k])[w];
+                if (inst_loud && fallbacks)
+                    ++*fallbacks;
             }
+            hint = loud;
         }
         for (; n < T; ++n)
             for (int w = 0; w < W; ++w)
                 y[row[w] * T + n] = clip_step<kModeApprox, false, false, PY> (c, x[row[w] * T + n], z[w]);
     }
+    if (mismatches != 0 && fallbacks)
+        *fallbacks = -mismatches;
 }
 
 // pairs = 0: one sequence per lane (f1), 1: two (f2, packed fp32x2 on the device)

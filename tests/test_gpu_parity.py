@@ -905,3 +905,24 @@ def test_asymmetric_law_with_a_long_circuit_memory(dwdf, oracle, p, B, T, gain, 
     den = np.maximum(np.max(np.abs(ref), axis=1), 1e-3 * np.max(np.abs(x), axis=1) + 1e-30)
     err = float(np.max(np.max(np.abs(y - ref), axis=1) / den))
     assert err < max(3e-6, 2.0 * cond), (err, cond)
+
+
+@pytest.mark.parametrize("ordering", ["plugin", "python"])
+def test_a_loud_neighbour_does_not_change_a_sequence(dwdf, oracle, tma, ordering):
+    """Approx root, two sequences per lane: a chunk in which ONE instance crosses omega3's log branch is redone with the LOUD
+    step for both, and a chunk that starts near the branch skips the plain step — the quiet instance must come out with the
+    same bits as when all its neighbours are quiet (and the loud ones within the forward bar of the reference)."""
+    oord = ORDER_PLUGIN if ordering == "plugin" else ORDER_PYTHON
+    p = ClipperParams()
+    B, T = 130, 1024
+    x = make_inputs(B, T, seed=91, amp=(0.1, 0.5))
+    xl = x.copy()
+    xl[1::2] *= 20.0  # every second sequence up to +-10 V: its lane partner stays quiet
+    xl[64:96] *= 0.0  # (and a few silent rows)
+    x[64:96] *= 0.0
+    circ, _ = make_clipper(dwdf, p, "approx", ordering)
+    yq = circ.forward(dev(x)).cpu().numpy()
+    yl = circ.forward(dev(xl)).cpu().numpy()
+    assert np.array_equal(yq[0::2], yl[0::2])
+    assert not yl[64:96].any()
+    assert seq_rel_err(yl, oracle.clipper_forward(xl, p, ordering=oord)) < FWD_TOL

@@ -140,6 +140,7 @@ def fast(hm, pairs, py, p, x):
     rc = hm.hm_clipper_fast(C.c_int(pairs), C.c_int(py), C.c_float(p.fs), C.c_float(p.R), C.c_float(p.C), C.c_float(p.Is), C.c_float(p.Vt), C.c_float(p.nabla), P(x), P(y), C.byref(nfb),
                             C.c_int64(x.shape[0]), C.c_int64(x.shape[1]))
     assert rc == 0
+    assert nfb.value >= 0, f"{-nfb.value} samples below omega3's log branch differ between the plain and the LOUD step"
     return y, nfb.value
 
 
@@ -147,8 +148,9 @@ def fast(hm, pairs, py, p, x):
 @pytest.mark.parametrize("py,oname", [(0, "plugin"), (1, "python")])
 def test_fast_forward_step_against_reference_vectors(hm, golden, circuit, py, oname):
     """clip_step_fastv — the forward kernels' sample (packed pairs f2 and its one-sequence twin f1) with
-    the per-instance loud-chunk fallback — against the reference's own outputs, quiet and loud
-    (+-10 V: nearly every chunk falls back); f1 and f2 agree bit for bit; silence stays exact silence."""
+    the loud chunks redone by the LOUD step (omega3's log branch, still packed) — against the reference's own
+    outputs, quiet and loud (+-10 V: nearly every chunk is loud); f1 and f2 agree bit for bit; an instance below the
+    branch gets the same bits from the plain and the LOUD step (checked on every chunk); silence stays exact silence."""
     p = ClipperParams() if circuit == "plugin" else ClipperParams(R=45000.0, C=4.7e-9)
     for xname, refname, expect_fallbacks in (("clip_x", f"clip_{circuit}_approx_{oname}_f32", False), ("clip_loud_x", "clip_loud_approx_python_f32", True)):
         if xname == "clip_loud_x" and (circuit != "plugin" or not py):
