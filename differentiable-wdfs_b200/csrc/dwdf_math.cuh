@@ -544,9 +544,9 @@ DWDF_HD float clip_step_scalar (const ClipConst& c, float x, float& z)
 //     anyway, z' = b + gamma (x - z) is taken as  -2V lambda (w0 - w1) + (2a - z),  and the Newton step
 //     y - (y - e)/(y + 1)  as  e r + y (1 - r),  r = 1/(y + 1);
 //   * omega3's x >= 8 branch (x - log_approx(x), ~11 instructions) is not evaluated: max(u0) is tracked
-//     per instance and the caller redoes a loud 4-sample chunk of THAT instance with the general
-//     clip_step (|a| > ~0.78 V for the 1N4148 clipper) — per instance, so a sequence's result never
-//     depends on which other sequences share its warp.
+//     per instance and the caller redoes a chunk with a loud instance (|a| > ~0.78 V for the 1N4148
+//     clipper) with the LOUD form of this step, which gives every instance below the branch the same
+//     bits — so a sequence's result never depends on which other sequences share its warp.
 // ~23 issue slots and ~14 fma-pipe cycles per sample instead of ~47 and ~17.
 // V = f2 (two instances, packed) or f1 (one instance; same operations in the same order, hence
 // bit-identical per sequence — the direct-access kernel and sub-warp batches use it).
