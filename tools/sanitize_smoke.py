@@ -86,5 +86,16 @@ for ordering in ("python", "plugin"):
                 yq = circ.forward(xq); circ.backward(target=(0.5 * yq).contiguous(), loss="mse+esr", skip=8)
                 circ.forward(xq); circ.backward(gy=torch.ones_like(xq), want_gx=True)
             dwdf.set_option(prev)
+# loud inputs (+-8 V on every second row): the warp-voted LOUD step of the approx root's forward kernels (pair, single, direct, forced chunks)
+for force in (0, 16, 2):
+    prev = dwdf.set_option(force)
+    Vs = dwdf.ResistiveVoltageSource(47000.0, True); Cc = dwdf.Capacitor(2.2e-9, 48000.0, True)
+    dp = dwdf.DiodePair(dwdf.Parallel(Vs, Cc), 4.352e-9, 25.85e-3, 1.906, trainable=True, mode="approx")
+    circ = dwdf.compile_circuit(dp, probe=Cc)
+    for Bq, Tq in ((70, 1024), (33, 203)):
+        xq = torch.from_numpy((rng.standard_normal((Bq, Tq)) * 0.3).astype(np.float32)).cuda()
+        xq[1::2] *= 25.0
+        yq = circ.forward(xq); circ.backward(target=(0.5 * yq).contiguous(), loss="mse", skip=8)
+    dwdf.set_option(prev)
 torch.cuda.synchronize()
 print("sanitize smoke done")
