@@ -1322,6 +1322,7 @@ struct TrainStateV
 {
     f2 z { 0.0f, 0.0f }, hz { 0.0f, 0.0f }, sg { 0.0f, 0.0f }, sl { 0.0f, 0.0f }, sv { 0.0f, 0.0f };
     f2 ag { 0.0f, 0.0f }, al { 0.0f, 0.0f }, av { 0.0f, 0.0f }, sse { 0.0f, 0.0f }, st2 { 0.0f, 0.0f };
+    template <bool LOUD = false> // (approx root) the step with omega3's log branch: see forward_chunk2
     __device__ __forceinline__ f2 step (const ClipConst& c, f2 x, f2 t, bool onA, bool onB, f2& umax)
     {
         StepTapeV<f2> tp;
@@ -1329,7 +1330,7 @@ struct TrainStateV
         if (MODE == kModeExact)
             y = clip_step_exact_tapev<f2, PY> (c, x, z, tp);
         else
-            y = clip_step_fastv_impl<f2, PY, true> (c, x, z, hz, umax, &tp);
+            y = clip_step_fastv_impl<f2, PY, true, LOUD> (c, x, z, hz, umax, &tp);
         const f2 e { onA ? y.x - t.x : 0.0f, onB ? y.y - t.y : 0.0f };
         const f2 tm { onA ? t.x : 0.0f, onB ? t.y : 0.0f };
         const f2 ng = fmav (tp.A, sg, tp.cg), nl = fmav (tp.A, sl, tp.cl), nv = fmav (tp.A, sv, tp.cv);
@@ -1410,6 +1411,7 @@ __global__ void __launch_bounds__ (kLanes) clipper_train_pair_tma (const __grid_
             load_stage (s);
     TrainStateV<MODE, PY> st;
     AdjAcc acc;
+    bool loud_hint = false; // the previous chunk's vote (never changes a result)
     for (int i = 0; i < ntiles; ++i)
     {
         const int s = i % kTrainPairStages;
@@ -1432,17 +1434,39 @@ __global__ void __launch_bounds__ (kLanes) clipper_train_pair_tma (const __grid_
                 f2 um { -1.0e30f, -1.0e30f };
                 if (fast)
                 {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    // approx root: a chunk in which any lane's instance crossed omega3's log branch again with the LOUD step, state and
+                    // tangents included, for the whole warp (a vote, not a per-lane branch; the chunk after a loud one goes straight
+                    // to it) — the same bits for every instance below the branch, as in the forward kernels (forward_chunk2)
+                    const unsigned active = __activemask ();
+                    bool redo = MODE != kModeExact && loud_hint;
+                    if (! redo)
                     {
-                        const bool on = n + k >= skip;
-                        const f2 y = st.step (c, f2 { xa[k], xb[k] }, f2 { tga[k], tgb[k] }, on && validA, on && validB, um);
-                        oa[k] = y.x, ob[k] = y.y;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const bool on = n + k >= skip;
+                            const f2 y = st.step (c, f2 { xa[k], xb[k] }, f2 { tga[k], tgb[k] }, on && validA, on && validB, um);
+                            oa[k] = y.x, ob[k] = y.y;
+                        }
+                        redo = MODE != kModeExact && __any_sync (active, fmaxf (um.x, um.y) >= kFastLoud) != 0;
+                        if (redo)
+                            st = saved;
+                    }
+                    if (redo)
+                    {
+                        um = f2 { -1.0e30f, -1.0e30f };
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const bool on = n + k >= skip;
+                            const f2 y = st.template step<true> (c, f2 { xa[k], xb[k] }, f2 { tga[k], tgb[k] }, on && validA, on && validB, um);
+                            oa[k] = y.x, ob[k] = y.y;
+                        }
+                        loud_hint = __any_sync (active, fmaxf (um.x, um.y) >= kFastLoud) != 0;
                     }
                 }
-                // an instance that crossed omega3's log branch in this chunk (or parameters outside the fast path's range):
-                // that instance's four samples again, the general way, from the state it had before the chunk
-                const bool redoA = ! fast || (MODE != kModeExact && um.x >= kFastLoud), redoB = ! fast || (MODE != kModeExact && um.y >= kFastLoud);
+                // parameters outside the fast path's range: both instances' four samples the general way
+                const bool redoA = ! fast, redoB = ! fast;
                 if (redoA || redoB)
                 {
 #pragma unroll
